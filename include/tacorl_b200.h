@@ -1,0 +1,161 @@
+/*
+ * tacorl_b200 — C ABI of the B200-native (sm_100a) PlayLMP / TACO-RL training hot path.
+ *
+ * The reference (ErickRosete/tacorl) is pure Python over torch.nn; it has no FFI.  Its plug-in
+ * boundary for this path is the Hydra `_target_` class paths + nn.Module method signatures
+ * (SURVEY.md §8b).  The Python mirror of those classes lives in `tacorl_b200/networks`,
+ * `tacorl_b200/modules`; every one of their tensor contractions / reductions calls one of the
+ * entry points below through ctypes (tacorl_b200/_lib.py).  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers to fp32 unless stated; no allocation happens inside: scratch
+ *     comes from the caller's `ws` (size from the matching *_ws_bytes query);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return 0 on success, <0 on error with a message in tacorl_last_error() (thread-local);
+ *   - random numbers are inputs (the host draws them with the reference's torch calls, in the
+ *     reference's order — SURVEY.md Appendix C);
+ *   - `prec`: TACORL_PREC_F32 = full-fp32 SIMT (parity path), TACORL_PREC_BF16 = bf16 tcgen05
+ *     tensor-core operands with fp32 accumulation (performance path).
+ *   - file:line citations are into /root/reference/src/tacorl/.
+ */
+#ifndef TACORL_B200_H_
+#define TACORL_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TACORL_B200_ABI_VERSION 1
+
+#define TACORL_PREC_F32 0
+#define TACORL_PREC_BF16 1
+
+#define TACORL_ACT_NONE 0
+#define TACORL_ACT_RELU 1
+#define TACORL_ACT_SILU 2
+
+const char* tacorl_last_error(void);
+int tacorl_abi_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py reports the delta) */
+unsigned long long tacorl_launch_count(void);
+
+/* ---- dense layers -------------------------------------------------------------------------
+ * C[M,N] = act(alpha * op(A)[M,K] op(B)[K,N] + beta * C + bias[N]); row-major with leading dims.
+ * transA: A stored [K,M]; transB: B stored [N,K] (a torch Linear weight).  Cpre (optional) receives
+ * the pre-activation.  Replaces every nn.Linear / F.linear on the path: encoder.py:398-403,
+ * goal_encoder.py:18-24, actor.py:252-266, critic.py:92-97, action_decoder_logistic.py:289-293,
+ * plan_recognition_tanh_net.py:44-45 — and the autograd GEMMs behind them. */
+int tacorl_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, long long lda,
+                const float* B, long long ldb, float beta, float* C, long long ldc, const float* bias, int act,
+                float* Cpre, long long ldpre, void* ws, size_t ws_bytes, int prec, void* stream);
+/* out[n] (+)= sum_m X[m*ldx+n]  (bias gradients) */
+int tacorl_colsum(int M, int N, const float* X, long long ldx, float* out, int accumulate, void* stream);
+/* dZ = dY * act'(.)   relu: pass the post-activation, silu: pass the pre-activation */
+int tacorl_act_bwd(int act, long long n, const float* dY, const float* y_or_pre, float* dZ, void* stream);
+/* out = x * (*dev_scalar or 1) * c */
+int tacorl_scale(long long n, const float* x, const float* dev_scalar, float c, float* out, void* stream);
+/* out[r][c] (+)= x[r][c] * row_scalars[r] * k */
+int tacorl_rowscale(long long rows, int L, const float* x, const float* row_scalars, float k, float* out,
+                    int accumulate, void* stream);
+
+/* ---- LMP vision encoder: encoder.py:369-419 (LMPVisionEncoder), utils.py:39-76 (SpatialSoftArgmax)
+ * x: (N,3,H,W) NCHW.  params/grads: 11 pointers in state_dict order
+ *   model.0.{weight,bias}, model.2.{weight,bias}, model.4.{weight,bias}, model.6.temperature,
+ *   fc_layers.0.{weight,bias}, fc_layers.3.{weight,bias}          
+ * Saved for backward (caller-owned; pass NULL for y1,y2[,y3,feat,smax,ssum,h4] in inference):
+ *   y1 (N,H1,W1,32), y2 (N,H2,W2,64), y3 (N,H3,W3,64) post-ReLU NHWC; feat (N,128);
+ *   smax, ssum (N,64) softmax statistics; h4 (N,hidden).   emb: (N,latent). */
+size_t tacorl_lmp_encoder_ws_bytes(int N, int H, int W, int hidden, int latent, int backward);
+int tacorl_lmp_encoder_fwd(const float* x, int N, int H, int W, const float* const* params, int hidden,
+                           int latent, float* y1, float* y2, float* y3, float* feat, float* smax,
+                           float* ssum, float* h4, float* emb, void* ws, size_t ws_bytes, int prec,
+                           void* stream);
+int tacorl_lmp_encoder_bwd(const float* x, int N, int H, int W, const float* const* params, int hidden,
+                           int latent, const float* y1, const float* y2, const float* y3,
+                           const float* feat, const float* smax, const float* ssum, const float* h4,
+                           const float* d_emb, float* const* grads, int accumulate, void* ws,
+                           size_t ws_bytes, int prec, void* stream);
+
+/* ---- ReLU RNN layer, one direction, time-major (T*B rows): nn.RNN(nonlinearity="relu") at
+ * rnn_models.py:5-16 (decoder) and plan_recognition_tanh_net.py:23-31 / plan_recognition_net.py:27-35
+ * (BiRNN).  h0 may be NULL (zeros).  reverse: recurrence runs t = T-1 .. T-n_steps.
+ * bwd: `dout` (dL/dout) is overwritten with dL/dpre; dx rows outside the active range are zeroed
+ * unless dx_accumulate.  Any of dx/dw_ih/dw_hh/db_ih/db_hh/dh0/dhn may be NULL. */
+size_t tacorl_rnn_layer_ws_bytes(int T, int B, int I, int H);
+int tacorl_rnn_layer_fwd(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
+                         const float* w_hh, const float* b_ih, const float* b_hh, const float* h0,
+                         int reverse, int n_steps, float* out, long long ldo, void* ws, size_t ws_bytes,
+                         int prec, void* stream);
+int tacorl_rnn_layer_bwd(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
+                         const float* w_hh, const float* h0, int reverse, int n_steps, const float* out,
+                         long long ldo, float* dout, long long lddo, const float* dhn, float* dx,
+                         long long lddx, int dx_accumulate, float* dw_ih, float* dw_hh, float* db_ih,
+                         float* db_hh, int accumulate, float* dh0, void* ws, size_t ws_bytes, int prec,
+                         void* stream);
+
+/* ---- action decoder losses: action_decoder_logistic.py:184-235 (_logistic_loss), :114-133 (_loss),
+ * :238-266 (_sample).  logits row = [prob A*10 | mean A*10 | log_scale A*10 | gripper 2].
+ * dlm_nll writes the mean loss to loss_out[0], per-term losses to row_loss (rows*(A+1)) and, if
+ * dlogits != NULL, dLoss/dlogits.  dlm_sample: u1 (rows,A,10), u2 (rows,A) ~ U[0,1); pred (rows,A+1);
+ * hit/acc_out optional gripper accuracy (play_lmp_for_rl.py:165-176). */
+int tacorl_dlm_nll(int rows, int act_dims, const float* logits, long long ld, const float* actions,
+                   long long lda, int num_classes, float act_min, float act_max, float gripper_alpha,
+                   float* row_loss, float* loss_out, float* dlogits, long long ldd, void* stream);
+int tacorl_dlm_sample(int rows, int act_dims, const float* logits, long long ld, const float* u1,
+                      const float* u2, const float* actions, long long lda, float grip_lo, float grip_hi,
+                      float* pred, float* hit, float* acc_out, void* stream);
+
+/* ---- distribution heads.  raw: (rows, 2L) = [mean | log_std or var].
+ * gauss_head: actor.py:259-266 (clamp +-9, exp(clamp(-5,2)));
+ * softplus_head: plan_recognition_tanh_net.py:44-46 (softplus + min_std). */
+int tacorl_gauss_head_fwd(int rows, int L, const float* raw, float* mean, float* stdv, void* stream);
+int tacorl_gauss_head_bwd(int rows, int L, const float* raw, const float* stdv, const float* dmean,
+                          const float* dstd, float* draw, void* stream);
+int tacorl_softplus_head_fwd(int rows, int L, const float* raw, float min_std, float* mean, float* stdv,
+                             void* stream);
+int tacorl_softplus_head_bwd(int rows, int L, const float* raw, const float* dmean, const float* dstd,
+                             float* draw, void* stream);
+/* balanced KL of the underlying Normals, play_lmp_for_rl.py:259-285; grads are d kl / d(.) */
+int tacorl_kl_balanced(int B, int L, const float* mu_q, const float* sd_q, const float* mu_p,
+                       const float* sd_p, float kl_alpha, int balancing, float* kl_out, float* dmu_q,
+                       float* dsd_q, float* dmu_p, float* dsd_p, void* stream);
+/* TanhNormal, utils/distributions.py:61-153.  rsample: a = tanh(mu + std*eps) (mu/std broadcast with
+ * period `bcast` elements for sample_n); logprob: (rows) with optional gradient outputs. */
+int tacorl_tanh_rsample_fwd(long long n, long long bcast, const float* mu, const float* sd, const float* eps,
+                            float* a, float* z, int apply_tanh, void* stream);
+int tacorl_tanh_rsample_bwd(long long n, const float* a, const float* eps, const float* da, const float* dz,
+                            float* dmu, float* dsd, int apply_tanh, void* stream);
+int tacorl_tanh_logprob(int rows, int L, int bcast_rows, const float* mu, const float* sd, const float* z,
+                        int from_value, float* logp, float* gmu, float* gsd, float* gz, void* stream);
+
+/* ---- CQL losses, cql_offline_lightning.py:284-406, 439-468.
+ * q*_all: [data (B) | rand (n,B) | curr (n,B) | next (n,B)].  scalars[14]:
+ *  0 bellman_q1, 1 bellman_q2, 2 conservative_q1, 3 conservative_q2, 4 alpha_prime, 5 alpha_prime_loss,
+ *  6 q1_loss, 7 q2_loss, 8 q1_data, 9 q1_random, 10 q1_policy, 11 q2_data, 12 q2_random, 13 q2_policy */
+#define TACORL_CQL_NUM_SCALARS 14
+int tacorl_cql_critic_loss(int B, int n, const float* q1_all, const float* q2_all, const float* lp_curr,
+                           const float* lp_next, const float* tq1, const float* tq2, const float* reward,
+                           const float* done, const float* log_alpha_prime, float rand_density, float discount,
+                           float reward_scale, float gap, float conservative_weight, float temp,
+                           int with_lagrange, float* scalars, float* dq1_all, float* dq2_all,
+                           float* d_log_alpha_prime, void* stream);
+/* mode 0: alpha loss; 1: actor loss, BC epochs (a = log-prob of data action);
+ * 2: actor loss, Q epochs (a,b = Q1,Q2 at the policy action).  out[0]=loss, out[1]=alpha (modes 1,2) */
+int tacorl_cql_actor_loss(int mode, int B, const float* log_pi, const float* a, const float* b,
+                          const float* log_alpha, float target_entropy, float* out, float* d_log_alpha,
+                          float* d_log_pi, float* da, float* db, void* stream);
+
+/* ---- optimiser side: Adam (play_lmp_for_rl.py:362-368, cql_offline_lightning.py:553-574) fused with
+ * clip_grad_norm_ (:522-537) over flat buffers; Polyak (:229-232); sum of squares (ws >= 592 floats) */
+int tacorl_adam_step(long long n, float* p, const float* g, float* m, float* v, float lr, float beta1,
+                     float beta2, float eps, int step, float grad_scale, const float* sqnorm, float max_norm,
+                     void* stream);
+int tacorl_polyak_update(long long n, float* target, const float* source, float tau, void* stream);
+int tacorl_sqnorm(long long n, const float* x, float* out, float* ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TACORL_B200_H_ */

@@ -1,0 +1,37 @@
+// Generic C-ABI entry points: error reporting, GEMM / linear-layer pieces.
+#include "common.cuh"
+#include "internal.h"
+#include "../../include/tacorl_b200.h"
+
+using namespace tacorl;
+
+extern "C" {
+
+const char* tacorl_last_error(void) { return last_error(); }
+
+int tacorl_abi_version(void) { return TACORL_B200_ABI_VERSION; }
+
+unsigned long long tacorl_launch_count(void) { return launch_count(); }
+
+int tacorl_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, long long lda,
+                const float* B, long long ldb, float beta, float* C, long long ldc, const float* bias, int act,
+                float* Cpre, long long ldpre, void* ws, size_t ws_bytes, int prec, void* stream) {
+  TACORL_REQUIRE(prec == PREC_F32 || prec == PREC_BF16, "gemm: unknown precision %d", prec);
+  GemmArgs g;
+  g.transA = transA; g.transB = transB; g.M = M; g.N = N; g.K = K; g.alpha = alpha;
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.beta = beta; g.C = C; g.ldc = ldc; g.bias = bias;
+  g.act = act; g.Cpre = Cpre; g.ldpre = ldpre; g.split_k = 0;
+  return gemm_f32(g, (float*)ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int tacorl_colsum(int M, int N, const float* X, long long ldx, float* out, int accumulate, void* stream) {
+  TACORL_REQUIRE(X && out, "colsum: null pointer");
+  return colsum_f32(M, N, X, ldx, out, accumulate, (cudaStream_t)stream);
+}
+
+int tacorl_act_bwd(int act, long long n, const float* dY, const float* y_or_pre, float* dZ, void* stream) {
+  TACORL_REQUIRE(dY && y_or_pre && dZ, "act_bwd: null pointer");
+  return act_bwd_f32(act, n, dY, y_or_pre, dZ, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+// fp32 building blocks of the LMP vision encoder (parity path): im2col / col2im around the
+// fp32 GEMM, weight-layout permutes, and the fused ReLU-aware spatial soft-argmax fwd/bwd.
+// Activations are kept NHWC internally: (frame, oy, ox, channel), channel fastest.
+// Reference: networks/visual_encoders/encoder.py:369-419, utils.py:39-76.
+#include "common.cuh"
+#include "internal.h"
+
+namespace tacorl {
+
+// col[m][k], m = (n, oy, ox) over `nframes` frames; k = (ky, kx, c) (c fastest) when korder == 1,
+// k = (c, ky, kx) (the torch weight layout) when korder == 0.
+// Input element (n, c, iy, ix) lives at x[n*sn + c*sc + iy*sh + ix*sw] (NCHW or NHWC by strides).
+__global__ void im2col_kernel(const float* __restrict__ x, long long sn, long long sc, long long sh,
+                              long long sw, int C, int KH, int KW, int stride, int OH, int OW,
+                              int nframes, float* __restrict__ col, int korder) {
+  const int K = KH * KW * C;
+  const long long total = (long long)nframes * OH * OW * K;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % K);
+    const long long m = idx / K;
+    int c, kx, ky;
+    if (korder) { c = k % C; kx = (k / C) % KW; ky = k / (C * KW); }
+    else { kx = k % KW; ky = (k / KW) % KH; c = k / (KW * KH); }
+    const int ox = (int)(m % OW), oy = (int)((m / OW) % OH);
+    const long long n = m / ((long long)OW * OH);
+    col[idx] = __ldg(x + n * sn + c * sc + (long long)(oy * stride + ky) * sh + (long long)(ox * stride + kx) * sw);
+  }
+}
+
+int im2col_f32(const float* x, long long sn, long long sc, long long sh, long long sw, int C, int KH,
+               int KW, int stride, int OH, int OW, int nframes, float* col, cudaStream_t st, int korder) {
+  long long total = (long long)nframes * OH * OW * KH * KW * C;
+  if (total == 0) return 0;
+  int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
+  im2col_kernel<<<blocks, 256, 0, st>>>(x, sn, sc, sh, sw, C, KH, KW, stride, OH, OW, nframes, col, korder);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
+// dX (NHWC) = mask(Y>0) * sum over the kernel taps that touch (iy, ix) of dcol.
+// dcol[m][k] with the same (ky,kx,c) ordering as im2col.  Gather form => deterministic.
+__global__ void col2im_kernel(const float* __restrict__ dcol, int C, int H, int W, int KH, int KW,
+                              int stride, int OH, int OW, int nframes, const float* __restrict__ ymask,
+                              float* __restrict__ dx) {
+  const int K = KH * KW * C;
+  const long long total = (long long)nframes * H * W * C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int ix = (int)((idx / C) % W), iy = (int)((idx / ((long long)C * W)) % H);
+    const long long n = idx / ((long long)C * W * H);
+    float s = 0.f;
+    if (!ymask || ymask[idx] > 0.f) {
+      for (int ky = 0; ky < KH; ++ky) {
+        const int ty = iy - ky;
+        if (ty < 0 || ty % stride) continue;
+        const int oy = ty / stride;
+        if (oy >= OH) continue;
+        for (int kx = 0; kx < KW; ++kx) {
+          const int tx = ix - kx;
+          if (tx < 0 || tx % stride) continue;
+          const int ox = tx / stride;
+          if (ox >= OW) continue;
+          s += dcol[((n * OH + oy) * OW + ox) * K + (ky * KW + kx) * C + c];
+        }
+      }
+    }
+    dx[idx] = s;
+  }
+}
+
+int col2im_f32(const float* dcol, int C, int H, int W, int KH, int KW, int stride, int OH, int OW,
+               int nframes, const float* ymask, float* dx, cudaStream_t st) {
+  long long total = (long long)nframes * H * W * C;
+  if (total == 0) return 0;
+  int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
+  col2im_kernel<<<blocks, 256, 0, st>>>(dcol, C, H, W, KH, KW, stride, OH, OW, nframes, ymask, dx);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
+// (oc, c, ky, kx) <-> (oc, ky, kx, c).  dir 0: torch -> khwc; dir 1: khwc -> torch.
+__global__ void permute_w_kernel(const float* __restrict__ src, float* __restrict__ dst, int OC, int C,
+                                 int KH, int KW, int dir) {
+  const int total = OC * C * KH * KW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    // i indexes the torch layout
+    const int kx = i % KW, ky = (i / KW) % KH, c = (i / (KW * KH)) % C, oc = i / (KW * KH * C);
+    const int j = ((oc * KH + ky) * KW + kx) * C + c;
+    if (dir == 0) dst[j] = src[i]; else dst[i] = src[j];
+  }
+}
+
+int permute_conv_weight_f32(const float* src, float* dst, int OC, int C, int KH, int KW, int dir,
+                            cudaStream_t st) {
+  int total = OC * C * KH * KW;
+  permute_w_kernel<<<cdiv(total, 256), 256, 0, st>>>(src, dst, OC, C, KH, KW, dir);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Spatial soft-argmax over an NHWC feature map y (already ReLU'd): per (frame, channel)
+//   p = softmax_i(y_i / tau),  f[2c] = sum p_i * col_i,  f[2c+1] = sum p_i * row_i.
+// One CTA per frame, blockDim = (C, G): thread (c, g) scans positions g, g+G, ... with an online
+// softmax, then the G partials are merged through shared memory.  Saves (max, sumexp) per (n,c).
+template <int G>
+__global__ void softargmax_fwd_kernel(const float* __restrict__ y, int P, int OW, int C,
+                                      const float* __restrict__ temperature, float* __restrict__ feat,
+                                      float* __restrict__ smax, float* __restrict__ ssum) {
+  extern __shared__ float sm[];  // 4 * G * C
+  const int c = threadIdx.x, g = threadIdx.y;
+  const long long n = blockIdx.x;
+  const float inv_t = 1.f / __ldg(temperature);
+  const float* yp = y + n * (long long)P * C;
+  float m = -INFINITY, s = 0.f, sx = 0.f, sy = 0.f;
+  for (int p = g; p < P; p += G) {
+    const float v = yp[(long long)p * C + c] * inv_t;
+    const float col = (float)(p % OW), row = (float)(p / OW);
+    if (v > m) {
+      const float sc = expf(m - v);
+      s = s * sc + 1.f; sx = sx * sc + col; sy = sy * sc + row; m = v;
+    } else {
+      const float e = expf(v - m);
+      s += e; sx += e * col; sy += e * row;
+    }
+  }
+  float* q = sm + (g * C + c) * 4;
+  q[0] = m; q[1] = s; q[2] = sx; q[3] = sy;
+  __syncthreads();
+  if (g == 0) {
+    float M = -INFINITY;
+    for (int i = 0; i < G; ++i) M = fmaxf(M, sm[(i * C + c) * 4]);
+    float S = 0.f, SX = 0.f, SY = 0.f;
+    for (int i = 0; i < G; ++i) {
+      const float* r = sm + (i * C + c) * 4;
+      if (r[1] > 0.f) {
+        const float sc = expf(r[0] - M);
+        S += r[1] * sc; SX += r[2] * sc; SY += r[3] * sc;
+      }
+    }
+    feat[n * 2 * C + 2 * c] = SX / S;
+    feat[n * 2 * C + 2 * c + 1] = SY / S;
+    smax[n * C + c] = M;
+    ssum[n * C + c] = S;
+  }
+}
+
+int softargmax_fwd_f32(const float* y, int N, int OH, int OW, int C, const float* temperature,
+                       float* feat, float* smax, float* ssum, cudaStream_t st) {
+  if (N == 0) return 0;
+  constexpr int G = 4;
+  TACORL_REQUIRE(C * G <= 1024, "softargmax: too many channels");
+  softargmax_fwd_kernel<G><<<N, dim3(C, G), 4 * G * C * sizeof(float), st>>>(y, OH * OW, OW, C, temperature,
+                                                                            feat, smax, ssum);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
+// Backward: dz_i = p_i * (gx*col_i + gy*row_i - (gx*fx + gy*fy));  dy_i = dz_i / tau * [y_i > 0]
+// dtau = sum_i dz_i * (-y_i / tau^2), reduced per frame into dtau_part[n] (summed by a colsum).
+template <int G>
+__global__ void softargmax_bwd_kernel(const float* __restrict__ y, int P, int OW, int C,
+                                      const float* __restrict__ temperature,
+                                      const float* __restrict__ feat, const float* __restrict__ smax,
+                                      const float* __restrict__ ssum, const float* __restrict__ dfeat,
+                                      float* __restrict__ dy, float* __restrict__ dtau_part) {
+  __shared__ float red[32];
+  const int c = threadIdx.x, g = threadIdx.y;
+  const long long n = blockIdx.x;
+  const float tau = __ldg(temperature), inv_t = 1.f / tau;
+  const float* yp = y + n * (long long)P * C;
+  float* dyp = dy + n * (long long)P * C;
+  const float gx = dfeat[n * 2 * C + 2 * c], gy = dfeat[n * 2 * C + 2 * c + 1];
+  const float fx = feat[n * 2 * C + 2 * c], fy = feat[n * 2 * C + 2 * c + 1];
+  const float M = smax[n * C + c], invS = 1.f / ssum[n * C + c];
+  const float dotg = gx * fx + gy * fy;
+  float dt = 0.f;
+  for (int p = g; p < P; p += G) {
+    const float yv = yp[(long long)p * C + c];
+    const float pr = expf(yv * inv_t - M) * invS;
+    const float dz = pr * (gx * (float)(p % OW) + gy * (float)(p / OW) - dotg);
+    dt += dz * yv;
+    dyp[(long long)p * C + c] = yv > 0.f ? dz * inv_t : 0.f;
+  }
+  dt = warp_sum(dt);
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nwarps = (blockDim.x * blockDim.y + 31) / 32;
+  if ((tid & 31) == 0) red[tid >> 5] = dt;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int i = 0; i < nwarps; ++i) t += red[i];
+    dtau_part[n] = -t * inv_t * inv_t;
+  }
+}
+
+int softargmax_bwd_f32(const float* y, int N, int OH, int OW, int C, const float* temperature,
+                       const float* feat, const float* smax, const float* ssum, const float* dfeat,
+                       float* dy, float* dtau_part, cudaStream_t st) {
+  if (N == 0) return 0;
+  constexpr int G = 4;
+  TACORL_REQUIRE(C * G <= 1024 && (C * G) % 32 == 0, "softargmax bwd: unsupported channel count");
+  softargmax_bwd_kernel<G><<<N, dim3(C, G), 0, st>>>(y, OH * OW, OW, C, temperature, feat, smax, ssum,
+                                                   dfeat, dy, dtau_part);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tacorl

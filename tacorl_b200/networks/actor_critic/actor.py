@@ -1,0 +1,88 @@
+"""Mirror of Actor / MLPPolicy, /root/reference/src/tacorl/networks/actor_critic/actor.py:18-156, 217-270
+(config/networks/actor_critic/actor/default.yaml: MLPPolicy, continuous actions)."""
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ...utils.config import instantiate, to_container
+from ...utils.distributions import TanhNormal
+from ..layers import Linear
+
+LOG_SIG_MAX = 2
+LOG_SIG_MIN = -5
+MEAN_MIN = -9.0
+MEAN_MAX = 9.0
+
+
+class MLPPolicy(nn.Module):
+    def __init__(self, input_dim: int, action_dim: int, num_layers: int = 2, hidden_dim: int = 256,
+                 init_w: float = 1e-3, discrete_gripper: bool = False):
+        super().__init__()
+        if discrete_gripper:
+            raise NotImplementedError("discrete-gripper policies belong to the flat-CQL baseline (out of scope)")
+        self.discrete_gripper = discrete_gripper
+        self.hidden_dim = hidden_dim
+        self.num_layers = num_layers
+        self.fc_layers = nn.ModuleList([Linear(input_dim, hidden_dim)] +
+                                       [Linear(hidden_dim, hidden_dim) for _ in range(num_layers - 1)])
+        self.fc_mean = Linear(hidden_dim, action_dim)
+        self.fc_log_std = Linear(hidden_dim, action_dim)
+        for lin in (self.fc_log_std, self.fc_mean):
+            lin.weight.data.uniform_(-init_w, init_w)
+            lin.bias.data.uniform_(-init_w, init_w)
+
+    def get_last_hidden_state(self, policy_input):
+        x = policy_input
+        for fc in self.fc_layers:
+            x = fc(x, act="silu")
+        return x
+
+    def forward(self, policy_input):
+        x = self.get_last_hidden_state(policy_input)
+        w = torch.cat([self.fc_mean.weight, self.fc_log_std.weight], dim=0)
+        b = torch.cat([self.fc_mean.bias, self.fc_log_std.bias], dim=0)
+        lead = x.shape[:-1]
+        mean, std = ops.gauss_head(ops.linear(x.reshape(-1, x.shape[-1]), w, b))
+        return mean.view(*lead, -1), std.view(*lead, -1)
+
+
+class Actor(nn.Module):
+    def __init__(self, state_dim: int, goal_dim: int = 0, action_dim: int = 16, policy: dict = {},
+                 discrete_gripper: bool = False):
+        super().__init__()
+        self.discrete_gripper = discrete_gripper
+        self.action_dim = action_dim
+        self.state_dim = state_dim
+        self.goal_dim = goal_dim
+        policy_cfg = to_container(policy)
+        policy_cfg.update({"input_dim": state_dim + goal_dim, "action_dim": action_dim,
+                           "discrete_gripper": discrete_gripper})
+        self.policy = instantiate(policy_cfg)
+
+    def forward(self, state_emb: torch.Tensor, goal_emb: Optional[torch.Tensor] = None):
+        x = torch.cat([state_emb, goal_emb], dim=-1) if goal_emb is not None else state_emb
+        return self.policy(x)
+
+    def get_dist(self, state_emb, goal_emb=None):
+        mean, std = self.forward(state_emb, goal_emb)
+        return TanhNormal(mean, std)
+
+    def get_actions(self, observation, deterministic: bool = False, reparameterize: bool = False):
+        mean, std = self.forward(observation)
+        if deterministic:
+            actions = torch.tanh(mean)
+            return actions, torch.zeros_like(actions)
+        dist = TanhNormal(mean, std)
+        return dist.rsample_and_logprob() if reparameterize else dist.sample_and_logprob()
+
+    def sample_n_with_log_prob(self, observation, n_actions: int):
+        mean, std = self.forward(observation)
+        dist = TanhNormal(mean, std)
+        actions, z = dist.sample_n(n_actions, return_pre_tanh_value=True)
+        return actions, dist.log_prob(actions, pre_tanh_value=z)
+
+    def log_prob(self, observations, actions):
+        mean, std = self.forward(observations)
+        return TanhNormal(mean, std).log_prob(value=actions)

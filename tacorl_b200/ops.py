@@ -1,0 +1,534 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels (include/tacorl_b200.h).
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every
+contraction / reduction / loss below runs in libtacorl_b200.so.  No CPU path exists.
+"""
+import ctypes
+import math
+
+import torch
+from torch.autograd import Function
+
+from . import _lib as L
+
+_STATE = {"prec": L.PREC_F32}
+_GEMM_WS = 96 << 20
+
+
+def set_precision(name):
+    """'fp32' = full-fp32 SIMT parity path; 'bf16' = bf16 tcgen05 operands, fp32 accumulate."""
+    _STATE["prec"] = {"fp32": L.PREC_F32, "bf16": L.PREC_BF16}[name]
+
+
+def get_precision():
+    return "bf16" if _STATE["prec"] == L.PREC_BF16 else "fp32"
+
+
+def _off(t, elems):
+    return ctypes.c_void_p(t.data_ptr() + 4 * elems)
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ld(t):
+    assert t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1), "row-major 2-D view expected"
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+def gemm(A, B, C, transA=False, transB=False, alpha=1.0, beta=0.0, bias=None, act=L.ACT_NONE, Cpre=None):
+    """C = act(alpha * op(A) op(B) + beta*C + bias); A, B, C are row-major 2-D (possibly strided rows)."""
+    M, N = C.shape
+    K = A.shape[0] if transA else A.shape[1]
+    assert (A.shape[1] if transA else A.shape[0]) == M, (A.shape, C.shape, transA)
+    assert (B.shape[0] if transB else B.shape[1]) == N and (B.shape[1] if transB else B.shape[0]) == K
+    ws = L.workspace(_GEMM_WS, C.device)
+    L.call("tacorl_gemm", int(transA), int(transB), M, N, K, float(alpha), L.ptr(A), _ld(A), L.ptr(B), _ld(B),
+           float(beta), L.ptr(C), _ld(C), L.ptr(bias), int(act), L.ptr(Cpre), _ld(Cpre) if Cpre is not None else 0,
+           ctypes.c_void_p(ws.data_ptr()), ws.numel(),
+           _STATE["prec"], L.stream())
+    return C
+
+
+def colsum(X, out=None, accumulate=False):
+    M, N = X.shape
+    if out is None:
+        out = torch.empty(N, device=X.device, dtype=torch.float32)
+    L.call("tacorl_colsum", M, N, L.ptr(X), _ld(X), L.ptr(out), int(accumulate), L.stream())
+    return out
+
+
+def scale(x, dev_scalar=None, c=1.0, out=None):
+    x = _c(x)
+    if out is None:
+        out = torch.empty_like(x)
+    L.call("tacorl_scale", x.numel(), L.ptr(x), L.ptr(dev_scalar), float(c), L.ptr(out), L.stream())
+    return out
+
+
+# --------------------------------------------------------------------------------------- linear
+class LinearFn(Function):
+    @staticmethod
+    def forward(ctx, x, W, b, act):
+        K = W.shape[1]
+        x2 = _c(x.reshape(-1, K))
+        Wc = _c(W)
+        out = torch.empty(x2.shape[0], W.shape[0], device=x.device, dtype=torch.float32)
+        pre = torch.empty_like(out) if act == L.ACT_SILU else None
+        gemm(x2, Wc, out, transB=True, bias=b, act=act, Cpre=pre)
+        ctx.act = act
+        ctx.has_bias = b is not None
+        ctx.xshape = x.shape
+        ctx.save_for_backward(x2, Wc, pre if act == L.ACT_SILU else (out if act == L.ACT_RELU else None))
+        return out.view(*x.shape[:-1], W.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, W, saved = ctx.saved_tensors
+        N = W.shape[0]
+        dz = _c(dy.reshape(-1, N))
+        if ctx.act != L.ACT_NONE:
+            dz2 = torch.empty_like(dz)
+            L.call("tacorl_act_bwd", ctx.act, dz.numel(), L.ptr(dz), L.ptr(saved), L.ptr(dz2), L.stream())
+            dz = dz2
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x2)
+            gemm(dz, W, dx)
+            dx = dx.view(ctx.xshape)
+        if ctx.needs_input_grad[1]:
+            dW = torch.empty_like(W)
+            gemm(dz, x2, dW, transA=True)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dz)
+        return dx, dW, db, None
+
+
+def linear(x, W, b=None, act=None):
+    return LinearFn.apply(x, W, b, L.ACTS[act] if not isinstance(act, int) else act)
+
+
+# --------------------------------------------------------------------------------------- encoder
+class LMPEncoderFn(Function):
+    """LMPVisionEncoder forward/backward as one op (tacorl_lmp_encoder_{fwd,bwd})."""
+
+    @staticmethod
+    def forward(ctx, x, save, *params):
+        N, C, H, W = x.shape
+        assert C == 3, "LMPVisionEncoder kernels are built for 3 input channels"
+        x = _c(x)
+        params = [_c(p) for p in params]
+        hidden, latent = params[7].shape[0], params[9].shape[0]
+        dev = x.device
+        H1, W1 = (H - 8) // 4 + 1, (W - 8) // 4 + 1
+        H2, W2 = (H1 - 4) // 2 + 1, (W1 - 4) // 2 + 1
+        H3, W3 = H2 - 2, W2 - 2
+        emb = torch.empty(N, latent, device=dev, dtype=torch.float32)
+        if save:
+            y1 = torch.empty(N, H1, W1, 32, device=dev)
+            y2 = torch.empty(N, H2, W2, 64, device=dev)
+            y3 = torch.empty(N, H3, W3, 64, device=dev)
+            feat = torch.empty(N, 128, device=dev)
+            smax = torch.empty(N, 64, device=dev)
+            ssum = torch.empty(N, 64, device=dev)
+            h4 = torch.empty(N, hidden, device=dev)
+        else:
+            y1 = y2 = y3 = feat = smax = ssum = h4 = None
+        nbytes = L.query("tacorl_lmp_encoder_ws_bytes", N, H, W, hidden, latent, 0)
+        ws = L.workspace(nbytes, dev)
+        L.call("tacorl_lmp_encoder_fwd", L.ptr(x), N, H, W, L.ptr_array(params), hidden, latent, L.ptr(y1),
+               L.ptr(y2), L.ptr(y3), L.ptr(feat), L.ptr(smax), L.ptr(ssum), L.ptr(h4), L.ptr(emb),
+               ctypes.c_void_p(ws.data_ptr()), ws.numel(), _STATE["prec"], L.stream())
+        if save:
+            ctx.save_for_backward(x, y1, y2, y3, feat, smax, ssum, h4, *params)
+        ctx.dims = (N, H, W, hidden, latent)
+        return emb
+
+    @staticmethod
+    def backward(ctx, d_emb):
+        x, y1, y2, y3, feat, smax, ssum, h4, *params = ctx.saved_tensors
+        N, H, W, hidden, latent = ctx.dims
+        grads = [torch.empty_like(p) for p in params]
+        nbytes = L.query("tacorl_lmp_encoder_ws_bytes", N, H, W, hidden, latent, 1)
+        ws = L.workspace(nbytes, x.device)
+        d_emb = _c(d_emb)
+        L.call("tacorl_lmp_encoder_bwd", L.ptr(x), N, H, W, L.ptr_array(params), hidden, latent, L.ptr(y1),
+               L.ptr(y2), L.ptr(y3), L.ptr(feat), L.ptr(smax), L.ptr(ssum), L.ptr(h4), L.ptr(d_emb),
+               L.ptr_array(grads), 0, ctypes.c_void_p(ws.data_ptr()), ws.numel(), _STATE["prec"], L.stream())
+        return (None, None, *grads)
+
+
+def lmp_encoder(x, params):
+    """params: the 11 tensors in state_dict order.  Images never receive a gradient."""
+    save = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    return LMPEncoderFn.apply(x, save, *params)
+
+
+# --------------------------------------------------------------------------------------- RNN
+class ReluRNNFn(Function):
+    """Multi-layer (bi)directional ReLU RNN on time-major input (T,B,I).
+    weights: per layer, per direction: w_ih, w_hh, b_ih, b_hh (torch nn.RNN order).
+    last_only: return only out[T-1] (B, D*H); the top layer's reverse direction then runs one step."""
+
+    @staticmethod
+    def forward(ctx, x, h0, num_layers, bidir, last_only, *weights):
+        T, B, I = x.shape
+        D = 2 if bidir else 1
+        H = weights[1].shape[0]
+        x = _c(x)
+        weights = [_c(w) for w in weights]
+        dev = x.device
+        outs = []
+        inp = x
+        hn = [] if not last_only else None
+        for l in range(num_layers):
+            Il = inp.shape[2]
+            out = torch.empty(T, B, D * H, device=dev, dtype=torch.float32)
+            for d in range(D):
+                w_ih, w_hh, b_ih, b_hh = weights[(l * D + d) * 4:(l * D + d) * 4 + 4]
+                n_steps = 1 if (last_only and l == num_layers - 1 and d == 1) else T
+                h0_ld = None if h0 is None else _c(h0[l * D + d])
+                ws = L.workspace(L.query("tacorl_rnn_layer_ws_bytes", T, B, Il, H), dev)
+                L.call("tacorl_rnn_layer_fwd", T, B, Il, H, L.ptr(inp), Il, L.ptr(w_ih), L.ptr(w_hh), L.ptr(b_ih),
+                       L.ptr(b_hh), L.ptr(h0_ld), d, n_steps, _off(out, d * H), D * H,
+                       ctypes.c_void_p(ws.data_ptr()), ws.numel(), _STATE["prec"], L.stream())
+                if hn is not None:
+                    hn.append(out[0 if d == 1 else T - 1, :, d * H:(d + 1) * H])
+            outs.append(out)
+            inp = out
+        ctx.cfg = (T, B, I, H, D, num_layers, last_only)
+        ctx.has_h0 = h0 is not None
+        ctx.save_for_backward(x, h0, *outs, *weights)
+        if last_only:
+            return inp[T - 1], None
+        return inp, torch.stack(hn, dim=0)
+
+    @staticmethod
+    def backward(ctx, d_out, d_hn):
+        T, B, I, H, D, num_layers, last_only = ctx.cfg
+        saved = ctx.saved_tensors
+        x, h0 = saved[0], saved[1]
+        outs = saved[2:2 + num_layers]
+        weights = saved[2 + num_layers:]
+        dev = x.device
+        if last_only:
+            dbuf = torch.zeros(T, B, D * H, device=dev, dtype=torch.float32)
+            dbuf[T - 1].copy_(d_out)
+        else:
+            dbuf = d_out.contiguous().clone() if d_out is not None else torch.zeros(T, B, D * H, device=dev)
+        wgrads = [None] * len(weights)
+        dh0 = torch.empty_like(h0) if (ctx.has_h0 and ctx.needs_input_grad[1]) else None
+        for l in range(num_layers - 1, -1, -1):
+            inp = x if l == 0 else outs[l - 1]
+            Il = inp.shape[2]
+            need_dx = l > 0 or ctx.needs_input_grad[0]
+            dx = torch.empty(T, B, Il, device=dev, dtype=torch.float32) if need_dx else None
+            for d in range(D):
+                k = (l * D + d) * 4
+                w_ih, w_hh = weights[k], weights[k + 1]
+                g = [torch.empty_like(weights[k + j]) for j in range(4)]
+                n_steps = 1 if (last_only and l == num_layers - 1 and d == 1) else T
+                h0_ld = None if h0 is None else _c(h0[l * D + d])
+                dhn_ld = None if d_hn is None else _c(d_hn[l * D + d])
+                dh0_ld = None if dh0 is None else dh0[l * D + d]
+                ws = L.workspace(L.query("tacorl_rnn_layer_ws_bytes", T, B, Il, H), dev)
+                L.call("tacorl_rnn_layer_bwd", T, B, Il, H, L.ptr(inp), Il, L.ptr(w_ih), L.ptr(w_hh), L.ptr(h0_ld),
+                       d, n_steps, _off(outs[l], d * H), D * H, _off(dbuf, d * H), D * H, L.ptr(dhn_ld),
+                       L.ptr(dx), Il, int(d == 1), L.ptr(g[0]), L.ptr(g[1]), L.ptr(g[2]), L.ptr(g[3]), 0,
+                       L.ptr(dh0_ld), ctypes.c_void_p(ws.data_ptr()), ws.numel(), _STATE["prec"], L.stream())
+                wgrads[k:k + 4] = g
+            dbuf = dx
+        return (dbuf if ctx.needs_input_grad[0] else None, dh0, None, None, None, *wgrads)
+
+
+def relu_rnn(x_tm, weights, num_layers, bidirectional, last_only=False, h0=None):
+    return ReluRNNFn.apply(x_tm, h0, num_layers, bidirectional, last_only, *weights)
+
+
+# --------------------------------------------------------------------------------------- losses
+class DlmLossFn(Function):
+    """Discretised logistic mixture NLL + gripper CE (mean over rows)."""
+
+    @staticmethod
+    def forward(ctx, logits, actions, num_classes, act_min, act_max, gripper_alpha):
+        logits, actions = _c(logits), _c(actions)
+        rows, A = logits.shape[0], actions.shape[1] - 1
+        assert logits.shape[1] == 3 * A * 10 + 2
+        dev = logits.device
+        row_loss = torch.empty(rows * (A + 1), device=dev)
+        loss = torch.empty(1, device=dev)
+        need = ctx.needs_input_grad[0]
+        dlog = torch.empty_like(logits) if need else None
+        L.call("tacorl_dlm_nll", rows, A, L.ptr(logits), logits.shape[1], L.ptr(actions), actions.shape[1],
+               int(num_classes), float(act_min), float(act_max), float(gripper_alpha), L.ptr(row_loss), L.ptr(loss),
+               L.ptr(dlog), logits.shape[1], L.stream())
+        if need:
+            ctx.save_for_backward(dlog)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlog,) = ctx.saved_tensors
+        return scale(dlog, _c(g.reshape(1))), None, None, None, None, None
+
+
+def dlm_loss(logits, actions, num_classes=10, act_min=-1.0, act_max=1.0, gripper_alpha=1.0):
+    return DlmLossFn.apply(logits, actions, num_classes, act_min, act_max, gripper_alpha)
+
+
+def dlm_sample(logits, u1, u2, actions=None, grip_lo=-1.0, grip_hi=1.0):
+    """Returns (pred (rows, A+1), gripper accuracy scalar or None).  No gradient."""
+    logits = _c(logits.detach())
+    rows = logits.shape[0]
+    A = (logits.shape[1] - 2) // 30
+    dev = logits.device
+    pred = torch.empty(rows, A + 1, device=dev)
+    hit = torch.empty(rows, device=dev) if actions is not None else None
+    acc = torch.empty(1, device=dev) if actions is not None else None
+    actions_c = _c(actions) if actions is not None else None
+    L.call("tacorl_dlm_sample", rows, A, L.ptr(logits), logits.shape[1], L.ptr(_c(u1)), L.ptr(_c(u2)),
+           L.ptr(actions_c), actions_c.shape[1] if actions is not None else 0, float(grip_lo), float(grip_hi),
+           L.ptr(pred), L.ptr(hit), L.ptr(acc), L.stream())
+    return pred, (acc.view(()) if acc is not None else None)
+
+
+class GaussHeadFn(Function):
+    """raw (rows, 2L) -> mean = clamp(+-9), std = exp(clamp(-5, 2))  (MLPPolicy.forward)."""
+
+    @staticmethod
+    def forward(ctx, raw):
+        raw = _c(raw)
+        rows, L2 = raw.shape
+        mean = torch.empty(rows, L2 // 2, device=raw.device)
+        std = torch.empty_like(mean)
+        L.call("tacorl_gauss_head_fwd", rows, L2 // 2, L.ptr(raw), L.ptr(mean), L.ptr(std), L.stream())
+        ctx.save_for_backward(raw, std)
+        return mean, std
+
+    @staticmethod
+    def backward(ctx, dmean, dstd):
+        raw, std = ctx.saved_tensors
+        draw = torch.empty_like(raw)
+        L.call("tacorl_gauss_head_bwd", raw.shape[0], raw.shape[1] // 2, L.ptr(raw), L.ptr(std),
+               L.ptr(_c(dmean) if dmean is not None else None), L.ptr(_c(dstd) if dstd is not None else None),
+               L.ptr(draw), L.stream())
+        return draw
+
+
+class SoftplusHeadFn(Function):
+    """raw (rows, 2L) -> mean, std = softplus(var) + min_std  (plan recognition heads)."""
+
+    @staticmethod
+    def forward(ctx, raw, min_std):
+        raw = _c(raw)
+        rows, L2 = raw.shape
+        mean = torch.empty(rows, L2 // 2, device=raw.device)
+        std = torch.empty_like(mean)
+        L.call("tacorl_softplus_head_fwd", rows, L2 // 2, L.ptr(raw), float(min_std), L.ptr(mean), L.ptr(std),
+               L.stream())
+        ctx.save_for_backward(raw)
+        return mean, std
+
+    @staticmethod
+    def backward(ctx, dmean, dstd):
+        (raw,) = ctx.saved_tensors
+        draw = torch.empty_like(raw)
+        L.call("tacorl_softplus_head_bwd", raw.shape[0], raw.shape[1] // 2, L.ptr(raw),
+               L.ptr(_c(dmean) if dmean is not None else None), L.ptr(_c(dstd) if dstd is not None else None),
+               L.ptr(draw), L.stream())
+        return draw, None
+
+
+def gauss_head(raw):
+    return GaussHeadFn.apply(raw)
+
+
+def softplus_head(raw, min_std):
+    return SoftplusHeadFn.apply(raw, min_std)
+
+
+class KLBalancedFn(Function):
+    @staticmethod
+    def forward(ctx, mu_q, sd_q, mu_p, sd_p, kl_alpha, balancing):
+        mu_q, sd_q, mu_p, sd_p = _c(mu_q), _c(sd_q), _c(mu_p), _c(sd_p)
+        B, Ld = mu_q.shape
+        kl = torch.empty(1, device=mu_q.device)
+        gs = [torch.empty_like(mu_q) for _ in range(4)]
+        L.call("tacorl_kl_balanced", B, Ld, L.ptr(mu_q), L.ptr(sd_q), L.ptr(mu_p), L.ptr(sd_p), float(kl_alpha),
+               int(balancing), L.ptr(kl), L.ptr(gs[0]), L.ptr(gs[1]), L.ptr(gs[2]), L.ptr(gs[3]), L.stream())
+        ctx.save_for_backward(*gs)
+        return kl.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _c(g.reshape(1))
+        return (*[scale(t, g) for t in ctx.saved_tensors], None, None)
+
+
+def kl_balanced(mu_q, sd_q, mu_p, sd_p, kl_alpha=0.8, balancing=True):
+    return KLBalancedFn.apply(mu_q, sd_q, mu_p, sd_p, kl_alpha, balancing)
+
+
+class TanhRsampleFn(Function):
+    """a = tanh(mu + std*eps) (or the raw z when apply_tanh=False); also returns z."""
+
+    @staticmethod
+    def forward(ctx, mu, sd, eps, apply_tanh):
+        mu, sd, eps = _c(mu), _c(sd), _c(eps)
+        a = torch.empty_like(eps)
+        z = torch.empty_like(eps)
+        L.call("tacorl_tanh_rsample_fwd", eps.numel(), mu.numel(), L.ptr(mu), L.ptr(sd), L.ptr(eps), L.ptr(a),
+               L.ptr(z), int(apply_tanh), L.stream())
+        ctx.apply_tanh = apply_tanh
+        ctx.same = eps.numel() == mu.numel()
+        ctx.save_for_backward(a, eps)
+        return a, z
+
+    @staticmethod
+    def backward(ctx, da, dz):
+        a, eps = ctx.saved_tensors
+        assert ctx.same, "gradient through sample_n broadcasting is not used by the reference"
+        dmu = torch.empty_like(a)
+        dsd = torch.empty_like(a)
+        L.call("tacorl_tanh_rsample_bwd", a.numel(), L.ptr(a), L.ptr(eps), L.ptr(_c(da) if da is not None else None),
+               L.ptr(_c(dz) if dz is not None else None), L.ptr(dmu), L.ptr(dsd), int(ctx.apply_tanh), L.stream())
+        return dmu, dsd, None, None
+
+
+def tanh_rsample(mu, sd, eps, apply_tanh=True):
+    return TanhRsampleFn.apply(mu, sd, eps, apply_tanh)
+
+
+class TanhLogProbFn(Function):
+    """TanhNormal.log_prob -> (rows, 1).  z is the pre-tanh value, or the tanh'ed value when from_value."""
+
+    @staticmethod
+    def forward(ctx, mu, sd, z, from_value):
+        mu, sd, z = _c(mu), _c(sd), _c(z)
+        Ld = z.shape[-1]
+        rows = z.numel() // Ld
+        brows = mu.numel() // Ld
+        logp = torch.empty(rows, device=z.device)
+        need = any(ctx.needs_input_grad[:3])
+        g = [torch.empty_like(z) for _ in range(3)] if need else [None] * 3
+        L.call("tacorl_tanh_logprob", rows, Ld, brows, L.ptr(mu), L.ptr(sd), L.ptr(z), int(from_value), L.ptr(logp),
+               L.ptr(g[0]), L.ptr(g[1]), L.ptr(g[2]), L.stream())
+        if need:
+            assert rows == brows, "gradient through a broadcast log_prob is not used by the reference"
+            ctx.save_for_backward(*g)
+        ctx.from_value = from_value
+        ctx.Ld = Ld
+        return logp.view(*z.shape[:-1], 1)
+
+    @staticmethod
+    def backward(ctx, dlogp):
+        gmu, gsd, gz = ctx.saved_tensors
+        d = _c(dlogp.reshape(-1))
+        rows = d.numel()
+
+        def rs(t):
+            o = torch.empty_like(t)
+            L.call("tacorl_rowscale", rows, ctx.Ld, L.ptr(t), L.ptr(d), 1.0, L.ptr(o), 0, L.stream())
+            return o
+
+        return (rs(gmu) if ctx.needs_input_grad[0] else None, rs(gsd) if ctx.needs_input_grad[1] else None,
+                rs(gz) if (ctx.needs_input_grad[2] and not ctx.from_value) else None, None)
+
+
+def tanh_logprob(mu, sd, z, from_value=False):
+    return TanhLogProbFn.apply(mu, sd, z, from_value)
+
+
+# --------------------------------------------------------------------------------------- CQL
+CQL_SCALARS = ("bellman_q1_loss", "bellman_q2_loss", "conservative_q1_loss", "conservative_q2_loss",
+               "alpha_prime", "alpha_prime_loss", "q1_loss", "q2_loss", "q1_data", "q1_random", "q1_policy",
+               "q2_data", "q2_random", "q2_policy")
+
+
+class CqlCriticLossFn(Function):
+    """Returns (q1_loss, q2_loss, scalars[14], d_log_alpha_prime).  Gradients flow to q1_all / q2_all only
+    (log_alpha_prime's own gradient — of alpha_prime_loss — is returned as a value, because the reference
+    steps alpha' from that loss alone and discards what the q-losses deposit)."""
+
+    @staticmethod
+    def forward(ctx, q1_all, q2_all, lp_curr, lp_next, tq1, tq2, reward, done, log_alpha_prime, n, rand_density,
+                discount, reward_scale, gap, cw, temp, with_lagrange):
+        q1_all, q2_all = _c(q1_all.reshape(-1)), _c(q2_all.reshape(-1))
+        B = tq1.numel()
+        dev = q1_all.device
+        scal = torch.empty(14, device=dev)
+        dq1, dq2 = torch.empty_like(q1_all), torch.empty_like(q2_all)
+        dlap = torch.empty(1, device=dev)
+        L.call("tacorl_cql_critic_loss", B, n, L.ptr(q1_all), L.ptr(q2_all), L.ptr(_c(lp_curr.reshape(-1))),
+               L.ptr(_c(lp_next.reshape(-1))), L.ptr(_c(tq1.reshape(-1))), L.ptr(_c(tq2.reshape(-1))),
+               L.ptr(_c(reward.reshape(-1))), L.ptr(_c(done.reshape(-1))),
+               L.ptr(log_alpha_prime) if with_lagrange else None, float(rand_density), float(discount),
+               float(reward_scale), float(gap), float(cw), float(temp), int(with_lagrange), L.ptr(scal),
+               L.ptr(dq1), L.ptr(dq2), L.ptr(dlap), L.stream())
+        ctx.save_for_backward(dq1, dq2)
+        ctx.mark_non_differentiable(scal, dlap)
+        return scal[6].clone(), scal[7].clone(), scal, dlap
+
+    @staticmethod
+    def backward(ctx, g1, g2, _gs, _gl):
+        dq1, dq2 = ctx.saved_tensors
+        r1 = scale(dq1, _c(g1.reshape(1))) if g1 is not None else None
+        r2 = scale(dq2, _c(g2.reshape(1))) if g2 is not None else None
+        return (r1, r2) + (None,) * 15
+
+
+class CqlActorLossFn(Function):
+    """mode 1: mean(alpha*log_pi - a); mode 2: mean(alpha*log_pi - min(a, b)).  alpha = exp(log_alpha) is
+    treated as a constant (its deposit is discarded by the reference, Appendix E.6)."""
+
+    @staticmethod
+    def forward(ctx, mode, log_pi, a, b, log_alpha):
+        log_pi, a = _c(log_pi.reshape(-1)), _c(a.reshape(-1))
+        b = _c(b.reshape(-1)) if b is not None else None
+        B = log_pi.numel()
+        dev = log_pi.device
+        out = torch.empty(2, device=dev)
+        dlp, da = torch.empty_like(log_pi), torch.empty_like(a)
+        db = torch.empty_like(b) if b is not None else None
+        L.call("tacorl_cql_actor_loss", mode, B, L.ptr(log_pi), L.ptr(a), L.ptr(b), L.ptr(log_alpha), 0.0,
+               L.ptr(out), None, L.ptr(dlp), L.ptr(da), L.ptr(db), L.stream())
+        ctx.save_for_backward(dlp, da, db)
+        ctx.shapes = None
+        ctx.mark_non_differentiable(out)
+        return out[0].clone(), out
+
+    @staticmethod
+    def backward(ctx, g, _go):
+        dlp, da, db = ctx.saved_tensors
+        g = _c(g.reshape(1))
+        return (None, scale(dlp, g).view(-1, 1), scale(da, g).view(-1, 1),
+                scale(db, g).view(-1, 1) if db is not None else None, None)
+
+
+def cql_alpha_loss(log_pi, log_alpha, target_entropy):
+    """Returns (alpha_loss value (1,), d alpha_loss / d log_alpha (1,)) — plain values, no graph."""
+    log_pi = _c(log_pi.detach().reshape(-1))
+    out = torch.empty(2, device=log_pi.device)
+    dla = torch.empty(1, device=log_pi.device)
+    L.call("tacorl_cql_actor_loss", 0, log_pi.numel(), L.ptr(log_pi), None, None, L.ptr(log_alpha),
+           float(target_entropy), L.ptr(out), L.ptr(dla), None, None, None, L.stream())
+    return out[:1], dla
+
+
+# --------------------------------------------------------------------------------------- optimiser kernels
+def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, sqnorm=None, max_norm=0.0):
+    L.call("tacorl_adam_step", p.numel(), L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), float(lr), float(beta1),
+           float(beta2), float(eps), int(step), float(grad_scale), L.ptr(sqnorm), float(max_norm), L.stream())
+
+
+def polyak_update(target, source, tau):
+    L.call("tacorl_polyak_update", target.numel(), L.ptr(target), L.ptr(source), float(tau), L.stream())
+
+
+def sqnorm(x, out=None):
+    if out is None:
+        out = torch.empty(1, device=x.device)
+    ws = torch.empty(592, device=x.device)
+    L.call("tacorl_sqnorm", x.numel(), L.ptr(x), L.ptr(out), L.ptr(ws), L.stream())
+    return out

@@ -1,0 +1,98 @@
+"""Flat-buffer optimiser pieces: one fused clip+Adam kernel launch per parameter group, Polyak over
+flat buffers, and the hook where the data-parallel gradient all-reduce plugs in.
+
+Replaces torch.optim.Adam / clip_grad_norm_ / soft_update_from_to at the reference call sites
+(play_lmp_for_rl.py:362-368; cql_offline_lightning.py:229-232, 519-542, 553-574)."""
+import torch
+
+from . import ops
+
+_ALIGN = 64   # elements (256 B): keeps every parameter view TMA/float4 friendly
+
+
+class FlatBuffer:
+    """Packs tensors into one contiguous fp32 buffer and re-points their .data at views of it."""
+
+    def __init__(self, tensors, repoint=True):
+        self.tensors = list(tensors)
+        self.offsets = []
+        off = 0
+        for t in self.tensors:
+            self.offsets.append(off)
+            off += (t.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.numel = max(off, _ALIGN)
+        dev = self.tensors[0].device if self.tensors else torch.device("cpu")
+        self.flat = torch.zeros(self.numel, device=dev, dtype=torch.float32)
+        self.views = []
+        for t, o in zip(self.tensors, self.offsets):
+            v = self.flat[o:o + t.numel()].view(t.shape)
+            if repoint:
+                v.copy_(t.data)
+                t.data = v
+            self.views.append(v)
+
+
+class FlatAdam(torch.optim.Optimizer):
+    """Adam over one flat parameter buffer (torch.optim.Adam semantics, no weight decay / amsgrad).
+
+    step(): gather .grad into the flat gradient buffer -> optional `grad_sync(flat_grad)` (the NCCL
+    all-reduce of tacorl_b200.parallel) -> optional global-norm clip -> ONE fused Adam kernel.
+    `grad_scale` (e.g. 1/world_size) and the clip coefficient are applied inside the kernel."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=None):
+        params = [p for p in params]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        ps = self.param_groups[0]["params"]
+        self.pbuf = FlatBuffer(ps, repoint=True)
+        self.flat_grad = torch.zeros_like(self.pbuf.flat)
+        self.exp_avg = torch.zeros_like(self.pbuf.flat)
+        self.exp_avg_sq = torch.zeros_like(self.pbuf.flat)
+        self.grad_views = [self.flat_grad[o:o + p.numel()].view(p.shape) for p, o in zip(ps, self.pbuf.offsets)]
+        self.max_grad_norm = max_grad_norm
+        self.grad_sync = None       # callable(flat_grad) -> None
+        self.grad_scale = 1.0
+        self.step_count = 0
+        self._sqnorm = torch.zeros(1, device=self.pbuf.flat.device)
+
+    @property
+    def flat_params(self):
+        return self.pbuf.flat
+
+    def gather_grads(self):
+        ps = self.param_groups[0]["params"]
+        dst, src, missing = [], [], []
+        for p, gv in zip(ps, self.grad_views):
+            if p.grad is None:
+                missing.append(gv)
+            else:
+                dst.append(gv)
+                src.append(p.grad)
+        if dst:
+            torch._foreach_copy_(dst, src)
+        for gv in missing:
+            gv.zero_()
+
+    @torch.no_grad()
+    def step(self, closure=None, gathered=False):
+        loss = closure() if closure is not None else None
+        if not gathered:
+            self.gather_grads()
+        if self.grad_sync is not None:
+            self.grad_sync(self.flat_grad)
+        g = self.param_groups[0]
+        self.step_count += 1
+        sq = None
+        if self.max_grad_norm is not None:
+            sq = ops.sqnorm(self.flat_grad, self._sqnorm)
+        ops.adam_step(self.pbuf.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], self.step_count,
+                      g["betas"][0], g["betas"][1], g["eps"], self.grad_scale, sq,
+                      float(self.max_grad_norm) if self.max_grad_norm is not None else 0.0)
+        return loss
+
+    def set_grad(self, flat_values):
+        """Directly provide the flat gradient (single-element groups such as log_alpha)."""
+        self.flat_grad[:flat_values.numel()].copy_(flat_values.reshape(-1))
+
+
+def polyak_update(target_buf: FlatBuffer, source_flat: torch.Tensor, tau: float):
+    ops.polyak_update(target_buf.flat, source_flat, tau)

@@ -1,0 +1,102 @@
+"""GPU parity tests, module level: tacorl_b200.modules.play_lmp.PlayLMP (CUDA path through the C ABI)
+against (a) the golden fixtures recorded from the unmodified reference and (b) the fp64 CPU oracle at
+the full network dimensions."""
+import pytest
+import torch
+
+from oracle import synth as S
+from oracle import tacorl_oracle as O
+from tests.gpu_util import DEV, assert_close, build_play_lmp, double_params, load_golden, play_lmp_tape, to_dev
+
+pytestmark = pytest.mark.gpu
+SCALARS = ["kl_loss", "kl_loss_scaled", "action_loss", "total_loss", "gripper_accuracy",
+           "random_plan_action_loss", "random_plan_gripper_accuracy"]
+
+
+def _setup():
+    from tacorl_b200 import ops
+    ops.set_precision("fp32")
+
+
+@pytest.mark.parametrize("name", ["playlmp_birnn_84", "playlmp_birnn_pad_128", "playlmp_multiview"])
+def test_play_lmp_matches_reference_golden(name):
+    """Same synthetic weights / batch / noise as oracle/make_golden.py fed to the CUDA modules; compared
+    with the numbers the reference itself produced (losses, every gradient, parameters after Adam)."""
+    _setup()
+    from tacorl_b200.utils.rng import noise_tape
+    rec = load_golden(name)
+    latent = rec["shapes"]["plan_recognition.mean_fc.weight"][0]
+    m = build_play_lmp(rec["pr_kind"], tuple(rec["modalities"]), rec["rnn_hidden"], latent, rec["T"])
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == rec["shapes"]
+    m.load_state_dict(S.synth_state_dict(rec["shapes"], rec["seed"]), strict=True)
+    m.to(DEV)
+    opt = m.configure_optimizers()
+    batch = S.synth_play_batch(rec["B"], rec["T"], rec["H"], rec["W"], rec["seed"],
+                               modalities=rec["modalities"], pad=rec["pad"])
+    for s, step in enumerate(rec["steps"]):
+        torch.manual_seed(rec["noise_seed_base"] + s)
+        noise = O.draw_play_lmp_noise(rec["B"], rec["T"], latent=latent)
+        opt.zero_grad()
+        with noise_tape(play_lmp_tape(noise, rec["B"])):
+            loss = m.training_step(to_dev(S.clone_batch(batch)), s)
+        loss.backward()
+        for k in SCALARS:
+            got, want = float(m.logged["train/" + k]), step["scalars"][k]
+            assert abs(got - want) <= 1e-4 * max(1.0, abs(want)), (name, s, k, got, want)
+        grads = {k: p.grad for k, p in m.named_parameters()}
+        for k, fp in step["grads"].items():
+            assert S.fingerprint_close(S.fingerprint(grads[k]), fp, 2e-4), (name, s, "grad", k, S.fingerprint(grads[k]), fp)
+        opt.step()
+        sd = m.state_dict()
+        for k, fp in step["params"].items():
+            assert S.fingerprint_close(S.fingerprint(sd[k]), fp, 2e-4), (name, s, "param", k)
+
+
+@pytest.mark.parametrize("B,T,H,W", [(8, 16, 200, 200), (2, 8, 128, 128)])
+def test_play_lmp_full_size_vs_fp64_oracle(B, T, H, W):
+    """BASELINE config 1 (8 windows x 16 frames, 200x200, hidden 2048): fwd/bwd parity, 1e-4 relative."""
+    _setup()
+    from tacorl_b200.utils.rng import noise_tape
+    torch.manual_seed(0)
+    m = build_play_lmp("tanh_net", ("rgb_static",), 2048, 16, T)
+    shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
+    sd = S.synth_state_dict(shapes, 5)
+    m.load_state_dict(sd)
+    m.to(DEV)
+    batch = S.synth_play_batch(B, T, H, W, 5)
+    torch.manual_seed(77)
+    noise = O.draw_play_lmp_noise(B, T)
+    with noise_tape(play_lmp_tape(noise, B)):
+        loss = m.training_step(to_dev(S.clone_batch(batch)), 0)
+    loss.backward()
+    P = double_params(sd)
+    b64 = {"states": {k: v.double() for k, v in batch["states"].items()}, "actions": batch["actions"].double()}
+    n64 = {k: v.double() for k, v in noise.items()}
+    out = O.play_lmp_forward(P, b64, n64)
+    out["total_loss"].backward()
+    for k in ["kl_loss", "action_loss", "total_loss", "random_plan_action_loss"]:
+        got, want = float(m.logged["train/" + k]), float(out[k])
+        assert abs(got - want) <= 1e-4 * max(1.0, abs(want)), (k, got, want)
+    worst = ("", 0.0)
+    for k, p in m.named_parameters():
+        want = P[k].grad
+        err = float((p.grad.double().cpu() - want).norm() / (want.norm() + 1e-30))
+        if err > worst[1]:
+            worst = (k, err)
+        assert_close(f"grad {k}", p.grad, want, 1e-4, atol=1e-9)
+    print("worst grad rel err", worst)
+
+
+def test_state_dict_round_trip_and_reference_class_paths():
+    _setup()
+    m = build_play_lmp("tanh_net", ("rgb_static",), 64, 16, 16)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m2 = build_play_lmp("tanh_net", ("rgb_static",), 64, 16, 16)
+    m2.load_state_dict(sd, strict=True)
+    m2.to(DEV)
+    opt = m2.configure_optimizers()     # flattening must keep names / shapes / values
+    sd2 = m2.state_dict()
+    assert list(sd2.keys()) == list(sd.keys())
+    for k in sd:
+        assert torch.equal(sd2[k].cpu(), sd[k]), k
+    assert opt.flat_params.numel() >= sum(p.numel() for p in m2.parameters())
