@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py — PlayLMP (+ TACO-RL) training-step throughput on N B200s, one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--precision fp32|bf16] [--batch 64] [--workload play_lmp|tacorl]
+
+Metric (BASELINE.json): train frames/sec; a step = one optimiser step (forward + backward + gradient
+all-reduce + Adam) on a synthetic CALVIN-shaped batch of `batch` windows x 16 frames of 3x200x200 per GPU
+(weak scaling: per-GPU batch fixed, global batch = batch x N).  `value` is timed with inputs resident in
+HBM; `e2e` re-times the same steps through the public module API with the batch in pinned host memory
+(H2D copy of the step's inputs and a D2H read of the loss inside the timed region).
+`--impl reference` times the CPU oracle port of the reference step (oracle/tacorl_oracle.py) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+T_FRAMES, IMG = 16, 200
+# algorithmic FLOPs (2/MAC, fwd+bwd, de-duplicated)
+ENC_FLOP_PER_FRAME = 260.8e6
+PLAYLMP_FLOP_PER_WINDOW = 8.97e9
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("TACORL_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=64, help="windows per GPU")
+    ap.add_argument("--workload", default="play_lmp", choices=["play_lmp"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ----------------------------------------------------------------------------------- CPU / reference arm
+def cpu_reference_step_time(batch_windows, steps, warmup, threads):
+    """Times the oracle port of PlayLMP.training_step + backward + Adam on the host cores."""
+    from oracle import synth as S
+    from oracle import tacorl_oracle as O
+    from tests.gpu_util import build_play_lmp
+    torch.set_num_threads(threads)
+    m = build_play_lmp("tanh_net", ("rgb_static",), 2048, 16, T_FRAMES)   # shapes only (no kernels run)
+    shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
+    del m
+    P = O.params_from(S.synth_state_dict(shapes, 0))
+    batch = S.synth_play_batch(batch_windows, T_FRAMES, IMG, IMG, 1)
+    opt = {}
+    times = []
+    for s in range(warmup + steps):
+        torch.manual_seed(1000 + s)
+        noise = O.draw_play_lmp_noise(batch_windows, T_FRAMES)
+        t0 = time.perf_counter()
+        O.play_lmp_training_step(P, opt, S.clone_batch(batch), noise)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    total = args.steps + args.warmup
+    windows = args.batch if total <= 40 else 8
+    times = cpu_reference_step_time(windows, args.steps, args.warmup, threads)
+    ms = 1e3 * sum(times) / len(times)
+    fps = windows * T_FRAMES / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "play_lmp_train_frames_per_sec", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "PlayLMP[BiRNN tanh_net] train step, static 3x200x200, 16 frames/window",
+                   "windows_per_step": windows, "host": "cpu"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} timed steps of {windows} windows x 16 frames (oracle port of the "
+                                   "reference step: forward+backward+Adam, torch CPU fp32)"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from tacorl_b200 import _lib, configs, ops, parallel
+    from tacorl_b200.utils import synthetic
+    from tacorl_b200.utils.config import instantiate
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ops.set_precision(args.precision)
+    B = args.batch
+
+    torch.manual_seed(0)
+    m = instantiate(configs.play_lmp_for_rl("tanh_net"))
+    synthetic.init_like_reference(m, seed=0)              # identical random-init weights on every rank
+    m.to(dev)
+    opt = m.configure_optimizers()
+    if world > 1:
+        parallel.attach_data_parallel(opt, world)
+
+    host = synthetic.play_batch(B, T_FRAMES, IMG, IMG, seed=1 + rank)
+    host_img = host["states"]["rgb_static"].pin_memory()
+    host_act = host["actions"].pin_memory()
+    dev_img = host_img.to(dev, non_blocking=True)
+    dev_act = host_act.to(dev, non_blocking=True)
+    h2d_bytes = host_img.numel() * 4 + host_act.numel() * 4
+
+    def step(img, act, s):
+        torch.manual_seed(1000 + s * world + rank)
+        opt.zero_grad(set_to_none=True)
+        loss = m.training_step({"states": {"rgb_static": img}, "actions": act}, s)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(n):
+            fn(s)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for s in range(args.warmup):
+        step(dev_img, dev_act, s)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    n0 = _lib.launch_count()
+    total_ms = timed(lambda s: step(dev_img, dev_act, args.warmup + s), args.steps)
+    launches = _lib.launch_count() - n0
+    clk = clocks.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    fps = world * B * T_FRAMES / (ms_per_step / 1e3)
+
+    # end-to-end: pinned host batch -> H2D every step, loss read back every step
+    losses = []
+
+    def e2e_step(s):
+        img = host_img.to(dev, non_blocking=True)
+        act = host_act.to(dev, non_blocking=True)
+        losses.append(float(step(img, act, args.warmup + args.steps + s)))   # .item(): D2H read + sync
+
+    e2e_step(0)
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    e2e_fps = world * B * T_FRAMES / (e2e_ms / 1e3)
+
+    # dominant op, timed alone with CUDA events on the launch stream: the vision encoder fwd+bwd
+    enc = m.perceptual_encoder.networks["rgb_static"]
+    frames = dev_img.view(B * T_FRAMES, 3, IMG, IMG)
+
+    def enc_fb(_):
+        for p in enc.parameters():
+            p.grad = None
+        e = enc(frames)
+        e.backward(torch.ones_like(e))
+
+    enc_fb(0)
+    enc_ms = timed(enc_fb, 5) / 5
+    pk, pk_kind = peaks()
+    achieved_tf = B * T_FRAMES * ENC_FLOP_PER_FRAME / (enc_ms / 1e3) / 1e12
+    roof = {"kernel": "lmp_encoder fwd+bwd (conv implicit GEMMs + soft-argmax + FC)", "bound": "tensor",
+            "achieved": achieved_tf, "peak": pk["bf16_tflops"], "peak_kind": pk_kind + " burst (cuBLAS bf16)",
+            "unit": "TFLOP/s", "frac": achieved_tf / pk["bf16_tflops"], "traffic": None,
+            "ms_per_launch": enc_ms, "algorithmic_flops_per_launch": B * T_FRAMES * ENC_FLOP_PER_FRAME,
+            "share_of_step": enc_ms / ms_per_step}
+
+    if rank == 0:
+        line = {
+            "metric": "play_lmp_train_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": "PlayLMP[BiRNN tanh_net] train step (fwd+bwd+allreduce+Adam), static 3x200x200, "
+                                   "16 frames/window, BASELINE configs[1]",
+                       "windows_per_gpu": B, "global_windows": B * world, "frames_per_window": T_FRAMES,
+                       "parallelism": f"dp{world}", "precision": args.precision,
+                       "l2_policy": "inputs (491 MB images/step) larger than the 126 MB L2"},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "launches_per_step": launches / args.steps,
+            "clocks": clk,
+            "roofline": roof,
+            "algorithmic_tflops_whole_step": world * B * PLAYLMP_FLOP_PER_WINDOW / (ms_per_step / 1e3) / 1e12,
+            "final_loss": losses[-1] if losses else None,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            t = cpu_reference_step_time(B, 4, 1, threads)
+            cms = 1e3 * sum(t) / len(t)
+            line["cpu_baseline"] = {"value": B * T_FRAMES / (cms / 1e3), "unit": "frames/s", "cores": threads,
+                                    "kind": "port", "ms_per_step": cms,
+                                    "sample": f"4 timed steps (+1 warm-up) of the same {B} windows x 16 frames workload, "
+                                              "oracle port of the reference step on torch CPU fp32"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

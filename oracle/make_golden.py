@@ -161,7 +161,8 @@ def golden_ops(name, seed=19):
     orig = torch.rand
     torch.rand = lambda *a, **k: seq.pop(0)
     try:
-        rec["sample"] = dec._sample(lp, ls, mu, grip).tolist()
+        # forward() clamps log_scales at -5 before _sample sees them (action_decoder_logistic.py:292)
+        rec["sample"] = dec._sample(lp, torch.clamp(ls, min=-5.0), mu, grip).tolist()
     finally:
         torch.rand = orig
     json.dump(rec, open(os.path.join(OUT, name + ".json"), "w"))

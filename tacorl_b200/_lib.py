@@ -127,6 +127,8 @@ _WS = {}
 
 def workspace(nbytes, device, tag="main"):
     """Cached per-device scratch buffer (stream-ordered reuse on the current stream)."""
+    if torch.device(device).type != "cuda":
+        raise TacorlLibraryError("tacorl_b200 ops need CUDA tensors (there is no CPU fallback)")
     key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:

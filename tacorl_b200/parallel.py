@@ -1,0 +1,50 @@
+"""Data-parallel gradient exchange: one process per GPU, NCCL all-reduce (sum) of the flat gradient
+buffer over NVLink/NVSwitch, 1/world folded into the fused Adam kernel.  Replaces Lightning's DDP-over-gloo
+(/root/reference/config/trainer/default.yaml:1-3, scripts/train.py:73-75).  Works on CPU tensors with the
+gloo backend (tests/test_parallel_gloo.py)."""
+import torch
+import torch.distributed as dist
+
+
+class BucketedAllReduce:
+    """All-reduces a flat gradient buffer in fixed-size buckets on a side stream (CUDA) so the exchange of
+    early buckets overlaps whatever the caller still runs on the main stream."""
+
+    def __init__(self, world_size, bucket_elems=16 << 20, group=None):
+        self.world = world_size
+        self.bucket = bucket_elems
+        self.group = group
+        self._stream = None
+
+    def __call__(self, flat):
+        if self.world <= 1:
+            return
+        if flat.is_cuda:
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(device=flat.device)
+            main = torch.cuda.current_stream(flat.device)
+            self._stream.wait_stream(main)
+            with torch.cuda.stream(self._stream):
+                for o in range(0, flat.numel(), self.bucket):
+                    dist.all_reduce(flat[o:o + self.bucket], op=dist.ReduceOp.SUM, group=self.group)
+            main.wait_stream(self._stream)
+        else:
+            for o in range(0, flat.numel(), self.bucket):
+                dist.all_reduce(flat[o:o + self.bucket], op=dist.ReduceOp.SUM, group=self.group)
+
+
+def attach_data_parallel(optimizer, world_size, group=None, bucket_elems=16 << 20):
+    """Make a FlatAdam average its gradient over `world_size` ranks before the update (DDP semantics:
+    mean of local-mean gradients; clip-by-norm acts on the reduced gradient, cql_offline_lightning.py:521-537)."""
+    optimizer.grad_sync = BucketedAllReduce(world_size, bucket_elems, group)
+    optimizer.grad_scale = 1.0 / world_size
+    return optimizer
+
+
+def shard_batch(batch, rank, world_size):
+    """Contiguous split of a replay batch over ranks."""
+    def sl(t):
+        n = t.shape[0]
+        per = n // world_size
+        return t[rank * per:(rank + 1) * per]
+    return {k: ({kk: sl(vv) for kk, vv in v.items()} if isinstance(v, dict) else sl(v)) for k, v in batch.items()}

@@ -74,16 +74,26 @@ def test_play_lmp_full_size_vs_fp64_oracle(B, T, H, W):
     n64 = {k: v.double() for k, v in noise.items()}
     out = O.play_lmp_forward(P, b64, n64)
     out["total_loss"].backward()
+    # the reference's own arithmetic: the same oracle in fp32 on the CPU.  Several gradients (conv stack,
+    # reverse RNN) are ill-conditioned sums whose fp32 evaluation is itself ~1e-3 away from fp64; the bar is
+    # 1e-4 relative OR no worse than 1.5x the fp32 reference's own distance to the fp64 arbiter.
+    P32 = O.params_from(sd)
+    out32 = O.play_lmp_forward(P32, S.clone_batch(batch), noise)
+    out32["total_loss"].backward()
     for k in ["kl_loss", "action_loss", "total_loss", "random_plan_action_loss"]:
         got, want = float(m.logged["train/" + k]), float(out[k])
         assert abs(got - want) <= 1e-4 * max(1.0, abs(want)), (k, got, want)
-    worst = ("", 0.0)
+    worst = ("", 0.0, 0.0)
+    bad = []
     for k, p in m.named_parameters():
         want = P[k].grad
         err = float((p.grad.double().cpu() - want).norm() / (want.norm() + 1e-30))
+        ref_err = float((P32[k].grad.double() - want).norm() / (want.norm() + 1e-30))
         if err > worst[1]:
-            worst = (k, err)
-        assert_close(f"grad {k}", p.grad, want, 1e-4, atol=1e-9)
+            worst = (k, err, ref_err)
+        if err > max(1e-4, 1.5 * ref_err):
+            bad.append((k, err, ref_err))
+    assert not bad, bad
     print("worst grad rel err", worst)
 
 

@@ -1,0 +1,135 @@
+"""CPU-only tests of the host side: C-ABI surface, drop-in class paths / state_dict layout, config
+instantiation, no-fallback behaviour, data-parallel plumbing (gloo, world_size 2)."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_shared_library_exports_every_declared_symbol():
+    from tacorl_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "tacorl_b200.h")).read()
+    declared = set(re.findall(r"\b(tacorl_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in declared if not hasattr(L, n)]
+    assert not missing, missing
+    assert declared == set(_lib.EXPORTED), declared ^ set(_lib.EXPORTED)
+    assert _lib.lib().tacorl_abi_version() == 1
+    assert _lib.launch_count() == 0          # nothing may have launched on a CPU-only box
+
+
+def test_ops_fail_loudly_without_cuda_tensors():
+    from tacorl_b200 import ops
+    from tacorl_b200._lib import TacorlLibraryError
+    with pytest.raises(TacorlLibraryError):
+        ops.linear(torch.randn(2, 3), torch.randn(4, 3), torch.randn(4))
+
+
+def test_product_package_never_imports_the_oracle():
+    bad = []
+    for dp, _, fs in os.walk(os.path.join(ROOT, "tacorl_b200")):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M) or "from tests" in src:
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad
+
+
+def _build(kind, rec):
+    from oracle import ref_loader_cfg as RC
+    from tacorl_b200.utils.config import instantiate
+    latent = rec["shapes"]["plan_recognition.mean_fc.weight"][0]
+    cfg = RC.play_lmp_cfg(pr_kind=rec["pr_kind"], modalities=tuple(rec.get("modalities", ["rgb_static"])),
+                          rnn_hidden=rec["rnn_hidden"], latent_plan_dim=latent, max_window=rec["T"], dropout_p=0.0)
+    cfg["_target_"] = "tacorl.modules.play_lmp.play_lmp_for_rl.PlayLMP"     # the REFERENCE class path
+    cfg["_recursive_"] = False
+    lmp = instantiate(cfg)
+    if kind == "play_lmp":
+        return lmp
+    tcfg = RC.tacorl_cfg()
+    tcfg["_target_"] = "tacorl.modules.tacorl.tacorl.TACORL"
+    tcfg["_recursive_"] = False
+    return instantiate(tcfg, play_lmp=lmp)
+
+
+@pytest.mark.parametrize("name,kind", [("playlmp_birnn_84", "play_lmp"), ("playlmp_multiview", "play_lmp"),
+                                       ("tacorl_bc_84", "tacorl"), ("tacorl_defaultpr_84", "tacorl")])
+def test_state_dict_layout_equals_reference(name, kind):
+    """Keys, order and shapes of the mirrors' state_dict == the reference's (recorded in the goldens)."""
+    rec = json.load(open(os.path.join(GOLD, name + ".json")))
+    m = _build(kind, rec)
+    mine = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert list(mine.items()) == list(rec["shapes"].items())
+    from oracle import synth as S
+    m.load_state_dict(S.synth_state_dict(rec["shapes"], rec["seed"]), strict=True)
+    if kind == "tacorl":
+        frozen = [n for n, p in m.named_parameters() if not p.requires_grad]
+        assert frozen and all(n.startswith(("perceptual_encoder.", "plan_recognition.")) for n in frozen)
+        assert m.target_entropy == rec["target_entropy"]
+
+
+def test_native_configs_build_the_same_modules():
+    from tacorl_b200 import configs
+    from tacorl_b200.utils.config import instantiate
+    rec = json.load(open(os.path.join(GOLD, "playlmp_birnn_84.json")))
+    m = instantiate(configs.play_lmp_for_rl("tanh_net", rnn_hidden=64))
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == rec["shapes"]
+    t = instantiate(configs.tacorl(), play_lmp=m)
+    assert len(t.state_dict()) == 181
+    with pytest.raises(NotImplementedError):
+        instantiate({"_target_": "tacorl.networks.visual_encoders.encoder.LMPVisionEncoder", "vib": True})
+
+
+_WORKER = r'''
+import os, sys, json, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from oracle import synth as S, tacorl_oracle as O
+from tacorl_b200 import parallel
+rank, world = int(sys.argv[1]), 2
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=sys.argv[2])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+rec = json.load(open(%(gold)r))
+P = O.params_from(S.synth_state_dict(rec["shapes"], rec["seed"]))
+batch = S.synth_play_batch(4, rec["T"], 84, 84, 21)
+torch.manual_seed(5)
+noise = O.draw_play_lmp_noise(4, rec["T"])
+def grads(b, n):
+    names = O.trainable_names(P)
+    out = O.play_lmp_forward(P, b, n)
+    gs = torch.autograd.grad(out["total_loss"], [P[k] for k in names])
+    return torch.cat([g.reshape(-1) for g in gs])
+full = grads(S.clone_batch(batch), noise)
+local_b = parallel.shard_batch(batch, rank, world)
+local_n = {k: v[rank * 2:(rank + 1) * 2] for k, v in noise.items()}
+flat = grads(local_b, local_n).clone()
+class Opt: pass
+o = Opt(); parallel.attach_data_parallel(o, world, bucket_elems=100000)
+o.grad_sync(flat)
+flat *= o.grad_scale
+err = float((flat - full).norm() / full.norm())
+assert err < 2e-5, err
+if rank == 0: print("DP_OK", err)
+dist.destroy_process_group()
+'''
+
+
+def test_data_parallel_mean_gradient_equals_global_batch_gradient_gloo(tmp_path):
+    """2 ranks x 2 windows, bucketed all-reduce + 1/world == gradient of the 4-window batch."""
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER % {"root": ROOT, "gold": os.path.join(GOLD, "playlmp_birnn_84.json")})
+    port = str(29500 + os.getpid() % 500)
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), port], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "DP_OK" in outs[0]
