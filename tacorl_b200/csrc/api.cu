@@ -21,7 +21,7 @@ int tacorl_gemm(int transA, int transB, int M, int N, int K, float alpha, const 
   g.transA = transA; g.transB = transB; g.M = M; g.N = N; g.K = K; g.alpha = alpha;
   g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.beta = beta; g.C = C; g.ldc = ldc; g.bias = bias;
   g.act = act; g.Cpre = Cpre; g.ldpre = ldpre; g.split_k = 0;
-  return gemm_f32(g, (float*)ws, ws_bytes, (cudaStream_t)stream);
+  return gemm_any(prec, g, (float*)ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int tacorl_colsum(int M, int N, const float* X, long long ldx, float* out, int accumulate, void* stream) {

@@ -1,0 +1,397 @@
+// bf16 tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory ->
+// tcgen05.mma (single-thread issue, cta_group::1, UMMA 128 x BN x 16) with the fp32 accumulator in TMEM ->
+// tcgen05.ld epilogue (alpha/beta/bias/activation, fp32 and/or bf16 stores, or split-K partials).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).  A kStages-deep mbarrier ring connects
+// producer and issuer; tcgen05.commit releases ring slots and finally signals the epilogue.
+//
+// Operand layouts: each operand is either K-major ([rows][K], K contiguous; one 64-wide K slab per
+// stage, canonical SW128 K-major atoms, SBO = 1024 B) or MN-major ([K][rows], rows contiguous; 64x64
+// boxes, canonical SW128 MN-major atoms, SBO = 1024 B between 8-row K groups, LBO = 8192 B between
+// 64-wide MN groups).  MN-major lets dX = dZ.W and dW = dZ^T.X run on the tensors as stored.
+#include "common.cuh"
+#include "internal.h"
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace tacorl {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;          // bf16 elements = 128 bytes = one swizzle row
+constexpr int TC_UMMA_K = 16;
+constexpr int TC_THREADS = 192;
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// SM100 shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct TcEpilogue {
+  float alpha, beta;
+  float* C; long long ldc;              // fp32 output (may be null if only bf16 output is wanted)
+  __nv_bfloat16* Cb; long long ldcb;    // optional bf16 copy of the (post-activation) output
+  const float* bias;                    // per column
+  int act;
+  float* Cpre; long long ldpre;
+  float* partial;                       // split-K: raw accumulators [z][M][N]
+};
+
+template <int BN, bool A_MN, bool B_MN, int kStages>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcEpilogue ep,
+               int M, int N, int K, int kblocks_per_split) {
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;     // 16 KB
+  constexpr uint32_t B_BYTES = BN * TC_BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  static_assert(!B_MN || BN % 64 == 0, "MN-major B needs 64-wide boxes");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + kStages * STAGE_BYTES);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int total_kb = (K + TC_BK - 1) / TC_BK;
+  const int kb_begin = blockIdx.z * kblocks_per_split;
+  const int kb_end = min(total_kb, kb_begin + kblocks_per_split);
+  const int nkb = kb_end - kb_begin;
+
+  const uint32_t smem_base = smem_u32(smem);
+  auto full_bar = [&](int s) { return smem_u32(bars + s); };
+  auto empty_bar = [&](int s) { return smem_u32(bars + kStages + s); };
+  const uint32_t tmem_full_bar = smem_u32(bars + 2 * kStages);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && nkb > 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        mbar_expect_tx(full_bar(s), STAGE_BYTES);
+        const int k0 = (kb_begin + i) * TC_BK;
+        const uint32_t a_dst = smem_base + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+        if (!A_MN) {
+          tma_load_2d(a_dst, &tmA, k0, m0, full_bar(s));
+        } else {
+          tma_load_2d(a_dst, &tmA, m0, k0, full_bar(s));
+          tma_load_2d(a_dst + 8192, &tmA, m0 + 64, k0, full_bar(s));
+        }
+        if (!B_MN) {
+          tma_load_2d(b_dst, &tmB, k0, n0, full_bar(s));
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, n0 + j * 64, k0, full_bar(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nkb > 0) {
+      // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, a_major bit15, b_major bit16,
+      // N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t a_src = smem_base + s * STAGE_BYTES, b_src = a_src + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+          // K-major: advance 16 elements (32 B) inside the 128 B swizzle row; MN-major: 16 K-rows of 128 B
+          const uint64_t ad = A_MN ? make_smem_desc(a_src + k * 2048, 8192, 1024) : make_smem_desc(a_src + k * 32, 16, 1024);
+          const uint64_t bd = B_MN ? make_smem_desc(b_src + k * 2048, 8192, 1024) : make_smem_desc(b_src + k * 32, 16, 1024);
+          tc_mma_bf16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(empty_bar(s));          // slot reusable once these MMAs have read it
+      }
+      tc_commit(tmem_full_bar);           // accumulator complete
+    }
+  } else {
+    // ---- epilogue: TMEM lane quarter q holds rows m0 + 32q .. +31
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    if (nkb > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t r[16];
+      if (nkb > 0) {
+        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = 0;
+      }
+      if (row < M) {
+        if (ep.partial) {
+          float* P = ep.partial + ((long long)blockIdx.z * M + row) * N;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + c0 + j < N) P[n0 + c0 + j] = __uint_as_float(r[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = n0 + c0 + j;
+            if (col < N) {
+              float v = ep.alpha * __uint_as_float(r[j]);
+              if (ep.beta != 0.f && ep.C) v = fmaf(ep.beta, ep.C[(long long)row * ep.ldc + col], v);
+              if (ep.bias) v += __ldg(ep.bias + col);
+              if (ep.Cpre) ep.Cpre[(long long)row * ep.ldpre + col] = v;
+              if (ep.act == ACT_RELU) v = fmaxf(v, 0.f);
+              else if (ep.act == ACT_SILU) v = v / (1.f + __expf(-v));
+              if (ep.C) ep.C[(long long)row * ep.ldc + col] = v;
+              if (ep.Cb) ep.Cb[(long long)row * ep.ldcb + col] = __float2bfloat16(v);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: inner dimension `inner` (contiguous), `outer` rows of pitch `ld` elements.
+static int make_tmap(CUtensorMap* tm, const void* base, long long inner, long long outer, long long ld,
+                     int box_inner, int box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  TACORL_REQUIRE(fn, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+  TACORL_REQUIRE(((uintptr_t)base & 15) == 0 && (ld * 2) % 16 == 0,
+                 "gemm_tc: TMA operand must be 16-byte aligned with a 16-byte multiple pitch (ld=%lld)", ld);
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TACORL_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld", (int)r,
+                 inner, outer, ld);
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcEpilogue& ep, int M, int N, int K,
+                     int splits, cudaStream_t st) {
+  constexpr int kStages = BN >= 128 ? 5 : 6;
+  constexpr size_t smem = (size_t)kStages * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + (2 * kStages + 1) * 8 + 16 + 1024;
+  static bool configured = false;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, kStages>;
+  if (!configured) {
+    TACORL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int total_kb = cdiv(K, TC_BK);
+  const int per = cdiv(total_kb, splits);
+  dim3 grid(cdiv(N, BN), cdiv(M, TC_BM), cdiv(total_kb, per));
+  kern<<<grid, TC_THREADS, smem, st>>>(ta, tb, ep, M, N, K, per);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void tc_splitk_reduce_kernel(int M, int N, int splits, const float* __restrict__ partial, TcEpilogue ep) {
+  const long long total = (long long)M * N;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(idx / N), col = (int)(idx % N);
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += partial[(long long)z * total + idx];
+    float v = ep.alpha * s;
+    if (ep.beta != 0.f && ep.C) v = fmaf(ep.beta, ep.C[(long long)row * ep.ldc + col], v);
+    if (ep.bias) v += __ldg(ep.bias + col);
+    if (ep.Cpre) ep.Cpre[(long long)row * ep.ldpre + col] = v;
+    if (ep.act == ACT_RELU) v = fmaxf(v, 0.f);
+    else if (ep.act == ACT_SILU) v = v / (1.f + __expf(-v));
+    if (ep.C) ep.C[(long long)row * ep.ldc + col] = v;
+    if (ep.Cb) ep.Cb[(long long)row * ep.ldcb + col] = __float2bfloat16(v);
+  }
+}
+
+// Core entry: bf16 operands already in global memory.
+//   A: a_mn ? stored [K][M] (pitch lda) : stored [M][K];   B: b_mn ? stored [K][N] : stored [N][K].
+int gemm_tc_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, int M, int N,
+                 int K, const TcArgs& e, float* ws, size_t ws_bytes, cudaStream_t st) {
+  if (M == 0 || N == 0) return 0;
+  TACORL_REQUIRE(K > 0, "gemm_tc: K must be positive");
+  int BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+  if (b_mn && BN < 64) BN = 64;
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = a_mn ? make_tmap(&ta, A, M, K, lda, 64, 64) : make_tmap(&ta, A, K, M, lda, 64, TC_BM))) return rc;
+  if ((rc = b_mn ? make_tmap(&tb, B, N, K, ldb, 64, 64) : make_tmap(&tb, B, K, N, ldb, 64, BN))) return rc;
+  const long long ctas = (long long)cdiv(M, TC_BM) * cdiv(N, BN);
+  const int total_kb = cdiv(K, TC_BK);
+  int splits = e.split_k;
+  if (splits <= 0) {
+    splits = 1;
+    if (ws && ctas < 74 && total_kb >= 8) splits = (int)min((long long)cdiv(148, ctas), (long long)(total_kb / 4));
+  }
+  if (splits > total_kb) splits = total_kb;
+  if (splits > 1 && (!ws || (size_t)splits * M * N * 4 > ws_bytes)) {
+    splits = ws ? (int)(ws_bytes / ((size_t)M * N * 4)) : 1;
+    if (splits < 1) splits = 1;
+  }
+  TcEpilogue ep;
+  ep.alpha = e.alpha; ep.beta = e.beta; ep.C = e.C; ep.ldc = e.ldc; ep.Cb = (__nv_bfloat16*)e.Cb; ep.ldcb = e.ldcb;
+  ep.bias = e.bias; ep.act = e.act; ep.Cpre = e.Cpre; ep.ldpre = e.ldpre; ep.partial = splits > 1 ? ws : nullptr;
+#define TC_DISPATCH(BNV)                                                                                   \
+  if (BN == BNV) {                                                                                         \
+    if (!a_mn && !b_mn) rc = launch_tc<BNV, false, false>(ta, tb, ep, M, N, K, splits, st);                \
+    else if (a_mn && !b_mn) rc = launch_tc<BNV, true, false>(ta, tb, ep, M, N, K, splits, st);             \
+    else if (!a_mn && b_mn) rc = launch_tc<(BNV < 64 ? 64 : BNV), false, true>(ta, tb, ep, M, N, K, splits, st); \
+    else rc = launch_tc<(BNV < 64 ? 64 : BNV), true, true>(ta, tb, ep, M, N, K, splits, st);               \
+  }
+  rc = -1;
+  TC_DISPATCH(32) TC_DISPATCH(64) TC_DISPATCH(128)
+#undef TC_DISPATCH
+  if (rc) return rc;
+  if (splits > 1) {
+    // the kernel may have used fewer z-slices than `splits` when the K blocks do not divide evenly
+    const int per = cdiv(total_kb, splits);
+    const int used = cdiv(total_kb, per);
+    ep.partial = nullptr;
+    long long total = (long long)M * N;
+    tc_splitk_reduce_kernel<<<(int)min((long long)1184, (total + 255) / 256), 256, 0, st>>>(M, N, used, ws, ep);
+    TACORL_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ fp32 -> bf16 staging
+__global__ void cast_bf16_2d_kernel(const float* __restrict__ src, long long lds, long long rows, int cols,
+                                    __nv_bfloat16* __restrict__ dst, long long ldd) {
+  const long long total = rows * ldd;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ldd; const int c = (int)(i % ldd);
+    dst[i] = __float2bfloat16(c < cols ? src[r * lds + c] : 0.f);
+  }
+}
+
+int cast_bf16_2d(const float* src, long long lds, long long rows, int cols, void* dst, long long ldd, cudaStream_t st) {
+  if (rows == 0) return 0;
+  long long total = rows * ldd;
+  cast_bf16_2d_kernel<<<(int)min((long long)148 * 8, (total + 255) / 256), 256, 0, st>>>(src, lds, rows, cols,
+                                                                                        (__nv_bfloat16*)dst, ldd);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
+// GemmArgs (fp32 operands, any transposition) on the tensor cores: operands are staged to bf16 in `ws`
+// in their stored orientation (no transposes: stored-[K][rows] operands use the MN-major descriptors).
+int gemm_tc_from_f32(const GemmArgs& g, float* ws, size_t ws_bytes, cudaStream_t st) {
+  if (g.M == 0 || g.N == 0) return 0;
+  TACORL_REQUIRE(ws, "gemm_tc: workspace required");
+  const long long a_rows = g.transA ? g.K : g.M, a_cols = g.transA ? g.M : g.K;
+  const long long b_rows = g.transB ? g.N : g.K, b_cols = g.transB ? g.K : g.N;
+  const long long lda = (a_cols + 7) & ~7LL, ldb = (b_cols + 7) & ~7LL;
+  Arena ar(ws, ws_bytes);
+  __nv_bfloat16* Ab = ar.take<__nv_bfloat16>((size_t)a_rows * lda);
+  __nv_bfloat16* Bb = ar.take<__nv_bfloat16>((size_t)b_rows * ldb);
+  TACORL_REQUIRE(Ab && Bb, "gemm_tc: workspace too small for bf16 staging (%lld + %lld elements)", a_rows * lda,
+                 b_rows * ldb);
+  int rc;
+  if ((rc = cast_bf16_2d(g.A, g.lda, a_rows, (int)a_cols, Ab, lda, st))) return rc;
+  if ((rc = cast_bf16_2d(g.B, g.ldb, b_rows, (int)b_cols, Bb, ldb, st))) return rc;
+  TcArgs e;
+  e.alpha = g.alpha; e.beta = g.beta; e.C = g.C; e.ldc = g.ldc; e.bias = g.bias; e.act = g.act; e.Cpre = g.Cpre;
+  e.ldpre = g.ldpre; e.split_k = g.split_k;
+  return gemm_tc_bf16(Ab, lda, g.transA ? 1 : 0, Bb, ldb, g.transB ? 0 : 1, g.M, g.N, g.K, e,
+                      (float*)(ar.base + ar.off), ar.left(), st);
+}
+
+}  // namespace tacorl

@@ -22,6 +22,26 @@ int softargmax_bwd_f32(const float* y, int N, int OH, int OW, int C, const float
                        const float* feat, const float* smax, const float* ssum, const float* dfeat,
                        float* dy, float* dtau_part, cudaStream_t st);
 
+// ---- bf16 tcgen05 GEMM (gemm_tc.cu)
+struct TcArgs {
+  float alpha = 1.f, beta = 0.f;
+  float* C = nullptr; long long ldc = 0;          // fp32 output
+  void* Cb = nullptr; long long ldcb = 0;         // optional bf16 copy of the output
+  const float* bias = nullptr;
+  int act = ACT_NONE;
+  float* Cpre = nullptr; long long ldpre = 0;
+  int split_k = 0;                                // 0 = auto
+};
+// bf16 operands in place: a_mn/b_mn = operand stored [K][rows] (rows contiguous) instead of [rows][K]
+int gemm_tc_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, int M, int N,
+                 int K, const TcArgs& e, float* ws, size_t ws_bytes, cudaStream_t st);
+int cast_bf16_2d(const float* src, long long lds, long long rows, int cols, void* dst, long long ldd, cudaStream_t st);
+int gemm_tc_from_f32(const GemmArgs& g, float* ws, size_t ws_bytes, cudaStream_t st);
+// precision dispatch used by the composite ops
+static inline int gemm_any(int prec, const GemmArgs& g, float* ws, size_t ws_bytes, cudaStream_t st) {
+  return prec == PREC_BF16 ? gemm_tc_from_f32(g, ws, ws_bytes, st) : gemm_f32(g, ws, ws_bytes, st);
+}
+
 // simple bump allocator over a caller-provided workspace (256-byte aligned slices)
 struct Arena {
   char* base; size_t cap; size_t off = 0;

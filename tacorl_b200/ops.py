@@ -454,6 +454,7 @@ class CqlCriticLossFn(Function):
     @staticmethod
     def forward(ctx, q1_all, q2_all, lp_curr, lp_next, tq1, tq2, reward, done, log_alpha_prime, n, rand_density,
                 discount, reward_scale, gap, cw, temp, with_lagrange):
+        ctx.qshapes = (q1_all.shape, q2_all.shape)
         q1_all, q2_all = _c(q1_all.reshape(-1)), _c(q2_all.reshape(-1))
         B = tq1.numel()
         dev = q1_all.device
@@ -473,8 +474,8 @@ class CqlCriticLossFn(Function):
     @staticmethod
     def backward(ctx, g1, g2, _gs, _gl):
         dq1, dq2 = ctx.saved_tensors
-        r1 = scale(dq1, _c(g1.reshape(1))) if g1 is not None else None
-        r2 = scale(dq2, _c(g2.reshape(1))) if g2 is not None else None
+        r1 = scale(dq1, _c(g1.reshape(1))).view(ctx.qshapes[0]) if g1 is not None else None
+        r2 = scale(dq2, _c(g2.reshape(1))).view(ctx.qshapes[1]) if g2 is not None else None
         return (r1, r2) + (None,) * 15
 
 
@@ -484,6 +485,7 @@ class CqlActorLossFn(Function):
 
     @staticmethod
     def forward(ctx, mode, log_pi, a, b, log_alpha):
+        ctx.in_shapes = (log_pi.shape, a.shape, b.shape if b is not None else None)
         log_pi, a = _c(log_pi.reshape(-1)), _c(a.reshape(-1))
         b = _c(b.reshape(-1)) if b is not None else None
         B = log_pi.numel()
@@ -502,8 +504,9 @@ class CqlActorLossFn(Function):
     def backward(ctx, g, _go):
         dlp, da, db = ctx.saved_tensors
         g = _c(g.reshape(1))
-        return (None, scale(dlp, g).view(-1, 1), scale(da, g).view(-1, 1),
-                scale(db, g).view(-1, 1) if db is not None else None, None)
+        sh = ctx.in_shapes
+        return (None, scale(dlp, g).view(sh[0]), scale(da, g).view(sh[1]),
+                scale(db, g).view(sh[2]) if db is not None else None, None)
 
 
 def cql_alpha_loss(log_pi, log_alpha, target_entropy):
