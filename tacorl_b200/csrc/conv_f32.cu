@@ -4,15 +4,22 @@
 // Reference: networks/visual_encoders/encoder.py:369-419, utils.py:39-76.
 #include "common.cuh"
 #include "internal.h"
+#include <cuda_bf16.h>
 
 namespace tacorl {
 
 // col[m][k], m = (n, oy, ox) over `nframes` frames; k = (ky, kx, c) (c fastest) when korder == 1,
 // k = (c, ky, kx) (the torch weight layout) when korder == 0.
 // Input element (n, c, iy, ix) lives at x[n*sn + c*sc + iy*sh + ix*sw] (NCHW or NHWC by strides).
+__device__ __forceinline__ void store_as(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_as(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+__device__ __forceinline__ float load_as(const float* p) { return *p; }
+__device__ __forceinline__ float load_as(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename OutT>
 __global__ void im2col_kernel(const float* __restrict__ x, long long sn, long long sc, long long sh,
                               long long sw, int C, int KH, int KW, int stride, int OH, int OW,
-                              int nframes, float* __restrict__ col, int korder) {
+                              int nframes, OutT* __restrict__ col, int korder) {
   const int K = KH * KW * C;
   const long long total = (long long)nframes * OH * OW * K;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -24,7 +31,7 @@ __global__ void im2col_kernel(const float* __restrict__ x, long long sn, long lo
     else { kx = k % KW; ky = (k / KW) % KH; c = k / (KW * KH); }
     const int ox = (int)(m % OW), oy = (int)((m / OW) % OH);
     const long long n = m / ((long long)OW * OH);
-    col[idx] = __ldg(x + n * sn + c * sc + (long long)(oy * stride + ky) * sh + (long long)(ox * stride + kx) * sw);
+    store_as(col + idx, __ldg(x + n * sn + c * sc + (long long)(oy * stride + ky) * sh + (long long)(ox * stride + kx) * sw));
   }
 }
 
@@ -33,16 +40,28 @@ int im2col_f32(const float* x, long long sn, long long sc, long long sh, long lo
   long long total = (long long)nframes * OH * OW * KH * KW * C;
   if (total == 0) return 0;
   int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
-  im2col_kernel<<<blocks, 256, 0, st>>>(x, sn, sc, sh, sw, C, KH, KW, stride, OH, OW, nframes, col, korder);
+  im2col_kernel<float><<<blocks, 256, 0, st>>>(x, sn, sc, sh, sw, C, KH, KW, stride, OH, OW, nframes, col, korder);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
+int im2col_bf16(const float* x, long long sn, long long sc, long long sh, long long sw, int C, int KH,
+                int KW, int stride, int OH, int OW, int nframes, void* col, cudaStream_t st, int korder) {
+  long long total = (long long)nframes * OH * OW * KH * KW * C;
+  if (total == 0) return 0;
+  int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
+  im2col_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(x, sn, sc, sh, sw, C, KH, KW, stride, OH, OW, nframes,
+                                                       (__nv_bfloat16*)col, korder);
   TACORL_LAUNCH_CHECK();
   return 0;
 }
 
 // dX (NHWC) = mask(Y>0) * sum over the kernel taps that touch (iy, ix) of dcol.
 // dcol[m][k] with the same (ky,kx,c) ordering as im2col.  Gather form => deterministic.
-__global__ void col2im_kernel(const float* __restrict__ dcol, int C, int H, int W, int KH, int KW,
+template <typename InT>
+__global__ void col2im_kernel(const InT* __restrict__ dcol, int C, int H, int W, int KH, int KW,
                               int stride, int OH, int OW, int nframes, const float* __restrict__ ymask,
-                              float* __restrict__ dx) {
+                              float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb) {
   const int K = KH * KW * C;
   const long long total = (long long)nframes * H * W * C;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -62,11 +81,12 @@ __global__ void col2im_kernel(const float* __restrict__ dcol, int C, int H, int 
           if (tx < 0 || tx % stride) continue;
           const int ox = tx / stride;
           if (ox >= OW) continue;
-          s += dcol[((n * OH + oy) * OW + ox) * K + (ky * KW + kx) * C + c];
+          s += load_as(dcol + ((n * OH + oy) * OW + ox) * K + (ky * KW + kx) * C + c);
         }
       }
     }
     dx[idx] = s;
+    if (dxb) dxb[idx] = __float2bfloat16(s);
   }
 }
 
@@ -75,7 +95,19 @@ int col2im_f32(const float* dcol, int C, int H, int W, int KH, int KW, int strid
   long long total = (long long)nframes * H * W * C;
   if (total == 0) return 0;
   int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
-  col2im_kernel<<<blocks, 256, 0, st>>>(dcol, C, H, W, KH, KW, stride, OH, OW, nframes, ymask, dx);
+  col2im_kernel<float><<<blocks, 256, 0, st>>>(dcol, C, H, W, KH, KW, stride, OH, OW, nframes, ymask, dx, nullptr);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
+// bf16 dcol in, fp32 dx out plus a dense bf16 copy of dx (the next GEMM's operand)
+int col2im_bf16(const void* dcol, int C, int H, int W, int KH, int KW, int stride, int OH, int OW,
+                int nframes, const float* ymask, float* dx, void* dxb, cudaStream_t st) {
+  long long total = (long long)nframes * H * W * C;
+  if (total == 0) return 0;
+  int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
+  col2im_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)dcol, C, H, W, KH, KW, stride, OH, OW,
+                                                       nframes, ymask, dx, (__nv_bfloat16*)dxb);
   TACORL_LAUNCH_CHECK();
   return 0;
 }

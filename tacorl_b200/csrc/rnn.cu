@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "internal.h"
 #include "../../include/tacorl_b200.h"
+#include <cuda_bf16.h>
 
 namespace tacorl {
 
@@ -19,26 +20,30 @@ __global__ void vec_add_kernel(int n, const float* a, const float* b, float* o) 
   if (i < n) o[i] = a[i] + b[i];
 }
 
-// rows x H block with row stride ld: p = relu(p)
-__global__ void relu_rows_kernel(long long rows, int H, float* p, long long ld) {
+// rows x H block with row stride ld: p = relu(p)  (+ optional dense bf16 copy, pitch H)
+__global__ void relu_rows_kernel(long long rows, int H, float* p, long long ld, __nv_bfloat16* pb) {
   const long long total = rows * H;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     float* q = p + (i / H) * ld + (i % H);
-    *q = fmaxf(*q, 0.f);
+    const float v = fmaxf(*q, 0.f);
+    *q = v;
+    if (pb) pb[i] = __float2bfloat16(v);
   }
 }
 
-// d = (d + add?) * [out > 0]
+// d = (d + add?) * [out > 0]  (+ optional dense bf16 copy, pitch H)
 __global__ void mask_rows_kernel(long long rows, int H, float* d, long long ldd, const float* out,
-                                 long long ldo, const float* add, long long lda) {
+                                 long long ldo, const float* add, long long lda, __nv_bfloat16* db) {
   const long long total = rows * H;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / H; const int c = (int)(i % H);
     float v = d[r * ldd + c];
     if (add) v += add[r * lda + c];
-    d[r * ldd + c] = out[r * ldo + c] > 0.f ? v : 0.f;
+    v = out[r * ldo + c] > 0.f ? v : 0.f;
+    d[r * ldd + c] = v;
+    if (db) db[i] = __float2bfloat16(v);
   }
 }
 
@@ -51,19 +56,19 @@ using namespace tacorl;
 extern "C" {
 
 size_t tacorl_rnn_layer_ws_bytes(int T, int B, int I, int H) {
-  (void)T; (void)I;
-  // bias sum + split-K partials for the recurrent GEMM (<= 16 splits of BxH) and the weight grads
+  // bias sum + split-K partials for the recurrent GEMM (<= 16 splits of BxH) and the weight grads;
+  // bf16 path: staged copies of W_ih, W_hh, x, h / dpre
+  const size_t mx = (size_t)(H > I ? H : I);
   size_t sk = (size_t)16 * B * H * 4;
-  size_t wg = (size_t)4 * H * (size_t)(H > I ? H : I) * 4;
-  return (size_t)H * 4 + 4096 + (sk > wg ? sk : wg) + (1 << 16);
+  size_t wg = (size_t)4 * H * mx * 4;
+  size_t bf = ((size_t)H * (I + 8) + (size_t)H * H + (size_t)T * B * (I + 8) + 2 * (size_t)T * B * H) * 2 + 8192;
+  return (size_t)H * 4 + 4096 + (sk > wg ? sk : wg) + bf + (1 << 16);
 }
 
-int tacorl_rnn_layer_fwd(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
-                         const float* w_hh, const float* b_ih, const float* b_hh, const float* h0,
-                         int reverse, int n_steps, float* out, long long ldo, void* ws, size_t ws_bytes,
-                         int prec, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  TACORL_REQUIRE(prec == PREC_F32, "rnn_layer_fwd: precision %d not built into this entry point", prec);
+static int rnn_fwd_f32(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
+                       const float* w_hh, const float* b_ih, const float* b_hh, const float* h0,
+                       int reverse, int n_steps, float* out, long long ldo, void* ws, size_t ws_bytes,
+                       cudaStream_t st) {
   TACORL_REQUIRE(x && w_ih && w_hh && b_ih && b_hh && out && ws, "rnn_layer_fwd: null pointer");
   TACORL_REQUIRE(n_steps >= 1 && n_steps <= T, "rnn_layer_fwd: n_steps %d out of range (T=%d)", n_steps, T);
   if (B == 0) return 0;
@@ -88,7 +93,7 @@ int tacorl_rnn_layer_fwd(int T, int B, int I, int H, const float* x, long long l
     if (s == 0) { hp = h0; ldh = H; }
     else { hp = out + (long long)(reverse ? t + 1 : t - 1) * B * ldo; ldh = ldo; }
     if (!hp) {
-      relu_rows_kernel<<<ew_blocks((long long)B * H), 256, 0, st>>>(B, H, ot, ldo);
+      relu_rows_kernel<<<ew_blocks((long long)B * H), 256, 0, st>>>(B, H, ot, ldo, nullptr);
       TACORL_LAUNCH_CHECK();
       continue;
     }
@@ -100,14 +105,11 @@ int tacorl_rnn_layer_fwd(int T, int B, int I, int H, const float* x, long long l
   return 0;
 }
 
-int tacorl_rnn_layer_bwd(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
-                         const float* w_hh, const float* h0, int reverse, int n_steps, const float* out,
-                         long long ldo, float* dout, long long lddo, const float* dhn, float* dx,
-                         long long lddx, int dx_accumulate, float* dw_ih, float* dw_hh, float* db_ih,
-                         float* db_hh, int accumulate, float* dh0, void* ws, size_t ws_bytes, int prec,
-                         void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  TACORL_REQUIRE(prec == PREC_F32, "rnn_layer_bwd: precision %d not built into this entry point", prec);
+static int rnn_bwd_f32(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
+                       const float* w_hh, const float* h0, int reverse, int n_steps, const float* out,
+                       long long ldo, float* dout, long long lddo, const float* dhn, float* dx,
+                       long long lddx, int dx_accumulate, float* dw_ih, float* dw_hh, float* db_ih,
+                       float* db_hh, int accumulate, float* dh0, void* ws, size_t ws_bytes, cudaStream_t st) {
   TACORL_REQUIRE(x && w_ih && w_hh && out && dout && ws, "rnn_layer_bwd: null pointer");
   TACORL_REQUIRE(n_steps >= 1 && n_steps <= T, "rnn_layer_bwd: n_steps out of range");
   if (B == 0) return 0;
@@ -122,7 +124,7 @@ int tacorl_rnn_layer_bwd(int T, int B, int I, int H, const float* x, long long l
     float* dt = dout + (long long)t * B * lddo;
     const float* ot = out + (long long)t * B * ldo;
     mask_rows_kernel<<<ew_blocks((long long)B * H), 256, 0, st>>>(
-        B, H, dt, lddo, ot, ldo, (s == n_steps - 1) ? dhn : nullptr, H);
+        B, H, dt, lddo, ot, ldo, (s == n_steps - 1) ? dhn : nullptr, H, nullptr);
     TACORL_LAUNCH_CHECK();
     if (s > 0) {  // dout[t_prev] += dpre[t] W_hh
       const int tp = reverse ? t + 1 : t - 1;
@@ -183,6 +185,163 @@ int tacorl_rnn_layer_bwd(int T, int B, int I, int H, const float* x, long long l
     if ((rc = gemm_f32(d, sk, sk_bytes, st))) return rc;
   }
   return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------ bf16 tensor-core path
+// Weights are staged to bf16 once per call; h_t / dpre_t are written in fp32 (saved / accumulated) and as
+// dense bf16 copies that feed the next step's tcgen05 GEMM.  No transposes: W_hh / W_ih / dpre / h / x are
+// consumed in their stored orientation through K-major or MN-major UMMA descriptors.
+static int rnn_fwd_bf16(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
+                        const float* w_hh, const float* b_ih, const float* b_hh, const float* h0,
+                        int reverse, int n_steps, float* out, long long ldo, void* ws, size_t ws_bytes,
+                        cudaStream_t st) {
+  const long long Ip = (I + 7) & ~7LL;
+  Arena ar(ws, ws_bytes);
+  float* bsum = ar.take<float>(H);
+  __nv_bfloat16* wih = ar.take<__nv_bfloat16>((size_t)H * Ip);
+  __nv_bfloat16* whh = ar.take<__nv_bfloat16>((size_t)H * H);
+  __nv_bfloat16* xb = ar.take<__nv_bfloat16>((size_t)n_steps * B * Ip);
+  __nv_bfloat16* hb = ar.take<__nv_bfloat16>((size_t)T * B * H);
+  __nv_bfloat16* h0b = h0 ? ar.take<__nv_bfloat16>((size_t)B * H) : nullptr;
+  TACORL_REQUIRE(bsum && wih && whh && xb && hb && (!h0 || h0b), "rnn_layer_fwd(bf16): workspace too small");
+  TACORL_REQUIRE(H % 8 == 0, "rnn_layer_fwd(bf16): hidden size must be a multiple of 8");
+  float* sk = (float*)(ar.base + ar.off);
+  size_t sk_bytes = ar.left();
+  const int t_lo = reverse ? T - n_steps : 0;
+  int rc;
+  vec_add_kernel<<<cdiv(H, 256), 256, 0, st>>>(H, b_ih, b_hh, bsum);
+  TACORL_LAUNCH_CHECK();
+  if ((rc = cast_bf16_2d(w_ih, I, H, I, wih, Ip, st))) return rc;
+  if ((rc = cast_bf16_2d(w_hh, H, H, H, whh, H, st))) return rc;
+  if ((rc = cast_bf16_2d(x + (long long)t_lo * B * ldx, ldx, (long long)n_steps * B, I, xb, Ip, st))) return rc;
+  if (h0 && (rc = cast_bf16_2d(h0, H, B, H, h0b, H, st))) return rc;
+  TcArgs in;
+  in.C = out + (long long)t_lo * B * ldo; in.ldc = ldo; in.bias = bsum; in.split_k = 1;
+  if ((rc = gemm_tc_bf16(xb, Ip, 0, wih, Ip, 0, n_steps * B, H, I, in, sk, sk_bytes, st))) return rc;
+  for (int s = 0; s < n_steps; ++s) {
+    const int t = reverse ? T - 1 - s : s;
+    float* ot = out + (long long)t * B * ldo;
+    __nv_bfloat16* hbt = hb + (long long)t * B * H;
+    const __nv_bfloat16* hp = (s == 0) ? h0b : hb + (long long)(reverse ? t + 1 : t - 1) * B * H;
+    if (!hp) {
+      relu_rows_kernel<<<ew_blocks((long long)B * H), 256, 0, st>>>(B, H, ot, ldo, hbt);
+      TACORL_LAUNCH_CHECK();
+      continue;
+    }
+    TcArgs r;
+    r.C = ot; r.ldc = ldo; r.beta = 1.f; r.act = ACT_RELU; r.Cb = hbt; r.ldcb = H; r.split_k = 1;
+    if ((rc = gemm_tc_bf16(hp, H, 0, whh, H, 0, B, H, H, r, sk, sk_bytes, st))) return rc;
+  }
+  return 0;
+}
+
+static int rnn_bwd_bf16(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
+                        const float* w_hh, const float* h0, int reverse, int n_steps, const float* out,
+                        long long ldo, float* dout, long long lddo, const float* dhn, float* dx,
+                        long long lddx, int dx_accumulate, float* dw_ih, float* dw_hh, float* db_ih,
+                        float* db_hh, int accumulate, float* dh0, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const long long Ip = (I + 7) & ~7LL;
+  Arena ar(ws, ws_bytes);
+  __nv_bfloat16* wih = ar.take<__nv_bfloat16>((size_t)H * Ip);
+  __nv_bfloat16* whh = ar.take<__nv_bfloat16>((size_t)H * H);
+  __nv_bfloat16* xb = ar.take<__nv_bfloat16>((size_t)n_steps * B * Ip);
+  __nv_bfloat16* hb = ar.take<__nv_bfloat16>((size_t)T * B * H);
+  __nv_bfloat16* db = ar.take<__nv_bfloat16>((size_t)T * B * H);
+  __nv_bfloat16* h0b = h0 ? ar.take<__nv_bfloat16>((size_t)B * H) : nullptr;
+  TACORL_REQUIRE(wih && whh && xb && hb && db && (!h0 || h0b), "rnn_layer_bwd(bf16): workspace too small");
+  float* sk = (float*)(ar.base + ar.off);
+  size_t sk_bytes = ar.left();
+  const float beta0 = accumulate ? 1.f : 0.f;
+  const int t_lo = reverse ? T - n_steps : 0;
+  const long long rows = (long long)n_steps * B;
+  int rc;
+  if ((rc = cast_bf16_2d(w_ih, I, H, I, wih, Ip, st))) return rc;
+  if ((rc = cast_bf16_2d(w_hh, H, H, H, whh, H, st))) return rc;
+  if ((rc = cast_bf16_2d(x + (long long)t_lo * B * ldx, ldx, rows, I, xb, Ip, st))) return rc;
+  if ((rc = cast_bf16_2d(out + (long long)t_lo * B * ldo, ldo, rows, H, hb + (long long)t_lo * B * H, H, st))) return rc;
+  if (h0 && (rc = cast_bf16_2d(h0, H, B, H, h0b, H, st))) return rc;
+  for (int s = n_steps - 1; s >= 0; --s) {
+    const int t = reverse ? T - 1 - s : s;
+    float* dt = dout + (long long)t * B * lddo;
+    __nv_bfloat16* dbt = db + (long long)t * B * H;
+    mask_rows_kernel<<<ew_blocks((long long)B * H), 256, 0, st>>>(
+        B, H, dt, lddo, out + (long long)t * B * ldo, ldo, (s == n_steps - 1) ? dhn : nullptr, H, dbt);
+    TACORL_LAUNCH_CHECK();
+    if (s > 0) {   // dout[t_prev] += dpre[t] W_hh   (B operand = W_hh as stored [K=H][N=H]: MN-major)
+      const int tp = reverse ? t + 1 : t - 1;
+      TcArgs c;
+      c.C = dout + (long long)tp * B * lddo; c.ldc = lddo; c.beta = 1.f; c.split_k = 1;
+      if ((rc = gemm_tc_bf16(dbt, H, 0, whh, H, 1, B, H, H, c, sk, sk_bytes, st))) return rc;
+    } else if (dh0) {
+      TcArgs c;
+      c.C = dh0; c.ldc = H; c.split_k = 1;
+      if ((rc = gemm_tc_bf16(dbt, H, 0, whh, H, 1, B, H, H, c, sk, sk_bytes, st))) return rc;
+    }
+  }
+  float* dpre = dout + (long long)t_lo * B * lddo;
+  const __nv_bfloat16* dpb = db + (long long)t_lo * B * H;
+  if (dw_hh) {
+    bool wrote = false;
+    if (n_steps > 1) {   // dW_hh = dpre[pairs]^T h[prev]: both operands stored [K=rows][H]: MN-major
+      const __nv_bfloat16 *a, *b;
+      if (!reverse) { a = dpb + (long long)B * H; b = hb; }
+      else { a = dpb; b = hb + (long long)(t_lo + 1) * B * H; }
+      TcArgs w;
+      w.C = dw_hh; w.ldc = H; w.beta = beta0; w.split_k = 0;
+      if ((rc = gemm_tc_bf16(a, H, 1, b, H, 1, H, H, (n_steps - 1) * B, w, sk, sk_bytes, st))) return rc;
+      wrote = true;
+    }
+    if (h0) {
+      const int t0 = reverse ? T - 1 : 0;
+      TcArgs w;
+      w.C = dw_hh; w.ldc = H; w.beta = wrote ? 1.f : beta0; w.split_k = 0;
+      if ((rc = gemm_tc_bf16(db + (long long)t0 * B * H, H, 1, h0b, H, 1, H, H, B, w, sk, sk_bytes, st))) return rc;
+      wrote = true;
+    }
+    if (!wrote && !accumulate) TACORL_CHECK_CUDA(cudaMemsetAsync(dw_hh, 0, (size_t)H * H * 4, st));
+  }
+  if (dw_ih) {
+    TcArgs w;
+    w.C = dw_ih; w.ldc = I; w.beta = beta0; w.split_k = 0;
+    if ((rc = gemm_tc_bf16(dpb, H, 1, xb, Ip, 1, H, I, (int)rows, w, sk, sk_bytes, st))) return rc;
+  }
+  if (db_ih) if ((rc = colsum_f32((int)rows, H, dpre, lddo, db_ih, accumulate, st))) return rc;
+  if (db_hh) if ((rc = colsum_f32((int)rows, H, dpre, lddo, db_hh, accumulate, st))) return rc;
+  if (dx) {
+    if (!dx_accumulate && n_steps < T) {
+      const long long lo_rows = (long long)t_lo * B, hi_rows = (long long)(T - t_lo - n_steps) * B;
+      if (lo_rows) TACORL_CHECK_CUDA(cudaMemset2DAsync(dx, lddx * 4, 0, (size_t)I * 4, lo_rows, st));
+      if (hi_rows) TACORL_CHECK_CUDA(cudaMemset2DAsync(dx + (long long)(t_lo + n_steps) * B * lddx, lddx * 4, 0,
+                                                       (size_t)I * 4, hi_rows, st));
+    }
+    TcArgs d;   // dx = dpre W_ih  (B operand = W_ih as stored [K=H][N=I]: MN-major)
+    d.C = dx + (long long)t_lo * B * lddx; d.ldc = lddx; d.beta = dx_accumulate ? 1.f : 0.f; d.split_k = 1;
+    if ((rc = gemm_tc_bf16(dpb, H, 0, wih, Ip, 1, (int)rows, I, H, d, sk, sk_bytes, st))) return rc;
+  }
+  return 0;
+}
+
+int tacorl_rnn_layer_fwd(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
+                         const float* w_hh, const float* b_ih, const float* b_hh, const float* h0,
+                         int reverse, int n_steps, float* out, long long ldo, void* ws, size_t ws_bytes,
+                         int prec, void* stream) {
+  TACORL_REQUIRE(prec == PREC_F32 || prec == PREC_BF16, "rnn_layer_fwd: unknown precision %d", prec);
+  auto fn = prec == PREC_BF16 ? rnn_fwd_bf16 : rnn_fwd_f32;
+  return fn(T, B, I, H, x, ldx, w_ih, w_hh, b_ih, b_hh, h0, reverse, n_steps, out, ldo, ws, ws_bytes,
+            (cudaStream_t)stream);
+}
+
+int tacorl_rnn_layer_bwd(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
+                         const float* w_hh, const float* h0, int reverse, int n_steps, const float* out,
+                         long long ldo, float* dout, long long lddo, const float* dhn, float* dx,
+                         long long lddx, int dx_accumulate, float* dw_ih, float* dw_hh, float* db_ih,
+                         float* db_hh, int accumulate, float* dh0, void* ws, size_t ws_bytes, int prec,
+                         void* stream) {
+  TACORL_REQUIRE(prec == PREC_F32 || prec == PREC_BF16, "rnn_layer_bwd: unknown precision %d", prec);
+  auto fn = prec == PREC_BF16 ? rnn_bwd_bf16 : rnn_bwd_f32;
+  return fn(T, B, I, H, x, ldx, w_ih, w_hh, h0, reverse, n_steps, out, ldo, dout, lddo, dhn, dx, lddx,
+            dx_accumulate, dw_ih, dw_hh, db_ih, db_hh, accumulate, dh0, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,121 @@
+"""GPU tests of the bf16 tcgen05 tensor-core path (TMA + TMEM GEMM, RNN, encoder, full PlayLMP step).
+Tolerance: 1e-2 relative on losses (BASELINE.json north_star bf16 bar); the raw GEMM is checked tightly
+on bf16-exact inputs so descriptor / layout errors cannot hide behind the loose tolerance."""
+import pytest
+import torch
+
+from oracle import synth as S
+from oracle import tacorl_oracle as O
+from tests.gpu_util import DEV, assert_close, build_play_lmp, load_golden, play_lmp_tape, rel_err, to_dev
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def bf16_ops():
+    from tacorl_b200 import ops
+    ops.set_precision("bf16")
+    yield ops
+    ops.set_precision("fp32")
+
+
+def _bf(t):
+    return t.bfloat16().float()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (64, 2048, 2048), (960, 182, 2048), (1024, 32, 192), (300, 64, 512),
+                                   (257, 130, 40), (64, 64, 1000), (2000, 256, 128), (5000, 576, 64), (64, 576, 5000),
+                                   (32, 192, 3000), (8, 16, 8)])
+@pytest.mark.parametrize("tA,tB", [(False, True), (False, False), (True, False), (True, True)])
+def test_tcgen05_gemm_all_operand_layouts(bf16_ops, M, N, K, tA, tB):
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
+    A = _bf(torch.randn((K, M) if tA else (M, K), generator=g))
+    B = _bf(torch.randn((N, K) if tB else (K, N), generator=g))
+    bias = torch.randn(N, generator=g)
+    C0 = torch.randn(M, N, generator=g)
+    want = (A.double().t() if tA else A.double()) @ (B.double().t() if tB else B.double())
+    want = 0.5 * want + 0.25 * C0.double() + bias.double()
+    C = C0.clone().to(DEV)
+    bf16_ops.gemm(A.to(DEV), B.to(DEV), C, transA=tA, transB=tB, alpha=0.5, beta=0.25, bias=bias.to(DEV))
+    assert_close(f"tc gemm tA={tA} tB={tB}", C, want, 2e-5)
+
+
+def test_tcgen05_gemm_relu_and_rounding(bf16_ops):
+    g = torch.Generator().manual_seed(1)
+    A, W = torch.randn(333, 200, generator=g), torch.randn(77, 200, generator=g)
+    out = torch.empty(333, 77, device=DEV)
+    bf16_ops.gemm(A.to(DEV), W.to(DEV), out, transB=True, act=1)
+    want = torch.relu(_bf(A).double() @ _bf(W).double().t())
+    assert_close("relu", out, want, 2e-5)
+    full = torch.relu(A.double() @ W.double().t())
+    assert rel_err(out, full) < 1e-2
+
+
+@pytest.mark.parametrize("bidir,last_only", [(False, False), (True, True)])
+def test_rnn_bf16_close_to_fp64(bf16_ops, bidir, last_only):
+    g = torch.Generator().manual_seed(5)
+    B, T, I, H = 64, 16, 32, 256
+    rnn = torch.nn.RNN(I, H, num_layers=2, nonlinearity="relu", bidirectional=bidir, batch_first=True)
+    sd = {k: v.detach().clone() for k, v in rnn.state_dict().items()}
+    names = list(sd.keys())
+    x = torch.randn(B, T, I, generator=g)
+    P = {"r." + k: v.double().requires_grad_(True) for k, v in sd.items()}
+    x64 = x.double().requires_grad_(True)
+    out, _ = O.rnn_stack(P, "r.", x64, 2, bidir)
+    want = out[:, -1] if last_only else out
+    cot = torch.randn(want.shape, generator=g)
+    (want * cot.double()).sum().backward()
+    ws = [sd[k].clone().to(DEV).requires_grad_(True) for k in names]
+    xd = x.to(DEV).requires_grad_(True)
+    got, _ = bf16_ops.relu_rnn(xd.transpose(0, 1), ws, 2, bidir, last_only, None)
+    if not last_only:
+        got = got.transpose(0, 1)
+    (got * cot.to(DEV)).sum().backward()
+    assert_close("out", got, want, 2e-2)
+    assert_close("dx", xd.grad, x64.grad, 3e-2)
+    for k, w in zip(names, ws):
+        assert_close(f"grad {k}", w.grad, P["r." + k].grad, 3e-2, atol=1e-5)
+
+
+@pytest.mark.parametrize("n,h,w", [(3, 84, 84), (2, 200, 200), (2, 150, 200)])
+def test_encoder_bf16_close_to_fp64(bf16_ops, n, h, w):
+    rec = load_golden("encoder_shapes")
+    sd = S.synth_state_dict(rec["shapes"], rec["seed"])
+    x = S.synth_images((n, 3, h, w), rec["seed"], f"enc{h}x{w}")
+    P = O.params_from({k: v.double() for k, v in sd.items()})
+    y = O.lmp_encoder(P, "", x.double())
+    cot = torch.rand(y.shape, generator=S._gen(rec["seed"], f"cot{h}x{w}")) * 2 - 1
+    (y * cot.double()).sum().backward()
+    names = list(rec["shapes"].keys())
+    params = [sd[k].clone().to(DEV).requires_grad_(True) for k in names]
+    emb = bf16_ops.lmp_encoder(x.to(DEV), params)
+    (emb * cot.to(DEV)).sum().backward()
+    assert_close("emb", emb, y, 2e-2)
+    errs = {k: rel_err(p.grad, P[k].grad) for k, p in zip(names, params)}
+    assert max(errs.values()) < 6e-2, errs
+
+
+def test_play_lmp_bf16_step_within_1e2_of_fp64_oracle(bf16_ops):
+    from tacorl_b200.utils.rng import noise_tape
+    B, T, H, W = 8, 16, 200, 200
+    m = build_play_lmp("tanh_net", ("rgb_static",), 2048, 16, T)
+    shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
+    sd = S.synth_state_dict(shapes, 5)
+    m.load_state_dict(sd)
+    m.to(DEV)
+    opt = m.configure_optimizers()
+    batch = S.synth_play_batch(B, T, H, W, 5)
+    P = O.params_from(sd)
+    ost = {}
+    for s in range(3):
+        torch.manual_seed(77 + s)
+        noise = O.draw_play_lmp_noise(B, T)
+        opt.zero_grad()
+        with noise_tape(play_lmp_tape(noise, B)):
+            loss = m.training_step(to_dev(S.clone_batch(batch)), s)
+        loss.backward()
+        opt.step()
+        out, _ = O.play_lmp_training_step(P, ost, S.clone_batch(batch), noise)
+        for k in ["kl_loss", "action_loss", "total_loss"]:
+            got, want = float(m.logged["train/" + k]), float(out[k])
+            assert abs(got - want) <= 1e-2 * max(1.0, abs(want)), (s, k, got, want)
