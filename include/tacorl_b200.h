@@ -149,9 +149,11 @@ int tacorl_cql_actor_loss(int mode, int B, const float* log_pi, const float* a, 
 
 /* ---- optimiser side: Adam (play_lmp_for_rl.py:362-368, cql_offline_lightning.py:553-574) fused with
  * clip_grad_norm_ (:522-537) over flat buffers; Polyak (:229-232); sum of squares (ws >= 592 floats) */
+/* step: host-side step count (>=1) used for the bias corrections, OR step_dev != NULL: a device int that the
+ * call increments and reads (so a captured CUDA graph replays with the right bias correction). */
 int tacorl_adam_step(long long n, float* p, const float* g, float* m, float* v, float lr, float beta1,
-                     float beta2, float eps, int step, float grad_scale, const float* sqnorm, float max_norm,
-                     void* stream);
+                     float beta2, float eps, int step, int* step_dev, float grad_scale, const float* sqnorm,
+                     float max_norm, void* stream);
 int tacorl_polyak_update(long long n, float* target, const float* source, float tau, void* stream);
 int tacorl_sqnorm(long long n, const float* x, float* out, float* ws, void* stream);
 

@@ -47,7 +47,7 @@ _SIGS = {
     "tacorl_cql_critic_loss": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _i,
                                _vp, _vp, _vp, _vp, _vp],
     "tacorl_cql_actor_loss": [_i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp],
-    "tacorl_adam_step": [_ll, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _f, _vp, _f, _vp],
+    "tacorl_adam_step": [_ll, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _vp, _f, _vp, _f, _vp],
     "tacorl_polyak_update": [_ll, _vp, _vp, _f, _vp],
     "tacorl_sqnorm": [_ll, _vp, _vp, _vp, _vp],
     "tacorl_last_error": [],

@@ -19,7 +19,12 @@ constexpr int kOptBlocks = 148 * 4;
 __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g,
                             float* __restrict__ m, float* __restrict__ v, float lr, float b1, float b2,
                             float eps, float bc1, float bc2_sqrt, float grad_scale,
-                            const float* __restrict__ sqnorm, float max_norm) {
+                            const float* __restrict__ sqnorm, float max_norm, const int* __restrict__ step_dev) {
+  if (step_dev) {   // CUDA-graph friendly: bias corrections from a device-resident step counter
+    const float t = (float)(*step_dev);
+    bc1 = 1.f - powf(b1, t);
+    bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  }
   float gs = grad_scale;
   if (sqnorm) {
     const float norm = sqrtf(*sqnorm) * grad_scale;
@@ -48,6 +53,8 @@ __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __r
     p[i] -= step * mm / (sqrtf(vv) / bc2_sqrt + eps);
   }
 }
+
+__global__ void increment_kernel(int* p) { *p += 1; }
 
 __global__ void polyak_kernel(long long n, float* __restrict__ tgt, const float* __restrict__ src, float tau) {
   const long long n4 = n >> 2;
@@ -98,17 +105,22 @@ using namespace tacorl;
 extern "C" {
 
 int tacorl_adam_step(long long n, float* p, const float* g, float* m, float* v, float lr, float beta1,
-                     float beta2, float eps, int step, float grad_scale, const float* sqnorm, float max_norm,
-                     void* stream) {
+                     float beta2, float eps, int step, int* step_dev, float grad_scale, const float* sqnorm,
+                     float max_norm, void* stream) {
   if (n == 0) return 0;
-  TACORL_REQUIRE(p && g && m && v && step >= 1, "adam_step: bad arguments");
+  TACORL_REQUIRE(p && g && m && v && (step >= 1 || step_dev), "adam_step: bad arguments");
+  if (step_dev) {
+    increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    TACORL_LAUNCH_CHECK();
+    if (step < 1) step = 1;
+  }
   TACORL_REQUIRE(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
                      ((uintptr_t)v % 16 == 0), "adam_step: buffers must be 16-byte aligned");
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
   int blocks = (int)min((long long)kOptBlocks, (n / 4 + 255) / 256 + 1);
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(n, p, g, m, v, lr, beta1, beta2, eps, bc1, sqrtf(bc2),
-                                                       grad_scale, sqnorm, max_norm);
+                                                       grad_scale, sqnorm, max_norm, step_dev);
   TACORL_LAUNCH_CHECK();
   return 0;
 }

@@ -230,7 +230,7 @@ static int rnn_fwd_bf16(int T, int B, int I, int H, const float* x, long long ld
       continue;
     }
     TcArgs r;
-    r.C = ot; r.ldc = ldo; r.beta = 1.f; r.act = ACT_RELU; r.Cb = hbt; r.ldcb = H; r.split_k = 1;
+    r.C = ot; r.ldc = ldo; r.beta = 1.f; r.act = ACT_RELU; r.Cb = hbt; r.ldcb = H; r.split_k = 0;
     if ((rc = gemm_tc_bf16(hp, H, 0, whh, H, 0, B, H, H, r, sk, sk_bytes, st))) return rc;
   }
   return 0;
@@ -271,7 +271,7 @@ static int rnn_bwd_bf16(int T, int B, int I, int H, const float* x, long long ld
     if (s > 0) {   // dout[t_prev] += dpre[t] W_hh   (B operand = W_hh as stored [K=H][N=H]: MN-major)
       const int tp = reverse ? t + 1 : t - 1;
       TcArgs c;
-      c.C = dout + (long long)tp * B * lddo; c.ldc = lddo; c.beta = 1.f; c.split_k = 1;
+      c.C = dout + (long long)tp * B * lddo; c.ldc = lddo; c.beta = 1.f; c.split_k = 0;
       if ((rc = gemm_tc_bf16(dbt, H, 0, whh, H, 1, B, H, H, c, sk, sk_bytes, st))) return rc;
     } else if (dh0) {
       TcArgs c;

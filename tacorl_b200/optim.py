@@ -53,6 +53,9 @@ class FlatAdam(torch.optim.Optimizer):
         self.grad_scale = 1.0
         self.step_count = 0
         self._sqnorm = torch.zeros(1, device=self.pbuf.flat.device)
+        # device-resident step counter: the bias correction stays right when the step is replayed from a CUDA graph
+        self._step_dev = (torch.zeros(1, dtype=torch.int32, device=self.pbuf.flat.device)
+                          if self.pbuf.flat.is_cuda else None)
 
     @property
     def flat_params(self):
@@ -86,7 +89,7 @@ class FlatAdam(torch.optim.Optimizer):
             sq = ops.sqnorm(self.flat_grad, self._sqnorm)
         ops.adam_step(self.pbuf.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], self.step_count,
                       g["betas"][0], g["betas"][1], g["eps"], self.grad_scale, sq,
-                      float(self.max_grad_norm) if self.max_grad_norm is not None else 0.0)
+                      float(self.max_grad_norm) if self.max_grad_norm is not None else 0.0, self._step_dev)
         return loss
 
     def set_grad(self, flat_values):

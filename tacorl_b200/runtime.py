@@ -1,0 +1,71 @@
+"""CUDA-graph execution of a whole training step (forward + backward + all-reduce + optimiser).
+
+The step issues several hundred small launches (per-timestep recurrent GEMMs, per-chunk conv GEMMs, loss
+kernels); replaying them from one captured graph removes the host launch / ctypes / autograd overhead that would
+otherwise dominate a ~ms step (SURVEY.md §7 "Host overhead").  Noise keeps advancing between replays (the torch
+CUDA generator is graph-aware) and the Adam bias correction reads a device-resident step counter."""
+import torch
+
+
+def _clone_to_static(batch, device):
+    out = {}
+    for k, v in batch.items():
+        if isinstance(v, dict):
+            out[k] = _clone_to_static(v, device)
+        elif torch.is_tensor(v):
+            out[k] = v.to(device, non_blocking=True).clone()
+        else:
+            out[k] = v
+    return out
+
+
+def _copy_into(static, batch):
+    for k, v in batch.items():
+        if isinstance(v, dict):
+            _copy_into(static[k], v)
+        elif torch.is_tensor(v):
+            static[k].copy_(v, non_blocking=True)
+
+
+class GraphedTrainStep:
+    """step_fn(static_batch) must run one full optimisation step and return a scalar device tensor (or None).
+    Usage:  g = GraphedTrainStep(step_fn, example_batch); loss = g(next_batch)"""
+
+    def __init__(self, step_fn, example_batch, device=None, warmup=3):
+        device = device or torch.device("cuda", torch.cuda.current_device())
+        self.static = _clone_to_static(example_batch, device)
+        self.step_fn = step_fn
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                step_fn(self.static)
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            out = step_fn(self.static)
+            self.out = out.detach() if torch.is_tensor(out) else None
+
+    def __call__(self, batch=None):
+        if batch is not None:
+            _copy_into(self.static, batch)
+        self.graph.replay()
+        return self.out
+
+
+def play_lmp_step_fn(module, optimizer):
+    def step(batch):
+        optimizer.zero_grad(set_to_none=True)
+        loss = module.training_step(batch, 0)
+        loss.backward()
+        optimizer.step()
+        return loss
+    return step
+
+
+def tacorl_step_fn(module):
+    def step(batch):
+        module.training_step(batch)
+        return module.logged.get("train/q1_loss")
+    return step
