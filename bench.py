@@ -221,8 +221,11 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
     n0 = _lib.launch_count()
+    r0 = graphed.replays if graphed is not None else 0
     total_ms = timed(lambda s: step(None, None, args.warmup + s), args.steps)
     launches = _lib.launch_count() - n0
+    if graphed is not None:     # replayed kernels: (kernels recorded in the graph) x (replays in the timed region)
+        launches += graphed.launches_per_replay * (graphed.replays - r0)
     clk = clocks.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
     fps = world * B * T_FRAMES / (ms_per_step / 1e3)

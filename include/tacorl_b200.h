@@ -65,7 +65,8 @@ int tacorl_rowscale(long long rows, int L, const float* x, const float* row_scal
  *   model.0.{weight,bias}, model.2.{weight,bias}, model.4.{weight,bias}, model.6.temperature,
  *   fc_layers.0.{weight,bias}, fc_layers.3.{weight,bias}          
  * Saved for backward (caller-owned; pass NULL for y1,y2[,y3,feat,smax,ssum,h4] in inference):
- *   y1 (N,H1,W1,32), y2 (N,H2,W2,64), y3 (N,H3,W3,64) post-ReLU NHWC; feat (N,128);
+ *   y1 (N,H1,W1,32), y2 (N,H2,W2,64) post-ReLU NHWC (fp32 for PREC_F32, bf16 for PREC_BF16),
+ *   y3 (N,H3,W3,64) post-ReLU NHWC fp32; feat (N,128);
  *   smax, ssum (N,64) softmax statistics; h4 (N,hidden).   emb: (N,latent). */
 size_t tacorl_lmp_encoder_ws_bytes(int N, int H, int W, int hidden, int latent, int backward);
 int tacorl_lmp_encoder_fwd(const float* x, int N, int H, int W, const float* const* params, int hidden,

@@ -115,6 +115,15 @@ def ptr(t, allow_none=True):
     return ctypes.c_void_p(t.data_ptr())
 
 
+def ptr_any(t):
+    """Device pointer of a contiguous CUDA tensor of any dtype (saved bf16 activations)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise TacorlLibraryError("tacorl_b200 ops need CUDA tensors (there is no CPU fallback)")
+    return ctypes.c_void_p(t.data_ptr())
+
+
 def ptr_array(tensors):
     arr = (ctypes.c_void_p * len(tensors))()
     for i, t in enumerate(tensors):

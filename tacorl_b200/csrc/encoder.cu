@@ -4,8 +4,8 @@
 // SpatialSoftArgmax.forward (networks/visual_encoders/utils.py:39-76):
 //   conv(3->32,k8,s4)+ReLU, conv(32->64,k4,s2)+ReLU, conv(64->64,k3,s1)+ReLU,
 //   spatial soft-argmax (learned temperature, pixel coordinates), FC 128->hidden+ReLU, FC hidden->latent.
-// Saved activations are NHWC fp32.  This file is the fp32 parity path (im2col + SIMT GEMM);
-// the bf16 tensor-core path plugs in behind the same entry points via `prec`.
+// Saved activations are NHWC: fp32 on the fp32 parity path (im2col + SIMT GEMM); on the bf16 tensor-core
+// path (`prec` = TACORL_PREC_BF16) y1 / y2 are bf16 (written by the tcgen05 GEMM epilogue) and y3 stays fp32.
 #include "common.cuh"
 #include "internal.h"
 #include "../../include/tacorl_b200.h"
@@ -108,20 +108,20 @@ static int enc_fwd(const float* x, int N, int H, int W, const float* const* para
     float* y2p = save12 ? y2 + n0 * g.P2 * 64 : y2c;
     float* y3p = y3 + n0 * g.P3 * 64;
     if (tc) {
-      // bf16 im2col straight into the TMA-fed tcgen05 GEMM (K-major A = col, K-major B = weights)
+      // bf16 path: vectorised bf16 im2col -> TMA-fed tcgen05 GEMM (K-major col x K-major weights) with the
+      // bias+ReLU epilogue writing the NHWC activation directly in bf16 (y1, y2) / fp32 (y3, for the soft-argmax)
+      __nv_bfloat16* y1b = (__nv_bfloat16*)(save12 ? (void*)y1 : (void*)y1c) + (save12 ? n0 * g.P1 * 32 : 0);
+      __nv_bfloat16* y2b = (__nv_bfloat16*)(save12 ? (void*)y2 : (void*)y2c) + (save12 ? n0 * g.P2 * 64 : 0);
       TcArgs e;
       e.act = ACT_RELU; e.split_k = 1;
-      if ((rc = im2col_bf16(x + n0 * 3 * H * W, 3LL * H * W, (long long)H * W, W, 1, 3, 8, 8, 4, g.H1, g.W1, nf,
-                            (void*)col, st, 0))) return rc;
-      e.C = y1p; e.ldc = 32; e.bias = params[P_B1];
+      if ((rc = im2col_conv1_bf16(x + n0 * 3 * H * W, H, W, g.H1, g.W1, nf, col, st))) return rc;
+      e.C = nullptr; e.Cb = y1b; e.ldcb = 32; e.bias = params[P_B1];
       if ((rc = gemm_tc_bf16(col, 192, 0, wb1, 192, 0, (int)(nf * g.P1), 32, 192, e, nullptr, 0, st))) return rc;
-      if ((rc = im2col_bf16(y1p, g.P1 * 32, 1, (long long)g.W1 * 32, 32, 32, 4, 4, 2, g.H2, g.W2, nf, col, st, 1)))
-        return rc;
-      e.C = y2p; e.ldc = 64; e.bias = params[P_B2];
+      if ((rc = im2col_nhwc_bf16(2, y1b, g.H1, g.W1, g.H2, g.W2, nf, col, st))) return rc;
+      e.Cb = y2b; e.ldcb = 64; e.bias = params[P_B2];
       if ((rc = gemm_tc_bf16(col, 512, 0, wb2, 512, 0, (int)(nf * g.P2), 64, 512, e, nullptr, 0, st))) return rc;
-      if ((rc = im2col_bf16(y2p, g.P2 * 64, 1, (long long)g.W2 * 64, 64, 64, 3, 3, 1, g.H3, g.W3, nf, col, st, 1)))
-        return rc;
-      e.C = y3p; e.ldc = 64; e.bias = params[P_B3];
+      if ((rc = im2col_nhwc_bf16(3, y2b, g.H2, g.W2, g.H3, g.W3, nf, col, st))) return rc;
+      e.C = y3p; e.ldc = 64; e.Cb = nullptr; e.bias = params[P_B3];
       if ((rc = gemm_tc_bf16(col, 576, 0, wb3, 576, 0, (int)(nf * g.P3), 64, 576, e, nullptr, 0, st))) return rc;
       continue;
     }
@@ -252,37 +252,36 @@ int tacorl_lmp_encoder_bwd(const float* x, int N, int H, int W, const float* con
     const float* dy3p = dy3 + n0 * g.P3 * 64;
     if (tc) {
       // Every GEMM below consumes its operands as stored: wgrad = (dy MN-major)^T (col MN-major),
-      // dgrad = (dy K-major) (W MN-major) -> bf16 dcol, gathered by col2im with the ReLU mask.
+      // dgrad = (dy K-major) (W MN-major) -> bf16 dcol, gathered by the vectorised col2im with the ReLU mask.
       if (n0 == 0) {
         if ((rc = cast_bf16_2d(w2p, 512, 64, 512, wb2, 512, st))) return rc;
         if ((rc = cast_bf16_2d(w3p, 576, 64, 576, wb3, 576, st))) return rc;
       }
+      const __nv_bfloat16* y1b = (const __nv_bfloat16*)(const void*)y1 + n0 * g.P1 * 32;
+      const __nv_bfloat16* y2b = (const __nv_bfloat16*)(const void*)y2 + n0 * g.P2 * 64;
       const int m3 = (int)(nf * g.P3), m2 = (int)(nf * g.P2), m1 = (int)(nf * g.P1);
       TcArgs w, d;
       w.beta = betac; w.split_k = 0;
-      d.split_k = 1;
+      d.split_k = 1; d.C = nullptr;
       // conv3
       if ((rc = cast_bf16_2d(dy3p, 64, m3, 64, dyb, 64, st))) return rc;
-      if ((rc = im2col_bf16(y2p, g.P2 * 64, 1, (long long)g.W2 * 64, 64, 64, 3, 3, 1, g.H3, g.W3, nf, colb, st, 1)))
-        return rc;
+      if ((rc = im2col_nhwc_bf16(3, y2b, g.H2, g.W2, g.H3, g.W3, nf, colb, st))) return rc;
       w.C = dw3p; w.ldc = 576;
       if ((rc = gemm_tc_bf16(dyb, 64, 1, colb, 576, 1, 64, 576, m3, w, skws, kSplitKWs, st))) return rc;
-      d.C = nullptr; d.Cb = dcolb; d.ldcb = 576;
+      d.Cb = dcolb; d.ldcb = 576;
       if ((rc = gemm_tc_bf16(dyb, 64, 0, wb3, 576, 1, m3, 576, 64, d, nullptr, 0, st))) return rc;
-      if ((rc = col2im_bf16(dcolb, 64, g.H2, g.W2, 3, 3, 1, g.H3, g.W3, nf, y2p, dy2c, dyb, st))) return rc;
-      if ((rc = colsum_tall_f32((long long)nf * g.P2, 64, dy2c, grads[P_B2], accc, csws, 592 * 64 * 4, st))) return rc;
+      if ((rc = col2im_nhwc_bf16(3, dcolb, g.H2, g.W2, g.H3, g.W3, nf, y2b, dyb, st))) return rc;
+      if ((rc = colsum_tall_bf16((long long)nf * g.P2, 64, dyb, grads[P_B2], accc, csws, 592 * 64 * 4, st))) return rc;
       // conv2
-      if ((rc = im2col_bf16(y1p, g.P1 * 32, 1, (long long)g.W1 * 32, 32, 32, 4, 4, 2, g.H2, g.W2, nf, colb, st, 1)))
-        return rc;
+      if ((rc = im2col_nhwc_bf16(2, y1b, g.H1, g.W1, g.H2, g.W2, nf, colb, st))) return rc;
       w.C = dw2p; w.ldc = 512;
       if ((rc = gemm_tc_bf16(dyb, 64, 1, colb, 512, 1, 64, 512, m2, w, skws, kSplitKWs, st))) return rc;
       d.Cb = dcolb; d.ldcb = 512;
       if ((rc = gemm_tc_bf16(dyb, 64, 0, wb2, 512, 1, m2, 512, 64, d, nullptr, 0, st))) return rc;
-      if ((rc = col2im_bf16(dcolb, 32, g.H1, g.W1, 4, 4, 2, g.H2, g.W2, nf, y1p, dy1c, dyb, st))) return rc;
-      if ((rc = colsum_tall_f32((long long)nf * g.P1, 32, dy1c, grads[P_B1], accc, csws, 592 * 64 * 4, st))) return rc;
+      if ((rc = col2im_nhwc_bf16(2, dcolb, g.H1, g.W1, g.H2, g.W2, nf, y1b, dyb, st))) return rc;
+      if ((rc = colsum_tall_bf16((long long)nf * g.P1, 32, dyb, grads[P_B1], accc, csws, 592 * 64 * 4, st))) return rc;
       // conv1 wgrad, torch K order (c,ky,kx)
-      if ((rc = im2col_bf16(x + n0 * 3 * H * W, 3LL * H * W, (long long)H * W, W, 1, 3, 8, 8, 4, g.H1, g.W1, nf,
-                            colb, st, 0))) return rc;
+      if ((rc = im2col_conv1_bf16(x + n0 * 3 * H * W, H, W, g.H1, g.W1, nf, colb, st))) return rc;
       w.C = grads[P_W1]; w.ldc = 192;
       if ((rc = gemm_tc_bf16(dyb, 32, 1, colb, 192, 1, 32, 192, m1, w, skws, kSplitKWs, st))) return rc;
       continue;

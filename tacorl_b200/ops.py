@@ -126,8 +126,9 @@ class LMPEncoderFn(Function):
         H3, W3 = H2 - 2, W2 - 2
         emb = torch.empty(N, latent, device=dev, dtype=torch.float32)
         if save:
-            y1 = torch.empty(N, H1, W1, 32, device=dev)
-            y2 = torch.empty(N, H2, W2, 64, device=dev)
+            adt = torch.bfloat16 if _STATE["prec"] == L.PREC_BF16 else torch.float32
+            y1 = torch.empty(N, H1, W1, 32, device=dev, dtype=adt)
+            y2 = torch.empty(N, H2, W2, 64, device=dev, dtype=adt)
             y3 = torch.empty(N, H3, W3, 64, device=dev)
             feat = torch.empty(N, 128, device=dev)
             smax = torch.empty(N, 64, device=dev)
@@ -137,8 +138,9 @@ class LMPEncoderFn(Function):
             y1 = y2 = y3 = feat = smax = ssum = h4 = None
         nbytes = L.query("tacorl_lmp_encoder_ws_bytes", N, H, W, hidden, latent, 0)
         ws = L.workspace(nbytes, dev)
-        L.call("tacorl_lmp_encoder_fwd", L.ptr(x), N, H, W, L.ptr_array(params), hidden, latent, L.ptr(y1),
-               L.ptr(y2), L.ptr(y3), L.ptr(feat), L.ptr(smax), L.ptr(ssum), L.ptr(h4), L.ptr(emb),
+        ctx.prec = _STATE["prec"]
+        L.call("tacorl_lmp_encoder_fwd", L.ptr(x), N, H, W, L.ptr_array(params), hidden, latent, L.ptr_any(y1),
+               L.ptr_any(y2), L.ptr(y3), L.ptr(feat), L.ptr(smax), L.ptr(ssum), L.ptr(h4), L.ptr(emb),
                ctypes.c_void_p(ws.data_ptr()), ws.numel(), _STATE["prec"], L.stream())
         if save:
             ctx.save_for_backward(x, y1, y2, y3, feat, smax, ssum, h4, *params)
@@ -153,9 +155,9 @@ class LMPEncoderFn(Function):
         nbytes = L.query("tacorl_lmp_encoder_ws_bytes", N, H, W, hidden, latent, 1)
         ws = L.workspace(nbytes, x.device)
         d_emb = _c(d_emb)
-        L.call("tacorl_lmp_encoder_bwd", L.ptr(x), N, H, W, L.ptr_array(params), hidden, latent, L.ptr(y1),
-               L.ptr(y2), L.ptr(y3), L.ptr(feat), L.ptr(smax), L.ptr(ssum), L.ptr(h4), L.ptr(d_emb),
-               L.ptr_array(grads), 0, ctypes.c_void_p(ws.data_ptr()), ws.numel(), _STATE["prec"], L.stream())
+        L.call("tacorl_lmp_encoder_bwd", L.ptr(x), N, H, W, L.ptr_array(params), hidden, latent, L.ptr_any(y1),
+               L.ptr_any(y2), L.ptr(y3), L.ptr(feat), L.ptr(smax), L.ptr(ssum), L.ptr(h4), L.ptr(d_emb),
+               L.ptr_array(grads), 0, ctypes.c_void_p(ws.data_ptr()), ws.numel(), ctx.prec, L.stream())
         return (None, None, *grads)
 
 

@@ -42,15 +42,21 @@ class GraphedTrainStep:
                 step_fn(self.static)
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
+        from . import _lib
         self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
         with torch.cuda.graph(self.graph):
             out = step_fn(self.static)
             self.out = out.detach() if torch.is_tensor(out) else None
+        # kernels of libtacorl_b200.so recorded in the graph = launched again by every replay
+        self.launches_per_replay = _lib.launch_count() - n0
+        self.replays = 0
 
     def __call__(self, batch=None):
         if batch is not None:
             _copy_into(self.static, batch)
         self.graph.replay()
+        self.replays += 1
         return self.out
 
 
