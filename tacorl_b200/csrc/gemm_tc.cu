@@ -90,6 +90,98 @@ struct TcEpilogue {
   float* partial;                       // split-K: raw accumulators [z][M][N]
 };
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Epilogue math for one 16-column chunk of one output row, with 16-byte vector accesses when the row is
+// aligned and the chunk is fully inside the matrix (scalar guarded accesses otherwise).
+__device__ __forceinline__ void tc_epilogue_chunk(const TcEpilogue& ep, const uint32_t (&r)[16], int row, int col0,
+                                                  int N, int zslice, int M) {
+  const bool full = col0 + 16 <= N;
+  if (ep.partial) {
+    float* P = ep.partial + ((long long)zslice * M + row) * N + col0;
+    if (full && (N & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        reinterpret_cast<float4*>(P)[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                      __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (col0 + j < N) P[j] = __uint_as_float(r[j]);
+    }
+    return;
+  }
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = ep.alpha * __uint_as_float(r[j]);
+  float* Crow = ep.C ? ep.C + (long long)row * ep.ldc + col0 : nullptr;
+  const bool vecC = full && Crow && ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0);
+  if (ep.beta != 0.f && Crow) {
+    if (vecC) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 c = reinterpret_cast<const float4*>(Crow)[j];
+        v[4 * j] = fmaf(ep.beta, c.x, v[4 * j]); v[4 * j + 1] = fmaf(ep.beta, c.y, v[4 * j + 1]);
+        v[4 * j + 2] = fmaf(ep.beta, c.z, v[4 * j + 2]); v[4 * j + 3] = fmaf(ep.beta, c.w, v[4 * j + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (col0 + j < N) v[j] = fmaf(ep.beta, Crow[j], v[j]);
+    }
+  }
+  if (ep.bias) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (col0 + j < N) v[j] += __ldg(ep.bias + col0 + j);
+  }
+  if (ep.Cpre) {
+    float* Prow = ep.Cpre + (long long)row * ep.ldpre + col0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (col0 + j < N) Prow[j] = v[j];
+  }
+  if (ep.act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (ep.act == ACT_SILU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = v[j] / (1.f + __expf(-v[j]));
+  }
+  if (Crow) {
+    if (vecC) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        reinterpret_cast<float4*>(Crow)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (col0 + j < N) Crow[j] = v[j];
+    }
+  }
+  if (ep.Cb) {
+    __nv_bfloat16* Brow = ep.Cb + (long long)row * ep.ldcb + col0;
+    if (full && ((ep.ldcb & 7) == 0) && ((reinterpret_cast<uintptr_t>(ep.Cb) & 15) == 0)) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        pk[j] = *reinterpret_cast<uint32_t*>(&t);
+      }
+      reinterpret_cast<uint4*>(Brow)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      reinterpret_cast<uint4*>(Brow)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (col0 + j < N) Brow[j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+// Persistent over output tiles: CTA b processes tiles b, b + gridDim.x, ...; two TMEM accumulator stages let the
+// epilogue of tile i overlap the MMAs of tile i+1; the smem ring runs continuously across tiles.
 template <int BN, bool A_MN, bool B_MN, int kStages>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcEpilogue ep,
@@ -97,29 +189,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;     // 16 KB
   constexpr uint32_t B_BYTES = BN * TC_BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;        // power of two >= 64
   static_assert(!B_MN || BN % 64 == 0, "MN-major B needs 64-wide boxes");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + kStages * STAGE_BYTES);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kStages + 1);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
   const int total_kb = (K + TC_BK - 1) / TC_BK;
   const int kb_begin = blockIdx.z * kblocks_per_split;
   const int kb_end = min(total_kb, kb_begin + kblocks_per_split);
   const int nkb = kb_end - kb_begin;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int num_tiles = ((M + TC_BM - 1) / TC_BM) * tiles_n;
 
   const uint32_t smem_base = smem_u32(smem);
   auto full_bar = [&](int s) { return smem_u32(bars + s); };
   auto empty_bar = [&](int s) { return smem_u32(bars + kStages + s); };
-  const uint32_t tmem_full_bar = smem_u32(bars + 2 * kStages);
+  auto tfull_bar = [&](int a) { return smem_u32(bars + 2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return smem_u32(bars + 2 * kStages + 2 + a); };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -134,24 +229,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0 && nkb > 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % kStages;
-        const uint32_t ph = (i / kStages) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
-        mbar_expect_tx(full_bar(s), STAGE_BYTES);
-        const int k0 = (kb_begin + i) * TC_BK;
-        const uint32_t a_dst = smem_base + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
-        if (!A_MN) {
-          tma_load_2d(a_dst, &tmA, k0, m0, full_bar(s));
-        } else {
-          tma_load_2d(a_dst, &tmA, m0, k0, full_bar(s));
-          tma_load_2d(a_dst + 8192, &tmA, m0 + 64, k0, full_bar(s));
-        }
-        if (!B_MN) {
-          tma_load_2d(b_dst, &tmB, k0, n0, full_bar(s));
-        } else {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          const int k0 = (kb_begin + i) * TC_BK;
+          const uint32_t a_dst = smem_base + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+          if (!A_MN) {
+            tma_load_2d(a_dst, &tmA, k0, m0, full_bar(s));
+          } else {
+            tma_load_2d(a_dst, &tmA, m0, k0, full_bar(s));
+            tma_load_2d(a_dst + 8192, &tmA, m0 + 64, k0, full_bar(s));
+          }
+          if (!B_MN) {
+            tma_load_2d(b_dst, &tmB, k0, n0, full_bar(s));
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, n0 + j * 64, k0, full_bar(s));
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, n0 + j * 64, k0, full_bar(s));
+          }
         }
       }
     }
@@ -161,62 +260,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % kStages;
-        const uint32_t ph = (i / kStages) & 1;
-        mbar_wait(full_bar(s), ph);
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t acc = lt & 1;
+        mbar_wait(tempty_bar(acc), ((lt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t a_src = smem_base + s * STAGE_BYTES, b_src = a_src + A_BYTES;
+        const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t a_src = smem_base + s * STAGE_BYTES, b_src = a_src + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-          // K-major: advance 16 elements (32 B) inside the 128 B swizzle row; MN-major: 16 K-rows of 128 B
-          const uint64_t ad = A_MN ? make_smem_desc(a_src + k * 2048, 8192, 1024) : make_smem_desc(a_src + k * 32, 16, 1024);
-          const uint64_t bd = B_MN ? make_smem_desc(b_src + k * 2048, 8192, 1024) : make_smem_desc(b_src + k * 32, 16, 1024);
-          tc_mma_bf16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+            // K-major: advance 16 elements (32 B) inside the 128 B swizzle row; MN-major: 16 K-rows of 128 B
+            const uint64_t ad = A_MN ? make_smem_desc(a_src + k * 2048, 8192, 1024) : make_smem_desc(a_src + k * 32, 16, 1024);
+            const uint64_t bd = B_MN ? make_smem_desc(b_src + k * 2048, 8192, 1024) : make_smem_desc(b_src + k * 32, 16, 1024);
+            tc_mma_bf16(tmem_d, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty_bar(s));          // slot reusable once these MMAs have read it
         }
-        tc_commit(empty_bar(s));          // slot reusable once these MMAs have read it
+        tc_commit(tfull_bar(acc));          // accumulator complete
       }
-      tc_commit(tmem_full_bar);           // accumulator complete
     }
   } else {
     // ---- epilogue: TMEM lane quarter q holds rows m0 + 32q .. +31
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
-    if (nkb > 0) {
-      mbar_wait(tmem_full_bar, 0);
-      tc_fence_after();
-    }
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t r[16];
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int m0 = (tile / tiles_n) * TC_BM, n0 = (tile % tiles_n) * BN;
+      const int row = m0 + q * 32 + lane;
+      const uint32_t acc = lt & 1;
       if (nkb > 0) {
-        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = 0;
+        mbar_wait(tfull_bar(acc), (lt >> 1) & 1);
+        tc_fence_after();
       }
-      if (row < M) {
-        if (ep.partial) {
-          float* P = ep.partial + ((long long)blockIdx.z * M + row) * N;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n0 + c0 + j < N) P[n0 + c0 + j] = __uint_as_float(r[j]);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[16];
+        if (nkb > 0) {
+          tc_ld16(tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16) + c0, r);
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = n0 + c0 + j;
-            if (col < N) {
-              float v = ep.alpha * __uint_as_float(r[j]);
-              if (ep.beta != 0.f && ep.C) v = fmaf(ep.beta, ep.C[(long long)row * ep.ldc + col], v);
-              if (ep.bias) v += __ldg(ep.bias + col);
-              if (ep.Cpre) ep.Cpre[(long long)row * ep.ldpre + col] = v;
-              if (ep.act == ACT_RELU) v = fmaxf(v, 0.f);
-              else if (ep.act == ACT_SILU) v = v / (1.f + __expf(-v));
-              if (ep.C) ep.C[(long long)row * ep.ldc + col] = v;
-              if (ep.Cb) ep.Cb[(long long)row * ep.ldcb + col] = __float2bfloat16(v);
-            }
-          }
+          for (int j = 0; j < 16; ++j) r[j] = 0;
         }
+        if (row < M && n0 + c0 < N) tc_epilogue_chunk(ep, r, row, n0 + c0, N, blockIdx.z, M);
+      }
+      if (nkb > 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));     // this warp's TMEM reads of the stage are complete
       }
     }
   }
@@ -268,7 +362,7 @@ template <int BN, bool A_MN, bool B_MN>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcEpilogue& ep, int M, int N, int K,
                      int splits, cudaStream_t st) {
   constexpr int kStages = BN >= 128 ? 5 : 6;
-  constexpr size_t smem = (size_t)kStages * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + (2 * kStages + 1) * 8 + 16 + 1024;
+  constexpr size_t smem = (size_t)kStages * (TC_BM * TC_BK * 2 + BN * TC_BK * 2) + (2 * kStages + 4) * 8 + 16 + 1024;
   static bool configured = false;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, kStages>;
   if (!configured) {
@@ -277,7 +371,10 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcEpilo
   }
   const int total_kb = cdiv(K, TC_BK);
   const int per = cdiv(total_kb, splits);
-  dim3 grid(cdiv(N, BN), cdiv(M, TC_BM), cdiv(total_kb, per));
+  const int zs = cdiv(total_kb, per);
+  const long long tiles = (long long)cdiv(N, BN) * cdiv(M, TC_BM);
+  const int ctas = (int)min(tiles, (long long)max(1, 148 / zs));   // persistent: ~one CTA per SM in total
+  dim3 grid(ctas, 1, zs);
   kern<<<grid, TC_THREADS, smem, st>>>(ta, tb, ep, M, N, K, per);
   TACORL_LAUNCH_CHECK();
   return 0;

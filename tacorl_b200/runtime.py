@@ -19,6 +19,14 @@ def _clone_to_static(batch, device):
     return out
 
 
+def _tensors(batch):
+    for v in batch.values():
+        if isinstance(v, dict):
+            yield from _tensors(v)
+        elif torch.is_tensor(v):
+            yield v
+
+
 def _copy_into(static, batch):
     for k, v in batch.items():
         if isinstance(v, dict):
@@ -55,9 +63,35 @@ class GraphedTrainStep:
     def __call__(self, batch=None):
         if batch is not None:
             _copy_into(self.static, batch)
+        elif self._staged:
+            # inputs prefetched by `prefetch()`: wait for the H2D, move them into the graph's static buffers
+            main = torch.cuda.current_stream()
+            main.wait_event(self._ready)
+            _copy_into(self.static, self._staging)
+            self._consumed.record(main)
+            self._staged = False
         self.graph.replay()
         self.replays += 1
         return self.out
+
+    _staged = False
+    _staging = None
+
+    def prefetch(self, host_batch):
+        """Start the host->device copy of the NEXT step's (pinned) batch on a side stream so it overlaps the
+        step that is running; the following `__call__()` consumes it (double buffering, like a pinned
+        DataLoader with non_blocking copies)."""
+        if self._staging is None:
+            self._staging = _clone_to_static(self.static, next(iter(_tensors(self.static))).device)
+            self._copy_stream = torch.cuda.Stream()
+            self._ready = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._consumed)
+            _copy_into(self._staging, host_batch)
+            self._ready.record(self._copy_stream)
+        self._staged = True
 
 
 def play_lmp_step_fn(module, optimizer):
