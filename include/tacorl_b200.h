@@ -131,6 +131,26 @@ int tacorl_tanh_rsample_bwd(long long n, const float* a, const float* eps, const
 int tacorl_tanh_logprob(int rows, int L, int bcast_rows, const float* mu, const float* sd, const float* z,
                         int from_value, float* logp, float* gmu, float* gsd, float* gz, void* stream);
 
+/* ---- transformer plan recogniser pieces: plan_recognition_transformer.py:70-105 (+ torch's
+ * nn.TransformerEncoderLayer: post-norm, ReLU, eps 1e-5, (T,B,D) layout).  Linear layers use tacorl_gemm.
+ * Dropout masks are pre-scaled keep masks (or NULL).  attn: T <= 32, head_dim <= 16; qkv (T,B,3D) = [q|k|v],
+ * P (B*heads,T,T) = saved softmax.  add_ln: y = LayerNorm(x + r*mask); bwd ACCUMULATES dw/db (zero them first). */
+int tacorl_posemb_fwd(int B, int T, int D0, int D, const float* emb, const float* pos, const float* mask, float* x,
+                      void* stream);
+int tacorl_posemb_bwd(int B, int T, int D0, int D, const float* dx, const float* mask, float* demb, float* dpos,
+                      void* stream);
+int tacorl_attn_fwd(int B, int T, int D, int heads, const float* qkv, const float* amask, float* P, float* out,
+                    void* stream);
+int tacorl_attn_bwd(int B, int T, int D, int heads, const float* qkv, const float* amask, const float* P,
+                    const float* dout, float* dqkv, void* stream);
+int tacorl_add_ln_fwd(int rows, int D, const float* x, const float* r, const float* mask, const float* w,
+                      const float* b, float eps, float* y, float* xhat, float* rstd, void* stream);
+int tacorl_add_ln_bwd(int rows, int D, const float* dy, const float* xhat, const float* rstd, const float* w,
+                      const float* mask, float* dx, float* dr, float* dw, float* db, void* stream);
+int tacorl_mean_t_fwd(int B, int T, int C, const float* x, float* y, void* stream);
+int tacorl_mean_t_bwd(int B, int T, int C, const float* dy, float* dx, void* stream);
+int tacorl_mul(long long n, const float* a, const float* b, float* out, void* stream);
+
 /* ---- CQL losses, cql_offline_lightning.py:284-406, 439-468.
  * q*_all: [data (B) | rand (n,B) | curr (n,B) | next (n,B)].  scalars[14]:
  *  0 bellman_q1, 1 bellman_q2, 2 conservative_q1, 3 conservative_q2, 4 alpha_prime, 5 alpha_prime_loss,

@@ -44,6 +44,15 @@ _SIGS = {
     "tacorl_tanh_rsample_fwd": [_ll, _ll, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "tacorl_tanh_rsample_bwd": [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "tacorl_tanh_logprob": [_i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp],
+    "tacorl_posemb_fwd": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "tacorl_posemb_bwd": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "tacorl_attn_fwd": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "tacorl_attn_bwd": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "tacorl_add_ln_fwd": [_i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp],
+    "tacorl_add_ln_bwd": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "tacorl_mean_t_fwd": [_i, _i, _i, _vp, _vp, _vp],
+    "tacorl_mean_t_bwd": [_i, _i, _i, _vp, _vp, _vp],
+    "tacorl_mul": [_ll, _vp, _vp, _vp, _vp],
     "tacorl_cql_critic_loss": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _i,
                                _vp, _vp, _vp, _vp, _vp],
     "tacorl_cql_actor_loss": [_i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -25,6 +25,12 @@ def plan_recognition(kind="tanh_net", latent_plan_dim=16, hidden_dim=2048, max_w
         return {"_target_": _N + "plan_encoders.plan_recognition_net.PlanRecognitionNetwork",
                 "state_dim": None, "latent_plan_dim": latent_plan_dim, "birnn_dropout_p": 0.0, "min_std": 0.0001,
                 "hidden_dim": hidden_dim}
+    if kind == "transformer":                                     # networks/plan_recognition/transformer.yaml
+        return {"_target_": _N + "plan_encoders.plan_recognition_transformer.PlanRecognitionTransformersNetwork",
+                "num_heads": 8, "num_layers": 2, "encoder_hidden_size": 2048, "fc_hidden_size": 4096,
+                "state_dim": None, "latent_plan_dim": latent_plan_dim, "min_std": 0.0001, "dropout_p": 0.1,
+                "encoder_normalize": False, "positional_normalize": False, "position_embedding": True,
+                "max_position_embeddings": max_window_size}
     raise ValueError(kind)
 
 

@@ -540,3 +540,138 @@ def sqnorm(x, out=None):
     ws = torch.empty(592, device=x.device)
     L.call("tacorl_sqnorm", x.numel(), L.ptr(x), L.ptr(out), L.ptr(ws), L.stream())
     return out
+
+
+# --------------------------------------------------------------------------------------- transformer pieces
+class PosEmbFn(Function):
+    """x (T,B,D) = (emb (B,T,D0) zero-padded to D + pos[:T]) * mask."""
+
+    @staticmethod
+    def forward(ctx, emb, pos, mask):
+        emb, pos = _c(emb), _c(pos)
+        B, T, D0 = emb.shape
+        D = pos.shape[1]
+        x = torch.empty(T, B, D, device=emb.device)
+        L.call("tacorl_posemb_fwd", B, T, D0, D, L.ptr(emb), L.ptr(pos), L.ptr(mask), L.ptr(x), L.stream())
+        ctx.dims = (B, T, D0, D, pos.shape[0])
+        ctx.save_for_backward(mask)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        (mask,) = ctx.saved_tensors
+        B, T, D0, D, npos = ctx.dims
+        demb = torch.empty(B, T, D0, device=dx.device) if ctx.needs_input_grad[0] else None
+        dpos = torch.zeros(npos, D, device=dx.device)
+        L.call("tacorl_posemb_bwd", B, T, D0, D, L.ptr(_c(dx)), L.ptr(mask), L.ptr(demb), L.ptr(dpos), L.stream())
+        return demb, dpos, None
+
+
+class AttentionFn(Function):
+    """Multi-head self-attention core on packed qkv (T,B,3D) -> (T,B,D)."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads, amask):
+        qkv = _c(qkv)
+        T, B, D3 = qkv.shape
+        D = D3 // 3
+        P = torch.empty(B * heads, T, T, device=qkv.device)
+        out = torch.empty(T, B, D, device=qkv.device)
+        L.call("tacorl_attn_fwd", B, T, D, heads, L.ptr(qkv), L.ptr(amask), L.ptr(P), L.ptr(out), L.stream())
+        ctx.heads = heads
+        ctx.save_for_backward(qkv, amask, P)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, amask, P = ctx.saved_tensors
+        T, B, D3 = qkv.shape
+        dqkv = torch.empty_like(qkv)
+        L.call("tacorl_attn_bwd", B, T, D3 // 3, ctx.heads, L.ptr(qkv), L.ptr(amask), L.ptr(P), L.ptr(_c(dout)),
+               L.ptr(dqkv), L.stream())
+        return dqkv, None, None
+
+
+class AddLayerNormFn(Function):
+    """LayerNorm(x + r*mask) over the last dim (post-norm residual block)."""
+
+    @staticmethod
+    def forward(ctx, x, r, mask, w, b, eps):
+        x, r = _c(x), _c(r)
+        D = x.shape[-1]
+        rows = x.numel() // D
+        y, xhat = torch.empty_like(x), torch.empty_like(x)
+        rstd = torch.empty(rows, device=x.device)
+        L.call("tacorl_add_ln_fwd", rows, D, L.ptr(x), L.ptr(r), L.ptr(mask), L.ptr(_c(w)), L.ptr(_c(b)), float(eps),
+               L.ptr(y), L.ptr(xhat), L.ptr(rstd), L.stream())
+        ctx.save_for_backward(xhat, rstd, w, mask)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xhat, rstd, w, mask = ctx.saved_tensors
+        D = xhat.shape[-1]
+        rows = xhat.numel() // D
+        dx, dr = torch.empty_like(xhat), torch.empty_like(xhat)
+        dw, db = torch.zeros(D, device=dy.device), torch.zeros(D, device=dy.device)
+        L.call("tacorl_add_ln_bwd", rows, D, L.ptr(_c(dy)), L.ptr(xhat), L.ptr(rstd), L.ptr(_c(w)), L.ptr(mask),
+               L.ptr(dx), L.ptr(dr), L.ptr(dw), L.ptr(db), L.stream())
+        return dx, dr, None, dw, db, None
+
+
+class MeanTimeFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        B, T, C = x.shape
+        y = torch.empty(B, C, device=x.device)
+        L.call("tacorl_mean_t_fwd", B, T, C, L.ptr(x), L.ptr(y), L.stream())
+        ctx.dims = (B, T, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, T, C = ctx.dims
+        dx = torch.empty(B, T, C, device=dy.device)
+        L.call("tacorl_mean_t_bwd", B, T, C, L.ptr(_c(dy)), L.ptr(dx), L.stream())
+        return dx
+
+
+class MaskMulFn(Function):
+    """x * mask (dropout with an explicit pre-scaled keep mask)."""
+
+    @staticmethod
+    def forward(ctx, x, mask):
+        x = _c(x)
+        out = torch.empty_like(x)
+        L.call("tacorl_mul", x.numel(), L.ptr(x), L.ptr(mask), L.ptr(out), L.stream())
+        ctx.save_for_backward(mask)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (mask,) = ctx.saved_tensors
+        dy = _c(dy)
+        dx = torch.empty_like(dy)
+        L.call("tacorl_mul", dy.numel(), L.ptr(dy), L.ptr(mask), L.ptr(dx), L.stream())
+        return dx, None
+
+
+def posemb(emb, pos, mask=None):
+    return PosEmbFn.apply(emb, pos, mask)
+
+
+def attention(qkv, heads, amask=None):
+    return AttentionFn.apply(qkv, heads, amask)
+
+
+def add_layernorm(x, r, w, b, mask=None, eps=1e-5):
+    return AddLayerNormFn.apply(x, r, mask, w, b, eps)
+
+
+def mean_time(x):
+    return MeanTimeFn.apply(x)
+
+
+def mask_mul(x, mask):
+    return x if mask is None else MaskMulFn.apply(x, mask)

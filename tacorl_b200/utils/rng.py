@@ -55,3 +55,12 @@ def uniform(shape, lo, hi, device):
     if _TAPE is not None:
         return _pop(shape, device)
     return torch.empty(shape, device=device, dtype=torch.float32).uniform_(lo, hi)
+
+
+def dropout_mask(shape, p, device, training=True):
+    """Pre-scaled keep mask (keep / (1-p)) of F.dropout, or None when dropout is inactive."""
+    if not training or p == 0.0:
+        return None
+    if _TAPE is not None:
+        return _pop(shape, device)
+    return torch.nn.functional.dropout(torch.ones(shape, device=device), p, True)

@@ -350,3 +350,56 @@ def test_library_fails_loudly_on_cpu_tensors():
     from tacorl_b200._lib import TacorlLibraryError
     with pytest.raises(TacorlLibraryError):
         ops.linear(torch.randn(2, 3), torch.randn(4, 3), torch.randn(4))
+
+
+def test_transformer_plan_recogniser_with_dropout_masks_vs_oracle():
+    """PlanRecognitionTransformersNetwork (training mode, dropout 0.1) with an explicit mask tape against the
+    oracle restatement fed the same masks: output distribution parameters and every gradient."""
+    _ops()
+    from tacorl_b200.networks.plan_encoders.plan_recognition_transformer import PlanRecognitionTransformersNetwork
+    from tacorl_b200.utils.rng import noise_tape
+    g = _g(41)
+    B, T, D, Hh, FF, p = 5, 8, 32, 8, 64, 0.1
+    net = PlanRecognitionTransformersNetwork(state_dim=D, latent_plan_dim=16, num_heads=Hh, num_layers=2,
+                                             encoder_hidden_size=FF, fc_hidden_size=96, max_position_embeddings=T,
+                                             dropout_p=p)
+    shapes = {k: list(v.shape) for k, v in net.state_dict().items()}
+    sd = S.synth_state_dict(shapes, 23)
+    net.load_state_dict(sd)
+    net.to(DEV).train()
+    emb = torch.randn(B, T, D, generator=g)
+
+    def mk(shape):
+        return (torch.rand(shape, generator=g) > p).float() / (1 - p)
+
+    masks = {"input": mk((T, B, D))}
+    tape = [masks["input"]]
+    for l in range(2):
+        masks[f"attn{l}"] = mk((B * Hh, T, T)); masks[f"drop1_{l}"] = mk((T, B, D))
+        masks[f"ff{l}"] = mk((T, B, FF)); masks[f"drop2_{l}"] = mk((T, B, D))
+        tape += [masks[f"attn{l}"], masks[f"drop1_{l}"], masks[f"ff{l}"], masks[f"drop2_{l}"]]
+    P = {"pr." + k: v.double().requires_grad_(True) for k, v in sd.items()}
+    e64 = emb.double().requires_grad_(True)
+    mu, sdv = O.plan_recognition_transformer(P, "pr.", e64, num_heads=Hh, num_layers=2,
+                                             masks={k: v.double() for k, v in masks.items()})
+    cm, cs = torch.randn(B, 16, generator=g), torch.randn(B, 16, generator=g)
+    ((mu * cm.double()).sum() + (sdv * cs.double()).sum()).backward()
+    ed = emb.to(DEV).requires_grad_(True)
+    with noise_tape(tape) as tp:
+        dist = net(ed)
+        assert len(tp) == 0
+    ((dist.normal_mean * cm.to(DEV)).sum() + (dist.normal_std * cs.to(DEV)).sum()).backward()
+    assert_close("mean", dist.normal_mean, mu, RTOL)
+    assert_close("std", dist.normal_std, sdv, RTOL)
+    assert_close("d emb", ed.grad, e64.grad, RTOL)
+    for k, prm in net.named_parameters():
+        want = P["pr." + k].grad
+        if want is None:
+            assert prm.grad is None, k
+            continue
+        assert_close(f"grad {k}", prm.grad, want, RTOL, atol=1e-6)
+    net.eval()
+    with torch.no_grad():
+        d2 = net(ed)
+    mu_e, _ = O.plan_recognition_transformer(P, "pr.", e64, num_heads=Hh, num_layers=2, masks=None)
+    assert_close("eval mean", d2.normal_mean, mu_e, RTOL)

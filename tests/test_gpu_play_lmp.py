@@ -18,7 +18,8 @@ def _setup():
     ops.set_precision("fp32")
 
 
-@pytest.mark.parametrize("name", ["playlmp_birnn_84", "playlmp_birnn_pad_128", "playlmp_multiview"])
+@pytest.mark.parametrize("name", ["playlmp_birnn_84", "playlmp_birnn_pad_128", "playlmp_multiview",
+                                  "playlmp_transformer_84"])
 def test_play_lmp_matches_reference_golden(name):
     """Same synthetic weights / batch / noise as oracle/make_golden.py fed to the CUDA modules; compared
     with the numbers the reference itself produced (losses, every gradient, parameters after Adam)."""
@@ -44,6 +45,7 @@ def test_play_lmp_matches_reference_golden(name):
             got, want = float(m.logged["train/" + k]), step["scalars"][k]
             assert abs(got - want) <= 1e-4 * max(1.0, abs(want)), (name, s, k, got, want)
         grads = {k: p.grad for k, p in m.named_parameters()}
+        assert {k for k, g in grads.items() if g is not None} == set(step["grads"])
         for k, fp in step["grads"].items():
             assert S.fingerprint_close(S.fingerprint(grads[k]), fp, 2e-4), (name, s, "grad", k, S.fingerprint(grads[k]), fp)
         opt.step()

@@ -29,7 +29,7 @@ def test_graphed_step_trains_and_counts_adam_steps():
     assert all(torch.isfinite(torch.tensor(losses)))
     assert losses[-1] < losses[0]
     assert not torch.equal(before, opt.flat_params)
-    assert int(opt._step_dev) == 2 + 1 + 6              # warm-up + capture + replays
+    assert int(opt._step_dev) == 2 + 6                  # warm-up + replays (capture records, it does not run)
     # host-fed path: pinned batch prefetched on the copy stream, consumed by the next call
     host = S.synth_play_batch(B, T, H, W, 5)
     host = {"states": {k: v.pin_memory() for k, v in host["states"].items()}, "actions": host["actions"].pin_memory()}
