@@ -58,6 +58,8 @@ struct GemmArgs {
 int gemm_f32(const GemmArgs& g, float* ws, size_t ws_bytes, cudaStream_t st);
 // out[n] (+)= sum_m X[m*ldx + n]
 int colsum_f32(int M, int N, const float* X, long long ldx, float* out, int accumulate, cudaStream_t st);
+int colsum2_f32(int M, int N, const float* X, long long ldx, float* out, int accumulate, float* ws, size_t ws_bytes,
+                cudaStream_t st);
 // dZ = dY * act'(.)  (relu: uses Y (post-act); silu: uses pre-activation)
 int act_bwd_f32(int act, long long n, const float* dY, const float* YorPre, float* dZ, cudaStream_t st);
 

@@ -201,11 +201,41 @@ __global__ void colsum_kernel(int M, int N, const float* __restrict__ X, long lo
   }
 }
 
+// slab-parallel variant: grid (N/32, slabs); part[slab][N]
+__global__ void colsum_slab_kernel(int M, int N, const float* __restrict__ X, long long ldx, float* __restrict__ part) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int beg = blockIdx.y * rows_per, end = min(M, beg + rows_per);
+  float s = 0.f;
+  if (n < N)
+    for (int m = beg + threadIdx.y; m < end; m += 8) s += X[(long long)m * ldx + n];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    part[(long long)blockIdx.y * N + n] = t;
+  }
+}
+
 int colsum_f32(int M, int N, const float* X, long long ldx, float* out, int accumulate, cudaStream_t st) {
   if (N == 0) return 0;
   colsum_kernel<<<cdiv(N, 32), dim3(32, 8), 0, st>>>(M, N, X, ldx, out, accumulate);
   TACORL_LAUNCH_CHECK();
   return 0;
+}
+
+// deterministic two-stage column sum that fills the machine when M is large and N moderate
+int colsum2_f32(int M, int N, const float* X, long long ldx, float* out, int accumulate, float* ws, size_t ws_bytes,
+                cudaStream_t st) {
+  if (N == 0) return 0;
+  int slabs = min(16, max(1, M / 64));
+  if (!ws || ws_bytes < (size_t)slabs * N * sizeof(float) || slabs == 1) return colsum_f32(M, N, X, ldx, out, accumulate, st);
+  colsum_slab_kernel<<<dim3(cdiv(N, 32), slabs), dim3(32, 8), 0, st>>>(M, N, X, ldx, ws);
+  TACORL_LAUNCH_CHECK();
+  return colsum_f32(slabs, N, ws, N, out, accumulate, st);
 }
 
 // two-stage column sum for very tall matrices (conv bias grads: M ~ 2.4M, N = 32/64)

@@ -88,6 +88,7 @@ struct TcEpilogue {
   int act;
   float* Cpre; long long ldpre;
   float* partial;                       // split-K: raw accumulators [z][M][N]
+  const float* gate; long long ldgate;  // optional ReLU gate: output forced to 0 where gate[row][col] <= 0
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -149,6 +150,12 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcEpilogue& ep, const ui
   } else if (ep.act == ACT_SILU) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = v[j] / (1.f + __expf(-v[j]));
+  }
+  if (ep.gate) {
+    const float* Grow = ep.gate + (long long)row * ep.ldgate + col0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (col0 + j < N && Grow[j] <= 0.f) v[j] = 0.f;
   }
   if (Crow) {
     if (vecC) {
@@ -393,6 +400,7 @@ __global__ void tc_splitk_reduce_kernel(int M, int N, int splits, const float* _
     if (ep.Cpre) ep.Cpre[(long long)row * ep.ldpre + col] = v;
     if (ep.act == ACT_RELU) v = fmaxf(v, 0.f);
     else if (ep.act == ACT_SILU) v = v / (1.f + __expf(-v));
+    if (ep.gate && ep.gate[(long long)row * ep.ldgate + col] <= 0.f) v = 0.f;
     if (ep.C) ep.C[(long long)row * ep.ldc + col] = v;
     if (ep.Cb) ep.Cb[(long long)row * ep.ldcb + col] = __float2bfloat16(v);
   }
@@ -405,6 +413,9 @@ int gemm_tc_bf16(const void* A, long long lda, int a_mn, const void* B, long lon
   if (M == 0 || N == 0) return 0;
   TACORL_REQUIRE(K > 0, "gemm_tc: K must be positive");
   int BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+  // skinny-M recurrent steps: many narrow N tiles (one fused kernel, no split-K round trip) beat 16 wide ones
+  const bool skinny = M <= TC_BM && N >= 512 && e.split_k == 0;
+  if (skinny) BN = b_mn ? 64 : 32;
   if (b_mn && BN < 64) BN = 64;
   CUtensorMap ta, tb;
   int rc;
@@ -415,7 +426,7 @@ int gemm_tc_bf16(const void* A, long long lda, int a_mn, const void* B, long lon
   int splits = e.split_k;
   if (splits <= 0) {
     splits = 1;
-    if (ws && ctas < 74 && total_kb >= 8) splits = (int)min((long long)cdiv(148, ctas), (long long)(total_kb / 4));
+    if (ws && !skinny && ctas < 74 && total_kb >= 8) splits = (int)min((long long)cdiv(148, ctas), (long long)(total_kb / 4));
   }
   if (splits > total_kb) splits = total_kb;
   if (splits > 1 && (!ws || (size_t)splits * M * N * 4 > ws_bytes)) {
@@ -425,6 +436,7 @@ int gemm_tc_bf16(const void* A, long long lda, int a_mn, const void* B, long lon
   TcEpilogue ep;
   ep.alpha = e.alpha; ep.beta = e.beta; ep.C = e.C; ep.ldc = e.ldc; ep.Cb = (__nv_bfloat16*)e.Cb; ep.ldcb = e.ldcb;
   ep.bias = e.bias; ep.act = e.act; ep.Cpre = e.Cpre; ep.ldpre = e.ldpre; ep.partial = splits > 1 ? ws : nullptr;
+  ep.gate = e.gate; ep.ldgate = e.ldgate;
 #define TC_DISPATCH(BNV)                                                                                   \
   if (BN == BNV) {                                                                                         \
     if (!a_mn && !b_mn) rc = launch_tc<BNV, false, false>(ta, tb, ep, M, N, K, splits, st);                \
@@ -464,6 +476,30 @@ int cast_bf16_2d(const float* src, long long lds, long long rows, int cols, void
   long long total = rows * ldd;
   cast_bf16_2d_kernel<<<(int)min((long long)148 * 8, (total + 255) / 256), 256, 0, st>>>(src, lds, rows, cols,
                                                                                         (__nv_bfloat16*)dst, ldd);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
+// dst[c][r] = bf16(src[r][c]) : 32x32 tiles through shared memory
+__global__ void cast_transpose_bf16_kernel(const float* __restrict__ src, long long lds, int rows, int cols,
+                                           __nv_bfloat16* __restrict__ dst, long long ldd) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(long long)r * lds + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) dst[(long long)c * ldd + r] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+
+int cast_transpose_bf16(const float* src, long long lds, int rows, int cols, void* dst, long long ldd, cudaStream_t st) {
+  if (rows == 0 || cols == 0) return 0;
+  cast_transpose_bf16_kernel<<<dim3(cdiv(cols, 32), cdiv(rows, 32)), dim3(32, 8), 0, st>>>(src, lds, rows, cols,
+                                                                                          (__nv_bfloat16*)dst, ldd);
   TACORL_LAUNCH_CHECK();
   return 0;
 }

@@ -41,11 +41,13 @@ struct TcArgs {
   int act = ACT_NONE;
   float* Cpre = nullptr; long long ldpre = 0;
   int split_k = 0;                                // 0 = auto
+  const float* gate = nullptr; long long ldgate = 0;   // optional ReLU gate applied to the output
 };
 // bf16 operands in place: a_mn/b_mn = operand stored [K][rows] (rows contiguous) instead of [rows][K]
 int gemm_tc_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, int M, int N,
                  int K, const TcArgs& e, float* ws, size_t ws_bytes, cudaStream_t st);
 int cast_bf16_2d(const float* src, long long lds, long long rows, int cols, void* dst, long long ldd, cudaStream_t st);
+int cast_transpose_bf16(const float* src, long long lds, int rows, int cols, void* dst, long long ldd, cudaStream_t st);
 int gemm_tc_from_f32(const GemmArgs& g, float* ws, size_t ws_bytes, cudaStream_t st);
 // precision dispatch used by the composite ops
 static inline int gemm_any(int prec, const GemmArgs& g, float* ws, size_t ws_bytes, cudaStream_t st) {

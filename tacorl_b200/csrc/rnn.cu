@@ -169,8 +169,17 @@ static int rnn_bwd_f32(int T, int B, int I, int H, const float* x, long long ldx
     w.B = x + (long long)t_lo * B * ldx; w.ldb = ldx; w.C = dw_ih; w.ldc = I; w.beta = beta0; w.split_k = 0;
     if ((rc = gemm_f32(w, sk, sk_bytes, st))) return rc;
   }
-  if (db_ih) if ((rc = colsum_f32((int)rows, H, dpre, lddo, db_ih, accumulate, st))) return rc;
-  if (db_hh) if ((rc = colsum_f32((int)rows, H, dpre, lddo, db_hh, accumulate, st))) return rc;
+  // db_ih == db_hh == column sums of dpre: reduce once, reuse
+  if (db_ih || db_hh) {
+    float* first = db_ih ? db_ih : db_hh;
+    if (!accumulate) {
+      if ((rc = colsum2_f32((int)rows, H, dpre, lddo, first, 0, sk, sk_bytes, st))) return rc;
+      if (db_ih && db_hh) TACORL_CHECK_CUDA(cudaMemcpyAsync(db_hh, db_ih, (size_t)H * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+      if (db_ih) if ((rc = colsum2_f32((int)rows, H, dpre, lddo, db_ih, 1, sk, sk_bytes, st))) return rc;
+      if (db_hh) if ((rc = colsum2_f32((int)rows, H, dpre, lddo, db_hh, 1, sk, sk_bytes, st))) return rc;
+    }
+  }
   if (dx) {
     if (!dx_accumulate && n_steps < T) {
       // rows outside the active range receive no gradient
@@ -257,26 +266,30 @@ static int rnn_bwd_bf16(int T, int B, int I, int H, const float* x, long long ld
   const long long rows = (long long)n_steps * B;
   int rc;
   if ((rc = cast_bf16_2d(w_ih, I, H, I, wih, Ip, st))) return rc;
-  if ((rc = cast_bf16_2d(w_hh, H, H, H, whh, H, st))) return rc;
+  if ((rc = cast_transpose_bf16(w_hh, H, H, H, whh, H, st))) return rc;     // whh = W_hh^T: K-major B for the carry GEMM
   if ((rc = cast_bf16_2d(x + (long long)t_lo * B * ldx, ldx, rows, I, xb, Ip, st))) return rc;
   if ((rc = cast_bf16_2d(out + (long long)t_lo * B * ldo, ldo, rows, H, hb + (long long)t_lo * B * H, H, st))) return rc;
   if (h0 && (rc = cast_bf16_2d(h0, H, B, H, h0b, H, st))) return rc;
+  {  // last step of the recurrence: dpre = (dout (+ dhn)) * [h > 0]
+    const int t = reverse ? T - n_steps : n_steps - 1;
+    mask_rows_kernel<<<ew_blocks((long long)B * H), 256, 0, st>>>(
+        B, H, dout + (long long)t * B * lddo, lddo, out + (long long)t * B * ldo, ldo, dhn, H, db + (long long)t * B * H);
+    TACORL_LAUNCH_CHECK();
+  }
   for (int s = n_steps - 1; s >= 0; --s) {
     const int t = reverse ? T - 1 - s : s;
-    float* dt = dout + (long long)t * B * lddo;
     __nv_bfloat16* dbt = db + (long long)t * B * H;
-    mask_rows_kernel<<<ew_blocks((long long)B * H), 256, 0, st>>>(
-        B, H, dt, lddo, out + (long long)t * B * ldo, ldo, (s == n_steps - 1) ? dhn : nullptr, H, dbt);
-    TACORL_LAUNCH_CHECK();
-    if (s > 0) {   // dout[t_prev] += dpre[t] W_hh   (B operand = W_hh as stored [K=H][N=H]: MN-major)
+    if (s > 0) {   // dpre[t_prev] = (dout[t_prev] + dpre[t] W_hh) * [h[t_prev] > 0], one fused GEMM (+ bf16 copy)
       const int tp = reverse ? t + 1 : t - 1;
       TcArgs c;
       c.C = dout + (long long)tp * B * lddo; c.ldc = lddo; c.beta = 1.f; c.split_k = 0;
-      if ((rc = gemm_tc_bf16(dbt, H, 0, whh, H, 1, B, H, H, c, sk, sk_bytes, st))) return rc;
+      c.gate = out + (long long)tp * B * ldo; c.ldgate = ldo;
+      c.Cb = db + (long long)tp * B * H; c.ldcb = H;
+      if ((rc = gemm_tc_bf16(dbt, H, 0, whh, H, 0, B, H, H, c, sk, sk_bytes, st))) return rc;
     } else if (dh0) {
       TcArgs c;
       c.C = dh0; c.ldc = H; c.split_k = 1;
-      if ((rc = gemm_tc_bf16(dbt, H, 0, whh, H, 1, B, H, H, c, sk, sk_bytes, st))) return rc;
+      if ((rc = gemm_tc_bf16(dbt, H, 0, whh, H, 0, B, H, H, c, sk, sk_bytes, st))) return rc;
     }
   }
   float* dpre = dout + (long long)t_lo * B * lddo;
@@ -306,8 +319,17 @@ static int rnn_bwd_bf16(int T, int B, int I, int H, const float* x, long long ld
     w.C = dw_ih; w.ldc = I; w.beta = beta0; w.split_k = 0;
     if ((rc = gemm_tc_bf16(dpb, H, 1, xb, Ip, 1, H, I, (int)rows, w, sk, sk_bytes, st))) return rc;
   }
-  if (db_ih) if ((rc = colsum_f32((int)rows, H, dpre, lddo, db_ih, accumulate, st))) return rc;
-  if (db_hh) if ((rc = colsum_f32((int)rows, H, dpre, lddo, db_hh, accumulate, st))) return rc;
+  // db_ih == db_hh == column sums of dpre: reduce once, reuse
+  if (db_ih || db_hh) {
+    float* first = db_ih ? db_ih : db_hh;
+    if (!accumulate) {
+      if ((rc = colsum2_f32((int)rows, H, dpre, lddo, first, 0, sk, sk_bytes, st))) return rc;
+      if (db_ih && db_hh) TACORL_CHECK_CUDA(cudaMemcpyAsync(db_hh, db_ih, (size_t)H * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+      if (db_ih) if ((rc = colsum2_f32((int)rows, H, dpre, lddo, db_ih, 1, sk, sk_bytes, st))) return rc;
+      if (db_hh) if ((rc = colsum2_f32((int)rows, H, dpre, lddo, db_hh, 1, sk, sk_bytes, st))) return rc;
+    }
+  }
   if (dx) {
     if (!dx_accumulate && n_steps < T) {
       const long long lo_rows = (long long)t_lo * B, hi_rows = (long long)(T - t_lo - n_steps) * B;
