@@ -10,6 +10,7 @@
 #include "internal.h"
 #include "../../include/tacorl_b200.h"
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace tacorl {
 
@@ -32,6 +33,18 @@ struct EncGeom {
 
 enum { P_W1 = 0, P_B1, P_W2, P_B2, P_W3, P_B3, P_TEMP, P_W4, P_B4, P_W5, P_B5, P_COUNT };
 static const size_t kSplitKWs = 64ull << 20;
+
+// Frames per im2col/GEMM chunk on the tensor-core path: small enough that a chunk's col matrix stays in the
+// 126 MB L2 between its producer and the GEMM that consumes it (TACORL_ENC_CHUNK overrides, for experiments).
+static int enc_chunk_cap() {
+  static int cap = 0;
+  if (!cap) {
+    const char* e = getenv("TACORL_ENC_CHUNK");
+    cap = e ? atoi(e) : 64;
+    if (cap < 1) cap = 64;
+  }
+  return cap;
+}
 
 static size_t fwd_fixed_bytes(const EncGeom& g, int hidden, bool need_y12, bool need_rest) {
   size_t b = (64 * 512 + 64 * 576) * 4 + 1024;
@@ -87,6 +100,7 @@ static int enc_fwd(const float* x, int N, int H, int W, const float* const* para
   if (!save12) per_frame += (g.P1 * 32 + g.P2 * 64) * 4 + 512;
   long long chunk = (long long)(ar.left() > 4096 ? (ar.left() - 4096) / per_frame : 0);
   if (chunk > N) chunk = N;
+  if (tc && chunk > enc_chunk_cap()) chunk = enc_chunk_cap();
   TACORL_REQUIRE(chunk >= 1, "lmp_encoder_fwd: workspace too small for one frame (%zu bytes left)", ar.left());
   float* col = ar.take<float>((size_t)chunk * g.col_floats_per_frame());
   float* y1c = save12 ? nullptr : ar.take<float>((size_t)chunk * g.P1 * 32);
@@ -195,6 +209,7 @@ int tacorl_lmp_encoder_bwd(const float* x, int N, int H, int W, const float* con
   const size_t reserve = 4096 + (tc ? (1 << 20) : 0);
   long long chunk = (long long)(ar.left() > reserve ? (ar.left() - reserve) / per_frame : 0);
   if (chunk > N) chunk = N;
+  if (tc && chunk > enc_chunk_cap()) chunk = enc_chunk_cap();
   TACORL_REQUIRE(chunk >= 1, "lmp_encoder_bwd: workspace too small for one frame");
   float* col = ar.take<float>((size_t)chunk * g.col_floats_per_frame());
   float* dy1c = ar.take<float>((size_t)chunk * g.P1 * 32);

@@ -414,7 +414,7 @@ int gemm_tc_bf16(const void* A, long long lda, int a_mn, const void* B, long lon
   TACORL_REQUIRE(K > 0, "gemm_tc: K must be positive");
   int BN = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
   // skinny-M recurrent steps: many narrow N tiles (one fused kernel, no split-K round trip) beat 16 wide ones
-  const bool skinny = M <= TC_BM && N >= 512 && e.split_k == 0;
+  const bool skinny = M <= TC_BM && N >= 512 && K <= 8192 && e.split_k == 0;
   if (skinny) BN = b_mn ? 64 : 32;
   if (b_mn && BN < 64) BN = 64;
   CUtensorMap ta, tb;
