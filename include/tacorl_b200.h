@@ -79,6 +79,14 @@ int tacorl_lmp_encoder_bwd(const float* x, int N, int H, int W, const float* con
                            const float* d_emb, float* const* grads, int accumulate, void* ws,
                            size_t ws_bytes, int prec, void* stream);
 
+/* Diagnostic hook for the implicit-GEMM convolution kernels behind tacorl_lmp_encoder_* (PREC_BF16):
+ * runs ONE op on fp32 NHWC inputs staged to bf16.  op 1/2/3: conv1/2/3 forward (in0 = image NCHW | y1 | y2);
+ * 4/5: conv3/conv2 data gradient (in0 = dY, in1 = saved activation gating the result);
+ * 6/7/8: conv3/conv2/conv1 weight gradient (in0 = dY, in1 = y2 | y1 | image) -> torch (oc,c,ky,kx) layout.
+ * H, W are the IMAGE dims the layer geometry derives from (encoder.py:369-390). */
+int tacorl_conv_tc_debug(int op, const float* in0, const float* in1, const float* Wt, const float* bias, int N,
+                         int H, int W, float* out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- ReLU RNN layer, one direction, time-major (T*B rows): nn.RNN(nonlinearity="relu") at
  * rnn_models.py:5-16 (decoder) and plan_recognition_tanh_net.py:23-31 / plan_recognition_net.py:27-35
  * (BiRNN).  h0 may be NULL (zeros).  reverse: recurrence runs t = T-1 .. T-n_steps.

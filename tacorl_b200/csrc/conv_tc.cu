@@ -1,0 +1,797 @@
+// Implicit-GEMM convolutions on the 5th-gen tensor cores (sm_100a): no im2col matrix is ever materialised.
+//
+//   rows (M)      = output pixels, 128 per tile, persistent CTAs loop over tiles
+//   K blocks      = filter taps (or tap pairs): 64 bf16 = one 128-byte NHWC pixel run of the source activation
+//   A operand     = gathered by 4 producer warps with 16-byte cp.async straight from the NHWC activation into
+//                   128B-swizzled shared memory (thread r owns tile row r; out-of-image taps are zero-filled),
+//                   fenced into the async proxy and handed to the MMA warp through an mbarrier ring
+//   B operand     = the layer's packed bf16 weights, TMA-loaded ONCE per CTA and kept resident in shared memory
+//   accumulator   = TMEM, double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1
+//   epilogue      = tcgen05.ld -> bias + ReLU (forward) or ReLU gate of the saved activation (dgrad) -> NHWC bf16/fp32
+//
+// The same kernel runs conv1 (as a 2x2/stride-1 conv over a space-to-depth(4) copy of the image), conv2, conv3 forward,
+// conv3 dgrad and the four stride-parity classes of conv2 dgrad.  conv_tc_wgrad_kernel computes the weight gradients
+// with both operands MN-major (pixels are the UMMA K dimension).
+// Reference semantics: nn.Conv2d x3 + ReLU of /root/reference/src/tacorl/networks/visual_encoders/encoder.py:369-390.
+#include "common.cuh"
+#include "internal.h"
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace tacorl {
+
+constexpr int CV_MAXT = 16;
+constexpr int CV_STAGES = 4;
+constexpr int CV_THREADS = 288;     // 4 producer warps, 1 MMA warp, 4 epilogue warps
+
+struct ConvGeom {
+  const __nv_bfloat16* src;         // NHWC source (N, SH, SW, SC)
+  int SH, SW, SC;
+  int kchunks;                      // valid 16-byte chunks per K-block row (<= 8); the rest is zero-filled
+  int RA, RB;                       // rows per frame = RA*RB (output-pixel grid of this launch)
+  int M;                            // total rows = frames * RA * RB
+  int sy, sx;                       // source pixel of tap t for row (a,b): (a*sy + dy[t], b*sx + dx[t])
+  int ntaps;
+  int dy[CV_MAXT], dx[CV_MAXT], coff[CV_MAXT];
+  int check_bounds;                 // zero-fill taps that fall outside the source image (dgrad)
+  // output pixel of row (a,b): (a*oys + oy0, b*oxs + ox0) in an (N, OH, OW, OC) tensor
+  int OH, OW, oys, oy0, oxs, ox0;
+};
+
+struct ConvEpi {
+  const float* bias;                // per output channel (forward) or null
+  int relu;
+  const __nv_bfloat16* gate;        // dgrad: saved activation at the output pixel; output zeroed where gate <= 0
+  __nv_bfloat16* out_bf16;          // (N, OH, OW, BN) or null
+  float* out_f32;                   // (N, OH, OW, BN) or null
+};
+
+// ---- PTX helpers (same conventions as gemm_tc.cu)
+__device__ __forceinline__ uint32_t cv_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cv_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void cv_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cv_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cv_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void cv_tma_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void cv_cp16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cv_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cv_wait_group() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void cv_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cv_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cv_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cv_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cv_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void cv_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint64_t cv_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------ forward / dgrad
+template <int BN>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ CUtensorMap tmW, const ConvEpi ep) {
+  constexpr uint32_t A_BYTES = 128 * 128;              // 128 rows x 64 bf16
+  constexpr uint32_t W_TAP_BYTES = BN * 128;           // [BN][64] bf16, K-major SW128
+  constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t w_base = cv_smem(smem);
+  const uint32_t a_base = w_base + g.ntaps * W_TAP_BYTES;            // multiple of 1024 (BN*128 with BN >= 32: 4096)
+  uint64_t* bars = (uint64_t*)(smem + g.ntaps * W_TAP_BYTES + CV_STAGES * A_BYTES);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * CV_STAGES + 5);
+  auto full_bar = [&](int s) { return cv_smem(bars + s); };
+  auto empty_bar = [&](int s) { return cv_smem(bars + CV_STAGES + s); };
+  auto tfull_bar = [&](int a) { return cv_smem(bars + 2 * CV_STAGES + a); };
+  auto tempty_bar = [&](int a) { return cv_smem(bars + 2 * CV_STAGES + 2 + a); };
+  const uint32_t w_bar = cv_smem(bars + 2 * CV_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (g.M + 127) / 128;
+  const int rows_per_frame = g.RA * g.RB;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < CV_STAGES; ++s) { cv_mbar_init(full_bar(s), 128); cv_mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { cv_mbar_init(tfull_bar(a), 1); cv_mbar_init(tempty_bar(a), 4); }
+    cv_mbar_init(w_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(cv_smem(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  cv_fence_before();
+  __syncthreads();
+  cv_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===== producers: thread r gathers tile row r, one 128-byte K-block row per stage
+    const int r = threadIdx.x;
+    const uint32_t row_off = (uint32_t)r * 128;
+    const uint32_t sw = (uint32_t)(r & 7);
+    uint32_t it = 0;
+    int pending = -1;                                    // stage whose copies are issued but not yet published
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m = tile * 128 + r;
+      const bool row_ok = m < g.M;
+      int n = 0, a = 0, b = 0;
+      if (row_ok) { n = m / rows_per_frame; const int rem = m - n * rows_per_frame; a = rem / g.RB; b = rem - a * g.RB; }
+      const int py0 = a * g.sy, px0 = b * g.sx;
+      const __nv_bfloat16* frame = g.src + (long long)n * g.SH * g.SW * g.SC;
+      for (int t = 0; t < g.ntaps; ++t, ++it) {
+        const int s = it % CV_STAGES;
+        const uint32_t ph = (it / CV_STAGES) & 1;
+        cv_mbar_wait(empty_bar(s), ph ^ 1);
+        const int py = py0 + g.dy[t], px = px0 + g.dx[t];
+        bool ok = row_ok;
+        if (g.check_bounds) ok = ok && py >= 0 && py < g.SH && px >= 0 && px < g.SW;
+        const __nv_bfloat16* srcp = ok ? frame + ((long long)py * g.SW + px) * g.SC + g.coff[t] : g.src;
+        const uint32_t dst = a_base + s * A_BYTES + row_off;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          cv_cp16(dst + ((j ^ sw) << 4), srcp + j * 8, (ok && j < g.kchunks) ? 16u : 0u);
+        cv_commit_group();
+        if (pending >= 0) {                               // publish the previous stage: its copies have landed
+          cv_wait_group<1>();
+          cv_fence_async();
+          cv_mbar_arrive(full_bar(pending));
+        }
+        pending = s;
+      }
+    }
+    if (pending >= 0) {
+      cv_wait_group<0>();
+      cv_fence_async();
+      cv_mbar_arrive(full_bar(pending));
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      // resident weights: one TMA box per tap
+      cv_mbar_expect_tx(w_bar, g.ntaps * W_TAP_BYTES);
+      for (int t = 0; t < g.ntaps; ++t) cv_tma_2d(w_base + t * W_TAP_BYTES, &tmW, 0, t * BN, w_bar);
+      cv_mbar_wait(w_bar, 0);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t acc = lt & 1;
+        cv_mbar_wait(tempty_bar(acc), ((lt >> 1) & 1) ^ 1);
+        cv_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
+        for (int t = 0; t < g.ntaps; ++t, ++it) {
+          const int s = it % CV_STAGES;
+          const uint32_t ph = (it / CV_STAGES) & 1;
+          cv_mbar_wait(full_bar(s), ph);
+          cv_fence_after();
+          const uint32_t a_src = a_base + s * A_BYTES, b_src = w_base + t * W_TAP_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            cv_mma(tmem_d, cv_desc(a_src + k * 32, 16, 1024), cv_desc(b_src + k * 32, 16, 1024), idesc,
+                   (t > 0 || k > 0) ? 1u : 0u);
+          cv_commit(empty_bar(s));
+        }
+        cv_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    // ===== epilogue warps 5..8: TMEM lane quarter = warp % 4
+    const int q = warp & 3;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t acc = lt & 1;
+      const int m = tile * 128 + q * 32 + lane;
+      const bool row_ok = m < g.M;
+      long long opix = 0;
+      if (row_ok) {
+        const int n = m / rows_per_frame; const int rem = m - n * rows_per_frame;
+        const int a = rem / g.RB, b = rem - a * g.RB;
+        opix = ((long long)n * g.OH + (a * g.oys + g.oy0)) * g.OW + (b * g.oxs + g.ox0);
+      }
+      cv_mbar_wait(tfull_bar(acc), (lt >> 1) & 1);
+      cv_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[16];
+        cv_ld16(tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16) + c0, r);
+        if (!row_ok) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        if (ep.bias) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += __ldg(ep.bias + c0 + j);
+        }
+        if (ep.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (ep.gate) {
+          const uint4* gp = reinterpret_cast<const uint4*>(ep.gate + opix * BN + c0);
+          const uint4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+          const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&g0);
+          const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&g1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f0 = __bfloat1622float2(h0[j]), f1 = __bfloat1622float2(h1[j]);
+            if (f0.x <= 0.f) v[2 * j] = 0.f;
+            if (f0.y <= 0.f) v[2 * j + 1] = 0.f;
+            if (f1.x <= 0.f) v[8 + 2 * j] = 0.f;
+            if (f1.y <= 0.f) v[8 + 2 * j + 1] = 0.f;
+          }
+        }
+        if (ep.out_bf16) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            pk[j] = *reinterpret_cast<uint32_t*>(&t2);
+          }
+          uint4* op = reinterpret_cast<uint4*>(ep.out_bf16 + opix * BN + c0);
+          op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        if (ep.out_f32) {
+          float4* op = reinterpret_cast<float4*>(ep.out_f32 + opix * BN + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+      cv_fence_before();
+      __syncwarp();
+      if (lane == 0) cv_mbar_arrive(tempty_bar(acc));
+    }
+  }
+  cv_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    cv_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*CvEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static CvEncodeFn cv_encode_fn() {
+  static CvEncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (CvEncodeFn)p;
+  }
+  return fn;
+}
+
+// packed weights: [ntaps * BN rows][64] bf16, K-major; one [64][BN] box per tap
+static int cv_weight_tmap(CUtensorMap* tm, const void* wp, int ntaps, int BN) {
+  CvEncodeFn fn = cv_encode_fn();
+  TACORL_REQUIRE(fn, "conv_tc: cuTensorMapEncodeTiled is not available");
+  TACORL_REQUIRE(((uintptr_t)wp & 15) == 0, "conv_tc: packed weights must be 16-byte aligned");
+  cuuint64_t dims[2] = {64, (cuuint64_t)ntaps * BN};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {64, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TACORL_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(weights) failed (%d)", (int)r);
+  return 0;
+}
+
+template <int BN>
+static int cv_launch(const ConvGeom& g, const void* wpacked, const ConvEpi& ep, cudaStream_t st) {
+  CUtensorMap tm;
+  int rc = cv_weight_tmap(&tm, wpacked, g.ntaps, BN);
+  if (rc) return rc;
+  const size_t smem = (size_t)g.ntaps * BN * 128 + CV_STAGES * 128 * 128 + (2 * CV_STAGES + 5) * 8 + 16 + 1024;
+  static size_t configured = 0;
+  auto kern = conv_tc_kernel<BN>;
+  if (smem > configured) {
+    TACORL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int tiles = (g.M + 127) / 128;
+  const int ctas = tiles < 148 ? tiles : 148;
+  kern<<<ctas, CV_THREADS, smem, st>>>(g, tm, ep);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
+int conv_tc_run(const ConvGeom& g, int BN, const void* wpacked, const ConvEpi& ep, cudaStream_t st) {
+  if (g.M == 0) return 0;
+  TACORL_REQUIRE(g.ntaps >= 1 && g.ntaps <= CV_MAXT, "conv_tc: bad tap count %d", g.ntaps);
+  TACORL_REQUIRE(((uintptr_t)g.src & 15) == 0 && (g.SC * 2) % 16 == 0, "conv_tc: source must be 16-byte aligned");
+  if (BN == 32) return cv_launch<32>(g, wpacked, ep, st);
+  if (BN == 64) return cv_launch<64>(g, wpacked, ep, st);
+  set_last_error("conv_tc: unsupported output width %d", BN);
+  return -1;
+}
+
+// ------------------------------------------------------------------------------------------ packing kernels
+// mode 0: conv3 fwd   Wp[t=(ky,kx)][oc][c]            = W3[oc][c][ky][kx]            (9 taps, BN=64)
+// mode 1: conv2 fwd   Wp[t=(ky,p)][oc][(kx-2p)*32+c]  = W2[oc][c][ky][kx]            (8 tap pairs, BN=64)
+// mode 2: conv1 fwd   Wp[t=(dy,dx)][oc][q]            = W1[oc][c][4dy+py][4dx+px], q=(py*4+px)*3+c (<48, else 0)  (4 taps, BN=32)
+// mode 3: conv3 dgrad Wp[t=(ky,kx)][c][oc]            = W3[oc][c][ky][kx]            (9 taps, BN=64)
+// mode 4: conv2 dgrad Wp[cls=(py,px)][t=(j,i)][c][oc] = W2[oc][c][py+2j][px+2i]      (4 classes x 4 taps, BN=32)
+__global__ void cv_pack_kernel(int mode, const float* __restrict__ W, __nv_bfloat16* __restrict__ Wp, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int k = i & 63;
+  float v = 0.f;
+  if (mode == 0) {
+    const int oc = (i >> 6) & 63, t = i >> 12, ky = t / 3, kx = t % 3;
+    v = W[((oc * 64 + k) * 3 + ky) * 3 + kx];
+  } else if (mode == 1) {
+    const int oc = (i >> 6) & 63, t = i >> 12, ky = t >> 1, p = t & 1, kx = 2 * p + (k >> 5), c = k & 31;
+    v = W[((oc * 32 + c) * 4 + ky) * 4 + kx];
+  } else if (mode == 2) {
+    const int oc = (i >> 6) & 31, t = i >> 11, dy = t >> 1, dx = t & 1;
+    if (k < 48) {
+      const int c = k % 3, pp = k / 3, py = pp >> 2, px = pp & 3;
+      v = W[((oc * 3 + c) * 8 + (4 * dy + py)) * 8 + (4 * dx + px)];
+    }
+  } else if (mode == 3) {
+    const int c = (i >> 6) & 63, t = i >> 12, ky = t / 3, kx = t % 3;
+    v = W[((k * 64 + c) * 3 + ky) * 3 + kx];
+  } else {
+    const int c = (i >> 6) & 31, t = (i >> 11) & 3, cls = i >> 13, py = cls >> 1, px = cls & 1, j = t >> 1, ii = t & 1;
+    v = W[((k * 32 + c) * 4 + (py + 2 * j)) * 4 + (px + 2 * ii)];
+  }
+  Wp[i] = __float2bfloat16(v);
+}
+
+int conv_tc_pack(int mode, const float* W, void* Wp, cudaStream_t st) {
+  static const int totals[5] = {9 * 64 * 64, 8 * 64 * 64, 4 * 32 * 64, 9 * 64 * 64, 16 * 32 * 64};
+  TACORL_REQUIRE(mode >= 0 && mode < 5, "conv_tc_pack: bad mode");
+  cv_pack_kernel<<<cdiv(totals[mode], 256), 256, 0, st>>>(mode, W, (__nv_bfloat16*)Wp, totals[mode]);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
+// fp32 NCHW image (N,3,H,W) -> bf16 space-to-depth(4) (N, SH, SW, 48), channel q = (py*4+px)*3 + c.
+// One thread per (n, Y, X, py): three float4 loads, 12 bf16 out (24 contiguous bytes).
+__global__ void cv_s2d_kernel(const float* __restrict__ x, int H, int W, int SH, int SW, long long total,
+                              __nv_bfloat16* __restrict__ xs) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int py = (int)(i & 3);
+    long long t = i >> 2;
+    const int X = (int)(t % SW); t /= SW;
+    const int Y = (int)(t % SH);
+    const long long n = t / SH;
+    const int iy = 4 * Y + py;
+    float4 c0 = make_float4(0, 0, 0, 0), c1 = c0, c2 = c0;
+    if (iy < H && 4 * X + 3 < W) {
+      const float* p = x + ((n * 3) * H + iy) * (long long)W + 4 * X;
+      c0 = __ldg(reinterpret_cast<const float4*>(p));
+      c1 = __ldg(reinterpret_cast<const float4*>(p + (long long)H * W));
+      c2 = __ldg(reinterpret_cast<const float4*>(p + 2LL * H * W));
+    }
+    __nv_bfloat16* o = xs + ((n * SH + Y) * (long long)SW + X) * 48 + py * 12;
+    const float v[12] = {c0.x, c1.x, c2.x, c0.y, c1.y, c2.y, c0.z, c1.z, c2.z, c0.w, c1.w, c2.w};
+    uint32_t pk[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      __nv_bfloat162 t2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      pk[j] = *reinterpret_cast<uint32_t*>(&t2);
+    }
+    uint2* op = reinterpret_cast<uint2*>(o);          // 24-byte run, 8-byte aligned (96 B pixel pitch)
+    op[0] = make_uint2(pk[0], pk[1]); op[1] = make_uint2(pk[2], pk[3]); op[2] = make_uint2(pk[4], pk[5]);
+  }
+}
+
+int conv_tc_s2d(const float* x, int N, int H, int W, int SH, int SW, void* xs, cudaStream_t st) {
+  TACORL_REQUIRE(W % 4 == 0 && ((uintptr_t)x & 15) == 0, "conv_tc_s2d: image width must be a multiple of 4");
+  const long long total = (long long)N * SH * SW * 4;
+  if (total == 0) return 0;
+  cv_s2d_kernel<<<(int)min((long long)148 * 16, (total + 255) / 256), 256, 0, st>>>(x, H, W, SH, SW, total,
+                                                                                  (__nv_bfloat16*)xs);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ layer drivers
+// conv1 forward on the s2d image: 2x2 taps, stride 1, C = 48 (6 chunks), BN = 32
+int conv_tc_conv1_fwd(const void* xs, int N, int H1, int W1, const void* wp, const float* bias, void* y1b,
+                      cudaStream_t st) {
+  ConvGeom g = {};
+  g.src = (const __nv_bfloat16*)xs; g.SH = H1 + 1; g.SW = W1 + 1; g.SC = 48; g.kchunks = 6;
+  g.RA = H1; g.RB = W1; g.M = N * H1 * W1; g.sy = 1; g.sx = 1; g.ntaps = 4;
+  for (int t = 0; t < 4; ++t) { g.dy[t] = t >> 1; g.dx[t] = t & 1; g.coff[t] = 0; }
+  g.OH = H1; g.OW = W1; g.oys = 1; g.oxs = 1;
+  ConvEpi e = {bias, 1, nullptr, (__nv_bfloat16*)y1b, nullptr};
+  return conv_tc_run(g, 32, wp, e, st);
+}
+// conv2 forward: 4x4 stride 2 over y1 (C = 32): 8 tap pairs
+int conv_tc_conv2_fwd(const void* y1b, int N, int H1, int W1, int H2, int W2, const void* wp, const float* bias,
+                      void* y2b, cudaStream_t st) {
+  ConvGeom g = {};
+  g.src = (const __nv_bfloat16*)y1b; g.SH = H1; g.SW = W1; g.SC = 32; g.kchunks = 8;
+  g.RA = H2; g.RB = W2; g.M = N * H2 * W2; g.sy = 2; g.sx = 2; g.ntaps = 8;
+  for (int t = 0; t < 8; ++t) { g.dy[t] = t >> 1; g.dx[t] = 2 * (t & 1); g.coff[t] = 0; }
+  g.OH = H2; g.OW = W2; g.oys = 1; g.oxs = 1;
+  ConvEpi e = {bias, 1, nullptr, (__nv_bfloat16*)y2b, nullptr};
+  return conv_tc_run(g, 64, wp, e, st);
+}
+// conv3 forward: 3x3 stride 1 over y2 (C = 64): 9 taps; fp32 output for the soft-argmax
+int conv_tc_conv3_fwd(const void* y2b, int N, int H2, int W2, int H3, int W3, const void* wp, const float* bias,
+                      float* y3, cudaStream_t st) {
+  ConvGeom g = {};
+  g.src = (const __nv_bfloat16*)y2b; g.SH = H2; g.SW = W2; g.SC = 64; g.kchunks = 8;
+  g.RA = H3; g.RB = W3; g.M = N * H3 * W3; g.sy = 1; g.sx = 1; g.ntaps = 9;
+  for (int t = 0; t < 9; ++t) { g.dy[t] = t / 3; g.dx[t] = t % 3; g.coff[t] = 0; }
+  g.OH = H3; g.OW = W3; g.oys = 1; g.oxs = 1;
+  ConvEpi e = {bias, 1, nullptr, nullptr, y3};
+  return conv_tc_run(g, 64, wp, e, st);
+}
+// conv3 dgrad: dy2[iy][ix][c] = [y2>0] * sum_{ky,kx,oc} dy3[iy-ky][ix-kx][oc] W3[oc][c][ky][kx]
+int conv_tc_conv3_dgrad(const void* dy3b, int N, int H2, int W2, int H3, int W3, const void* wp, const void* y2b,
+                        void* dy2b, cudaStream_t st) {
+  ConvGeom g = {};
+  g.src = (const __nv_bfloat16*)dy3b; g.SH = H3; g.SW = W3; g.SC = 64; g.kchunks = 8;
+  g.RA = H2; g.RB = W2; g.M = N * H2 * W2; g.sy = 1; g.sx = 1; g.ntaps = 9; g.check_bounds = 1;
+  for (int t = 0; t < 9; ++t) { g.dy[t] = -(t / 3); g.dx[t] = -(t % 3); g.coff[t] = 0; }
+  g.OH = H2; g.OW = W2; g.oys = 1; g.oxs = 1;
+  ConvEpi e = {nullptr, 0, (const __nv_bfloat16*)y2b, (__nv_bfloat16*)dy2b, nullptr};
+  return conv_tc_run(g, 64, wp, e, st);
+}
+// conv2 dgrad: four stride-parity classes (py,px); class rows (a,b) -> dy1 pixel (2a+py, 2b+px),
+//   dy1 = [y1>0] * sum_{j,i in {0,1}, oc} dy2[a-j][b-i][oc] W2[oc][c][py+2j][px+2i]
+int conv_tc_conv2_dgrad(const void* dy2b, int N, int H1, int W1, int H2, int W2, const void* wp_classes,
+                        const void* y1b, void* dy1b, cudaStream_t st) {
+  for (int cls = 0; cls < 4; ++cls) {
+    const int py = cls >> 1, px = cls & 1;
+    ConvGeom g = {};
+    g.src = (const __nv_bfloat16*)dy2b; g.SH = H2; g.SW = W2; g.SC = 64; g.kchunks = 8;
+    g.RA = (H1 - py + 1) / 2; g.RB = (W1 - px + 1) / 2; g.M = N * g.RA * g.RB; g.sy = 1; g.sx = 1; g.ntaps = 4;
+    g.check_bounds = 1;
+    for (int t = 0; t < 4; ++t) { g.dy[t] = -(t >> 1); g.dx[t] = -(t & 1); g.coff[t] = 0; }
+    g.OH = H1; g.OW = W1; g.oys = 2; g.oy0 = py; g.oxs = 2; g.ox0 = px;
+    ConvEpi e = {nullptr, 0, (const __nv_bfloat16*)y1b, (__nv_bfloat16*)dy1b, nullptr};
+    int rc = conv_tc_run(g, 32, (const __nv_bfloat16*)wp_classes + (size_t)cls * 4 * 32 * 64, e, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace tacorl
+
+// ==========================================================================================
+// Weight gradients: dW[oc][tap][c] = sum over output pixels m of dY[m][oc] * X[src_pixel(m, tap)][c].
+// Pixels are the UMMA K dimension, so both operands are MN-major tiles of 64 pixel rows x 128 bytes:
+//   A = dY rows (OC channels, zero-filled to 128 B), padded to M = 128 with a shared all-zero tile,
+//   B = NT gathered activation tiles (one per tap / tap pair), N = NT*64 accumulator columns.
+// Each CTA owns one tap group and one slice of the pixel range; partial sums go to a workspace and a small
+// kernel reduces the slices and scatters into the torch weight-gradient layout.
+namespace tacorl {
+
+constexpr int WG_STAGES = 4;
+constexpr int WG_THREADS = 224;       // 2 producer warps (64 pixel rows), 1 MMA warp, 4 epilogue warps
+
+struct WgradGeom {
+  const __nv_bfloat16* dy;            // (M, OC) output gradient, NHWC rows
+  int OC, dy_chunks;                  // OC*2/16 valid chunks per dY row
+  const __nv_bfloat16* src;           // NHWC source activation (N, SH, SW, SC)
+  int SH, SW, SC, kchunks;
+  int RA, RB, M;                      // output pixel grid per frame, total rows
+  int sy, sx;
+  int NT;                             // taps per CTA (N = NT*64)
+  int groups;                         // tap groups (gridDim.y)
+  int dy_t[CV_MAXT], dx_t[CV_MAXT], coff[CV_MAXT];   // per (group*NT + j) source offsets
+  int rows_per_split;                 // multiple of 64
+  float* partial;                     // [splits][groups][OC][NT*64]
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) conv_tc_wgrad_kernel(const __grid_constant__ WgradGeom g) {
+  constexpr uint32_t TILE = 64 * 128;                   // one 64-row x 128-byte MN-major tile
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t stage_bytes = (1 + g.NT) * TILE;
+  const uint32_t base = cv_smem(smem);
+  const uint32_t zero_tile = base + WG_STAGES * stage_bytes;
+  uint64_t* bars = (uint64_t*)(smem + WG_STAGES * stage_bytes + TILE);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * WG_STAGES + 1);
+  auto full_bar = [&](int s) { return cv_smem(bars + s); };
+  auto empty_bar = [&](int s) { return cv_smem(bars + WG_STAGES + s); };
+  const uint32_t done_bar = cv_smem(bars + 2 * WG_STAGES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NCOLS = g.NT * 64;
+  const uint32_t tmem_cols = NCOLS <= 64 ? 64 : (NCOLS <= 128 ? 128 : 256);
+
+  const int m_begin = blockIdx.x * g.rows_per_split;
+  const int m_end = min(g.M, m_begin + g.rows_per_split);
+  const int nkb = m_end > m_begin ? (m_end - m_begin + 63) / 64 : 0;
+  const int grp = blockIdx.y;
+  const int rows_per_frame = g.RA * g.RB;
+
+  // zero tile (upper half of the M = 128 A operand)
+  for (int i = threadIdx.x; i < (int)(TILE / 16); i += blockDim.x)
+    reinterpret_cast<uint4*>(smem + WG_STAGES * stage_bytes)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) { cv_mbar_init(full_bar(s), 64); cv_mbar_init(empty_bar(s), 1); }
+    cv_mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(cv_smem(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  cv_fence_async();          // the generic-proxy zero fill must be visible to the tensor core (async proxy)
+  cv_fence_before();
+  __syncthreads();
+  cv_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 2) {
+    const int r = threadIdx.x;                                   // pixel row within the K block
+    const uint32_t row_off = (uint32_t)r * 128, sw = (uint32_t)(r & 7);
+    int pending = -1;
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % WG_STAGES;
+      const uint32_t ph = (i / WG_STAGES) & 1;
+      cv_mbar_wait(empty_bar(s), ph ^ 1);
+      const int m = m_begin + i * 64 + r;
+      const bool ok = m < m_end;
+      int n = 0, a = 0, b = 0;
+      if (ok) { n = m / rows_per_frame; const int rem = m - n * rows_per_frame; a = rem / g.RB; b = rem - a * g.RB; }
+      const uint32_t st = base + s * stage_bytes;
+      const __nv_bfloat16* dyp = g.dy + (long long)(ok ? m : 0) * g.OC;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cv_cp16(st + row_off + ((j ^ sw) << 4), dyp + j * 8, (ok && j < g.dy_chunks) ? 16u : 0u);
+      const __nv_bfloat16* frame = g.src + (long long)n * g.SH * g.SW * g.SC;
+      for (int t = 0; t < g.NT; ++t) {
+        const int tt = grp * g.NT + t;
+        const __nv_bfloat16* sp = frame + ((long long)(a * g.sy + g.dy_t[tt]) * g.SW + (b * g.sx + g.dx_t[tt])) * g.SC + g.coff[tt];
+        const uint32_t dst = st + (1 + t) * TILE + row_off;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cv_cp16(dst + ((j ^ sw) << 4), sp + j * 8, (ok && j < g.kchunks) ? 16u : 0u);
+      }
+      cv_commit_group();
+      if (pending >= 0) { cv_wait_group<1>(); cv_fence_async(); cv_mbar_arrive(full_bar(pending)); }
+      pending = s;
+    }
+    if (pending >= 0) { cv_wait_group<0>(); cv_fence_async(); cv_mbar_arrive(full_bar(pending)); }
+  } else if (warp == 2) {
+    if (lane == 0 && nkb > 0) {
+      // A and B MN-major (bits 15, 16), D = f32, bf16 inputs, M = 128, N = NT*64
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(NCOLS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % WG_STAGES;
+        const uint32_t ph = (i / WG_STAGES) & 1;
+        cv_mbar_wait(full_bar(s), ph);
+        cv_fence_after();
+        const uint32_t a_src = base + s * stage_bytes, b_src = a_src + TILE;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)     // 16 pixel rows (2048 B) per UMMA K step
+          cv_mma(tmem_base, cv_desc(a_src + k * 2048, zero_tile - a_src, 1024), cv_desc(b_src + k * 2048, TILE, 1024),
+                 idesc, (i > 0 || k > 0) ? 1u : 0u);
+        cv_commit(empty_bar(s));
+      }
+      cv_commit(done_bar);
+    }
+  } else {
+    const int q = warp & 3;                     // warps 3..6 -> quarters 3,0,1,2
+    const int oc = q * 32 + lane;
+    if (nkb > 0) { cv_mbar_wait(done_bar, 0); cv_fence_after(); }
+    float* P = g.partial + (((long long)blockIdx.x * g.groups + grp) * g.OC + oc) * NCOLS;
+    if (q * 32 < g.OC) {
+      for (int c0 = 0; c0 < NCOLS; c0 += 16) {
+        uint32_t r[16];
+        if (nkb > 0) cv_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
+        else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = 0;
+        }
+        if (oc < g.OC) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            reinterpret_cast<float4*>(P + c0)[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
+      }
+    }
+  }
+  cv_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    cv_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// dW (torch layout) = beta*dW + sum over splits of partial, with the per-layer column -> (c, ky, kx) mapping
+// layer 3: groups = 3 (ky), col = kx*64 + c;  layer 2: groups = 2, col = (kyl*2 + p)*64 + k, ky = 2g+kyl, kx = 2p+(k>>5), c = k&31;
+// layer 1: groups = 1, col = t*64 + q (q < 48), t = (dy,dx), q = (py*4+px)*3 + c, ky = 4dy+py, kx = 4dx+px.
+__global__ void conv_tc_wgrad_reduce_kernel(int layer, int splits, int groups, int OC, int NCOLS,
+                                            const float* __restrict__ partial, float beta, float* __restrict__ dW) {
+  const int total = groups * OC * NCOLS;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int col = i % NCOLS, oc = (i / NCOLS) % OC, grp = i / (NCOLS * OC);
+  int idx = -1;
+  if (layer == 3) {
+    const int kx = col >> 6, c = col & 63;
+    idx = ((oc * 64 + c) * 3 + grp) * 3 + kx;
+  } else if (layer == 2) {
+    const int k = col & 63, tp = col >> 6, kyl = tp >> 1, p = tp & 1;
+    idx = ((oc * 32 + (k & 31)) * 4 + (2 * grp + kyl)) * 4 + (2 * p + (k >> 5));
+  } else {
+    const int q = col & 63, t = col >> 6;
+    if (q < 48) {
+      const int c = q % 3, pp = q / 3, py = pp >> 2, px = pp & 3;
+      idx = ((oc * 3 + c) * 8 + (4 * (t >> 1) + py)) * 8 + (4 * (t & 1) + px);
+    }
+  }
+  if (idx < 0) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += partial[(((long long)z * groups + grp) * OC + oc) * NCOLS + col];
+  dW[idx] = beta != 0.f ? fmaf(beta, dW[idx], s) : s;
+}
+
+// layer: 1 (conv1 on the s2d image), 2, 3.  dyb: (N*RA*RB, OC) bf16; src: NHWC bf16 input activation of the layer.
+int conv_tc_wgrad(int layer, const void* dyb, const void* src, int N, int SH, int SW, int RA, int RB, float beta,
+                  float* dW, float* ws, size_t ws_bytes, cudaStream_t st) {
+  WgradGeom g = {};
+  g.dy = (const __nv_bfloat16*)dyb; g.src = (const __nv_bfloat16*)src;
+  g.SH = SH; g.SW = SW; g.RA = RA; g.RB = RB; g.M = N * RA * RB;
+  if (layer == 3) {
+    g.OC = 64; g.SC = 64; g.kchunks = 8; g.sy = g.sx = 1; g.NT = 3; g.groups = 3;
+    for (int t = 0; t < 9; ++t) { g.dy_t[t] = t / 3; g.dx_t[t] = t % 3; g.coff[t] = 0; }
+  } else if (layer == 2) {
+    g.OC = 64; g.SC = 32; g.kchunks = 8; g.sy = g.sx = 2; g.NT = 4; g.groups = 2;
+    for (int t = 0; t < 8; ++t) { g.dy_t[t] = t >> 1; g.dx_t[t] = 2 * (t & 1); g.coff[t] = 0; }
+  } else {
+    g.OC = 32; g.SC = 48; g.kchunks = 6; g.sy = g.sx = 1; g.NT = 4; g.groups = 1;
+    for (int t = 0; t < 4; ++t) { g.dy_t[t] = t >> 1; g.dx_t[t] = t & 1; g.coff[t] = 0; }
+  }
+  g.dy_chunks = g.OC / 8;
+  if (g.M == 0) return 0;
+  const int NCOLS = g.NT * 64;
+  int splits = 148 / g.groups;
+  const int kblocks = (g.M + 63) / 64;
+  if (splits > kblocks) splits = kblocks;
+  const size_t per_split = (size_t)g.groups * g.OC * NCOLS * sizeof(float);
+  if ((size_t)splits * per_split > ws_bytes) splits = (int)(ws_bytes / per_split);
+  TACORL_REQUIRE(ws && splits >= 1, "conv_tc_wgrad: workspace too small");
+  g.rows_per_split = ((kblocks + splits - 1) / splits) * 64;
+  splits = (g.M + g.rows_per_split - 1) / g.rows_per_split;
+  g.partial = ws;
+  const size_t smem = (size_t)WG_STAGES * (1 + g.NT) * 8192 + 8192 + (2 * WG_STAGES + 1) * 8 + 16 + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    TACORL_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  conv_tc_wgrad_kernel<<<dim3(splits, g.groups), WG_THREADS, smem, st>>>(g);
+  TACORL_LAUNCH_CHECK();
+  const int total = g.groups * g.OC * NCOLS;
+  conv_tc_wgrad_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(layer, splits, g.groups, g.OC, NCOLS, ws, beta, dW);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tacorl
+
+// ==========================================================================================
+// Diagnostic entry point (tests/test_gpu_conv_tc.py): runs ONE implicit-GEMM convolution op on fp32 inputs
+// (staged to bf16 exactly as the encoder does) so each kernel can be checked tightly against torch's conv in fp64.
+namespace tacorl {
+__global__ void cv_bf16_to_f32_kernel(long long n, const __nv_bfloat16* __restrict__ a, float* __restrict__ o) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    o[i] = __bfloat162float(a[i]);
+}
+static int cv_to_f32(long long n, const void* a, float* o, cudaStream_t st) {
+  cv_bf16_to_f32_kernel<<<(int)min((long long)1184, (n + 255) / 256), 256, 0, st>>>(n, (const __nv_bfloat16*)a, o);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace tacorl
+
+extern "C" int tacorl_conv_tc_debug(int op, const float* in0, const float* in1, const float* Wt, const float* bias, int N,
+                                    int H, int W, float* out, void* ws, size_t ws_bytes, void* stream) {
+  using namespace tacorl;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H1 = (H - 8) / 4 + 1, W1 = (W - 8) / 4 + 1, H2 = (H1 - 4) / 2 + 1, W2 = (W1 - 4) / 2 + 1, H3 = H2 - 2, W3 = W2 - 2;
+  const long long P1 = (long long)H1 * W1, P2 = (long long)H2 * W2, P3 = (long long)H3 * W3;
+  Arena ar(ws, ws_bytes);
+  __nv_bfloat16* wp = ar.take<__nv_bfloat16>(16 * 64 * 64);
+  __nv_bfloat16* a0 = ar.take<__nv_bfloat16>((size_t)N * (H1 + 1) * (W1 + 1) * 48 + (size_t)N * P1 * 64);
+  __nv_bfloat16* a1 = ar.take<__nv_bfloat16>((size_t)N * (H1 + 1) * (W1 + 1) * 48 + (size_t)N * P1 * 64);
+  __nv_bfloat16* ob = ar.take<__nv_bfloat16>((size_t)N * P1 * 64);
+  float* wsf = ar.take<float>((32 << 20) / 4);
+  TACORL_REQUIRE(wp && a0 && a1 && ob && wsf, "conv_tc_debug: workspace too small");
+  int rc;
+  switch (op) {
+    case 1:
+      if ((rc = conv_tc_pack(2, Wt, wp, st))) return rc;
+      if ((rc = conv_tc_s2d(in0, N, H, W, H1 + 1, W1 + 1, a0, st))) return rc;
+      if ((rc = conv_tc_conv1_fwd(a0, N, H1, W1, wp, bias, ob, st))) return rc;
+      return cv_to_f32(N * P1 * 32, ob, out, st);
+    case 2:
+      if ((rc = conv_tc_pack(1, Wt, wp, st))) return rc;
+      if ((rc = cast_bf16_2d(in0, 32, N * P1, 32, a0, 32, st))) return rc;
+      if ((rc = conv_tc_conv2_fwd(a0, N, H1, W1, H2, W2, wp, bias, ob, st))) return rc;
+      return cv_to_f32(N * P2 * 64, ob, out, st);
+    case 3:
+      if ((rc = conv_tc_pack(0, Wt, wp, st))) return rc;
+      if ((rc = cast_bf16_2d(in0, 64, N * P2, 64, a0, 64, st))) return rc;
+      return conv_tc_conv3_fwd(a0, N, H2, W2, H3, W3, wp, bias, out, st);
+    case 4:
+      if ((rc = conv_tc_pack(3, Wt, wp, st))) return rc;
+      if ((rc = cast_bf16_2d(in0, 64, N * P3, 64, a0, 64, st))) return rc;
+      if ((rc = cast_bf16_2d(in1, 64, N * P2, 64, a1, 64, st))) return rc;
+      if ((rc = conv_tc_conv3_dgrad(a0, N, H2, W2, H3, W3, wp, a1, ob, st))) return rc;
+      return cv_to_f32(N * P2 * 64, ob, out, st);
+    case 5:
+      if ((rc = conv_tc_pack(4, Wt, wp, st))) return rc;
+      if ((rc = cast_bf16_2d(in0, 64, N * P2, 64, a0, 64, st))) return rc;
+      if ((rc = cast_bf16_2d(in1, 32, N * P1, 32, a1, 32, st))) return rc;
+      if ((rc = conv_tc_conv2_dgrad(a0, N, H1, W1, H2, W2, wp, a1, ob, st))) return rc;
+      return cv_to_f32(N * P1 * 32, ob, out, st);
+    case 6:
+      if ((rc = cast_bf16_2d(in0, 64, N * P3, 64, a0, 64, st))) return rc;
+      if ((rc = cast_bf16_2d(in1, 64, N * P2, 64, a1, 64, st))) return rc;
+      return conv_tc_wgrad(3, a0, a1, N, H2, W2, H3, W3, 0.f, out, wsf, 32 << 20, st);
+    case 7:
+      if ((rc = cast_bf16_2d(in0, 64, N * P2, 64, a0, 64, st))) return rc;
+      if ((rc = cast_bf16_2d(in1, 32, N * P1, 32, a1, 32, st))) return rc;
+      return conv_tc_wgrad(2, a0, a1, N, H1, W1, H2, W2, 0.f, out, wsf, 32 << 20, st);
+    case 8:
+      if ((rc = cast_bf16_2d(in0, 32, N * P1, 32, a0, 32, st))) return rc;
+      if ((rc = conv_tc_s2d(in1, N, H, W, H1 + 1, W1 + 1, a1, st))) return rc;
+      return conv_tc_wgrad(1, a0, a1, N, H1 + 1, W1 + 1, H1, W1, 0.f, out, wsf, 32 << 20, st);
+    default:
+      set_last_error("conv_tc_debug: unknown op %d", op);
+      return -1;
+  }
+}

@@ -40,8 +40,8 @@ static int enc_chunk_cap() {
   static int cap = 0;
   if (!cap) {
     const char* e = getenv("TACORL_ENC_CHUNK");
-    cap = e ? atoi(e) : 64;
-    if (cap < 1) cap = 64;
+    cap = e ? atoi(e) : 256;
+    if (cap < 1) cap = 256;
   }
   return cap;
 }
@@ -67,7 +67,111 @@ size_t tacorl_lmp_encoder_ws_bytes(int N, int H, int W, int hidden, int latent, 
   size_t fixed = fwd_fixed_bytes(g, hidden, true, true) + kSplitKWs + (8 << 20);
   if (backward) fixed += (size_t)N * (hidden + 128 + g.P3 * 64 + 1) * 4 + 4 * (64 * 576) * 4 + (1 << 20);
   (void)latent;
-  return fixed + per_frame * chunk;
+  // implicit-GEMM tensor-core path: no col matrix, whole-batch bf16 gradient / s2d buffers instead
+  size_t tc = (size_t)N * ((size_t)(g.H1 + 1) * (g.W1 + 1) * 96 + g.P1 * 64 + g.P2 * 128 + g.P3 * 64 * 6 +
+                           (g.P1 * 64 + g.P2 * 128) + (128 + 64 + 64 + hidden + 128 + hidden) * 4 + 4096) +
+              kSplitKWs + (32 << 20);
+  size_t legacy = fixed + per_frame * chunk;
+  return tc > legacy ? tc : legacy;
+}
+
+// ------------------------------------------------------------------------------------------ tensor-core path
+// conv stack as implicit GEMMs (conv_tc.cu): x -> space-to-depth bf16 -> conv1 -> conv2 -> conv3, NHWC bf16
+// activations, packed bf16 weights resident in shared memory, no im2col buffers.
+static int enc_fwd_tc(const float* x, int N, int H, int W, const float* const* params, int hidden, int latent,
+                      void* y1, void* y2, float* y3, float* feat, float* smax, float* ssum, float* h4, float* emb,
+                      void* ws, size_t ws_bytes, cudaStream_t st) {
+  EncGeom g(N, H, W);
+  Arena ar(ws, ws_bytes);
+  __nv_bfloat16* wp1 = ar.take<__nv_bfloat16>(4 * 32 * 64);
+  __nv_bfloat16* wp2 = ar.take<__nv_bfloat16>(8 * 64 * 64);
+  __nv_bfloat16* wp3 = ar.take<__nv_bfloat16>(9 * 64 * 64);
+  float* fcws = ar.take<float>((8 << 20) / 4);
+  __nv_bfloat16* xs = ar.take<__nv_bfloat16>((size_t)N * (g.H1 + 1) * (g.W1 + 1) * 48);
+  __nv_bfloat16* y1b = y1 ? (__nv_bfloat16*)y1 : ar.take<__nv_bfloat16>((size_t)N * g.P1 * 32);
+  __nv_bfloat16* y2b = y2 ? (__nv_bfloat16*)y2 : ar.take<__nv_bfloat16>((size_t)N * g.P2 * 64);
+  if (!y3) y3 = ar.take<float>((size_t)N * g.P3 * 64);
+  if (!feat) feat = ar.take<float>((size_t)N * 128);
+  if (!smax) smax = ar.take<float>((size_t)N * 64);
+  if (!ssum) ssum = ar.take<float>((size_t)N * 64);
+  if (!h4) h4 = ar.take<float>((size_t)N * hidden);
+  TACORL_REQUIRE(wp1 && wp2 && wp3 && fcws && xs && y1b && y2b && y3 && feat && smax && ssum && h4,
+                 "lmp_encoder_fwd(bf16): workspace too small (%zu bytes)", ws_bytes);
+  int rc;
+  if ((rc = conv_tc_pack(2, params[P_W1], wp1, st))) return rc;
+  if ((rc = conv_tc_pack(1, params[P_W2], wp2, st))) return rc;
+  if ((rc = conv_tc_pack(0, params[P_W3], wp3, st))) return rc;
+  if ((rc = conv_tc_s2d(x, N, H, W, g.H1 + 1, g.W1 + 1, xs, st))) return rc;
+  if ((rc = conv_tc_conv1_fwd(xs, N, g.H1, g.W1, wp1, params[P_B1], y1b, st))) return rc;
+  if ((rc = conv_tc_conv2_fwd(y1b, N, g.H1, g.W1, g.H2, g.W2, wp2, params[P_B2], y2b, st))) return rc;
+  if ((rc = conv_tc_conv3_fwd(y2b, N, g.H2, g.W2, g.H3, g.W3, wp3, params[P_B3], y3, st))) return rc;
+  if ((rc = softargmax_fwd_f32(y3, N, g.H3, g.W3, 64, params[P_TEMP], feat, smax, ssum, st))) return rc;
+  GemmArgs f;
+  f.transB = 1; f.M = N; f.N = hidden; f.K = 128; f.A = feat; f.lda = 128; f.B = params[P_W4]; f.ldb = 128;
+  f.C = h4; f.ldc = hidden; f.bias = params[P_B4]; f.act = ACT_RELU; f.split_k = 1;
+  if ((rc = gemm_tc_from_f32(f, fcws, 8 << 20, st))) return rc;
+  f.N = latent; f.K = hidden; f.A = h4; f.lda = hidden; f.B = params[P_W5]; f.ldb = hidden; f.C = emb;
+  f.ldc = latent; f.bias = params[P_B5]; f.act = ACT_NONE;
+  return gemm_tc_from_f32(f, fcws, 8 << 20, st);
+}
+
+static int enc_bwd_tc(const float* x, int N, int H, int W, const float* const* params, int hidden, int latent,
+                      const void* y1, const void* y2, const float* y3, const float* feat, const float* smax,
+                      const float* ssum, const float* h4, const float* d_emb, float* const* grads, int accumulate,
+                      void* ws, size_t ws_bytes, cudaStream_t st) {
+  EncGeom g(N, H, W);
+  const float beta0 = accumulate ? 1.f : 0.f;
+  Arena ar(ws, ws_bytes);
+  __nv_bfloat16* wd3 = ar.take<__nv_bfloat16>(9 * 64 * 64);
+  __nv_bfloat16* wd2 = ar.take<__nv_bfloat16>(16 * 32 * 64);
+  float* dh4 = ar.take<float>((size_t)N * hidden);
+  float* dfeat = ar.take<float>((size_t)N * 128);
+  float* dtau = ar.take<float>(N);
+  float* csws = ar.take<float>(592 * 64);
+  float* skws = ar.take<float>(kSplitKWs / 4);
+  float* dy3 = ar.take<float>((size_t)N * g.P3 * 64);
+  __nv_bfloat16* dy3b = ar.take<__nv_bfloat16>((size_t)N * g.P3 * 64);
+  __nv_bfloat16* dy2b = ar.take<__nv_bfloat16>((size_t)N * g.P2 * 64);
+  __nv_bfloat16* dy1b = ar.take<__nv_bfloat16>((size_t)N * g.P1 * 32);
+  __nv_bfloat16* xs = ar.take<__nv_bfloat16>((size_t)N * (g.H1 + 1) * (g.W1 + 1) * 48);
+  TACORL_REQUIRE(wd3 && wd2 && dh4 && dfeat && dtau && csws && skws && dy3 && dy3b && dy2b && dy1b && xs,
+                 "lmp_encoder_bwd(bf16): workspace too small (%zu bytes)", ws_bytes);
+  int rc;
+  // ---- FC head (small GEMMs, fp32 operands staged to bf16)
+  GemmArgs a;
+  a.transA = 1; a.transB = 0; a.M = latent; a.N = hidden; a.K = N; a.A = d_emb; a.lda = latent; a.B = h4;
+  a.ldb = hidden; a.C = grads[P_W5]; a.ldc = hidden; a.beta = beta0; a.split_k = 0;
+  if ((rc = gemm_tc_from_f32(a, skws, kSplitKWs, st))) return rc;
+  if ((rc = colsum_f32(N, latent, d_emb, latent, grads[P_B5], accumulate, st))) return rc;
+  GemmArgs b;
+  b.M = N; b.N = hidden; b.K = latent; b.A = d_emb; b.lda = latent; b.B = params[P_W5]; b.ldb = hidden;
+  b.C = dh4; b.ldc = hidden; b.split_k = 1;
+  if ((rc = gemm_tc_from_f32(b, skws, kSplitKWs, st))) return rc;
+  if ((rc = act_bwd_f32(ACT_RELU, (long long)N * hidden, dh4, h4, dh4, st))) return rc;
+  a.M = hidden; a.N = 128; a.A = dh4; a.lda = hidden; a.B = feat; a.ldb = 128; a.C = grads[P_W4]; a.ldc = 128;
+  if ((rc = gemm_tc_from_f32(a, skws, kSplitKWs, st))) return rc;
+  if ((rc = colsum_f32(N, hidden, dh4, hidden, grads[P_B4], accumulate, st))) return rc;
+  b.N = 128; b.K = hidden; b.A = dh4; b.lda = hidden; b.B = params[P_W4]; b.ldb = 128; b.C = dfeat; b.ldc = 128;
+  if ((rc = gemm_tc_from_f32(b, skws, kSplitKWs, st))) return rc;
+  // ---- soft-argmax backward (applies conv3's ReLU mask), temperature and conv3-bias gradients
+  if ((rc = softargmax_bwd_f32(y3, N, g.H3, g.W3, 64, params[P_TEMP], feat, smax, ssum, dfeat, dy3, dtau, st)))
+    return rc;
+  if ((rc = colsum_f32(N, 1, dtau, 1, grads[P_TEMP], accumulate, st))) return rc;
+  if ((rc = colsum_tall_f32((long long)N * g.P3, 64, dy3, grads[P_B3], accumulate, csws, 592 * 64 * 4, st))) return rc;
+  if ((rc = cast_bf16_2d(dy3, 64, (long long)N * g.P3, 64, dy3b, 64, st))) return rc;
+  // ---- conv3: weight gradient, then data gradient gated by y2's ReLU
+  if ((rc = conv_tc_pack(3, params[P_W3], wd3, st))) return rc;
+  if ((rc = conv_tc_pack(4, params[P_W2], wd2, st))) return rc;
+  if ((rc = conv_tc_wgrad(3, dy3b, y2, N, g.H2, g.W2, g.H3, g.W3, beta0, grads[P_W3], skws, kSplitKWs, st))) return rc;
+  if ((rc = conv_tc_conv3_dgrad(dy3b, N, g.H2, g.W2, g.H3, g.W3, wd3, y2, dy2b, st))) return rc;
+  if ((rc = colsum_tall_bf16((long long)N * g.P2, 64, dy2b, grads[P_B2], accumulate, csws, 592 * 64 * 4, st))) return rc;
+  // ---- conv2
+  if ((rc = conv_tc_wgrad(2, dy2b, y1, N, g.H1, g.W1, g.H2, g.W2, beta0, grads[P_W2], skws, kSplitKWs, st))) return rc;
+  if ((rc = conv_tc_conv2_dgrad(dy2b, N, g.H1, g.W1, g.H2, g.W2, wd2, y1, dy1b, st))) return rc;
+  if ((rc = colsum_tall_bf16((long long)N * g.P1, 32, dy1b, grads[P_B1], accumulate, csws, 592 * 64 * 4, st))) return rc;
+  // ---- conv1 (weight gradient only; images receive no gradient)
+  if ((rc = conv_tc_s2d(x, N, H, W, g.H1 + 1, g.W1 + 1, xs, st))) return rc;
+  return conv_tc_wgrad(1, dy1b, xs, N, g.H1 + 1, g.W1 + 1, g.H1, g.W1, beta0, grads[P_W1], skws, kSplitKWs, st);
 }
 
 static int enc_fwd(const float* x, int N, int H, int W, const float* const* params, int hidden,
@@ -75,11 +179,16 @@ static int enc_fwd(const float* x, int N, int H, int W, const float* const* para
                    float* ssum, float* h4, float* emb, void* ws, size_t ws_bytes, int prec,
                    cudaStream_t st) {
   EncGeom g(N, H, W);
-  const bool tc = prec == PREC_BF16;
+  const bool tc = false;   // the explicit-im2col tensor-core variant below is superseded by enc_fwd_tc
   TACORL_REQUIRE(g.ok, "lmp_encoder_fwd: image %dx%d too small", H, W);
   TACORL_REQUIRE(prec == PREC_F32 || prec == PREC_BF16, "lmp_encoder_fwd: unknown precision %d", prec);
   TACORL_REQUIRE(x && params && emb && ws, "lmp_encoder_fwd: null pointer");
   if (N == 0) return 0;
+  if (prec == PREC_BF16) {
+    TACORL_REQUIRE(W % 4 == 0, "lmp_encoder_fwd(bf16): image width must be a multiple of 4 (got %d)", W);
+    return enc_fwd_tc(x, N, H, W, params, hidden, latent, (void*)y1, (void*)y2, y3, feat, smax, ssum, h4, emb, ws,
+                      ws_bytes, st);
+  }
   Arena ar(ws, ws_bytes);
   float* w2p = ar.take<float>(64 * 512);
   float* w3p = ar.take<float>(64 * 576);
@@ -185,12 +294,15 @@ int tacorl_lmp_encoder_bwd(const float* x, int N, int H, int W, const float* con
                            size_t ws_bytes, int prec, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   EncGeom g(N, H, W);
-  const bool tc = prec == PREC_BF16;
+  const bool tc = false;   // the explicit-im2col tensor-core variant below is superseded by enc_bwd_tc
   TACORL_REQUIRE(g.ok, "lmp_encoder_bwd: image %dx%d too small", H, W);
   TACORL_REQUIRE(prec == PREC_F32 || prec == PREC_BF16, "lmp_encoder_bwd: unknown precision %d", prec);
   TACORL_REQUIRE(x && params && grads && y1 && y2 && y3 && feat && smax && ssum && h4 && d_emb && ws,
                  "lmp_encoder_bwd: null pointer");
   if (N == 0) return 0;
+  if (prec == PREC_BF16)
+    return enc_bwd_tc(x, N, H, W, params, hidden, latent, (const void*)y1, (const void*)y2, y3, feat, smax, ssum, h4,
+                      d_emb, grads, accumulate, ws, ws_bytes, st);
   const float beta0 = accumulate ? 1.f : 0.f;
   Arena ar(ws, ws_bytes);
   float* w2p = ar.take<float>(64 * 512);

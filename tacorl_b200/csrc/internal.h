@@ -54,6 +54,21 @@ static inline int gemm_any(int prec, const GemmArgs& g, float* ws, size_t ws_byt
   return prec == PREC_BF16 ? gemm_tc_from_f32(g, ws, ws_bytes, st) : gemm_f32(g, ws, ws_bytes, st);
 }
 
+// ---- implicit-GEMM convolutions (conv_tc.cu); all activations NHWC bf16
+int conv_tc_pack(int mode, const float* W, void* Wp, cudaStream_t st);
+int conv_tc_s2d(const float* x, int N, int H, int W, int SH, int SW, void* xs, cudaStream_t st);
+int conv_tc_conv1_fwd(const void* xs, int N, int H1, int W1, const void* wp, const float* bias, void* y1b, cudaStream_t st);
+int conv_tc_conv2_fwd(const void* y1b, int N, int H1, int W1, int H2, int W2, const void* wp, const float* bias,
+                      void* y2b, cudaStream_t st);
+int conv_tc_conv3_fwd(const void* y2b, int N, int H2, int W2, int H3, int W3, const void* wp, const float* bias,
+                      float* y3, cudaStream_t st);
+int conv_tc_conv3_dgrad(const void* dy3b, int N, int H2, int W2, int H3, int W3, const void* wp, const void* y2b,
+                        void* dy2b, cudaStream_t st);
+int conv_tc_conv2_dgrad(const void* dy2b, int N, int H1, int W1, int H2, int W2, const void* wp_classes,
+                        const void* y1b, void* dy1b, cudaStream_t st);
+int conv_tc_wgrad(int layer, const void* dyb, const void* src, int N, int SH, int SW, int RA, int RB, float beta,
+                  float* dW, float* ws, size_t ws_bytes, cudaStream_t st);
+
 // simple bump allocator over a caller-provided workspace (256-byte aligned slices)
 struct Arena {
   char* base; size_t cap; size_t off = 0;

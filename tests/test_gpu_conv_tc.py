@@ -1,0 +1,89 @@
+"""Tight per-kernel checks of the implicit-GEMM tcgen05 convolutions (conv_tc.cu) against torch's conv in fp64 on
+bf16-exact operands: forward (bias+ReLU), data gradients (ReLU-gated, incl. the stride-2 parity classes) and weight
+gradients of all three encoder layers, at every image size the encoder must support."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.gpu_util import DEV, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(t):
+    return t.bfloat16().float()
+
+
+def _run(op, in0, in1, Wt, bias, N, H, W, out_shape):
+    from tacorl_b200 import _lib as L
+    out = torch.full(out_shape, float("nan"), device=DEV)
+    ws = L.workspace(1 << 30, torch.device(DEV), tag="convdbg")
+    L.call("tacorl_conv_tc_debug", op, L.ptr(in0.to(DEV).contiguous()), L.ptr(in1.to(DEV).contiguous() if in1 is not None else None),
+           L.ptr(Wt.to(DEV).contiguous() if Wt is not None else None), L.ptr(bias.to(DEV) if bias is not None else None),
+           N, H, W, L.ptr(out), ctypes.c_void_p(ws.data_ptr()), ws.numel(), L.stream())
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+def _geom(H, W):
+    H1, W1 = (H - 8) // 4 + 1, (W - 8) // 4 + 1
+    H2, W2 = (H1 - 4) // 2 + 1, (W1 - 4) // 2 + 1
+    return H1, W1, H2, W2, H2 - 2, W2 - 2
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("N,H,W", [(3, 84, 84), (2, 200, 200), (2, 150, 200), (5, 128, 128), (70, 84, 84)])
+def test_implicit_gemm_convs_match_torch(N, H, W):
+    g = torch.Generator().manual_seed(N * 1000 + H + W)
+    H1, W1, H2, W2, H3, W3 = _geom(H, W)
+    x = _bf(torch.rand(N, 3, H, W, generator=g) * 2 - 1)
+    W1t, W2t, W3t = (_bf(torch.randn(s, generator=g) * sc) for s, sc in (((32, 3, 8, 8), 0.1), ((64, 32, 4, 4), 0.06),
+                                                                         ((64, 64, 3, 3), 0.06)))
+    b1, b2, b3 = (torch.randn(n, generator=g) * 0.1 for n in (32, 64, 64))
+    xd = x.double()
+    y1 = F.relu(F.conv2d(xd, W1t.double(), b1.double(), stride=4))
+    got = _run(1, x, None, W1t, b1, N, H, W, (N, H1, W1, 32))
+    assert_close("conv1 fwd", got, nhwc(y1), 6e-3)
+    y1b = _bf(nhwc(y1).float())                         # what the next layer actually consumes
+    y1n = y1b.permute(0, 3, 1, 2).double()
+    y2 = F.relu(F.conv2d(y1n, W2t.double(), b2.double(), stride=2))
+    got = _run(2, y1b, None, W2t, b2, N, H, W, (N, H2, W2, 64))
+    assert_close("conv2 fwd", got, nhwc(y2), 6e-3)
+    y2b = _bf(nhwc(y2).float())
+    y2n = y2b.permute(0, 3, 1, 2).double()
+    y3 = F.relu(F.conv2d(y2n, W3t.double(), b3.double(), stride=1))
+    got = _run(3, y2b, None, W3t, b3, N, H, W, (N, H3, W3, 64))
+    assert_close("conv3 fwd", got, nhwc(y3), 1e-4)
+    # ---- data gradients
+    dy3 = _bf(torch.randn(N, H3, W3, 64, generator=g))
+    dy3n = dy3.permute(0, 3, 1, 2).double()
+    dy2 = F.conv_transpose2d(dy3n, W3t.double(), stride=1) * (y2n > 0)
+    got = _run(4, dy3, y2b, W3t, None, N, H, W, (N, H2, W2, 64))
+    assert_close("conv3 dgrad", got, nhwc(dy2), 6e-3)
+    dy2b = _bf(torch.randn(N, H2, W2, 64, generator=g))
+    dy2n = dy2b.permute(0, 3, 1, 2).double()
+    full = F.conv_transpose2d(dy2n, W2t.double(), stride=2)
+    pad_h, pad_w = H1 - full.shape[2], W1 - full.shape[3]          # rows/cols no output pixel reaches
+    full = F.pad(full, (0, pad_w, 0, pad_h))
+    dy1 = full * (y1n > 0)
+    got = _run(5, dy2b, y1b, W2t, None, N, H, W, (N, H1, W1, 32))
+    assert_close("conv2 dgrad", got, nhwc(dy1), 6e-3)
+    # ---- weight gradients (fp32 accumulation, fp32 output)
+    w = W3t.double().requires_grad_(True)
+    (F.conv2d(y2n, w, stride=1) * dy3n).sum().backward()
+    got = _run(6, dy3, y2b, None, None, N, H, W, (64, 64, 3, 3))
+    assert_close("conv3 wgrad", got, w.grad, 2e-4)
+    w = W2t.double().requires_grad_(True)
+    (F.conv2d(y1n, w, stride=2) * dy2n).sum().backward()
+    got = _run(7, dy2b, y1b, None, None, N, H, W, (64, 32, 4, 4))
+    assert_close("conv2 wgrad", got, w.grad, 2e-4)
+    dy1b = _bf(torch.randn(N, H1, W1, 32, generator=g))
+    w = W1t.double().requires_grad_(True)
+    (F.conv2d(xd, w, stride=4) * dy1b.permute(0, 3, 1, 2).double()).sum().backward()
+    got = _run(8, dy1b, x, None, None, N, H, W, (32, 3, 8, 8))
+    assert_close("conv1 wgrad", got, w.grad, 2e-4)
