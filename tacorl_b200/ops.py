@@ -289,7 +289,8 @@ def dlm_sample(logits, u1, u2, actions=None, grip_lo=-1.0, grip_hi=1.0):
     hit = torch.empty(rows, device=dev) if actions is not None else None
     acc = torch.empty(1, device=dev) if actions is not None else None
     actions_c = _c(actions) if actions is not None else None
-    L.call("tacorl_dlm_sample", rows, A, L.ptr(logits), logits.shape[1], L.ptr(_c(u1)), L.ptr(_c(u2)),
+    u1, u2 = _c(u1), _c(u2)          # keep the (possibly copied) operands alive until the launch is enqueued
+    L.call("tacorl_dlm_sample", rows, A, L.ptr(logits), logits.shape[1], L.ptr(u1), L.ptr(u2),
            L.ptr(actions_c), actions_c.shape[1] if actions is not None else 0, float(grip_lo), float(grip_hi),
            L.ptr(pred), L.ptr(hit), L.ptr(acc), L.stream())
     return pred, (acc.view(()) if acc is not None else None)
@@ -312,9 +313,10 @@ class GaussHeadFn(Function):
     def backward(ctx, dmean, dstd):
         raw, std = ctx.saved_tensors
         draw = torch.empty_like(raw)
+        dmean = _c(dmean) if dmean is not None else None
+        dstd = _c(dstd) if dstd is not None else None
         L.call("tacorl_gauss_head_bwd", raw.shape[0], raw.shape[1] // 2, L.ptr(raw), L.ptr(std),
-               L.ptr(_c(dmean) if dmean is not None else None), L.ptr(_c(dstd) if dstd is not None else None),
-               L.ptr(draw), L.stream())
+               L.ptr(dmean), L.ptr(dstd), L.ptr(draw), L.stream())
         return draw
 
 
@@ -336,8 +338,9 @@ class SoftplusHeadFn(Function):
     def backward(ctx, dmean, dstd):
         (raw,) = ctx.saved_tensors
         draw = torch.empty_like(raw)
-        L.call("tacorl_softplus_head_bwd", raw.shape[0], raw.shape[1] // 2, L.ptr(raw),
-               L.ptr(_c(dmean) if dmean is not None else None), L.ptr(_c(dstd) if dstd is not None else None),
+        dmean = _c(dmean) if dmean is not None else None
+        dstd = _c(dstd) if dstd is not None else None
+        L.call("tacorl_softplus_head_bwd", raw.shape[0], raw.shape[1] // 2, L.ptr(raw), L.ptr(dmean), L.ptr(dstd),
                L.ptr(draw), L.stream())
         return draw, None
 
@@ -393,8 +396,10 @@ class TanhRsampleFn(Function):
         assert ctx.same, "gradient through sample_n broadcasting is not used by the reference"
         dmu = torch.empty_like(a)
         dsd = torch.empty_like(a)
-        L.call("tacorl_tanh_rsample_bwd", a.numel(), L.ptr(a), L.ptr(eps), L.ptr(_c(da) if da is not None else None),
-               L.ptr(_c(dz) if dz is not None else None), L.ptr(dmu), L.ptr(dsd), int(ctx.apply_tanh), L.stream())
+        da = _c(da) if da is not None else None
+        dz = _c(dz) if dz is not None else None
+        L.call("tacorl_tanh_rsample_bwd", a.numel(), L.ptr(a), L.ptr(eps), L.ptr(da), L.ptr(dz), L.ptr(dmu), L.ptr(dsd),
+               int(ctx.apply_tanh), L.stream())
         return dmu, dsd, None, None
 
 
@@ -463,9 +468,12 @@ class CqlCriticLossFn(Function):
         scal = torch.empty(14, device=dev)
         dq1, dq2 = torch.empty_like(q1_all), torch.empty_like(q2_all)
         dlap = torch.empty(1, device=dev)
-        L.call("tacorl_cql_critic_loss", B, n, L.ptr(q1_all), L.ptr(q2_all), L.ptr(_c(lp_curr.reshape(-1))),
-               L.ptr(_c(lp_next.reshape(-1))), L.ptr(_c(tq1.reshape(-1))), L.ptr(_c(tq2.reshape(-1))),
-               L.ptr(_c(reward.reshape(-1))), L.ptr(_c(done.reshape(-1))),
+        lp_curr, lp_next = _c(lp_curr.reshape(-1)), _c(lp_next.reshape(-1))
+        tq1, tq2 = _c(tq1.reshape(-1)), _c(tq2.reshape(-1))
+        reward, done = _c(reward.reshape(-1)), _c(done.reshape(-1))
+        L.call("tacorl_cql_critic_loss", B, n, L.ptr(q1_all), L.ptr(q2_all), L.ptr(lp_curr),
+               L.ptr(lp_next), L.ptr(tq1), L.ptr(tq2),
+               L.ptr(reward), L.ptr(done),
                L.ptr(log_alpha_prime) if with_lagrange else None, float(rand_density), float(discount),
                float(reward_scale), float(gap), float(cw), float(temp), int(with_lagrange), L.ptr(scal),
                L.ptr(dq1), L.ptr(dq2), L.ptr(dlap), L.stream())
@@ -602,7 +610,8 @@ class AddLayerNormFn(Function):
         rows = x.numel() // D
         y, xhat = torch.empty_like(x), torch.empty_like(x)
         rstd = torch.empty(rows, device=x.device)
-        L.call("tacorl_add_ln_fwd", rows, D, L.ptr(x), L.ptr(r), L.ptr(mask), L.ptr(_c(w)), L.ptr(_c(b)), float(eps),
+        w, b = _c(w), _c(b)
+        L.call("tacorl_add_ln_fwd", rows, D, L.ptr(x), L.ptr(r), L.ptr(mask), L.ptr(w), L.ptr(b), float(eps),
                L.ptr(y), L.ptr(xhat), L.ptr(rstd), L.stream())
         ctx.save_for_backward(xhat, rstd, w, mask)
         return y
@@ -614,7 +623,8 @@ class AddLayerNormFn(Function):
         rows = xhat.numel() // D
         dx, dr = torch.empty_like(xhat), torch.empty_like(xhat)
         dw, db = torch.zeros(D, device=dy.device), torch.zeros(D, device=dy.device)
-        L.call("tacorl_add_ln_bwd", rows, D, L.ptr(_c(dy)), L.ptr(xhat), L.ptr(rstd), L.ptr(_c(w)), L.ptr(mask),
+        dy, w = _c(dy), _c(w)
+        L.call("tacorl_add_ln_bwd", rows, D, L.ptr(dy), L.ptr(xhat), L.ptr(rstd), L.ptr(w), L.ptr(mask),
                L.ptr(dx), L.ptr(dr), L.ptr(dw), L.ptr(db), L.stream())
         return dx, dr, None, dw, db, None
 

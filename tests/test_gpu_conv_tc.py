@@ -20,10 +20,16 @@ def _run(op, in0, in1, Wt, bias, N, H, W, out_shape):
     from tacorl_b200 import _lib as L
     out = torch.full(out_shape, float("nan"), device=DEV)
     ws = L.workspace(1 << 30, torch.device(DEV), tag="convdbg")
-    L.call("tacorl_conv_tc_debug", op, L.ptr(in0.to(DEV).contiguous()), L.ptr(in1.to(DEV).contiguous() if in1 is not None else None),
-           L.ptr(Wt.to(DEV).contiguous() if Wt is not None else None), L.ptr(bias.to(DEV) if bias is not None else None),
-           N, H, W, L.ptr(out), ctypes.c_void_p(ws.data_ptr()), ws.numel(), L.stream())
+    # keep every device tensor referenced until the kernels have run (a freed temporary would be recycled by the
+    # caching allocator for the next H2D copy before the launch executes)
+    d0 = in0.to(DEV).contiguous()
+    d1 = in1.to(DEV).contiguous() if in1 is not None else None
+    dw = Wt.to(DEV).contiguous() if Wt is not None else None
+    db = bias.to(DEV).contiguous() if bias is not None else None
+    L.call("tacorl_conv_tc_debug", op, L.ptr(d0), L.ptr(d1), L.ptr(dw), L.ptr(db), N, H, W, L.ptr(out),
+           ctypes.c_void_p(ws.data_ptr()), ws.numel(), L.stream())
     torch.cuda.synchronize()
+    del d0, d1, dw, db
     return out.cpu()
 
 
