@@ -45,17 +45,6 @@ int im2col_f32(const float* x, long long sn, long long sc, long long sh, long lo
   return 0;
 }
 
-int im2col_bf16(const float* x, long long sn, long long sc, long long sh, long long sw, int C, int KH,
-                int KW, int stride, int OH, int OW, int nframes, void* col, cudaStream_t st, int korder) {
-  long long total = (long long)nframes * OH * OW * KH * KW * C;
-  if (total == 0) return 0;
-  int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
-  im2col_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(x, sn, sc, sh, sw, C, KH, KW, stride, OH, OW, nframes,
-                                                       (__nv_bfloat16*)col, korder);
-  TACORL_LAUNCH_CHECK();
-  return 0;
-}
-
 // dX (NHWC) = mask(Y>0) * sum over the kernel taps that touch (iy, ix) of dcol.
 // dcol[m][k] with the same (ky,kx,c) ordering as im2col.  Gather form => deterministic.
 template <typename InT>
@@ -96,18 +85,6 @@ int col2im_f32(const float* dcol, int C, int H, int W, int KH, int KW, int strid
   if (total == 0) return 0;
   int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
   col2im_kernel<float><<<blocks, 256, 0, st>>>(dcol, C, H, W, KH, KW, stride, OH, OW, nframes, ymask, dx, nullptr);
-  TACORL_LAUNCH_CHECK();
-  return 0;
-}
-
-// bf16 dcol in, fp32 dx out plus a dense bf16 copy of dx (the next GEMM's operand)
-int col2im_bf16(const void* dcol, int C, int H, int W, int KH, int KW, int stride, int OH, int OW,
-                int nframes, const float* ymask, float* dx, void* dxb, cudaStream_t st) {
-  long long total = (long long)nframes * H * W * C;
-  if (total == 0) return 0;
-  int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
-  col2im_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)dcol, C, H, W, KH, KW, stride, OH, OW,
-                                                       nframes, ymask, dx, (__nv_bfloat16*)dxb);
   TACORL_LAUNCH_CHECK();
   return 0;
 }
@@ -243,105 +220,7 @@ int softargmax_bwd_f32(const float* y, int N, int OH, int OW, int C, const float
 }  // namespace tacorl
 
 // ==========================================================================================
-// Vectorised bf16 staging kernels for the tensor-core path: every thread moves one 16-byte chunk
-// (8 bf16), index arithmetic is on compile-time constants, all accesses are 16-byte aligned.
 namespace tacorl {
-
-// conv1: fp32 NCHW image -> bf16 col[m][k], k = (c, ky, kx) with KW = 8: one thread per (m, c, ky)
-// reads 8 contiguous floats (two float4) and writes 8 bf16.
-__global__ void im2col_conv1_bf16_kernel(const float* __restrict__ x, int H, int W, int OH, int OW, long long total,
-                                         uint4* __restrict__ col) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cky = (int)(i % 24);            // c*8 + ky
-    const long long m = i / 24;
-    const int c = cky >> 3, ky = cky & 7;
-    const int ox = (int)(m % OW);
-    const long long t = m / OW;
-    const int oy = (int)(t % OH);
-    const long long n = t / OH;
-    const float4* src = reinterpret_cast<const float4*>(x + ((n * 3 + c) * H + (oy * 4 + ky)) * (long long)W + ox * 4);
-    const float4 a = __ldg(src), b = __ldg(src + 1);
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
-    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
-    uint4 o;
-    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
-    col[i] = o;
-  }
-}
-
-// NHWC bf16 activation -> bf16 col[m][k], k = (ky, kx, c): pure 16-byte chunk copies.
-template <int C, int KH, int KW, int S>
-__global__ void im2col_nhwc_bf16_kernel(const uint4* __restrict__ y, int H, int W, int OH, int OW, long long total,
-                                        uint4* __restrict__ col) {
-  constexpr int CH = C / 8;                   // 16-byte chunks per pixel
-  constexpr int KCH = KH * KW * CH;           // chunks per col row
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int kc = (int)(i % KCH);
-    const long long m = i / KCH;
-    const int ch = kc % CH, kx = (kc / CH) % KW, ky = kc / (CH * KW);
-    const int ox = (int)(m % OW);
-    const long long t = m / OW;
-    const int oy = (int)(t % OH);
-    const long long n = t / OH;
-    col[i] = __ldg(y + ((n * H + oy * S + ky) * (long long)W + ox * S + kx) * CH + ch);
-  }
-}
-
-__device__ __forceinline__ void acc_bf16x8(float (&s)[8], const uint4& v) {
-  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(p[j]); s[2 * j] += f.x; s[2 * j + 1] += f.y; }
-}
-
-// dX (NHWC, bf16) = [Y > 0] * gather of dcol (bf16) over the taps touching each input pixel; also emits the
-// per-channel sums needed for the bias gradient? (no: bias grads are column sums of dX, done separately)
-template <int C, int KH, int KW, int S>
-__global__ void col2im_nhwc_bf16_kernel(const uint4* __restrict__ dcol, int H, int W, int OH, int OW, long long total,
-                                        const uint4* __restrict__ ymask, uint4* __restrict__ dx) {
-  constexpr int CH = C / 8;
-  constexpr int KCH = KH * KW * CH;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % CH);
-    const long long p = i / CH;
-    const int ix = (int)(p % W);
-    const long long t = p / W;
-    const int iy = (int)(t % H);
-    const long long n = t / H;
-    float s[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = 0.f;
-#pragma unroll
-    for (int ky = 0; ky < KH; ++ky) {
-      const int ty = iy - ky;
-      if (ty < 0 || (ty % S) != 0) continue;
-      const int oy = ty / S;
-      if (oy >= OH) continue;
-#pragma unroll
-      for (int kx = 0; kx < KW; ++kx) {
-        const int tx = ix - kx;
-        if (tx < 0 || (tx % S) != 0) continue;
-        const int ox = tx / S;
-        if (ox >= OW) continue;
-        acc_bf16x8(s, __ldg(dcol + ((n * OH + oy) * (long long)OW + ox) * KCH + (ky * KW + kx) * CH + ch));
-      }
-    }
-    const uint4 mk = __ldg(ymask + i);
-    const __nv_bfloat162* mp = reinterpret_cast<const __nv_bfloat162*>(&mk);
-    uint4 o;
-    uint32_t* op = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 mf = __bfloat1622float2(mp[j]);
-      __nv_bfloat162 r = __floats2bfloat162_rn(mf.x > 0.f ? s[2 * j] : 0.f, mf.y > 0.f ? s[2 * j + 1] : 0.f);
-      op[j] = *reinterpret_cast<uint32_t*>(&r);
-    }
-    dx[i] = o;
-  }
-}
 
 // column sums of a tall bf16 matrix [M][N] (bias gradients), two-stage like colsum_tall_kernel
 __global__ void colsum_tall_bf16_kernel(long long M, int N, const __nv_bfloat16* __restrict__ X, float* __restrict__ part) {
@@ -358,48 +237,6 @@ __global__ void colsum_tall_bf16_kernel(long long M, int N, const __nv_bfloat16*
     for (int i = 0; i < R; ++i) t += sm[i * N + n];
     part[(long long)blockIdx.x * N + n] = t;
   }
-}
-
-static inline int vec_blocks(long long total) { return (int)min((long long)148 * 16, (total + 255) / 256); }
-
-int im2col_conv1_bf16(const float* x, int H, int W, int OH, int OW, int nframes, void* col, cudaStream_t st) {
-  TACORL_REQUIRE(W % 4 == 0 && ((uintptr_t)x & 15) == 0, "im2col_conv1_bf16: image width must be a multiple of 4");
-  const long long total = (long long)nframes * OH * OW * 24;
-  if (total == 0) return 0;
-  im2col_conv1_bf16_kernel<<<vec_blocks(total), 256, 0, st>>>(x, H, W, OH, OW, total, (uint4*)col);
-  TACORL_LAUNCH_CHECK();
-  return 0;
-}
-
-int im2col_nhwc_bf16(int layer, const void* y, int H, int W, int OH, int OW, int nframes, void* col, cudaStream_t st) {
-  if (layer == 2) {
-    const long long total = (long long)nframes * OH * OW * (4 * 4 * 32 / 8);
-    if (total == 0) return 0;
-    im2col_nhwc_bf16_kernel<32, 4, 4, 2><<<vec_blocks(total), 256, 0, st>>>((const uint4*)y, H, W, OH, OW, total, (uint4*)col);
-  } else {
-    const long long total = (long long)nframes * OH * OW * (3 * 3 * 64 / 8);
-    if (total == 0) return 0;
-    im2col_nhwc_bf16_kernel<64, 3, 3, 1><<<vec_blocks(total), 256, 0, st>>>((const uint4*)y, H, W, OH, OW, total, (uint4*)col);
-  }
-  TACORL_LAUNCH_CHECK();
-  return 0;
-}
-
-int col2im_nhwc_bf16(int layer, const void* dcol, int H, int W, int OH, int OW, int nframes, const void* ymask,
-                     void* dx, cudaStream_t st) {
-  if (layer == 2) {
-    const long long total = (long long)nframes * H * W * (32 / 8);
-    if (total == 0) return 0;
-    col2im_nhwc_bf16_kernel<32, 4, 4, 2><<<vec_blocks(total), 256, 0, st>>>((const uint4*)dcol, H, W, OH, OW, total,
-                                                                          (const uint4*)ymask, (uint4*)dx);
-  } else {
-    const long long total = (long long)nframes * H * W * (64 / 8);
-    if (total == 0) return 0;
-    col2im_nhwc_bf16_kernel<64, 3, 3, 1><<<vec_blocks(total), 256, 0, st>>>((const uint4*)dcol, H, W, OH, OW, total,
-                                                                          (const uint4*)ymask, (uint4*)dx);
-  }
-  TACORL_LAUNCH_CHECK();
-  return 0;
 }
 
 int colsum_tall_bf16(long long M, int N, const void* X, float* out, int accumulate, float* ws, size_t ws_bytes,

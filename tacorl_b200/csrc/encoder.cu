@@ -34,18 +34,6 @@ struct EncGeom {
 enum { P_W1 = 0, P_B1, P_W2, P_B2, P_W3, P_B3, P_TEMP, P_W4, P_B4, P_W5, P_B5, P_COUNT };
 static const size_t kSplitKWs = 64ull << 20;
 
-// Frames per im2col/GEMM chunk on the tensor-core path: small enough that a chunk's col matrix stays in the
-// 126 MB L2 between its producer and the GEMM that consumes it (TACORL_ENC_CHUNK overrides, for experiments).
-static int enc_chunk_cap() {
-  static int cap = 0;
-  if (!cap) {
-    const char* e = getenv("TACORL_ENC_CHUNK");
-    cap = e ? atoi(e) : 256;
-    if (cap < 1) cap = 256;
-  }
-  return cap;
-}
-
 static size_t fwd_fixed_bytes(const EncGeom& g, int hidden, bool need_y12, bool need_rest) {
   size_t b = (64 * 512 + 64 * 576) * 4 + 1024;
   if (need_rest) b += (size_t)g.N * (g.P3 * 64 + 128 + 64 + 64 + hidden) * 4 + 2048;
@@ -179,7 +167,6 @@ static int enc_fwd(const float* x, int N, int H, int W, const float* const* para
                    float* ssum, float* h4, float* emb, void* ws, size_t ws_bytes, int prec,
                    cudaStream_t st) {
   EncGeom g(N, H, W);
-  const bool tc = false;   // the explicit-im2col tensor-core variant below is superseded by enc_fwd_tc
   TACORL_REQUIRE(g.ok, "lmp_encoder_fwd: image %dx%d too small", H, W);
   TACORL_REQUIRE(prec == PREC_F32 || prec == PREC_BF16, "lmp_encoder_fwd: unknown precision %d", prec);
   TACORL_REQUIRE(x && params && emb && ws, "lmp_encoder_fwd: null pointer");
@@ -192,11 +179,6 @@ static int enc_fwd(const float* x, int N, int H, int W, const float* const* para
   Arena ar(ws, ws_bytes);
   float* w2p = ar.take<float>(64 * 512);
   float* w3p = ar.take<float>(64 * 576);
-  __nv_bfloat16* wb1 = tc ? ar.take<__nv_bfloat16>(32 * 192) : nullptr;   // bf16 copies for the tensor-core path
-  __nv_bfloat16* wb2 = tc ? ar.take<__nv_bfloat16>(64 * 512) : nullptr;
-  __nv_bfloat16* wb3 = tc ? ar.take<__nv_bfloat16>(64 * 576) : nullptr;
-  float* fcws = tc ? ar.take<float>((4 << 20) / 4) : nullptr;
-  TACORL_REQUIRE(!tc || (wb1 && wb2 && wb3 && fcws), "lmp_encoder_fwd: workspace too small");
   const bool save12 = (y1 != nullptr);   // y1/y2 null => chunk-local scratch (inference / no_grad)
   TACORL_REQUIRE((y1 == nullptr) == (y2 == nullptr), "lmp_encoder_fwd: y1/y2 must both be given or both null");
   if (!y3) y3 = ar.take<float>((size_t)N * g.P3 * 64);
@@ -209,7 +191,6 @@ static int enc_fwd(const float* x, int N, int H, int W, const float* const* para
   if (!save12) per_frame += (g.P1 * 32 + g.P2 * 64) * 4 + 512;
   long long chunk = (long long)(ar.left() > 4096 ? (ar.left() - 4096) / per_frame : 0);
   if (chunk > N) chunk = N;
-  if (tc && chunk > enc_chunk_cap()) chunk = enc_chunk_cap();
   TACORL_REQUIRE(chunk >= 1, "lmp_encoder_fwd: workspace too small for one frame (%zu bytes left)", ar.left());
   float* col = ar.take<float>((size_t)chunk * g.col_floats_per_frame());
   float* y1c = save12 ? nullptr : ar.take<float>((size_t)chunk * g.P1 * 32);
@@ -219,35 +200,12 @@ static int enc_fwd(const float* x, int N, int H, int W, const float* const* para
   int rc;
   if ((rc = permute_conv_weight_f32(params[P_W2], w2p, 64, 32, 4, 4, 0, st))) return rc;
   if ((rc = permute_conv_weight_f32(params[P_W3], w3p, 64, 64, 3, 3, 0, st))) return rc;
-  if (tc) {
-    if ((rc = cast_bf16_2d(params[P_W1], 192, 32, 192, wb1, 192, st))) return rc;
-    if ((rc = cast_bf16_2d(w2p, 512, 64, 512, wb2, 512, st))) return rc;
-    if ((rc = cast_bf16_2d(w3p, 576, 64, 576, wb3, 576, st))) return rc;
-  }
 
   for (long long n0 = 0; n0 < N; n0 += chunk) {
     const int nf = (int)((N - n0) < chunk ? (N - n0) : chunk);
     float* y1p = save12 ? y1 + n0 * g.P1 * 32 : y1c;
     float* y2p = save12 ? y2 + n0 * g.P2 * 64 : y2c;
     float* y3p = y3 + n0 * g.P3 * 64;
-    if (tc) {
-      // bf16 path: vectorised bf16 im2col -> TMA-fed tcgen05 GEMM (K-major col x K-major weights) with the
-      // bias+ReLU epilogue writing the NHWC activation directly in bf16 (y1, y2) / fp32 (y3, for the soft-argmax)
-      __nv_bfloat16* y1b = (__nv_bfloat16*)(save12 ? (void*)y1 : (void*)y1c) + (save12 ? n0 * g.P1 * 32 : 0);
-      __nv_bfloat16* y2b = (__nv_bfloat16*)(save12 ? (void*)y2 : (void*)y2c) + (save12 ? n0 * g.P2 * 64 : 0);
-      TcArgs e;
-      e.act = ACT_RELU; e.split_k = 1;
-      if ((rc = im2col_conv1_bf16(x + n0 * 3 * H * W, H, W, g.H1, g.W1, nf, col, st))) return rc;
-      e.C = nullptr; e.Cb = y1b; e.ldcb = 32; e.bias = params[P_B1];
-      if ((rc = gemm_tc_bf16(col, 192, 0, wb1, 192, 0, (int)(nf * g.P1), 32, 192, e, nullptr, 0, st))) return rc;
-      if ((rc = im2col_nhwc_bf16(2, y1b, g.H1, g.W1, g.H2, g.W2, nf, col, st))) return rc;
-      e.Cb = y2b; e.ldcb = 64; e.bias = params[P_B2];
-      if ((rc = gemm_tc_bf16(col, 512, 0, wb2, 512, 0, (int)(nf * g.P2), 64, 512, e, nullptr, 0, st))) return rc;
-      if ((rc = im2col_nhwc_bf16(3, y2b, g.H2, g.W2, g.H3, g.W3, nf, col, st))) return rc;
-      e.C = y3p; e.ldc = 64; e.Cb = nullptr; e.bias = params[P_B3];
-      if ((rc = gemm_tc_bf16(col, 576, 0, wb3, 576, 0, (int)(nf * g.P3), 64, 576, e, nullptr, 0, st))) return rc;
-      continue;
-    }
     // conv1: NCHW input, K order (c,ky,kx) == torch weight layout
     if ((rc = im2col_f32(x + n0 * 3 * H * W, 3LL * H * W, (long long)H * W, W, 1, 3, 8, 8, 4, g.H1, g.W1, nf,
                          col, st, 0))) return rc;
@@ -273,10 +231,10 @@ static int enc_fwd(const float* x, int N, int H, int W, const float* const* para
   GemmArgs f;
   f.transB = 1; f.M = N; f.N = hidden; f.K = 128; f.A = feat; f.lda = 128; f.B = params[P_W4]; f.ldb = 128;
   f.C = h4; f.ldc = hidden; f.bias = params[P_B4]; f.act = ACT_RELU; f.split_k = 1;
-  if ((rc = gemm_any(prec, f, fcws, 4 << 20, st))) return rc;
+  if ((rc = gemm_f32(f, nullptr, 0, st))) return rc;
   f.N = latent; f.K = hidden; f.A = h4; f.lda = hidden; f.B = params[P_W5]; f.ldb = hidden; f.C = emb;
   f.ldc = latent; f.bias = params[P_B5]; f.act = ACT_NONE;
-  return gemm_any(prec, f, fcws, 4 << 20, st);
+  return gemm_f32(f, nullptr, 0, st);
 }
 
 int tacorl_lmp_encoder_fwd(const float* x, int N, int H, int W, const float* const* params, int hidden,
@@ -294,7 +252,6 @@ int tacorl_lmp_encoder_bwd(const float* x, int N, int H, int W, const float* con
                            size_t ws_bytes, int prec, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   EncGeom g(N, H, W);
-  const bool tc = false;   // the explicit-im2col tensor-core variant below is superseded by enc_bwd_tc
   TACORL_REQUIRE(g.ok, "lmp_encoder_bwd: image %dx%d too small", H, W);
   TACORL_REQUIRE(prec == PREC_F32 || prec == PREC_BF16, "lmp_encoder_bwd: unknown precision %d", prec);
   TACORL_REQUIRE(x && params && grads && y1 && y2 && y3 && feat && smax && ssum && h4 && d_emb && ws,
@@ -317,46 +274,31 @@ int tacorl_lmp_encoder_bwd(const float* x, int N, int H, int W, const float* con
   float* csws = ar.take<float>(592 * 64);
   TACORL_REQUIRE(w2p && w3p && dw2p && dw3p && dh4 && dfeat && dy3 && dtau && skws && csws,
                  "lmp_encoder_bwd: workspace too small");
-  size_t per_frame = (size_t)g.col_floats_per_frame() * 4 + (g.P1 * 32 + g.P2 * 64) * (tc ? 6 : 4) + 1024;
-  const size_t reserve = 4096 + (tc ? (1 << 20) : 0);
-  long long chunk = (long long)(ar.left() > reserve ? (ar.left() - reserve) / per_frame : 0);
+  size_t per_frame = (size_t)g.col_floats_per_frame() * 4 + (g.P1 * 32 + g.P2 * 64) * 4 + 1024;
+  long long chunk = (long long)(ar.left() > 4096 ? (ar.left() - 4096) / per_frame : 0);
   if (chunk > N) chunk = N;
-  if (tc && chunk > enc_chunk_cap()) chunk = enc_chunk_cap();
   TACORL_REQUIRE(chunk >= 1, "lmp_encoder_bwd: workspace too small for one frame");
   float* col = ar.take<float>((size_t)chunk * g.col_floats_per_frame());
   float* dy1c = ar.take<float>((size_t)chunk * g.P1 * 32);
   float* dy2c = ar.take<float>((size_t)chunk * g.P2 * 64);
   TACORL_REQUIRE(col && dy1c && dy2c, "lmp_encoder_bwd: workspace carve failed");
-  // tensor-core path: the fp32 col buffer is split into a bf16 col (first half) and a bf16 dcol (second half);
-  // dyb holds the bf16 copy of the current layer's output gradient
-  __nv_bfloat16* colb = (__nv_bfloat16*)col;
-  __nv_bfloat16* dcolb = colb + (size_t)chunk * g.col_floats_per_frame();
-  __nv_bfloat16 *dyb = nullptr, *wb2 = nullptr, *wb3 = nullptr;
-  if (tc) {
-    dyb = ar.take<__nv_bfloat16>((size_t)chunk * g.P1 * 32 > (size_t)chunk * g.P2 * 64 ? (size_t)chunk * g.P1 * 32
-                                                                                       : (size_t)chunk * g.P2 * 64);
-    wb2 = ar.take<__nv_bfloat16>(64 * 512);
-    wb3 = ar.take<__nv_bfloat16>(64 * 576);
-    TACORL_REQUIRE(dyb && wb2 && wb3, "lmp_encoder_bwd: workspace too small for the bf16 staging buffers");
-  }
-
   int rc;
   // ---- FC head
   GemmArgs a;
   a.transA = 1; a.transB = 0; a.M = latent; a.N = hidden; a.K = N; a.A = d_emb; a.lda = latent; a.B = h4;
   a.ldb = hidden; a.C = grads[P_W5]; a.ldc = hidden; a.beta = beta0; a.split_k = 0;
-  if ((rc = gemm_any(prec, a, skws, kSplitKWs, st))) return rc;                 // dW5 = d_emb^T h4
+  if ((rc = gemm_f32(a, skws, kSplitKWs, st))) return rc;                 // dW5 = d_emb^T h4
   if ((rc = colsum_f32(N, latent, d_emb, latent, grads[P_B5], accumulate, st))) return rc;
   GemmArgs b;
   b.M = N; b.N = hidden; b.K = latent; b.A = d_emb; b.lda = latent; b.B = params[P_W5]; b.ldb = hidden;
   b.C = dh4; b.ldc = hidden; b.split_k = 1;
-  if ((rc = gemm_any(prec, b, skws, kSplitKWs, st))) return rc;                 // dh4 = d_emb W5
+  if ((rc = gemm_f32(b, skws, kSplitKWs, st))) return rc;                 // dh4 = d_emb W5
   if ((rc = act_bwd_f32(ACT_RELU, (long long)N * hidden, dh4, h4, dh4, st))) return rc;
   a.M = hidden; a.N = 128; a.A = dh4; a.lda = hidden; a.B = feat; a.ldb = 128; a.C = grads[P_W4]; a.ldc = 128;
-  if ((rc = gemm_any(prec, a, skws, kSplitKWs, st))) return rc;                 // dW4 = dh4^T feat
+  if ((rc = gemm_f32(a, skws, kSplitKWs, st))) return rc;                 // dW4 = dh4^T feat
   if ((rc = colsum_f32(N, hidden, dh4, hidden, grads[P_B4], accumulate, st))) return rc;
   b.N = 128; b.K = hidden; b.A = dh4; b.lda = hidden; b.B = params[P_W4]; b.ldb = 128; b.C = dfeat; b.ldc = 128;
-  if ((rc = gemm_any(prec, b, skws, kSplitKWs, st))) return rc;                 // dfeat = dh4 W4
+  if ((rc = gemm_f32(b, skws, kSplitKWs, st))) return rc;                 // dfeat = dh4 W4
   // ---- soft-argmax (also applies conv3's ReLU mask) and temperature grad
   if ((rc = softargmax_bwd_f32(y3, N, g.H3, g.W3, 64, params[P_TEMP], feat, smax, ssum, dfeat, dy3, dtau, st)))
     return rc;
@@ -377,42 +319,6 @@ int tacorl_lmp_encoder_bwd(const float* x, int N, int H, int W, const float* con
     const float* y1p = y1 + n0 * g.P1 * 32;
     const float* y2p = y2 + n0 * g.P2 * 64;
     const float* dy3p = dy3 + n0 * g.P3 * 64;
-    if (tc) {
-      // Every GEMM below consumes its operands as stored: wgrad = (dy MN-major)^T (col MN-major),
-      // dgrad = (dy K-major) (W MN-major) -> bf16 dcol, gathered by the vectorised col2im with the ReLU mask.
-      if (n0 == 0) {
-        if ((rc = cast_bf16_2d(w2p, 512, 64, 512, wb2, 512, st))) return rc;
-        if ((rc = cast_bf16_2d(w3p, 576, 64, 576, wb3, 576, st))) return rc;
-      }
-      const __nv_bfloat16* y1b = (const __nv_bfloat16*)(const void*)y1 + n0 * g.P1 * 32;
-      const __nv_bfloat16* y2b = (const __nv_bfloat16*)(const void*)y2 + n0 * g.P2 * 64;
-      const int m3 = (int)(nf * g.P3), m2 = (int)(nf * g.P2), m1 = (int)(nf * g.P1);
-      TcArgs w, d;
-      w.beta = betac; w.split_k = 0;
-      d.split_k = 1; d.C = nullptr;
-      // conv3
-      if ((rc = cast_bf16_2d(dy3p, 64, m3, 64, dyb, 64, st))) return rc;
-      if ((rc = im2col_nhwc_bf16(3, y2b, g.H2, g.W2, g.H3, g.W3, nf, colb, st))) return rc;
-      w.C = dw3p; w.ldc = 576;
-      if ((rc = gemm_tc_bf16(dyb, 64, 1, colb, 576, 1, 64, 576, m3, w, skws, kSplitKWs, st))) return rc;
-      d.Cb = dcolb; d.ldcb = 576;
-      if ((rc = gemm_tc_bf16(dyb, 64, 0, wb3, 576, 1, m3, 576, 64, d, nullptr, 0, st))) return rc;
-      if ((rc = col2im_nhwc_bf16(3, dcolb, g.H2, g.W2, g.H3, g.W3, nf, y2b, dyb, st))) return rc;
-      if ((rc = colsum_tall_bf16((long long)nf * g.P2, 64, dyb, grads[P_B2], accc, csws, 592 * 64 * 4, st))) return rc;
-      // conv2
-      if ((rc = im2col_nhwc_bf16(2, y1b, g.H1, g.W1, g.H2, g.W2, nf, colb, st))) return rc;
-      w.C = dw2p; w.ldc = 512;
-      if ((rc = gemm_tc_bf16(dyb, 64, 1, colb, 512, 1, 64, 512, m2, w, skws, kSplitKWs, st))) return rc;
-      d.Cb = dcolb; d.ldcb = 512;
-      if ((rc = gemm_tc_bf16(dyb, 64, 0, wb2, 512, 1, m2, 512, 64, d, nullptr, 0, st))) return rc;
-      if ((rc = col2im_nhwc_bf16(2, dcolb, g.H1, g.W1, g.H2, g.W2, nf, y1b, dyb, st))) return rc;
-      if ((rc = colsum_tall_bf16((long long)nf * g.P1, 32, dyb, grads[P_B1], accc, csws, 592 * 64 * 4, st))) return rc;
-      // conv1 wgrad, torch K order (c,ky,kx)
-      if ((rc = im2col_conv1_bf16(x + n0 * 3 * H * W, H, W, g.H1, g.W1, nf, colb, st))) return rc;
-      w.C = grads[P_W1]; w.ldc = 192;
-      if ((rc = gemm_tc_bf16(dyb, 32, 1, colb, 192, 1, 32, 192, m1, w, skws, kSplitKWs, st))) return rc;
-      continue;
-    }
     // conv3 wgrad: dW3p[oc][k] (+)= sum_m dy3[m][oc] col3[m][k]
     if ((rc = im2col_f32(y2p, g.P2 * 64, 1, (long long)g.W2 * 64, 64, 64, 3, 3, 1, g.H3, g.W3, nf, col, st, 1)))
       return rc;

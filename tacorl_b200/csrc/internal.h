@@ -12,14 +12,6 @@ int colsum_tall_f32(long long M, int N, const float* X, float* out, int accumula
 
 int im2col_f32(const float* x, long long sn, long long sc, long long sh, long long sw, int C, int KH,
                int KW, int stride, int OH, int OW, int nframes, float* col, cudaStream_t st, int korder);
-int im2col_bf16(const float* x, long long sn, long long sc, long long sh, long long sw, int C, int KH,
-                int KW, int stride, int OH, int OW, int nframes, void* col, cudaStream_t st, int korder);
-int col2im_bf16(const void* dcol, int C, int H, int W, int KH, int KW, int stride, int OH, int OW,
-                int nframes, const float* ymask, float* dx, void* dxb, cudaStream_t st);
-int im2col_conv1_bf16(const float* x, int H, int W, int OH, int OW, int nframes, void* col, cudaStream_t st);
-int im2col_nhwc_bf16(int layer, const void* y, int H, int W, int OH, int OW, int nframes, void* col, cudaStream_t st);
-int col2im_nhwc_bf16(int layer, const void* dcol, int H, int W, int OH, int OW, int nframes, const void* ymask,
-                     void* dx, cudaStream_t st);
 int colsum_tall_bf16(long long M, int N, const void* X, float* out, int accumulate, float* ws, size_t ws_bytes,
                      cudaStream_t st);
 int col2im_f32(const float* dcol, int C, int H, int W, int KH, int KW, int stride, int OH, int OW,
