@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("TACORL_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=64, help="windows per GPU")
     ap.add_argument("--workload", default="play_lmp", choices=["play_lmp"])
+    ap.add_argument("--no-tacorl", action="store_true", help="skip the secondary TACO-RL (CQL) step measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
@@ -147,6 +148,49 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ----------------------------------------------------------------------------------- TACO-RL (secondary line item)
+def measure_tacorl(args, dev, world, rank, timed):
+    """TACORL.training_step (frozen LMP encode + decoder finetune + CQL actor/twin-Q/Lagrange update + Polyak) on
+    `batch` windows x 16 frames + 1 goal image per GPU (BASELINE configs[2]); weak scaling like the main metric."""
+    from tacorl_b200 import _lib, configs, parallel, runtime
+    from tacorl_b200.utils import synthetic
+    from tacorl_b200.utils.config import instantiate
+    B = args.batch
+    lmp = instantiate(configs.play_lmp_for_rl("tanh_net"))
+    t = instantiate(configs.tacorl(), play_lmp=lmp)
+    synthetic.init_like_reference(t, seed=0)
+    t.to(dev)
+    opts = t.optimizers()
+    if world > 1:
+        for o in opts:
+            parallel.attach_data_parallel(o, world)
+    host = synthetic.play_batch(B, T_FRAMES, IMG, IMG, seed=11 + rank, with_goal=True)
+    batch = {"states": {"rgb_static": host["states"]["rgb_static"].to(dev)}, "actions": host["actions"].to(dev),
+             "goal": {"rgb_static": host["goal"]["rgb_static"].to(dev)}, "disp": host["disp"].to(dev)}
+    fn = runtime.tacorl_step_fn(t)
+    graphed = None
+    if not args.no_graph:
+        try:
+            graphed = runtime.GraphedTrainStep(fn, batch, device=dev, warmup=3)
+        except Exception as e:  # pragma: no cover
+            sys.stderr.write(f"[bench] TACO-RL CUDA-graph capture failed, running eagerly: {e!r}\n")
+    run = (lambda s: graphed()) if graphed is not None else (lambda s: fn(batch))
+    for s in range(args.warmup):
+        run(s)
+    n0 = _lib.launch_count()
+    r0 = graphed.replays if graphed is not None else 0
+    ms = timed(run, args.steps) / args.steps
+    launches = _lib.launch_count() - n0
+    if graphed is not None:
+        launches += graphed.launches_per_replay * (graphed.replays - r0)
+    return {"metric": "tacorl_train_frames_per_sec", "value": world * B * T_FRAMES / (ms / 1e3), "unit": "frames/s",
+            "windows_per_sec": world * B / (ms / 1e3), "ms_per_step": ms, "launches_per_step": launches / args.steps,
+            "cuda_graph": used_graph,
+            "workload": "TACORL[BiRNN PR] train step: frozen LMP encode (16 frames) + decoder finetune + CQL update "
+                        "(n_action_samples 4, Lagrange, BC epoch), static 3x200x200, BASELINE configs[2]",
+            "q1_loss": float(t.logged["train/q1_loss"])}
+
+
 # ----------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch.distributed as dist
@@ -215,6 +259,7 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    used_graph = graphed is not None
     for s in range(args.warmup):
         step(None, None, s)
     clocks = ClockSampler(local)
@@ -270,6 +315,15 @@ def run_ours(args):
             "ms_per_launch": enc_ms, "algorithmic_flops_per_launch": B * T_FRAMES * ENC_FLOP_PER_FRAME,
             "share_of_step": enc_ms / ms_per_step}
 
+    tac = None
+    if not args.no_tacorl:
+        graphed = None   # release the PlayLMP graph before building the TACO-RL one
+        try:
+            tac = measure_tacorl(args, dev, world, rank, timed)
+        except Exception as e:  # pragma: no cover - reported, never fatal for the headline metric
+            sys.stderr.write(f"[bench] TACO-RL measurement failed: {e!r}\n")
+            tac = {"error": repr(e)}
+
     if rank == 0:
         line = {
             "metric": "play_lmp_train_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world,
@@ -280,7 +334,7 @@ def run_ours(args):
                                    "16 frames/window, BASELINE configs[1]",
                        "windows_per_gpu": B, "global_windows": B * world, "frames_per_window": T_FRAMES,
                        "parallelism": f"dp{world}", "precision": args.precision,
-                       "cuda_graph": graphed is not None,
+                       "cuda_graph": used_graph,
                        "l2_policy": "inputs (491 MB images/step) larger than the 126 MB L2"},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4},
@@ -291,6 +345,8 @@ def run_ours(args):
             "algorithmic_tflops_whole_step": world * B * PLAYLMP_FLOP_PER_WINDOW / (ms_per_step / 1e3) / 1e12,
             "final_loss": losses[-1] if losses else None,
         }
+        if tac is not None:
+            line["tacorl"] = tac
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             t = cpu_reference_step_time(B, 4, 1, threads)
