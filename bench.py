@@ -185,7 +185,7 @@ def measure_tacorl(args, dev, world, rank, timed):
         launches += graphed.launches_per_replay * (graphed.replays - r0)
     return {"metric": "tacorl_train_frames_per_sec", "value": world * B * T_FRAMES / (ms / 1e3), "unit": "frames/s",
             "windows_per_sec": world * B / (ms / 1e3), "ms_per_step": ms, "launches_per_step": launches / args.steps,
-            "cuda_graph": used_graph,
+            "cuda_graph": graphed is not None,
             "workload": "TACORL[BiRNN PR] train step: frozen LMP encode (16 frames) + decoder finetune + CQL update "
                         "(n_action_samples 4, Lagrange, BC epoch), static 3x200x200, BASELINE configs[2]",
             "q1_loss": float(t.logged["train/q1_loss"])}

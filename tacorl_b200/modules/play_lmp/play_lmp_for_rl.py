@@ -111,17 +111,28 @@ class PlayLMP(LightningModule):
         emb_states, pp_dist, pr_dist, lat_goal = self.process_batch(batch)
         kl_loss = self.compute_kl_loss(pr_dist=pr_dist, pp_dist=pp_dist, stage=stage)
         ad_states = self._cat([emb_states[k] for k in self.action_decoder_modalities])
-        action_loss = self.compute_action_loss(emb_states=ad_states, actions=batch["actions"],
-                                               latent_plan=pr_dist.rsample(), stage=stage, latent_goal=lat_goal)
-        # random-plan decoder pass: logging only unless add_random_plan_loss (:243-256)
+        latent_plan = pr_dist.rsample()
         mean_shape = pr_dist.normal.mean.shape if isinstance(pr_dist, TanhNormal) else pr_dist.mean.shape
-        random_plan = rng.uniform(mean_shape, -1.0, 1.0, lat_goal.device)
-        rng.uniform(lat_goal.shape, -1.0, 1.0, lat_goal.device)     # the reference also draws an (unused) goal
-        if self.add_random_plan_loss:
+        dec = self.action_decoder
+        if self.add_random_plan_loss or not hasattr(dec, "loss_and_act_two_plans"):
+            action_loss = self.compute_action_loss(emb_states=ad_states, actions=batch["actions"],
+                                                   latent_plan=latent_plan, stage=stage, latent_goal=lat_goal)
+            random_plan = rng.uniform(mean_shape, -1.0, 1.0, lat_goal.device)
+            rng.uniform(lat_goal.shape, -1.0, 1.0, lat_goal.device)   # the reference also draws an (unused) goal
             rp_loss = self.compute_action_loss(ad_states, batch["actions"], random_plan, stage, "random_plan_")
         else:
-            with torch.no_grad():
-                rp_loss = self.compute_action_loss(ad_states, batch["actions"], random_plan, stage, "random_plan_")
+            # sampled plan and random plan (logging only, :243-256) share ONE batched decoder pass; the noise is
+            # drawn in the reference's order: _sample(u1,u2) -> random plan -> (unused) random goal -> _sample
+            Bn, Tn = ad_states.shape[0], ad_states.shape[1] - 1
+            noise = dec._draw_sample_noise(Bn, Tn, lat_goal.device)
+            random_plan = rng.uniform(mean_shape, -1.0, 1.0, lat_goal.device)
+            rng.uniform(lat_goal.shape, -1.0, 1.0, lat_goal.device)
+            noise_rp = dec._draw_sample_noise(Bn, Tn, lat_goal.device)
+            (action_loss, _, acc), (rp_loss, _, acc_rp) = dec.loss_and_act_two_plans(
+                latent_plan, random_plan, ad_states[:, :-1], batch["actions"][:, :-1], noise, noise_rp)
+            for prefix, l_, a_ in (("", action_loss, acc), ("random_plan_", rp_loss, acc_rp)):
+                self.log(f"{stage}/{prefix}action_loss", l_, on_step=True, on_epoch=True, sync_dist=True)
+                self.log(f"{stage}/{prefix}gripper_accuracy", a_, on_step=True, on_epoch=True, sync_dist=True)
         total_loss = kl_loss + action_loss
         if self.add_random_plan_loss:
             total_loss = total_loss - rp_loss

@@ -92,6 +92,27 @@ class ActionDecoderLogistic(ActionDecoder):
         self.last_gripper_accuracy = acc
         return loss, pred.view(T, B, -1).transpose(0, 1)
 
+    def loss_and_act_two_plans(self, latent_plan, other_plan, perceptual_emb, actions, noise, other_noise):
+        """One batched decoder pass for two latent plans over the same window (PlayLMP evaluates the sampled plan AND a
+        random plan every step, play_lmp_for_rl.py:235-252).  The first plan carries gradients; the second is
+        logging-only.  noise / other_noise = (u1, u2) drawn by the caller in the reference's order.
+        Returns (loss, pred, acc), (other_loss, other_pred, other_acc)."""
+        B = latent_plan.shape[0]
+        plans = torch.cat([latent_plan, other_plan.detach()], dim=0)
+        embs = torch.cat([perceptual_emb, perceptual_emb.detach()], dim=0)
+        logits, _, (B2, T) = self._logits_time_major(plans, embs)
+        lg = logits.view(T, B2, -1)
+        la = lg[:, :B].reshape(T * B, -1)
+        lb = lg[:, B:].reshape(T * B, -1).detach()
+        acts = self._tm(actions)
+        pred, acc = ops.dlm_sample(la, noise[0], noise[1], acts, *self._grip)
+        loss = ops.dlm_loss(la, acts, self.num_classes, self._act_min, self._act_max, self.gripper_alpha)
+        with torch.no_grad():
+            pred_b, acc_b = ops.dlm_sample(lb, other_noise[0], other_noise[1], acts, *self._grip)
+            loss_b = ops.dlm_loss(lb, acts, self.num_classes, self._act_min, self._act_max, self.gripper_alpha)
+        return ((loss, pred.view(T, B, -1).transpose(0, 1), acc),
+                (loss_b, pred_b.view(T, B, -1).transpose(0, 1), acc_b))
+
     def act(self, latent_plan, perceptual_emb, latent_goal=None):
         with torch.no_grad():
             logits, self.hidden_state, (B, T) = self._logits_time_major(latent_plan, perceptual_emb,

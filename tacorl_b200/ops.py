@@ -24,6 +24,16 @@ def get_precision():
     return "bf16" if _STATE["prec"] == L.PREC_BF16 else "fp32"
 
 
+_SIDE = {}
+
+
+def _side_stream(dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
 def _off(t, elems):
     return ctypes.c_void_p(t.data_ptr() + 4 * elems)
 
@@ -187,15 +197,30 @@ class ReluRNNFn(Function):
         for l in range(num_layers):
             Il = inp.shape[2]
             out = torch.empty(T, B, D * H, device=dev, dtype=torch.float32)
-            for d in range(D):
+            nbytes = L.query("tacorl_rnn_layer_ws_bytes", T, B, Il, H)
+
+            def run_dir(d, tag):
                 w_ih, w_hh, b_ih, b_hh = weights[(l * D + d) * 4:(l * D + d) * 4 + 4]
                 n_steps = 1 if (last_only and l == num_layers - 1 and d == 1) else T
                 h0_ld = None if h0 is None else _c(h0[l * D + d])
-                ws = L.workspace(L.query("tacorl_rnn_layer_ws_bytes", T, B, Il, H), dev)
+                ws = L.workspace(nbytes, dev, tag)
                 L.call("tacorl_rnn_layer_fwd", T, B, Il, H, L.ptr(inp), Il, L.ptr(w_ih), L.ptr(w_hh), L.ptr(b_ih),
                        L.ptr(b_hh), L.ptr(h0_ld), d, n_steps, _off(out, d * H), D * H,
                        ctypes.c_void_p(ws.data_ptr()), ws.numel(), _STATE["prec"], L.stream())
-                if hn is not None:
+
+            if D == 2:
+                # the two directions of a layer are independent: the reverse one runs on a side stream
+                # (own workspace), joined before the next layer reads the concatenated output
+                main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    run_dir(1, "rnn_side")
+                run_dir(0, "main")
+                main.wait_stream(side)
+            else:
+                run_dir(0, "main")
+            if hn is not None:
+                for d in range(D):
                     hn.append(out[0 if d == 1 else T - 1, :, d * H:(d + 1) * H])
             outs.append(out)
             inp = out
@@ -226,7 +251,10 @@ class ReluRNNFn(Function):
             Il = inp.shape[2]
             need_dx = l > 0 or ctx.needs_input_grad[0]
             dx = torch.empty(T, B, Il, device=dev, dtype=torch.float32) if need_dx else None
-            for d in range(D):
+            dx_rev = torch.empty(T, B, Il, device=dev, dtype=torch.float32) if (need_dx and D == 2) else None
+            nbytes = L.query("tacorl_rnn_layer_ws_bytes", T, B, Il, H)
+
+            def run_dir(d, tag, dx_buf):
                 k = (l * D + d) * 4
                 w_ih, w_hh = weights[k], weights[k + 1]
                 g = [torch.empty_like(weights[k + j]) for j in range(4)]
@@ -234,12 +262,24 @@ class ReluRNNFn(Function):
                 h0_ld = None if h0 is None else _c(h0[l * D + d])
                 dhn_ld = None if d_hn is None else _c(d_hn[l * D + d])
                 dh0_ld = None if dh0 is None else dh0[l * D + d]
-                ws = L.workspace(L.query("tacorl_rnn_layer_ws_bytes", T, B, Il, H), dev)
+                ws = L.workspace(nbytes, dev, tag)
                 L.call("tacorl_rnn_layer_bwd", T, B, Il, H, L.ptr(inp), Il, L.ptr(w_ih), L.ptr(w_hh), L.ptr(h0_ld),
                        d, n_steps, _off(outs[l], d * H), D * H, _off(dbuf, d * H), D * H, L.ptr(dhn_ld),
-                       L.ptr(dx), Il, int(d == 1), L.ptr(g[0]), L.ptr(g[1]), L.ptr(g[2]), L.ptr(g[3]), 0,
+                       L.ptr(dx_buf), Il, 0, L.ptr(g[0]), L.ptr(g[1]), L.ptr(g[2]), L.ptr(g[3]), 0,
                        L.ptr(dh0_ld), ctypes.c_void_p(ws.data_ptr()), ws.numel(), _STATE["prec"], L.stream())
                 wgrads[k:k + 4] = g
+
+            if D == 2:
+                main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    run_dir(1, "rnn_side", dx_rev)
+                run_dir(0, "main", dx)
+                main.wait_stream(side)
+                if need_dx:
+                    dx.add_(dx_rev)
+            else:
+                run_dir(0, "main", dx)
             dbuf = dx
         return (dbuf if ctx.needs_input_grad[0] else None, dh0, None, None, None, *wgrads)
 
