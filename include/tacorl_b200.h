@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TACORL_B200_ABI_VERSION 1
+#define TACORL_B200_ABI_VERSION 2
 
 #define TACORL_PREC_F32 0
 #define TACORL_PREC_BF16 1
@@ -61,7 +61,9 @@ int tacorl_rowscale(long long rows, int L, const float* x, const float* row_scal
                     int accumulate, void* stream);
 
 /* ---- LMP vision encoder: encoder.py:369-419 (LMPVisionEncoder), utils.py:39-76 (SpatialSoftArgmax)
- * x: (N,3,H,W) NCHW.  params/grads: 11 pointers in state_dict order
+ * x: (N,3,H,W) NCHW; x_dtype 0 = fp32 (already normalised, the reference's batch contract) or 1 = uint8 raw frames
+ * normalised on the fly as v = u8 * x_scale + x_shift (ScaleImageTensor + Normalize of utils/transforms.py:87-101 /
+ * config rl_train.yaml:2-14 fused into the first load).  params/grads: 11 pointers in state_dict order
  *   model.0.{weight,bias}, model.2.{weight,bias}, model.4.{weight,bias}, model.6.temperature,
  *   fc_layers.0.{weight,bias}, fc_layers.3.{weight,bias}          
  * Saved for backward (caller-owned; pass NULL for y1,y2[,y3,feat,smax,ssum,h4] in inference):
@@ -69,11 +71,13 @@ int tacorl_rowscale(long long rows, int L, const float* x, const float* row_scal
  *   y3 (N,H3,W3,64) post-ReLU NHWC fp32; feat (N,128);
  *   smax, ssum (N,64) softmax statistics; h4 (N,hidden).   emb: (N,latent). */
 size_t tacorl_lmp_encoder_ws_bytes(int N, int H, int W, int hidden, int latent, int backward);
-int tacorl_lmp_encoder_fwd(const float* x, int N, int H, int W, const float* const* params, int hidden,
+int tacorl_lmp_encoder_fwd(const void* x, int x_dtype, float x_scale, float x_shift, int N, int H, int W,
+                           const float* const* params, int hidden,
                            int latent, float* y1, float* y2, float* y3, float* feat, float* smax,
                            float* ssum, float* h4, float* emb, void* ws, size_t ws_bytes, int prec,
                            void* stream);
-int tacorl_lmp_encoder_bwd(const float* x, int N, int H, int W, const float* const* params, int hidden,
+int tacorl_lmp_encoder_bwd(const void* x, int x_dtype, float x_scale, float x_shift, int N, int H, int W,
+                           const float* const* params, int hidden,
                            int latent, const float* y1, const float* y2, const float* y3,
                            const float* feat, const float* smax, const float* ssum, const float* h4,
                            const float* d_emb, float* const* grads, int accumulate, void* ws,

@@ -428,6 +428,66 @@ __global__ void cv_s2d_kernel(const float* __restrict__ x, int H, int W, int SH,
   }
 }
 
+// uint8 NCHW frames: scale/normalise (v = u8*scale + shift, i.e. ScaleImageTensor + Normalize of
+// /root/reference/src/tacorl/utils/transforms.py:87-101 fused into the load) and space-to-depth in one pass.
+__global__ void cv_s2d_u8_kernel(const unsigned char* __restrict__ x, int H, int W, int SH, int SW, long long total,
+                                 float scale, float shift, __nv_bfloat16* __restrict__ xs) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int py = (int)(i & 3);
+    long long t = i >> 2;
+    const int X = (int)(t % SW); t /= SW;
+    const int Y = (int)(t % SH);
+    const long long n = t / SH;
+    const int iy = 4 * Y + py;
+    float v[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) v[j] = 0.f;
+    if (iy < H && 4 * X + 3 < W) {
+      const unsigned char* p = x + ((n * 3) * H + iy) * (long long)W + 4 * X;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(p + (long long)c * H * W));
+        v[c] = fmaf((float)u.x, scale, shift); v[3 + c] = fmaf((float)u.y, scale, shift);
+        v[6 + c] = fmaf((float)u.z, scale, shift); v[9 + c] = fmaf((float)u.w, scale, shift);
+      }
+    }
+    __nv_bfloat16* o = xs + ((n * SH + Y) * (long long)SW + X) * 48 + py * 12;
+    uint32_t pk[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      __nv_bfloat162 t2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      pk[j] = *reinterpret_cast<uint32_t*>(&t2);
+    }
+    uint2* op = reinterpret_cast<uint2*>(o);
+    op[0] = make_uint2(pk[0], pk[1]); op[1] = make_uint2(pk[2], pk[3]); op[2] = make_uint2(pk[4], pk[5]);
+  }
+}
+
+int conv_tc_s2d_u8(const unsigned char* x, int N, int H, int W, int SH, int SW, float scale, float shift, void* xs,
+                   cudaStream_t st) {
+  TACORL_REQUIRE(W % 4 == 0 && ((uintptr_t)x & 3) == 0, "conv_tc_s2d_u8: image width must be a multiple of 4");
+  const long long total = (long long)N * SH * SW * 4;
+  if (total == 0) return 0;
+  cv_s2d_u8_kernel<<<(int)min((long long)148 * 16, (total + 255) / 256), 256, 0, st>>>(x, H, W, SH, SW, total, scale,
+                                                                                     shift, (__nv_bfloat16*)xs);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void cv_u8_to_f32_kernel(long long n, const unsigned char* __restrict__ x, float scale, float shift,
+                                    float* __restrict__ o) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    o[i] = fmaf((float)x[i], scale, shift);
+}
+
+int u8_to_f32_normalized(long long n, const unsigned char* x, float scale, float shift, float* out, cudaStream_t st) {
+  if (n == 0) return 0;
+  cv_u8_to_f32_kernel<<<(int)min((long long)148 * 16, (n + 255) / 256), 256, 0, st>>>(n, x, scale, shift, out);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
 int conv_tc_s2d(const float* x, int N, int H, int W, int SH, int SW, void* xs, cudaStream_t st) {
   TACORL_REQUIRE(W % 4 == 0 && ((uintptr_t)x & 15) == 0, "conv_tc_s2d: image width must be a multiple of 4");
   const long long total = (long long)N * SH * SW * 4;

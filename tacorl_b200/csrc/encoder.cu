@@ -59,14 +59,14 @@ size_t tacorl_lmp_encoder_ws_bytes(int N, int H, int W, int hidden, int latent, 
   size_t tc = (size_t)N * ((size_t)(g.H1 + 1) * (g.W1 + 1) * 96 + g.P1 * 64 + g.P2 * 128 + g.P3 * 64 * 6 +
                            (g.P1 * 64 + g.P2 * 128) + (128 + 64 + 64 + hidden + 128 + hidden) * 4 + 4096) +
               kSplitKWs + (32 << 20);
-  size_t legacy = fixed + per_frame * chunk;
+  size_t legacy = fixed + per_frame * chunk + (size_t)N * 3 * H * W * 4 + 4096;   // (+ fp32 copy of uint8 frames)
   return tc > legacy ? tc : legacy;
 }
 
 // ------------------------------------------------------------------------------------------ tensor-core path
 // conv stack as implicit GEMMs (conv_tc.cu): x -> space-to-depth bf16 -> conv1 -> conv2 -> conv3, NHWC bf16
 // activations, packed bf16 weights resident in shared memory, no im2col buffers.
-static int enc_fwd_tc(const float* x, int N, int H, int W, const float* const* params, int hidden, int latent,
+static int enc_fwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, int N, int H, int W, const float* const* params, int hidden, int latent,
                       void* y1, void* y2, float* y3, float* feat, float* smax, float* ssum, float* h4, float* emb,
                       void* ws, size_t ws_bytes, cudaStream_t st) {
   EncGeom g(N, H, W);
@@ -89,7 +89,8 @@ static int enc_fwd_tc(const float* x, int N, int H, int W, const float* const* p
   if ((rc = conv_tc_pack(2, params[P_W1], wp1, st))) return rc;
   if ((rc = conv_tc_pack(1, params[P_W2], wp2, st))) return rc;
   if ((rc = conv_tc_pack(0, params[P_W3], wp3, st))) return rc;
-  if ((rc = conv_tc_s2d(x, N, H, W, g.H1 + 1, g.W1 + 1, xs, st))) return rc;
+  if ((rc = x_u8 ? conv_tc_s2d_u8((const unsigned char*)xv, N, H, W, g.H1 + 1, g.W1 + 1, x_scale, x_shift, xs, st)
+                 : conv_tc_s2d((const float*)xv, N, H, W, g.H1 + 1, g.W1 + 1, xs, st))) return rc;
   if ((rc = conv_tc_conv1_fwd(xs, N, g.H1, g.W1, wp1, params[P_B1], y1b, st))) return rc;
   if ((rc = conv_tc_conv2_fwd(y1b, N, g.H1, g.W1, g.H2, g.W2, wp2, params[P_B2], y2b, st))) return rc;
   if ((rc = conv_tc_conv3_fwd(y2b, N, g.H2, g.W2, g.H3, g.W3, wp3, params[P_B3], y3, st))) return rc;
@@ -103,7 +104,7 @@ static int enc_fwd_tc(const float* x, int N, int H, int W, const float* const* p
   return gemm_tc_from_f32(f, fcws, 8 << 20, st);
 }
 
-static int enc_bwd_tc(const float* x, int N, int H, int W, const float* const* params, int hidden, int latent,
+static int enc_bwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, int N, int H, int W, const float* const* params, int hidden, int latent,
                       const void* y1, const void* y2, const float* y3, const float* feat, const float* smax,
                       const float* ssum, const float* h4, const float* d_emb, float* const* grads, int accumulate,
                       void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -158,25 +159,35 @@ static int enc_bwd_tc(const float* x, int N, int H, int W, const float* const* p
   if ((rc = conv_tc_conv2_dgrad(dy2b, N, g.H1, g.W1, g.H2, g.W2, wd2, y1, dy1b, st))) return rc;
   if ((rc = colsum_tall_bf16((long long)N * g.P1, 32, dy1b, grads[P_B1], accumulate, csws, 592 * 64 * 4, st))) return rc;
   // ---- conv1 (weight gradient only; images receive no gradient)
-  if ((rc = conv_tc_s2d(x, N, H, W, g.H1 + 1, g.W1 + 1, xs, st))) return rc;
+  if ((rc = x_u8 ? conv_tc_s2d_u8((const unsigned char*)xv, N, H, W, g.H1 + 1, g.W1 + 1, x_scale, x_shift, xs, st)
+                 : conv_tc_s2d((const float*)xv, N, H, W, g.H1 + 1, g.W1 + 1, xs, st))) return rc;
   return conv_tc_wgrad(1, dy1b, xs, N, g.H1 + 1, g.W1 + 1, g.H1, g.W1, beta0, grads[P_W1], skws, kSplitKWs, st);
 }
 
-static int enc_fwd(const float* x, int N, int H, int W, const float* const* params, int hidden,
+static int enc_fwd(const void* xv, int x_u8, float x_scale, float x_shift, int N, int H, int W,
+                   const float* const* params, int hidden,
                    int latent, float* y1, float* y2, float* y3, float* feat, float* smax,
                    float* ssum, float* h4, float* emb, void* ws, size_t ws_bytes, int prec,
                    cudaStream_t st) {
   EncGeom g(N, H, W);
+  const float* x = (const float*)xv;
   TACORL_REQUIRE(g.ok, "lmp_encoder_fwd: image %dx%d too small", H, W);
   TACORL_REQUIRE(prec == PREC_F32 || prec == PREC_BF16, "lmp_encoder_fwd: unknown precision %d", prec);
   TACORL_REQUIRE(x && params && emb && ws, "lmp_encoder_fwd: null pointer");
   if (N == 0) return 0;
   if (prec == PREC_BF16) {
     TACORL_REQUIRE(W % 4 == 0, "lmp_encoder_fwd(bf16): image width must be a multiple of 4 (got %d)", W);
-    return enc_fwd_tc(x, N, H, W, params, hidden, latent, (void*)y1, (void*)y2, y3, feat, smax, ssum, h4, emb, ws,
-                      ws_bytes, st);
+    return enc_fwd_tc(xv, x_u8, x_scale, x_shift, N, H, W, params, hidden, latent, (void*)y1, (void*)y2, y3, feat,
+                      smax, ssum, h4, emb, ws, ws_bytes, st);
   }
   Arena ar(ws, ws_bytes);
+  if (x_u8) {   // fp32 parity path: materialise the normalised fp32 image once
+    float* xf = ar.take<float>((size_t)N * 3 * H * W);
+    TACORL_REQUIRE(xf, "lmp_encoder_fwd: workspace too small for the uint8 -> fp32 image");
+    int rcu = u8_to_f32_normalized((long long)N * 3 * H * W, (const unsigned char*)xv, x_scale, x_shift, xf, st);
+    if (rcu) return rcu;
+    x = xf;
+  }
   float* w2p = ar.take<float>(64 * 512);
   float* w3p = ar.take<float>(64 * 576);
   const bool save12 = (y1 != nullptr);   // y1/y2 null => chunk-local scratch (inference / no_grad)
@@ -237,31 +248,43 @@ static int enc_fwd(const float* x, int N, int H, int W, const float* const* para
   return gemm_f32(f, nullptr, 0, st);
 }
 
-int tacorl_lmp_encoder_fwd(const float* x, int N, int H, int W, const float* const* params, int hidden,
+int tacorl_lmp_encoder_fwd(const void* x, int x_dtype, float x_scale, float x_shift, int N, int H, int W,
+                           const float* const* params, int hidden,
                            int latent, float* y1, float* y2, float* y3, float* feat, float* smax,
                            float* ssum, float* h4, float* emb, void* ws, size_t ws_bytes, int prec,
                            void* stream) {
-  return enc_fwd(x, N, H, W, params, hidden, latent, y1, y2, y3, feat, smax, ssum, h4, emb, ws, ws_bytes, prec,
-                 (cudaStream_t)stream);
+  TACORL_REQUIRE(x_dtype == 0 || x_dtype == 1, "lmp_encoder_fwd: x_dtype must be 0 (fp32) or 1 (uint8)");
+  return enc_fwd(x, x_dtype, x_scale, x_shift, N, H, W, params, hidden, latent, y1, y2, y3, feat, smax, ssum, h4, emb,
+                 ws, ws_bytes, prec, (cudaStream_t)stream);
 }
 
-int tacorl_lmp_encoder_bwd(const float* x, int N, int H, int W, const float* const* params, int hidden,
+int tacorl_lmp_encoder_bwd(const void* xv, int x_dtype, float x_scale, float x_shift, int N, int H, int W,
+                           const float* const* params, int hidden,
                            int latent, const float* y1, const float* y2, const float* y3,
                            const float* feat, const float* smax, const float* ssum, const float* h4,
                            const float* d_emb, float* const* grads, int accumulate, void* ws,
                            size_t ws_bytes, int prec, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   EncGeom g(N, H, W);
+  const float* x = (const float*)xv;
+  TACORL_REQUIRE(x_dtype == 0 || x_dtype == 1, "lmp_encoder_bwd: x_dtype must be 0 (fp32) or 1 (uint8)");
   TACORL_REQUIRE(g.ok, "lmp_encoder_bwd: image %dx%d too small", H, W);
   TACORL_REQUIRE(prec == PREC_F32 || prec == PREC_BF16, "lmp_encoder_bwd: unknown precision %d", prec);
   TACORL_REQUIRE(x && params && grads && y1 && y2 && y3 && feat && smax && ssum && h4 && d_emb && ws,
                  "lmp_encoder_bwd: null pointer");
   if (N == 0) return 0;
   if (prec == PREC_BF16)
-    return enc_bwd_tc(x, N, H, W, params, hidden, latent, (const void*)y1, (const void*)y2, y3, feat, smax, ssum, h4,
-                      d_emb, grads, accumulate, ws, ws_bytes, st);
+    return enc_bwd_tc(xv, x_dtype, x_scale, x_shift, N, H, W, params, hidden, latent, (const void*)y1, (const void*)y2,
+                      y3, feat, smax, ssum, h4, d_emb, grads, accumulate, ws, ws_bytes, st);
   const float beta0 = accumulate ? 1.f : 0.f;
   Arena ar(ws, ws_bytes);
+  if (x_dtype == 1) {   // fp32 parity path: normalised fp32 copy of the uint8 frames (conv1 weight gradient)
+    float* xf = ar.take<float>((size_t)N * 3 * H * W);
+    TACORL_REQUIRE(xf, "lmp_encoder_bwd: workspace too small for the uint8 -> fp32 image");
+    int rcu = u8_to_f32_normalized((long long)N * 3 * H * W, (const unsigned char*)xv, x_scale, x_shift, xf, st);
+    if (rcu) return rcu;
+    x = xf;
+  }
   float* w2p = ar.take<float>(64 * 512);
   float* w3p = ar.take<float>(64 * 576);
   float* dw2p = ar.take<float>(64 * 512);

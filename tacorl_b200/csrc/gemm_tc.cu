@@ -508,6 +508,9 @@ int cast_transpose_bf16(const float* src, long long lds, int rows, int cols, voi
 // in their stored orientation (no transposes: stored-[K][rows] operands use the MN-major descriptors).
 int gemm_tc_from_f32(const GemmArgs& g, float* ws, size_t ws_bytes, cudaStream_t st) {
   if (g.M == 0 || g.N == 0) return 0;
+  // tiny contractions (goal-encoder / policy / Q MLPs at batch 64, distribution heads): two staging casts plus a
+  // 148-SM tensor-core launch cost more than the whole fp32 FFMA GEMM, and fp32 is strictly more accurate
+  if ((long long)g.M * g.N * g.K < (1LL << 24)) return gemm_f32(g, ws, ws_bytes, st);
   TACORL_REQUIRE(ws, "gemm_tc: workspace required");
   const long long a_rows = g.transA ? g.K : g.M, a_cols = g.transA ? g.M : g.K;
   const long long b_rows = g.transB ? g.N : g.K, b_cols = g.transB ? g.K : g.N;

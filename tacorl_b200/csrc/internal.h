@@ -49,6 +49,9 @@ static inline int gemm_any(int prec, const GemmArgs& g, float* ws, size_t ws_byt
 // ---- implicit-GEMM convolutions (conv_tc.cu); all activations NHWC bf16
 int conv_tc_pack(int mode, const float* W, void* Wp, cudaStream_t st);
 int conv_tc_s2d(const float* x, int N, int H, int W, int SH, int SW, void* xs, cudaStream_t st);
+int conv_tc_s2d_u8(const unsigned char* x, int N, int H, int W, int SH, int SW, float scale, float shift, void* xs,
+                   cudaStream_t st);
+int u8_to_f32_normalized(long long n, const unsigned char* x, float scale, float shift, float* out, cudaStream_t st);
 int conv_tc_conv1_fwd(const void* xs, int N, int H1, int W1, const void* wp, const float* bias, void* y1b, cudaStream_t st);
 int conv_tc_conv2_fwd(const void* y1b, int N, int H1, int W1, int H2, int W2, const void* wp, const float* bias,
                       void* y2b, cudaStream_t st);

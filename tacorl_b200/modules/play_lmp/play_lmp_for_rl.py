@@ -99,6 +99,7 @@ class PlayLMP(LightningModule):
 
     def process_batch(self, batch):                                               # :200-219
         emb_states = self.get_emb_states(batch["states"], modalities=self.all_modalities)
+        self._overlap_grad_sync(emb_states)
         pp_state = self._cat([emb_states[k][:, 0] for k in self.plan_proposal_obs_modalities])
         pp_goal = self._cat([emb_states[k][:, -1] for k in self.plan_proposal_goal_modalities])
         pp_goal = self.goal_encoder(pp_goal)
@@ -163,4 +164,30 @@ class PlayLMP(LightningModule):
         return {"idx": batch.get("idx"), "sampled_plan_pp": pp_dist.sample()}
 
     def configure_optimizers(self):                                               # :362-368
-        return FlatAdam(filter(lambda p: p.requires_grad, self.parameters()), lr=self.lr)
+        self._flat_opt = FlatAdam(filter(lambda p: p.requires_grad, self.parameters()), lr=self.lr)
+        return self._flat_opt
+
+    _flat_opt = None
+
+    def _overlap_grad_sync(self, emb_states):
+        """Data parallel: everything behind the vision encoders (RNNs, decoder, MLPs = 99.7 % of the parameters)
+        has its final gradient before the encoders' backward starts.  A hook on the embeddings starts the
+        all-reduce of that slice at exactly that moment, so it overlaps the encoder backward."""
+        opt = self._flat_opt
+        if opt is None or opt.grad_sync is None or not torch.is_grad_enabled():
+            return
+        enc_ids = {id(p) for p in self.perceptual_encoder.parameters()}
+        rest = [p for p in opt.param_groups[0]["params"] if id(p) not in enc_ids]
+        pending = [len(emb_states)]
+
+        def hook(grad):
+            pending[0] -= 1
+            if pending[0] == 0:
+                opt.begin_overlapped_sync(rest)
+            return None
+
+        for v in emb_states.values():
+            if v.requires_grad:
+                v.register_hook(hook)
+            else:
+                pending[0] -= 1

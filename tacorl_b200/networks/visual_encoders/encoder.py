@@ -19,6 +19,9 @@ class LMPVisionEncoder(nn.Module):
                 "the B200 encoder kernels cover the shipped lmp_vision_encoder.yaml configuration "
                 "(3 input channels, ReLU, dropout 0, no output LayerNorm, no VIB)")
         self.latent_dim = latent_dim
+        # uint8 frames may be fed directly: ScaleImageTensor + Normalize(mean, std) of the reference's transform
+        # pipeline (config/datamodule/transform_manager/rl_train.yaml:2-14) are then fused into the first kernel
+        self.input_mean, self.input_std = 0.5, 0.5
         self.normalize_output = normalize_output
         self.vib = vib
         self.model = nn.Sequential(
@@ -35,4 +38,4 @@ class LMPVisionEncoder(nn.Module):
                 f[0].weight, f[0].bias, f[3].weight, f[3].bias]
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return ops.lmp_encoder(x, self.kernel_params())
+        return ops.lmp_encoder(x, self.kernel_params(), (self.input_mean, self.input_std))

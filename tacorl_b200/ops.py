@@ -124,10 +124,16 @@ class LMPEncoderFn(Function):
     """LMPVisionEncoder forward/backward as one op (tacorl_lmp_encoder_{fwd,bwd})."""
 
     @staticmethod
-    def forward(ctx, x, save, *params):
+    def forward(ctx, x, save, norm, *params):
         N, C, H, W = x.shape
         assert C == 3, "LMPVisionEncoder kernels are built for 3 input channels"
         x = _c(x)
+        if x.dtype == torch.uint8:       # raw frames: (u8/255 - mean)/std fused into the first kernel
+            mean, std = norm
+            ctx.xnorm = (1, 1.0 / (255.0 * std), -mean / std)
+        else:
+            assert x.dtype == torch.float32, f"images must be float32 or uint8, got {x.dtype}"
+            ctx.xnorm = (0, 1.0, 0.0)
         params = [_c(p) for p in params]
         hidden, latent = params[7].shape[0], params[9].shape[0]
         dev = x.device
@@ -149,7 +155,7 @@ class LMPEncoderFn(Function):
         nbytes = L.query("tacorl_lmp_encoder_ws_bytes", N, H, W, hidden, latent, 0)
         ws = L.workspace(nbytes, dev)
         ctx.prec = _STATE["prec"]
-        L.call("tacorl_lmp_encoder_fwd", L.ptr(x), N, H, W, L.ptr_array(params), hidden, latent, L.ptr_any(y1),
+        L.call("tacorl_lmp_encoder_fwd", L.ptr_any(x), *ctx.xnorm, N, H, W, L.ptr_array(params), hidden, latent, L.ptr_any(y1),
                L.ptr_any(y2), L.ptr(y3), L.ptr(feat), L.ptr(smax), L.ptr(ssum), L.ptr(h4), L.ptr(emb),
                ctypes.c_void_p(ws.data_ptr()), ws.numel(), _STATE["prec"], L.stream())
         if save:
@@ -165,16 +171,17 @@ class LMPEncoderFn(Function):
         nbytes = L.query("tacorl_lmp_encoder_ws_bytes", N, H, W, hidden, latent, 1)
         ws = L.workspace(nbytes, x.device)
         d_emb = _c(d_emb)
-        L.call("tacorl_lmp_encoder_bwd", L.ptr(x), N, H, W, L.ptr_array(params), hidden, latent, L.ptr_any(y1),
+        L.call("tacorl_lmp_encoder_bwd", L.ptr_any(x), *ctx.xnorm, N, H, W, L.ptr_array(params), hidden, latent, L.ptr_any(y1),
                L.ptr_any(y2), L.ptr(y3), L.ptr(feat), L.ptr(smax), L.ptr(ssum), L.ptr(h4), L.ptr(d_emb),
                L.ptr_array(grads), 0, ctypes.c_void_p(ws.data_ptr()), ws.numel(), ctx.prec, L.stream())
-        return (None, None, *grads)
+        return (None, None, None, *grads)
 
 
-def lmp_encoder(x, params):
-    """params: the 11 tensors in state_dict order.  Images never receive a gradient."""
+def lmp_encoder(x, params, norm=(0.5, 0.5)):
+    """params: the 11 tensors in state_dict order.  Images never receive a gradient.
+    x: float32 (N,3,H,W) already normalised, or uint8 raw frames normalised on the device with norm=(mean, std)."""
     save = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-    return LMPEncoderFn.apply(x, save, *params)
+    return LMPEncoderFn.apply(x, save, norm, *params)
 
 
 # --------------------------------------------------------------------------------------- RNN

@@ -61,10 +61,37 @@ class FlatAdam(torch.optim.Optimizer):
     def flat_params(self):
         return self.pbuf.flat
 
-    def gather_grads(self):
+    def _range_of(self, params):
+        ids = {id(p) for p in params}
+        idx = [i for i, p in enumerate(self.param_groups[0]["params"]) if id(p) in ids]
+        if not idx:
+            return None
+        lo, hi = min(idx), max(idx)
+        assert hi - lo + 1 == len(idx), "overlapped sync needs a contiguous run of parameters"
         ps = self.param_groups[0]["params"]
+        end = self.pbuf.offsets[hi + 1] if hi + 1 < len(ps) else self.pbuf.numel
+        return lo, hi + 1, self.pbuf.offsets[lo], end
+
+    def begin_overlapped_sync(self, params):
+        """Call when the gradients of `params` (a contiguous run, e.g. everything behind the vision encoder) are
+        final while backward is still running: their slice of the flat gradient is gathered and its all-reduce is
+        started on the side stream, overlapping the rest of backward.  step() then only exchanges what is left."""
+        if self.grad_sync is None:
+            return
+        r = self._range_of(params)
+        if r is None:
+            return
+        lo, hi, e0, e1 = r
+        self.gather_grads(lo, hi)
+        self.grad_sync.start(self.flat_grad[e0:e1])
+        self._synced = (lo, hi, e0, e1)
+
+    _synced = None
+
+    def gather_grads(self, lo=0, hi=None):
+        ps = self.param_groups[0]["params"][lo:hi]
         dst, src, missing = [], [], []
-        for p, gv in zip(ps, self.grad_views):
+        for p, gv in zip(ps, self.grad_views[lo:hi]):
             if p.grad is None:
                 missing.append(gv)
             else:
@@ -78,10 +105,25 @@ class FlatAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None, gathered=False):
         loss = closure() if closure is not None else None
-        if not gathered:
-            self.gather_grads()
-        if self.grad_sync is not None:
-            self.grad_sync(self.flat_grad)
+        if self._synced is not None and self.grad_sync is not None:
+            lo, hi, e0, e1 = self._synced          # [lo,hi) already gathered and in flight on the side stream
+            n = len(self.param_groups[0]["params"])
+            if not gathered:
+                if lo > 0:
+                    self.gather_grads(0, lo)
+                if hi < n:
+                    self.gather_grads(hi, n)
+            if e0 > 0:
+                self.grad_sync.start(self.flat_grad[:e0])
+            if e1 < self.pbuf.numel:
+                self.grad_sync.start(self.flat_grad[e1:])
+            self.grad_sync.finish()
+            self._synced = None
+        else:
+            if not gathered:
+                self.gather_grads()
+            if self.grad_sync is not None:
+                self.grad_sync(self.flat_grad)
         g = self.param_groups[0]
         self.step_count += 1
         sq = None

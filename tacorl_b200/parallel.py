@@ -16,21 +16,32 @@ class BucketedAllReduce:
         self.group = group
         self._stream = None
 
-    def __call__(self, flat):
-        if self.world <= 1:
+    def start(self, flat):
+        """Enqueue the all-reduce of `flat` on the side stream (after everything already queued on the current
+        stream) and return immediately; `finish()` makes the current stream wait for it."""
+        if self.world <= 1 or flat.numel() == 0:
             return
         if flat.is_cuda:
             if self._stream is None:
                 self._stream = torch.cuda.Stream(device=flat.device)
-            main = torch.cuda.current_stream(flat.device)
-            self._stream.wait_stream(main)
+            self._device = flat.device
+            self._stream.wait_stream(torch.cuda.current_stream(flat.device))
             with torch.cuda.stream(self._stream):
                 for o in range(0, flat.numel(), self.bucket):
                     dist.all_reduce(flat[o:o + self.bucket], op=dist.ReduceOp.SUM, group=self.group)
-            main.wait_stream(self._stream)
         else:
             for o in range(0, flat.numel(), self.bucket):
                 dist.all_reduce(flat[o:o + self.bucket], op=dist.ReduceOp.SUM, group=self.group)
+
+    def finish(self):
+        if self._stream is not None:
+            torch.cuda.current_stream(self._device).wait_stream(self._stream)
+
+    _device = None
+
+    def __call__(self, flat):
+        self.start(flat)
+        self.finish()
 
 
 def attach_data_parallel(optimizer, world_size, group=None, bucket_elems=16 << 20):

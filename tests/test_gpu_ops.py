@@ -403,3 +403,29 @@ def test_transformer_plan_recogniser_with_dropout_masks_vs_oracle():
         d2 = net(ed)
     mu_e, _ = O.plan_recognition_transformer(P, "pr.", e64, num_heads=Hh, num_layers=2, masks=None)
     assert_close("eval mean", d2.normal_mean, mu_e, RTOL)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_uint8_frames_equal_prenormalised_float_frames(prec):
+    """raw uint8 frames with ScaleImageTensor+Normalize fused into the first kernel give the same
+    embeddings and gradients as feeding the reference's pre-normalised float images."""
+    from tacorl_b200 import ops
+    ops.set_precision(prec)
+    try:
+        rec = load_golden("encoder_shapes")
+        sd = S.synth_state_dict(rec["shapes"], rec["seed"])
+        names = list(rec["shapes"].keys())
+        u8 = torch.randint(0, 256, (3, 3, 84, 84), generator=_g(77), dtype=torch.uint8)
+        xf = (u8.float() / 255.0 - 0.5) / 0.5
+        outs = []
+        for x in (xf, u8):
+            params = [sd[k].clone().to(DEV).requires_grad_(True) for k in names]
+            emb = ops.lmp_encoder(x.to(DEV), params, (0.5, 0.5))
+            emb.sum().backward()
+            outs.append((emb.detach(), [p.grad for p in params]))
+        tol = 1e-5 if prec == "fp32" else 2e-3
+        assert_close("emb", outs[1][0], outs[0][0], tol)
+        for k, a, b in zip(names, outs[1][1], outs[0][1]):
+            assert_close(f"grad {k}", a, b, tol * 10, atol=1e-6)
+    finally:
+        ops.set_precision("fp32")
