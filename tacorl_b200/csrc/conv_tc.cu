@@ -21,7 +21,8 @@
 namespace tacorl {
 
 constexpr int CV_MAXT = 16;
-constexpr int CV_STAGES = 4;
+constexpr int CV_STAGES = 6;
+constexpr int CV_LAG = 4;           // cp.async groups kept in flight per producer thread before a stage is published
 constexpr int CV_THREADS = 288;     // 4 producer warps, 1 MMA warp, 4 epilogue warps
 
 struct ConvGeom {
@@ -78,6 +79,15 @@ __device__ __forceinline__ void cv_cp16(uint32_t dst, const void* src, uint32_t 
 __device__ __forceinline__ void cv_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cv_wait_group() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void cv_wait_group_dyn(int n) {   // n in [0, 4]
+  switch (n) {
+    case 0: cv_wait_group<0>(); break;
+    case 1: cv_wait_group<1>(); break;
+    case 2: cv_wait_group<2>(); break;
+    case 3: cv_wait_group<3>(); break;
+    default: cv_wait_group<4>(); break;
+  }
 }
 __device__ __forceinline__ void cv_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void cv_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -155,8 +165,7 @@ conv_tc_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ CUten
     const int r = threadIdx.x;
     const uint32_t row_off = (uint32_t)r * 128;
     const uint32_t sw = (uint32_t)(r & 7);
-    uint32_t it = 0;
-    int pending = -1;                                    // stage whose copies are issued but not yet published
+    uint32_t it = 0;                                     // K blocks issued so far (stage = it % CV_STAGES)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m = tile * 128 + r;
       const bool row_ok = m < g.M;
@@ -177,18 +186,17 @@ conv_tc_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ CUten
         for (int j = 0; j < 8; ++j)
           cv_cp16(dst + ((j ^ sw) << 4), srcp + j * 8, (ok && j < g.kchunks) ? 16u : 0u);
         cv_commit_group();
-        if (pending >= 0) {                               // publish the previous stage: its copies have landed
-          cv_wait_group<1>();
+        if (it >= CV_LAG) {                               // the group issued CV_LAG blocks ago has landed: publish it
+          cv_wait_group<CV_LAG>();
           cv_fence_async();
-          cv_mbar_arrive(full_bar(pending));
+          cv_mbar_arrive(full_bar((it - CV_LAG) % CV_STAGES));
         }
-        pending = s;
       }
     }
-    if (pending >= 0) {
-      cv_wait_group<0>();
+    for (int rem = (int)min(it, (uint32_t)CV_LAG) - 1; rem >= 0; --rem) {   // drain
+      cv_wait_group_dyn(rem);
       cv_fence_async();
-      cv_mbar_arrive(full_bar(pending));
+      cv_mbar_arrive(full_bar((it - 1 - rem) % CV_STAGES));
     }
   } else if (warp == 4) {
     if (lane == 0) {
@@ -573,7 +581,8 @@ int conv_tc_conv2_dgrad(const void* dy2b, int N, int H1, int W1, int H2, int W2,
 // kernel reduces the slices and scatters into the torch weight-gradient layout.
 namespace tacorl {
 
-constexpr int WG_STAGES = 4;
+constexpr int WG_STAGES = 5;
+constexpr int WG_LAG = 3;
 constexpr int WG_THREADS = 224;       // 2 producer warps (64 pixel rows), 1 MMA warp, 4 epilogue warps
 
 struct WgradGeom {
@@ -634,7 +643,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_tc_wgrad_kernel(const __gr
   if (warp < 2) {
     const int r = threadIdx.x;                                   // pixel row within the K block
     const uint32_t row_off = (uint32_t)r * 128, sw = (uint32_t)(r & 7);
-    int pending = -1;
     for (int i = 0; i < nkb; ++i) {
       const int s = i % WG_STAGES;
       const uint32_t ph = (i / WG_STAGES) & 1;
@@ -656,10 +664,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_tc_wgrad_kernel(const __gr
         for (int j = 0; j < 8; ++j) cv_cp16(dst + ((j ^ sw) << 4), sp + j * 8, (ok && j < g.kchunks) ? 16u : 0u);
       }
       cv_commit_group();
-      if (pending >= 0) { cv_wait_group<1>(); cv_fence_async(); cv_mbar_arrive(full_bar(pending)); }
-      pending = s;
+      if (i >= WG_LAG) { cv_wait_group<WG_LAG>(); cv_fence_async(); cv_mbar_arrive(full_bar((i - WG_LAG) % WG_STAGES)); }
     }
-    if (pending >= 0) { cv_wait_group<0>(); cv_fence_async(); cv_mbar_arrive(full_bar(pending)); }
+    for (int rem = min(nkb, WG_LAG) - 1; rem >= 0; --rem) {
+      cv_wait_group_dyn(rem);
+      cv_fence_async();
+      cv_mbar_arrive(full_bar((nkb - 1 - rem) % WG_STAGES));
+    }
   } else if (warp == 2) {
     if (lane == 0 && nkb > 0) {
       // A and B MN-major (bits 15, 16), D = f32, bf16 inputs, M = 128, N = NT*64

@@ -23,9 +23,9 @@ def _bf(t):
     return t.bfloat16().float()
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (64, 2048, 2048), (960, 182, 2048), (1024, 32, 192), (300, 64, 512),
-                                   (257, 130, 40), (64, 64, 1000), (2000, 256, 128), (5000, 576, 64), (64, 576, 5000),
-                                   (32, 192, 3000), (8, 16, 8)])
+@pytest.mark.parametrize("M,N,K", [(1280, 1280, 64), (64, 2048, 2048), (960, 182, 2048), (10240, 32, 192), (3000, 64, 512),
+                                   (2570, 1300, 40), (640, 640, 1000), (2000, 256, 128), (5000, 576, 64), (64, 576, 5000),
+                                   (32, 192, 30000), (8, 16, 8)])   # all but the last exceed the 2^24-MAC fp32 cut-off
 @pytest.mark.parametrize("tA,tB", [(False, True), (False, False), (True, False), (True, True)])
 def test_tcgen05_gemm_all_operand_layouts(bf16_ops, M, N, K, tA, tB):
     g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
@@ -42,8 +42,8 @@ def test_tcgen05_gemm_all_operand_layouts(bf16_ops, M, N, K, tA, tB):
 
 def test_tcgen05_gemm_relu_and_rounding(bf16_ops):
     g = torch.Generator().manual_seed(1)
-    A, W = torch.randn(333, 200, generator=g), torch.randn(77, 200, generator=g)
-    out = torch.empty(333, 77, device=DEV)
+    A, W = torch.randn(1333, 200, generator=g), torch.randn(277, 200, generator=g)   # > 2^24 MACs: tensor-core route
+    out = torch.empty(1333, 277, device=DEV)
     bf16_ops.gemm(A.to(DEV), W.to(DEV), out, transB=True, act=1)
     want = torch.relu(_bf(A).double() @ _bf(W).double().t())
     assert_close("relu", out, want, 2e-5)
