@@ -76,6 +76,15 @@ __device__ __forceinline__ void cv_tma_2d(uint32_t dst, const CUtensorMap* tm, i
 __device__ __forceinline__ void cv_cp16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// arrive on `bar` once all cp.async issued so far by this thread have landed (no thread stall; the barrier's
+// expected count already includes this arrival)
+__device__ __forceinline__ void cv_cp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cv_st32(void* p, const uint32_t (&v)[8]) {     // one full 32-byte sector per lane
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 __device__ __forceinline__ void cv_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cv_wait_group() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -143,6 +152,8 @@ conv_tc_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ CUten
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (g.M + 127) / 128;
   const int rows_per_frame = g.RA * g.RB;
+  __shared__ float s_bias[BN];
+  if (threadIdx.x < BN) s_bias[threadIdx.x] = ep.bias ? ep.bias[threadIdx.x] : 0.f;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < CV_STAGES; ++s) { cv_mbar_init(full_bar(s), 128); cv_mbar_init(empty_bar(s), 1); }
@@ -161,42 +172,44 @@ conv_tc_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ CUten
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    // ===== producers: thread r gathers tile row r, one 128-byte K-block row per stage
-    const int r = threadIdx.x;
-    const uint32_t row_off = (uint32_t)r * 128;
-    const uint32_t sw = (uint32_t)(r & 7);
+    // ===== producers: a lane pair gathers tile rows p and p+64; lane h of the pair takes the odd/even 16-byte chunks so
+    // every warp-wide cp.async covers whole 32-byte sectors (a thread-per-row mapping fetches each sector twice)
+    const int h = threadIdx.x & 1, p = threadIdx.x >> 1;
     uint32_t it = 0;                                     // K blocks issued so far (stage = it % CV_STAGES)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m = tile * 128 + r;
-      const bool row_ok = m < g.M;
-      int n = 0, a = 0, b = 0;
-      if (row_ok) { n = m / rows_per_frame; const int rem = m - n * rows_per_frame; a = rem / g.RB; b = rem - a * g.RB; }
-      const int py0 = a * g.sy, px0 = b * g.sx;
-      const __nv_bfloat16* frame = g.src + (long long)n * g.SH * g.SW * g.SC;
+      const __nv_bfloat16* frame[2];
+      int py0[2], px0[2];
+      bool row_ok[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int m = tile * 128 + p + 64 * u;
+        row_ok[u] = m < g.M;
+        int n = 0, a = 0, b = 0;
+        if (row_ok[u]) { n = m / rows_per_frame; const int rem = m - n * rows_per_frame; a = rem / g.RB; b = rem - a * g.RB; }
+        py0[u] = a * g.sy; px0[u] = b * g.sx;
+        frame[u] = g.src + (long long)n * g.SH * g.SW * g.SC;
+      }
       for (int t = 0; t < g.ntaps; ++t, ++it) {
         const int s = it % CV_STAGES;
         const uint32_t ph = (it / CV_STAGES) & 1;
         cv_mbar_wait(empty_bar(s), ph ^ 1);
-        const int py = py0 + g.dy[t], px = px0 + g.dx[t];
-        bool ok = row_ok;
-        if (g.check_bounds) ok = ok && py >= 0 && py < g.SH && px >= 0 && px < g.SW;
-        const __nv_bfloat16* srcp = ok ? frame + ((long long)py * g.SW + px) * g.SC + g.coff[t] : g.src;
-        const uint32_t dst = a_base + s * A_BYTES + row_off;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          cv_cp16(dst + ((j ^ sw) << 4), srcp + j * 8, (ok && j < g.kchunks) ? 16u : 0u);
-        cv_commit_group();
-        if (it >= CV_LAG) {                               // the group issued CV_LAG blocks ago has landed: publish it
-          cv_wait_group<CV_LAG>();
-          cv_fence_async();
-          cv_mbar_arrive(full_bar((it - CV_LAG) % CV_STAGES));
+        for (int u = 0; u < 2; ++u) {
+          const int row = p + 64 * u;
+          const int py = py0[u] + g.dy[t], px = px0[u] + g.dx[t];
+          bool ok = row_ok[u];
+          if (g.check_bounds) ok = ok && py >= 0 && py < g.SH && px >= 0 && px < g.SW;
+          const __nv_bfloat16* srcp = ok ? frame[u] + ((long long)py * g.SW + px) * g.SC + g.coff[t] : g.src;
+          const uint32_t dst = a_base + s * A_BYTES + (uint32_t)row * 128;
+          const uint32_t sw = (uint32_t)(row & 7);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = 2 * i + h;
+            cv_cp16(dst + ((j ^ sw) << 4), srcp + j * 8, (ok && j < g.kchunks) ? 16u : 0u);
+          }
         }
+        cv_cp_async_arrive(full_bar(s));                  // fires when this thread's copies of the stage have landed
       }
-    }
-    for (int rem = (int)min(it, (uint32_t)CV_LAG) - 1; rem >= 0; --rem) {   // drain
-      cv_wait_group_dyn(rem);
-      cv_fence_async();
-      cv_mbar_arrive(full_bar((it - 1 - rem) % CV_STAGES));
     }
   } else if (warp == 4) {
     if (lane == 0) {
@@ -215,6 +228,7 @@ conv_tc_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ CUten
           const int s = it % CV_STAGES;
           const uint32_t ph = (it / CV_STAGES) & 1;
           cv_mbar_wait(full_bar(s), ph);
+          cv_fence_async();                 // cp.async (generic proxy) writes -> visible to the tensor core (async proxy)
           cv_fence_after();
           const uint32_t a_src = a_base + s * A_BYTES, b_src = w_base + t * W_TAP_BYTES;
 #pragma unroll
@@ -240,27 +254,29 @@ conv_tc_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ CUten
         const int a = rem / g.RB, b = rem - a * g.RB;
         opix = ((long long)n * g.OH + (a * g.oys + g.oy0)) * g.OW + (b * g.oxs + g.ox0);
       }
+      // prefetch the ReLU gate of this row (global latency) before blocking on the accumulator
+      uint4 gate[BN / 8];
+      if (ep.gate && row_ok) {
+        const uint4* gp = reinterpret_cast<const uint4*>(ep.gate + opix * BN);
+#pragma unroll
+        for (int j = 0; j < BN / 8; ++j) gate[j] = __ldg(gp + j);
+      }
       cv_mbar_wait(tfull_bar(acc), (lt >> 1) & 1);
       cv_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 16) {
         uint32_t r[16];
         cv_ld16(tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16) + c0, r);
         if (!row_ok) continue;
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-        if (ep.bias) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += __ldg(ep.bias + c0 + j);
-        }
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
         if (ep.relu) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (ep.gate) {
-          const uint4* gp = reinterpret_cast<const uint4*>(ep.gate + opix * BN + c0);
-          const uint4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+          const uint4 g0 = gate[c0 / 8], g1 = gate[c0 / 8 + 1];
           const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&g0);
           const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&g1);
 #pragma unroll
@@ -279,14 +295,14 @@ conv_tc_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ CUten
             __nv_bfloat162 t2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
             pk[j] = *reinterpret_cast<uint32_t*>(&t2);
           }
-          uint4* op = reinterpret_cast<uint4*>(ep.out_bf16 + opix * BN + c0);
-          op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          cv_st32(ep.out_bf16 + opix * BN + c0, pk);
         }
         if (ep.out_f32) {
-          float4* op = reinterpret_cast<float4*>(ep.out_f32 + opix * BN + c0);
+          uint32_t lo[8], hi[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < 8; ++j) { lo[j] = __float_as_uint(v[j]); hi[j] = __float_as_uint(v[8 + j]); }
+          cv_st32(ep.out_f32 + opix * BN + c0, lo);
+          cv_st32(ep.out_f32 + opix * BN + c0 + 8, hi);
         }
       }
       cv_fence_before();
@@ -641,35 +657,40 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_tc_wgrad_kernel(const __gr
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 2) {
-    const int r = threadIdx.x;                                   // pixel row within the K block
-    const uint32_t row_off = (uint32_t)r * 128, sw = (uint32_t)(r & 7);
+    // a lane pair gathers pixel rows p and p+32 of the K block; lane h takes the chunks 2i+h (whole sectors per warp)
+    const int h = threadIdx.x & 1, p = threadIdx.x >> 1;
     for (int i = 0; i < nkb; ++i) {
       const int s = i % WG_STAGES;
       const uint32_t ph = (i / WG_STAGES) & 1;
       cv_mbar_wait(empty_bar(s), ph ^ 1);
-      const int m = m_begin + i * 64 + r;
-      const bool ok = m < m_end;
-      int n = 0, a = 0, b = 0;
-      if (ok) { n = m / rows_per_frame; const int rem = m - n * rows_per_frame; a = rem / g.RB; b = rem - a * g.RB; }
       const uint32_t st = base + s * stage_bytes;
-      const __nv_bfloat16* dyp = g.dy + (long long)(ok ? m : 0) * g.OC;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) cv_cp16(st + row_off + ((j ^ sw) << 4), dyp + j * 8, (ok && j < g.dy_chunks) ? 16u : 0u);
-      const __nv_bfloat16* frame = g.src + (long long)n * g.SH * g.SW * g.SC;
-      for (int t = 0; t < g.NT; ++t) {
-        const int tt = grp * g.NT + t;
-        const __nv_bfloat16* sp = frame + ((long long)(a * g.sy + g.dy_t[tt]) * g.SW + (b * g.sx + g.dx_t[tt])) * g.SC + g.coff[tt];
-        const uint32_t dst = st + (1 + t) * TILE + row_off;
+      for (int u = 0; u < 2; ++u) {
+        const int r = p + 32 * u;
+        const uint32_t row_off = (uint32_t)r * 128, sw = (uint32_t)(r & 7);
+        const int m = m_begin + i * 64 + r;
+        const bool ok = m < m_end;
+        int n = 0, a = 0, b = 0;
+        if (ok) { n = m / rows_per_frame; const int rem = m - n * rows_per_frame; a = rem / g.RB; b = rem - a * g.RB; }
+        const __nv_bfloat16* dyp = g.dy + (long long)(ok ? m : 0) * g.OC;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) cv_cp16(dst + ((j ^ sw) << 4), sp + j * 8, (ok && j < g.kchunks) ? 16u : 0u);
+        for (int c = 0; c < 4; ++c) {
+          const int j = 2 * c + h;
+          cv_cp16(st + row_off + ((j ^ sw) << 4), dyp + j * 8, (ok && j < g.dy_chunks) ? 16u : 0u);
+        }
+        const __nv_bfloat16* frame = g.src + (long long)n * g.SH * g.SW * g.SC;
+        for (int t = 0; t < g.NT; ++t) {
+          const int tt = grp * g.NT + t;
+          const __nv_bfloat16* sp = frame + ((long long)(a * g.sy + g.dy_t[tt]) * g.SW + (b * g.sx + g.dx_t[tt])) * g.SC + g.coff[tt];
+          const uint32_t dst = st + (1 + t) * TILE + row_off;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int j = 2 * c + h;
+            cv_cp16(dst + ((j ^ sw) << 4), sp + j * 8, (ok && j < g.kchunks) ? 16u : 0u);
+          }
+        }
       }
-      cv_commit_group();
-      if (i >= WG_LAG) { cv_wait_group<WG_LAG>(); cv_fence_async(); cv_mbar_arrive(full_bar((i - WG_LAG) % WG_STAGES)); }
-    }
-    for (int rem = min(nkb, WG_LAG) - 1; rem >= 0; --rem) {
-      cv_wait_group_dyn(rem);
-      cv_fence_async();
-      cv_mbar_arrive(full_bar((nkb - 1 - rem) % WG_STAGES));
+      cv_cp_async_arrive(full_bar(s));
     }
   } else if (warp == 2) {
     if (lane == 0 && nkb > 0) {
@@ -680,6 +701,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_tc_wgrad_kernel(const __gr
         const int s = i % WG_STAGES;
         const uint32_t ph = (i / WG_STAGES) & 1;
         cv_mbar_wait(full_bar(s), ph);
+        cv_fence_async();
         cv_fence_after();
         const uint32_t a_src = base + s * stage_bytes, b_src = a_src + TILE;
 #pragma unroll
