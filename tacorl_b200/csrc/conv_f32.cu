@@ -159,7 +159,7 @@ __global__ void softargmax_fwd_kernel(const float* __restrict__ y, int P, int OW
 int softargmax_fwd_f32(const float* y, int N, int OH, int OW, int C, const float* temperature,
                        float* feat, float* smax, float* ssum, cudaStream_t st) {
   if (N == 0) return 0;
-  constexpr int G = 4;
+  constexpr int G = 16;
   TACORL_REQUIRE(C * G <= 1024, "softargmax: too many channels");
   softargmax_fwd_kernel<G><<<N, dim3(C, G), 4 * G * C * sizeof(float), st>>>(y, OH * OW, OW, C, temperature,
                                                                             feat, smax, ssum);
@@ -169,18 +169,21 @@ int softargmax_fwd_f32(const float* y, int N, int OH, int OW, int C, const float
 
 // Backward: dz_i = p_i * (gx*col_i + gy*row_i - (gx*fx + gy*fy));  dy_i = dz_i / tau * [y_i > 0]
 // dtau = sum_i dz_i * (-y_i / tau^2), reduced per frame into dtau_part[n] (summed by a colsum).
-template <int G>
+__device__ __forceinline__ void sa_store(float* p, float v) { *p = v; }
+__device__ __forceinline__ void sa_store(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <int G, typename OutT>
 __global__ void softargmax_bwd_kernel(const float* __restrict__ y, int P, int OW, int C,
                                       const float* __restrict__ temperature,
                                       const float* __restrict__ feat, const float* __restrict__ smax,
                                       const float* __restrict__ ssum, const float* __restrict__ dfeat,
-                                      float* __restrict__ dy, float* __restrict__ dtau_part) {
+                                      OutT* __restrict__ dy, float* __restrict__ dtau_part) {
   __shared__ float red[32];
   const int c = threadIdx.x, g = threadIdx.y;
   const long long n = blockIdx.x;
   const float tau = __ldg(temperature), inv_t = 1.f / tau;
   const float* yp = y + n * (long long)P * C;
-  float* dyp = dy + n * (long long)P * C;
+  OutT* dyp = dy + n * (long long)P * C;
   const float gx = dfeat[n * 2 * C + 2 * c], gy = dfeat[n * 2 * C + 2 * c + 1];
   const float fx = feat[n * 2 * C + 2 * c], fy = feat[n * 2 * C + 2 * c + 1];
   const float M = smax[n * C + c], invS = 1.f / ssum[n * C + c];
@@ -191,7 +194,7 @@ __global__ void softargmax_bwd_kernel(const float* __restrict__ y, int P, int OW
     const float pr = expf(yv * inv_t - M) * invS;
     const float dz = pr * (gx * (float)(p % OW) + gy * (float)(p / OW) - dotg);
     dt += dz * yv;
-    dyp[(long long)p * C + c] = yv > 0.f ? dz * inv_t : 0.f;
+    sa_store(dyp + (long long)p * C + c, yv > 0.f ? dz * inv_t : 0.f);
   }
   dt = warp_sum(dt);
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -211,8 +214,21 @@ int softargmax_bwd_f32(const float* y, int N, int OH, int OW, int C, const float
   if (N == 0) return 0;
   constexpr int G = 4;
   TACORL_REQUIRE(C * G <= 1024 && (C * G) % 32 == 0, "softargmax bwd: unsupported channel count");
-  softargmax_bwd_kernel<G><<<N, dim3(C, G), 0, st>>>(y, OH * OW, OW, C, temperature, feat, smax, ssum,
-                                                   dfeat, dy, dtau_part);
+  softargmax_bwd_kernel<G, float><<<N, dim3(C, G), 0, st>>>(y, OH * OW, OW, C, temperature, feat, smax, ssum,
+                                                          dfeat, dy, dtau_part);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
+// same, gradient written as bf16 (operand of the tensor-core conv3 weight / data gradient kernels)
+int softargmax_bwd_bf16out(const float* y, int N, int OH, int OW, int C, const float* temperature,
+                           const float* feat, const float* smax, const float* ssum, const float* dfeat,
+                           void* dy_bf16, float* dtau_part, cudaStream_t st) {
+  if (N == 0) return 0;
+  constexpr int G = 16;
+  TACORL_REQUIRE(C * G <= 1024 && (C * G) % 32 == 0, "softargmax bwd: unsupported channel count");
+  softargmax_bwd_kernel<G, __nv_bfloat16><<<N, dim3(C, G), 0, st>>>(y, OH * OW, OW, C, temperature, feat, smax, ssum,
+                                                                  dfeat, (__nv_bfloat16*)dy_bf16, dtau_part);
   TACORL_LAUNCH_CHECK();
   return 0;
 }

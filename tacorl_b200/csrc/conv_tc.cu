@@ -613,6 +613,7 @@ struct WgradGeom {
   int dy_t[CV_MAXT], dx_t[CV_MAXT], coff[CV_MAXT];   // per (group*NT + j) source offsets
   int rows_per_split;                 // multiple of 64
   float* partial;                     // [splits][groups][OC][NT*64]
+  float* bias_partial;                // [splits][OC] column sums of dY (bias gradient), written by group 0; may be null
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1) conv_tc_wgrad_kernel(const __grid_constant__ WgradGeom g) {
@@ -622,14 +623,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_tc_wgrad_kernel(const __gr
   const uint32_t stage_bytes = (1 + g.NT) * TILE;
   const uint32_t base = cv_smem(smem);
   const uint32_t zero_tile = base + WG_STAGES * stage_bytes;
-  uint64_t* bars = (uint64_t*)(smem + WG_STAGES * stage_bytes + TILE);
+  const uint32_t ones_tile = zero_tile + TILE;          // all-ones B operand: dY^T x 1 = bias gradient
+  uint64_t* bars = (uint64_t*)(smem + WG_STAGES * stage_bytes + 2 * TILE);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * WG_STAGES + 1);
   auto full_bar = [&](int s) { return cv_smem(bars + s); };
   auto empty_bar = [&](int s) { return cv_smem(bars + WG_STAGES + s); };
   const uint32_t done_bar = cv_smem(bars + 2 * WG_STAGES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NCOLS = g.NT * 64;
-  const uint32_t tmem_cols = NCOLS <= 64 ? 64 : (NCOLS <= 128 ? 128 : 256);
+  const bool with_bias = g.bias_partial != nullptr && blockIdx.y == 0;
+  const int acc_cols = NCOLS + 16;                      // + one N = 16 accumulator block for the bias gradient
+  const uint32_t tmem_cols = acc_cols <= 128 ? 128 : (acc_cols <= 256 ? 256 : 512);
 
   const int m_begin = blockIdx.x * g.rows_per_split;
   const int m_end = min(g.M, m_begin + g.rows_per_split);
@@ -638,8 +642,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_tc_wgrad_kernel(const __gr
   const int rows_per_frame = g.RA * g.RB;
 
   // zero tile (upper half of the M = 128 A operand)
-  for (int i = threadIdx.x; i < (int)(TILE / 16); i += blockDim.x)
+  for (int i = threadIdx.x; i < (int)(TILE / 16); i += blockDim.x) {
     reinterpret_cast<uint4*>(smem + WG_STAGES * stage_bytes)[i] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4*>(smem + WG_STAGES * stage_bytes + TILE)[i] =
+        make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);          // bf16 1.0 pairs
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < WG_STAGES; ++s) { cv_mbar_init(full_bar(s), 64); cv_mbar_init(empty_bar(s), 1); }
     cv_mbar_init(done_bar, 1);
@@ -697,6 +704,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_tc_wgrad_kernel(const __gr
       // A and B MN-major (bits 15, 16), D = f32, bf16 inputs, M = 128, N = NT*64
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(NCOLS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc_b = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       for (int i = 0; i < nkb; ++i) {
         const int s = i % WG_STAGES;
         const uint32_t ph = (i / WG_STAGES) & 1;
@@ -708,6 +717,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_tc_wgrad_kernel(const __gr
         for (int k = 0; k < 4; ++k)     // 16 pixel rows (2048 B) per UMMA K step
           cv_mma(tmem_base, cv_desc(a_src + k * 2048, zero_tile - a_src, 1024), cv_desc(b_src + k * 2048, TILE, 1024),
                  idesc, (i > 0 || k > 0) ? 1u : 0u);
+        if (with_bias) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            cv_mma(tmem_base + NCOLS, cv_desc(a_src + k * 2048, zero_tile - a_src, 1024), cv_desc(ones_tile, TILE, 1024),
+                   idesc_b, (i > 0 || k > 0) ? 1u : 0u);
+        }
         cv_commit(empty_bar(s));
       }
       cv_commit(done_bar);
@@ -732,6 +747,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_tc_wgrad_kernel(const __gr
                                                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
         }
       }
+      if (with_bias) {
+        uint32_t r[16];
+        if (nkb > 0) cv_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + NCOLS, r);
+        else r[0] = 0;
+        if (oc < g.OC) g.bias_partial[(long long)blockIdx.x * g.OC + oc] = __uint_as_float(r[0]);
+      }
     }
   }
   cv_fence_before();
@@ -746,10 +767,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_tc_wgrad_kernel(const __gr
 // layer 3: groups = 3 (ky), col = kx*64 + c;  layer 2: groups = 2, col = (kyl*2 + p)*64 + k, ky = 2g+kyl, kx = 2p+(k>>5), c = k&31;
 // layer 1: groups = 1, col = t*64 + q (q < 48), t = (dy,dx), q = (py*4+px)*3 + c, ky = 4dy+py, kx = 4dx+px.
 __global__ void conv_tc_wgrad_reduce_kernel(int layer, int splits, int groups, int OC, int NCOLS,
-                                            const float* __restrict__ partial, float beta, float* __restrict__ dW) {
+                                            const float* __restrict__ partial, float beta, float* __restrict__ dW,
+                                            const float* __restrict__ bias_partial, float* __restrict__ db) {
   const int total = groups * OC * NCOLS;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+  if (i >= total) {
+    const int oc = i - total;
+    if (db && oc < OC) {
+      float s = 0.f;
+      for (int z = 0; z < splits; ++z) s += bias_partial[(long long)z * OC + oc];
+      db[oc] = beta != 0.f ? fmaf(beta, db[oc], s) : s;
+    }
+    return;
+  }
   const int col = i % NCOLS, oc = (i / NCOLS) % OC, grp = i / (NCOLS * OC);
   int idx = -1;
   if (layer == 3) {
@@ -772,8 +802,9 @@ __global__ void conv_tc_wgrad_reduce_kernel(int layer, int splits, int groups, i
 }
 
 // layer: 1 (conv1 on the s2d image), 2, 3.  dyb: (N*RA*RB, OC) bf16; src: NHWC bf16 input activation of the layer.
+// db (optional): bias gradient = column sums of dyb, from an extra N = 16 MMA against an all-ones operand.
 int conv_tc_wgrad(int layer, const void* dyb, const void* src, int N, int SH, int SW, int RA, int RB, float beta,
-                  float* dW, float* ws, size_t ws_bytes, cudaStream_t st) {
+                  float* dW, float* db, float* ws, size_t ws_bytes, cudaStream_t st) {
   WgradGeom g = {};
   g.dy = (const __nv_bfloat16*)dyb; g.src = (const __nv_bfloat16*)src;
   g.SH = SH; g.SW = SW; g.RA = RA; g.RB = RB; g.M = N * RA * RB;
@@ -793,13 +824,14 @@ int conv_tc_wgrad(int layer, const void* dyb, const void* src, int N, int SH, in
   int splits = 148 / g.groups;
   const int kblocks = (g.M + 63) / 64;
   if (splits > kblocks) splits = kblocks;
-  const size_t per_split = (size_t)g.groups * g.OC * NCOLS * sizeof(float);
+  const size_t per_split = ((size_t)g.groups * g.OC * NCOLS + g.OC) * sizeof(float);
   if ((size_t)splits * per_split > ws_bytes) splits = (int)(ws_bytes / per_split);
   TACORL_REQUIRE(ws && splits >= 1, "conv_tc_wgrad: workspace too small");
   g.rows_per_split = ((kblocks + splits - 1) / splits) * 64;
   splits = (g.M + g.rows_per_split - 1) / g.rows_per_split;
   g.partial = ws;
-  const size_t smem = (size_t)WG_STAGES * (1 + g.NT) * 8192 + 8192 + (2 * WG_STAGES + 1) * 8 + 16 + 1024;
+  g.bias_partial = db ? ws + (size_t)splits * g.groups * g.OC * NCOLS : nullptr;
+  const size_t smem = (size_t)WG_STAGES * (1 + g.NT) * 8192 + 2 * 8192 + (2 * WG_STAGES + 1) * 8 + 16 + 1024;
   static size_t configured = 0;
   if (smem > configured) {
     TACORL_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -808,7 +840,8 @@ int conv_tc_wgrad(int layer, const void* dyb, const void* src, int N, int SH, in
   conv_tc_wgrad_kernel<<<dim3(splits, g.groups), WG_THREADS, smem, st>>>(g);
   TACORL_LAUNCH_CHECK();
   const int total = g.groups * g.OC * NCOLS;
-  conv_tc_wgrad_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(layer, splits, g.groups, g.OC, NCOLS, ws, beta, dW);
+  conv_tc_wgrad_reduce_kernel<<<cdiv(total + g.OC, 256), 256, 0, st>>>(layer, splits, g.groups, g.OC, NCOLS, ws, beta, dW,
+                                                                       g.bias_partial, db);
   TACORL_LAUNCH_CHECK();
   return 0;
 }
@@ -874,15 +907,15 @@ extern "C" int tacorl_conv_tc_debug(int op, const float* in0, const float* in1, 
     case 6:
       if ((rc = cast_bf16_2d(in0, 64, N * P3, 64, a0, 64, st))) return rc;
       if ((rc = cast_bf16_2d(in1, 64, N * P2, 64, a1, 64, st))) return rc;
-      return conv_tc_wgrad(3, a0, a1, N, H2, W2, H3, W3, 0.f, out, wsf, 32 << 20, st);
+      return conv_tc_wgrad(3, a0, a1, N, H2, W2, H3, W3, 0.f, out, out + 64 * 64 * 9, wsf, 32 << 20, st);
     case 7:
       if ((rc = cast_bf16_2d(in0, 64, N * P2, 64, a0, 64, st))) return rc;
       if ((rc = cast_bf16_2d(in1, 32, N * P1, 32, a1, 32, st))) return rc;
-      return conv_tc_wgrad(2, a0, a1, N, H1, W1, H2, W2, 0.f, out, wsf, 32 << 20, st);
+      return conv_tc_wgrad(2, a0, a1, N, H1, W1, H2, W2, 0.f, out, out + 64 * 32 * 16, wsf, 32 << 20, st);
     case 8:
       if ((rc = cast_bf16_2d(in0, 32, N * P1, 32, a0, 32, st))) return rc;
       if ((rc = conv_tc_s2d(in1, N, H, W, H1 + 1, W1 + 1, a1, st))) return rc;
-      return conv_tc_wgrad(1, a0, a1, N, H1 + 1, W1 + 1, H1, W1, 0.f, out, wsf, 32 << 20, st);
+      return conv_tc_wgrad(1, a0, a1, N, H1 + 1, W1 + 1, H1, W1, 0.f, out, out + 32 * 3 * 64, wsf, 32 << 20, st);
     default:
       set_last_error("conv_tc_debug: unknown op %d", op);
       return -1;

@@ -100,7 +100,7 @@ static int enc_fwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
   f.C = h4; f.ldc = hidden; f.bias = params[P_B4]; f.act = ACT_RELU; f.split_k = 1;
   if ((rc = gemm_tc_from_f32(f, fcws, 8 << 20, st))) return rc;
   f.N = latent; f.K = hidden; f.A = h4; f.lda = hidden; f.B = params[P_W5]; f.ldb = hidden; f.C = emb;
-  f.ldc = latent; f.bias = params[P_B5]; f.act = ACT_NONE;
+  f.ldc = latent; f.bias = params[P_B5]; f.act = ACT_NONE; f.split_k = 0;
   return gemm_tc_from_f32(f, fcws, 8 << 20, st);
 }
 
@@ -118,12 +118,11 @@ static int enc_bwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
   float* dtau = ar.take<float>(N);
   float* csws = ar.take<float>(592 * 64);
   float* skws = ar.take<float>(kSplitKWs / 4);
-  float* dy3 = ar.take<float>((size_t)N * g.P3 * 64);
   __nv_bfloat16* dy3b = ar.take<__nv_bfloat16>((size_t)N * g.P3 * 64);
   __nv_bfloat16* dy2b = ar.take<__nv_bfloat16>((size_t)N * g.P2 * 64);
   __nv_bfloat16* dy1b = ar.take<__nv_bfloat16>((size_t)N * g.P1 * 32);
   __nv_bfloat16* xs = ar.take<__nv_bfloat16>((size_t)N * (g.H1 + 1) * (g.W1 + 1) * 48);
-  TACORL_REQUIRE(wd3 && wd2 && dh4 && dfeat && dtau && csws && skws && dy3 && dy3b && dy2b && dy1b && xs,
+  TACORL_REQUIRE(wd3 && wd2 && dh4 && dfeat && dtau && csws && skws && dy3b && dy2b && dy1b && xs,
                  "lmp_encoder_bwd(bf16): workspace too small (%zu bytes)", ws_bytes);
   int rc;
   // ---- FC head (small GEMMs, fp32 operands staged to bf16)
@@ -142,26 +141,21 @@ static int enc_bwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
   if ((rc = colsum_f32(N, hidden, dh4, hidden, grads[P_B4], accumulate, st))) return rc;
   b.N = 128; b.K = hidden; b.A = dh4; b.lda = hidden; b.B = params[P_W4]; b.ldb = 128; b.C = dfeat; b.ldc = 128;
   if ((rc = gemm_tc_from_f32(b, skws, kSplitKWs, st))) return rc;
-  // ---- soft-argmax backward (applies conv3's ReLU mask), temperature and conv3-bias gradients
-  if ((rc = softargmax_bwd_f32(y3, N, g.H3, g.W3, 64, params[P_TEMP], feat, smax, ssum, dfeat, dy3, dtau, st)))
+  // ---- soft-argmax backward (applies conv3's ReLU mask, writes the bf16 operand directly) and temperature gradient
+  if ((rc = softargmax_bwd_bf16out(y3, N, g.H3, g.W3, 64, params[P_TEMP], feat, smax, ssum, dfeat, dy3b, dtau, st)))
     return rc;
   if ((rc = colsum_f32(N, 1, dtau, 1, grads[P_TEMP], accumulate, st))) return rc;
-  if ((rc = colsum_tall_f32((long long)N * g.P3, 64, dy3, grads[P_B3], accumulate, csws, 592 * 64 * 4, st))) return rc;
-  if ((rc = cast_bf16_2d(dy3, 64, (long long)N * g.P3, 64, dy3b, 64, st))) return rc;
-  // ---- conv3: weight gradient, then data gradient gated by y2's ReLU
+  // ---- per layer: weight + bias gradient (one kernel), then the data gradient gated by the input's ReLU
   if ((rc = conv_tc_pack(3, params[P_W3], wd3, st))) return rc;
   if ((rc = conv_tc_pack(4, params[P_W2], wd2, st))) return rc;
-  if ((rc = conv_tc_wgrad(3, dy3b, y2, N, g.H2, g.W2, g.H3, g.W3, beta0, grads[P_W3], skws, kSplitKWs, st))) return rc;
+  if ((rc = conv_tc_wgrad(3, dy3b, y2, N, g.H2, g.W2, g.H3, g.W3, beta0, grads[P_W3], grads[P_B3], skws, kSplitKWs, st))) return rc;
   if ((rc = conv_tc_conv3_dgrad(dy3b, N, g.H2, g.W2, g.H3, g.W3, wd3, y2, dy2b, st))) return rc;
-  if ((rc = colsum_tall_bf16((long long)N * g.P2, 64, dy2b, grads[P_B2], accumulate, csws, 592 * 64 * 4, st))) return rc;
-  // ---- conv2
-  if ((rc = conv_tc_wgrad(2, dy2b, y1, N, g.H1, g.W1, g.H2, g.W2, beta0, grads[P_W2], skws, kSplitKWs, st))) return rc;
+  if ((rc = conv_tc_wgrad(2, dy2b, y1, N, g.H1, g.W1, g.H2, g.W2, beta0, grads[P_W2], grads[P_B2], skws, kSplitKWs, st))) return rc;
   if ((rc = conv_tc_conv2_dgrad(dy2b, N, g.H1, g.W1, g.H2, g.W2, wd2, y1, dy1b, st))) return rc;
-  if ((rc = colsum_tall_bf16((long long)N * g.P1, 32, dy1b, grads[P_B1], accumulate, csws, 592 * 64 * 4, st))) return rc;
   // ---- conv1 (weight gradient only; images receive no gradient)
   if ((rc = x_u8 ? conv_tc_s2d_u8((const unsigned char*)xv, N, H, W, g.H1 + 1, g.W1 + 1, x_scale, x_shift, xs, st)
                  : conv_tc_s2d((const float*)xv, N, H, W, g.H1 + 1, g.W1 + 1, xs, st))) return rc;
-  return conv_tc_wgrad(1, dy1b, xs, N, g.H1 + 1, g.W1 + 1, g.H1, g.W1, beta0, grads[P_W1], skws, kSplitKWs, st);
+  return conv_tc_wgrad(1, dy1b, xs, N, g.H1 + 1, g.W1 + 1, g.H1, g.W1, beta0, grads[P_W1], grads[P_B1], skws, kSplitKWs, st);
 }
 
 static int enc_fwd(const void* xv, int x_u8, float x_scale, float x_shift, int N, int H, int W,

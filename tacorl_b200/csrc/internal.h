@@ -61,8 +61,11 @@ int conv_tc_conv3_dgrad(const void* dy3b, int N, int H2, int W2, int H3, int W3,
                         void* dy2b, cudaStream_t st);
 int conv_tc_conv2_dgrad(const void* dy2b, int N, int H1, int W1, int H2, int W2, const void* wp_classes,
                         const void* y1b, void* dy1b, cudaStream_t st);
+int softargmax_bwd_bf16out(const float* y, int N, int OH, int OW, int C, const float* temperature, const float* feat,
+                           const float* smax, const float* ssum, const float* dfeat, void* dy_bf16, float* dtau_part,
+                           cudaStream_t st);
 int conv_tc_wgrad(int layer, const void* dyb, const void* src, int N, int SH, int SW, int RA, int RB, float beta,
-                  float* dW, float* ws, size_t ws_bytes, cudaStream_t st);
+                  float* dW, float* db, float* ws, size_t ws_bytes, cudaStream_t st);
 
 // simple bump allocator over a caller-provided workspace (256-byte aligned slices)
 struct Arena {

@@ -82,14 +82,17 @@ def test_implicit_gemm_convs_match_torch(N, H, W):
     # ---- weight gradients (fp32 accumulation, fp32 output)
     w = W3t.double().requires_grad_(True)
     (F.conv2d(y2n, w, stride=1) * dy3n).sum().backward()
-    got = _run(6, dy3, y2b, None, None, N, H, W, (64, 64, 3, 3))
-    assert_close("conv3 wgrad", got, w.grad, 2e-4)
+    got = _run(6, dy3, y2b, None, None, N, H, W, (64 * 64 * 9 + 64,))
+    assert_close("conv3 wgrad", got[:-64].view(64, 64, 3, 3), w.grad, 2e-4)
+    assert_close("conv3 bias grad", got[-64:], dy3n.sum((0, 2, 3)), 2e-4)
     w = W2t.double().requires_grad_(True)
     (F.conv2d(y1n, w, stride=2) * dy2n).sum().backward()
-    got = _run(7, dy2b, y1b, None, None, N, H, W, (64, 32, 4, 4))
-    assert_close("conv2 wgrad", got, w.grad, 2e-4)
+    got = _run(7, dy2b, y1b, None, None, N, H, W, (64 * 32 * 16 + 64,))
+    assert_close("conv2 wgrad", got[:-64].view(64, 32, 4, 4), w.grad, 2e-4)
+    assert_close("conv2 bias grad", got[-64:], dy2n.sum((0, 2, 3)), 2e-4)
     dy1b = _bf(torch.randn(N, H1, W1, 32, generator=g))
     w = W1t.double().requires_grad_(True)
     (F.conv2d(xd, w, stride=4) * dy1b.permute(0, 3, 1, 2).double()).sum().backward()
-    got = _run(8, dy1b, x, None, None, N, H, W, (32, 3, 8, 8))
-    assert_close("conv1 wgrad", got, w.grad, 2e-4)
+    got = _run(8, dy1b, x, None, None, N, H, W, (32 * 3 * 64 + 32,))
+    assert_close("conv1 wgrad", got[:-32].view(32, 3, 8, 8), w.grad, 2e-4)
+    assert_close("conv1 bias grad", got[-32:], dy1b.double().sum((0, 1, 2)), 2e-4)
