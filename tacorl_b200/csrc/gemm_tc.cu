@@ -14,6 +14,7 @@
 #include "internal.h"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <algorithm>
 
 namespace tacorl {
 
@@ -329,6 +330,259 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ skinny cluster split-K
+// Recurrent steps (h_t = act(C + h_{t-1} W^T), batch <= 128 rows, 2048 x 2048 weights) are latency bound: every
+// CTA of an ordinary N-tiled GEMM streams the whole K extent of both operands through one SM.  Here a cluster of
+// RS_KS CTAs splits K instead: CTA r loads K slab r of the activations (UMMA M = 128 rows, only the batch rows are
+// fetched) and of one NT-column weight tile (UMMA N), keeps its partial accumulator in TMEM, spills it to its own
+// shared memory, and after one cluster barrier pulls a 1/RS_KS slice of the batch rows from all peers through
+// distributed shared memory (16-byte ld.shared::cluster; measured faster than pushing with st.shared::cluster),
+// sums them in a fixed order and applies the fused epilogue.  No partial sums travel through L2 and there is no
+// second kernel.  At most 15 clusters of 8 CTAs are co-resident on a B200 (148 SMs in GPCs of 16-20), so N is cut
+// into <= 15 tiles of NT = 16*ceil(N/240) columns: one wave, 120 SMs busy.
+constexpr int RS_KS = 8;
+constexpr int RS_MAX_TILES = 15;
+constexpr int RS_EPI = 512;          // 16 epilogue warps: enough loads in flight to hide the DSMEM / global latency
+constexpr int RS_THREADS = RS_EPI + 32;   // + warp 16: barrier setup, TMEM allocation, TMA and MMA issue
+constexpr int RS_MAXE = 2;           // float4 elements per thread in the reduction: 16 rows x 256 columns / 4 / 512 threads
+#ifdef TACORL_STEP_PROFILE
+__device__ unsigned long long g_step_prof[16];
+__device__ unsigned long long g_cta_prof[2][256][2];     // [previous / last launch][cta][start, end]
+#define RS_CTA_STAMP(which)                                                              \
+  if (tid == 0) {                                                                        \
+    const int c_ = blockIdx.y * gridDim.x + blockIdx.x;                                  \
+    unsigned long long t_;                                                               \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                             \
+    if (which == 0) { g_cta_prof[0][c_][0] = g_cta_prof[1][c_][0]; g_cta_prof[0][c_][1] = g_cta_prof[1][c_][1]; } \
+    g_cta_prof[1][c_][which] = t_;                                                       \
+  }
+#define RS_STAMP(i)                                                                      \
+  if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {                                  \
+    unsigned long long t_;                                                               \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                             \
+    g_step_prof[i] = t_;                                                                 \
+  }                                                                                      \
+  __syncwarp();
+#define RS_STAMP_T(i)                                                                    \
+  if (blockIdx.x == 0 && blockIdx.y == 0) {                                              \
+    unsigned long long t_;                                                               \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                             \
+    g_step_prof[i] = t_;                                                                 \
+  }
+#else
+#define RS_STAMP(i)
+#define RS_STAMP_T(i)
+#define RS_CTA_STAMP(which)
+#endif
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_dsmem_v4(uint32_t local_addr, uint32_t cta) {
+  uint32_t remote;
+  float4 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta));
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote)
+               : "memory");
+  return v;
+}
+
+// grid (RS_KS, tiles): blockIdx.x = K slab = cluster rank, blockIdx.y = N tile.  A: [M][K] bf16, W: [N][K] bf16.
+__global__ void __cluster_dims__(RS_KS, 1, 1) __launch_bounds__(RS_THREADS, 1)
+skinny_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                      const TcEpilogue ep, int M, int Mpad, int N, int NT, int kb_per_cta) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t A_TILE = 128 * 128, W_BYTES = (uint32_t)NT * 128, STAGE = A_TILE + ((W_BYTES + 1023) & ~1023u);
+  const int SP = NT + 4;                                                       // padded row pitch of S (floats)
+  const int per = Mpad / RS_KS;                                                // batch rows finished by each CTA
+  const size_t stage_total = (size_t)kb_per_cta * STAGE, s_bytes = (size_t)Mpad * SP * 4;
+  float* S = (float*)smem;                                                     // partial D, aliases the drained stages
+  uint64_t* bars = (uint64_t*)(smem + (stage_total > s_bytes ? stage_total : ((s_bytes + 1023) & ~(size_t)1023)));
+  uint32_t* tmem_slot = (uint32_t*)(bars + 9);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = blockIdx.x;                                            // == %cluster_ctarank (grid.x == RS_KS)
+  const int n0 = blockIdx.y * NT;
+  const uint32_t tmem_cols = NT <= 32 ? 32 : (NT <= 64 ? 64 : (NT <= 128 ? 128 : 256));
+  const uint32_t done_bar = smem_u32(bars + 8);
+  RS_CTA_STAMP(0)
+  RS_STAMP(0)
+
+  if (tid == RS_EPI) {
+    for (int s = 0; s < kb_per_cta; ++s) mbar_init(smem_u32(bars + s), 1);
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == RS_EPI / 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  RS_STAMP(1)
+
+  if (tid == RS_EPI) {
+    const int k_begin = (int)rank * kb_per_cta * TC_BK;
+    for (int s = 0; s < kb_per_cta; ++s) {                                     // the whole slab is in flight at once
+      const uint32_t bar = smem_u32(bars + s), dst = smem_u32(smem + (size_t)s * STAGE);
+      mbar_expect_tx(bar, (uint32_t)Mpad * 128 + W_BYTES);
+      tma_load_2d(dst, &tmA, k_begin + s * TC_BK, 0, bar);                     // Mpad batch rows (rows >= M zero-filled)
+      tma_load_2d(dst + A_TILE, &tmW, k_begin + s * TC_BK, n0, bar);           // NT weight rows (rows >= N zero-filled)
+    }
+    // UMMA rows Mpad..127 read stale shared memory: those accumulator lanes are never drained
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    RS_STAMP_T(2)
+    for (int s = 0; s < kb_per_cta; ++s) {
+      mbar_wait(smem_u32(bars + s), 0);
+      tc_fence_after();
+      if (s == 0) { RS_STAMP_T(3) }
+      const uint32_t a_src = smem_u32(smem + (size_t)s * STAGE), w_src = a_src + A_TILE;
+#pragma unroll
+      for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+        tc_mma_bf16(tmem_base, make_smem_desc(a_src + k * 32, 16, 1024), make_smem_desc(w_src + k * 32, 16, 1024), idesc,
+                    (s > 0 || k > 0) ? 1u : 0u);
+    }
+    tc_commit(done_bar);
+    RS_STAMP_T(4)
+  }
+  // This CTA finishes batch rows [rank*per, (rank+1)*per) of the tile in groups of 4 columns: element e = (row, group)
+  // = (e / NT4, e % NT4); epilogue thread t takes e = t, t + 512.  Fetch the epilogue operands (old C, gate, bias)
+  // now: they do not depend on the accumulators.
+  const int NT4 = NT >> 2, elems = per * NT4;
+  float4 cold[RS_MAXE], gt[RS_MAXE], bs[RS_MAXE];
+  if (tid < RS_EPI) {
+    // branch-free addressing (masked elements read element 0) so the loads of one operand issue back to back
+    long long offc[RS_MAXE], offg[RS_MAXE];
+    int colc[RS_MAXE];
+#pragma unroll
+    for (int i = 0; i < RS_MAXE; ++i) {
+      const int e = tid + i * RS_EPI;
+      const int bi = e / NT4, n = (e - bi * NT4) * 4, b = (int)rank * per + bi, col = n0 + n;
+#ifdef RS_EXP_NOPREFETCH
+      const bool ok = false;
+#else
+      const bool ok = e < elems && b < M && col < N;
+#endif
+      offc[i] = ok ? (long long)b * ep.ldc + col : 0;
+      offg[i] = ok ? (long long)b * ep.ldgate + col : 0;
+      colc[i] = ok ? col : 0;
+    }
+    const bool has_c = ep.beta != 0.f && ep.C != nullptr;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f), one = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+    for (int i = 0; i < RS_MAXE; ++i) cold[i] = has_c ? *reinterpret_cast<const float4*>(ep.C + offc[i]) : zero;
+#pragma unroll
+    for (int i = 0; i < RS_MAXE; ++i) gt[i] = ep.gate ? *reinterpret_cast<const float4*>(ep.gate + offg[i]) : one;
+#pragma unroll
+    for (int i = 0; i < RS_MAXE; ++i) bs[i] = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + colc[i])) : zero;
+  }
+#ifdef TACORL_STEP_PROFILE
+  RS_STAMP(12)
+#endif
+  if (tid < RS_EPI) {
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+  }
+  RS_STAMP(5)
+  // partial accumulator -> shared memory S[b][n] (row pitch NT + 4 floats: conflict-free float4 stores); warp w drains
+  // TMEM lane quarter w % 4 (batch rows), column chunks w / 4, w / 4 + 4, ...
+  if (tid < RS_EPI) {
+    const int q = warp & 3;
+    if (q * 32 < Mpad) {
+      float* Srow = S + (q * 32 + lane) * SP;
+      for (int c0 = (warp >> 2) * 16; c0 < NT; c0 += 64) {
+        uint32_t r[16];
+        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          reinterpret_cast<float4*>(Srow + c0)[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  RS_STAMP(6)
+  cluster_sync_all();
+  RS_STAMP(7)
+  if (tid >= RS_EPI) {                      // issuer warp: TMEM is drained; stay for the closing cluster barrier
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+    return;
+  }
+  // pull the RS_KS peers' partials of my rows (16-byte DSMEM loads, all in flight before the first use) and sum
+  // them in a fixed order
+  float4 acc[RS_MAXE];
+  {
+    float4 part[RS_MAXE][RS_KS];
+#pragma unroll
+    for (int i = 0; i < RS_MAXE; ++i) {
+      const int e = tid + i * RS_EPI;
+      const int bi = e / NT4, n = (e - bi * NT4) * 4;
+      const uint32_t addr = smem_u32(S + ((int)rank * per + (e < elems ? bi : 0)) * SP + (e < elems ? n : 0));
+#pragma unroll
+      for (int q = 0; q < RS_KS; ++q) part[i][q] = ld_dsmem_v4(addr, q);
+    }
+#pragma unroll
+    for (int i = 0; i < RS_MAXE; ++i) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < RS_KS; ++q) { v.x += part[i][q].x; v.y += part[i][q].y; v.z += part[i][q].z; v.w += part[i][q].w; }
+      acc[i] = v;
+    }
+  }
+  RS_STAMP(8)
+  // My reads of the peers' shared memory are done (the register operand makes the arrive wait for the loaded
+  // values): arrive now, wait only before exiting.  (A relaxed arrive here faults intermittently for >= 96 rows.)
+  {
+    float dep = 0.f;
+#pragma unroll
+    for (int i = 0; i < RS_MAXE; ++i) dep += acc[i].x + acc[i].y + acc[i].z + acc[i].w;
+#ifndef RS_EXP_LATEARRIVE
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::"f"(dep) : "memory");
+#endif
+  }
+#pragma unroll
+  for (int i = 0; i < RS_MAXE; ++i) {
+    const int e = tid + i * RS_EPI;
+    const int bi = e / NT4, n = (e - bi * NT4) * 4, b = (int)rank * per + bi, col = n0 + n;
+    if (e >= elems || b >= M || col >= N) continue;
+    float v[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
+    const float c4[4] = {cold[i].x, cold[i].y, cold[i].z, cold[i].w};
+    const float g4[4] = {gt[i].x, gt[i].y, gt[i].z, gt[i].w};
+    const float b4[4] = {bs[i].x, bs[i].y, bs[i].z, bs[i].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = fmaf(ep.beta, c4[j], ep.alpha * v[j]) + b4[j];
+    if (ep.Cpre) *reinterpret_cast<float4*>(ep.Cpre + (long long)b * ep.ldpre + col) = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (ep.act == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+      else if (ep.act == ACT_SILU) v[j] = v[j] / (1.f + __expf(-v[j]));
+      if (g4[j] <= 0.f) v[j] = 0.f;
+    }
+    if (ep.C) *reinterpret_cast<float4*>(ep.C + (long long)b * ep.ldc + col) = make_float4(v[0], v[1], v[2], v[3]);
+    if (ep.Cb) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+      uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      *reinterpret_cast<uint2*>(ep.Cb + (long long)b * ep.ldcb + col) = pk;
+    }
+  }
+  RS_STAMP(9)
+#ifdef RS_EXP_LATEARRIVE
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+#endif
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");             // peers may still be reading my partials
+  RS_STAMP(10)
+  RS_STAMP(11)
+  RS_CTA_STAMP(1)
+}
+
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -406,6 +660,36 @@ __global__ void tc_splitk_reduce_kernel(int M, int N, int splits, const float* _
   }
 }
 
+// C[M][N] = epilogue(A[M][K] . W[N][K]^T) for M <= 128 through skinny_cluster_kernel; returns 1 when the shape is
+// outside what the kernel covers (the caller then uses the tiled kernel).
+static int launch_skinny_cluster(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
+                                 const TcEpilogue& ep, cudaStream_t st) {
+  if (M < 1 || M > 128 || K % (TC_BK * RS_KS) != 0 || N % 4 != 0) return 1;
+  auto al16 = [](const void* p, long long ld, int elt) { return p == nullptr || (((uintptr_t)p & 15) == 0 && (ld * elt) % 16 == 0); };
+  if (!al16(ep.C, ep.ldc, 4) || !al16(ep.gate, ep.ldgate, 4) || !al16(ep.Cpre, ep.ldpre, 4) || !al16(ep.bias, 4, 4) ||
+      !(ep.Cb == nullptr || (((uintptr_t)ep.Cb & 7) == 0 && ep.ldcb % 4 == 0)))
+    return 1;
+  const int Mpad = (M + 15) & ~15, kb = K / (TC_BK * RS_KS);
+  const int NT = 16 * cdiv(N, 16 * RS_MAX_TILES), tiles = cdiv(N, NT);
+  if (NT > 256 || kb > 8 || (Mpad / RS_KS) * (NT / 4) > RS_MAXE * RS_EPI) return 1;
+  const size_t stage = 128 * 128 + (((size_t)NT * 128 + 1023) & ~(size_t)1023);
+  const size_t s_bytes = ((size_t)Mpad * (NT + 4) * 4 + 1023) & ~(size_t)1023;
+  const size_t smem = std::max((size_t)kb * stage, s_bytes) + 9 * 8 + 16 + 1024;
+  if (smem > 227 * 1024) return 1;
+  CUtensorMap ta, tw;
+  int rc;
+  if ((rc = make_tmap(&ta, A, K, M, lda, 64, Mpad))) return rc;
+  if ((rc = make_tmap(&tw, W, K, N, ldw, 64, NT))) return rc;
+  static size_t configured = 0;
+  if (smem > configured) {
+    TACORL_CHECK_CUDA(cudaFuncSetAttribute(skinny_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  skinny_cluster_kernel<<<dim3(RS_KS, tiles), RS_THREADS, smem, st>>>(ta, tw, ep, M, Mpad, N, NT, kb);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
 // Core entry: bf16 operands already in global memory.
 //   A: a_mn ? stored [K][M] (pitch lda) : stored [M][K];   B: b_mn ? stored [K][N] : stored [N][K].
 int gemm_tc_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, int M, int N,
@@ -417,8 +701,16 @@ int gemm_tc_bf16(const void* A, long long lda, int a_mn, const void* B, long lon
   const bool skinny = M <= TC_BM && N >= 512 && K <= 8192 && e.split_k == 0;
   if (skinny) BN = b_mn ? 64 : 32;
   if (b_mn && BN < 64) BN = 64;
-  CUtensorMap ta, tb;
   int rc;
+  if (skinny && !a_mn && !b_mn) {   // recurrent steps: cluster split-K with an in-cluster reduction
+    TcEpilogue ep;
+    ep.alpha = e.alpha; ep.beta = e.beta; ep.C = e.C; ep.ldc = e.ldc; ep.Cb = (__nv_bfloat16*)e.Cb; ep.ldcb = e.ldcb;
+    ep.bias = e.bias; ep.act = e.act; ep.Cpre = e.Cpre; ep.ldpre = e.ldpre; ep.partial = nullptr;
+    ep.gate = e.gate; ep.ldgate = e.ldgate;
+    rc = launch_skinny_cluster(A, lda, B, ldb, M, N, K, ep, st);
+    if (rc <= 0) return rc;
+  }
+  CUtensorMap ta, tb;
   if ((rc = a_mn ? make_tmap(&ta, A, M, K, lda, 64, 64) : make_tmap(&ta, A, K, M, lda, 64, TC_BM))) return rc;
   if ((rc = b_mn ? make_tmap(&tb, B, N, K, ldb, 64, 64) : make_tmap(&tb, B, K, N, ldb, 64, BN))) return rc;
   const long long ctas = (long long)cdiv(M, TC_BM) * cdiv(N, BN);

@@ -25,7 +25,9 @@ def _bf(t):
 
 @pytest.mark.parametrize("M,N,K", [(1280, 1280, 64), (64, 2048, 2048), (960, 182, 2048), (10240, 32, 192), (3000, 64, 512),
                                    (2570, 1300, 40), (640, 640, 1000), (2000, 256, 128), (5000, 576, 64), (64, 576, 5000),
-                                   (32, 192, 30000), (8, 16, 8)])   # all but the last exceed the 2^24-MAC fp32 cut-off
+                                   (32, 192, 30000), (8, 16, 8),    # all but this one exceed the 2^24-MAC fp32 cut-off
+                                   # skinny recurrent-step shapes -> cluster split-K kernel (DSMEM reduction)
+                                   (128, 2048, 2048), (70, 512, 1024), (9, 2048, 1024), (100, 1024, 4096)])
 @pytest.mark.parametrize("tA,tB", [(False, True), (False, False), (True, False), (True, True)])
 def test_tcgen05_gemm_all_operand_layouts(bf16_ops, M, N, K, tA, tB):
     g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
@@ -51,10 +53,11 @@ def test_tcgen05_gemm_relu_and_rounding(bf16_ops):
     assert rel_err(out, full) < 1e-2
 
 
+@pytest.mark.parametrize("H", [256, 512])        # 512: recurrent steps take the cluster split-K kernel
 @pytest.mark.parametrize("bidir,last_only", [(False, False), (True, True)])
-def test_rnn_bf16_close_to_fp64(bf16_ops, bidir, last_only):
+def test_rnn_bf16_close_to_fp64(bf16_ops, bidir, last_only, H):
     g = torch.Generator().manual_seed(5)
-    B, T, I, H = 64, 16, 32, 256
+    B, T, I = 64, 16, 32
     rnn = torch.nn.RNN(I, H, num_layers=2, nonlinearity="relu", bidirectional=bidir, batch_first=True)
     sd = {k: v.detach().clone() for k, v in rnn.state_dict().items()}
     names = list(sd.keys())
