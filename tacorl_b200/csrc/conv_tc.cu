@@ -21,20 +21,15 @@
 namespace tacorl {
 
 constexpr int CV_MAXT = 16;
-constexpr int CV_STAGES = 6;
-constexpr int CV_LAG = 4;           // cp.async groups kept in flight per producer thread before a stage is published
-constexpr int CV_THREADS = 288;     // 4 producer warps, 1 MMA warp, 4 epilogue warps
+constexpr int CV_STAGES = 8;
+constexpr int CV_THREADS = 192;     // TMA warp, MMA warp, 4 epilogue warps
 
 struct ConvGeom {
-  const __nv_bfloat16* src;         // NHWC source (N, SH, SW, SC)
-  int SH, SW, SC;
-  int kchunks;                      // valid 16-byte chunks per K-block row (<= 8); the rest is zero-filled
-  int RA, RB;                       // rows per frame = RA*RB (output-pixel grid of this launch)
-  int M;                            // total rows = frames * RA * RB
-  int sy, sx;                       // source pixel of tap t for row (a,b): (a*sy + dy[t], b*sx + dx[t])
+  int BW, BH;                       // output patch per tile: BW x BH pixels, tile row r = a_l*BW + b_l, BW*BH <= 128
+  int tiles_x, tiles_y, num_tiles;  // tiles per frame, total tiles (frames * tiles_x * tiles_y)
   int ntaps;
-  int dy[CV_MAXT], dx[CV_MAXT], coff[CV_MAXT];
-  int check_bounds;                 // zero-fill taps that fall outside the source image (dgrad)
+  int tap_x[CV_MAXT], tap_p[CV_MAXT], tap_y[CV_MAXT];   // source-view coordinates of tap t relative to the patch origin
+  int RA, RB;                       // valid output-pixel grid of this launch per frame (a < RA, b < RB)
   // output pixel of row (a,b): (a*oys + oy0, b*oxs + ox0) in an (N, OH, OW, OC) tensor
   int OH, OW, oys, oy0, oxs, ox0;
 };
@@ -72,6 +67,12 @@ __device__ __forceinline__ void cv_tma_2d(uint32_t dst, const CUtensorMap* tm, i
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void cv_tma_5d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4,
+                                          uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void cv_cp16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -130,9 +131,15 @@ __device__ __forceinline__ uint64_t cv_desc(uint32_t saddr, uint32_t lbo, uint32
 }
 
 // ------------------------------------------------------------------------------------------ forward / dgrad
+// One tile = a BW x BH patch of output pixels of one frame (row r = a_l*BW + b_l, BW*BH <= 128).  For filter tap t
+// the A operand of that tile is the same patch of the source activation shifted by the tap offset: ONE 5-D TMA box
+// (64 channels x BW x 1 x BH x 1 frame) written straight into a 128B-swizzled stage.  Out-of-image taps (data
+// gradients) and the ragged patch edges are zero-filled by TMA; stride-2 layers address the source through a
+// (pixel pair, row parity) view so no element strides are needed.
 template <int BN>
 __global__ void __launch_bounds__(CV_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ CUtensorMap tmW, const ConvEpi ep) {
+conv_tc_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ CUtensorMap tmA,
+               const __grid_constant__ CUtensorMap tmW, const ConvEpi ep) {
   constexpr uint32_t A_BYTES = 128 * 128;              // 128 rows x 64 bf16
   constexpr uint32_t W_TAP_BYTES = BN * 128;           // [BN][64] bf16, K-major SW128
   constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;
@@ -150,18 +157,17 @@ conv_tc_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ CUten
   const uint32_t w_bar = cv_smem(bars + 2 * CV_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = (g.M + 127) / 128;
-  const int rows_per_frame = g.RA * g.RB;
+  const int tiles_per_frame = g.tiles_x * g.tiles_y;
   __shared__ float s_bias[BN];
   if (threadIdx.x < BN) s_bias[threadIdx.x] = ep.bias ? ep.bias[threadIdx.x] : 0.f;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < CV_STAGES; ++s) { cv_mbar_init(full_bar(s), 128); cv_mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < CV_STAGES; ++s) { cv_mbar_init(full_bar(s), 1); cv_mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { cv_mbar_init(tfull_bar(a), 1); cv_mbar_init(tempty_bar(a), 4); }
     cv_mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(cv_smem(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -171,64 +177,38 @@ conv_tc_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ CUten
   cv_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // ===== producers: a lane pair gathers tile rows p and p+64; lane h of the pair takes the odd/even 16-byte chunks so
-    // every warp-wide cp.async covers whole 32-byte sectors (a thread-per-row mapping fetches each sector twice)
-    const int h = threadIdx.x & 1, p = threadIdx.x >> 1;
-    uint32_t it = 0;                                     // K blocks issued so far (stage = it % CV_STAGES)
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const __nv_bfloat16* frame[2];
-      int py0[2], px0[2];
-      bool row_ok[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int m = tile * 128 + p + 64 * u;
-        row_ok[u] = m < g.M;
-        int n = 0, a = 0, b = 0;
-        if (row_ok[u]) { n = m / rows_per_frame; const int rem = m - n * rows_per_frame; a = rem / g.RB; b = rem - a * g.RB; }
-        py0[u] = a * g.sy; px0[u] = b * g.sx;
-        frame[u] = g.src + (long long)n * g.SH * g.SW * g.SC;
-      }
-      for (int t = 0; t < g.ntaps; ++t, ++it) {
-        const int s = it % CV_STAGES;
-        const uint32_t ph = (it / CV_STAGES) & 1;
-        cv_mbar_wait(empty_bar(s), ph ^ 1);
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int row = p + 64 * u;
-          const int py = py0[u] + g.dy[t], px = px0[u] + g.dx[t];
-          bool ok = row_ok[u];
-          if (g.check_bounds) ok = ok && py >= 0 && py < g.SH && px >= 0 && px < g.SW;
-          const __nv_bfloat16* srcp = ok ? frame[u] + ((long long)py * g.SW + px) * g.SC + g.coff[t] : g.src;
-          const uint32_t dst = a_base + s * A_BYTES + (uint32_t)row * 128;
-          const uint32_t sw = (uint32_t)(row & 7);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int j = 2 * i + h;
-            cv_cp16(dst + ((j ^ sw) << 4), srcp + j * 8, (ok && j < g.kchunks) ? 16u : 0u);
-          }
-        }
-        cv_cp_async_arrive(full_bar(s));                  // fires when this thread's copies of the stage have landed
-      }
-    }
-  } else if (warp == 4) {
+  if (warp == 0) {
     if (lane == 0) {
-      // resident weights: one TMA box per tap
+      // ===== TMA producer: resident weights (one box per tap), then one activation box per (tile, tap)
       cv_mbar_expect_tx(w_bar, g.ntaps * W_TAP_BYTES);
       for (int t = 0; t < g.ntaps; ++t) cv_tma_2d(w_base + t * W_TAP_BYTES, &tmW, 0, t * BN, w_bar);
+      const uint32_t box_bytes = (uint32_t)(g.BW * g.BH) * 128;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        const int n = tile / tiles_per_frame, rem = tile - n * tiles_per_frame;
+        const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
+        const int x0 = tx * g.BW, y0 = ty * g.BH;
+        for (int t = 0; t < g.ntaps; ++t, ++it) {
+          const int s = it % CV_STAGES;
+          cv_mbar_wait(empty_bar(s), ((it / CV_STAGES) & 1) ^ 1);
+          cv_mbar_expect_tx(full_bar(s), box_bytes);
+          cv_tma_5d(a_base + s * A_BYTES, &tmA, 0, x0 + g.tap_x[t], g.tap_p[t], y0 + g.tap_y[t], n, full_bar(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
       cv_mbar_wait(w_bar, 0);
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       uint32_t it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++lt) {
         const uint32_t acc = lt & 1;
         cv_mbar_wait(tempty_bar(acc), ((lt >> 1) & 1) ^ 1);
         cv_fence_after();
         const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
         for (int t = 0; t < g.ntaps; ++t, ++it) {
           const int s = it % CV_STAGES;
-          const uint32_t ph = (it / CV_STAGES) & 1;
-          cv_mbar_wait(full_bar(s), ph);
-          cv_fence_async();                 // cp.async (generic proxy) writes -> visible to the tensor core (async proxy)
+          cv_mbar_wait(full_bar(s), (it / CV_STAGES) & 1);
           cv_fence_after();
           const uint32_t a_src = a_base + s * A_BYTES, b_src = w_base + t * W_TAP_BYTES;
 #pragma unroll
@@ -241,19 +221,18 @@ conv_tc_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ CUten
       }
     }
   } else {
-    // ===== epilogue warps 5..8: TMEM lane quarter = warp % 4
+    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4; lane r of the tile is patch pixel (r / BW, r % BW)
     const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int a_l = r / g.BW, b_l = r - a_l * g.BW;
     uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++lt) {
       const uint32_t acc = lt & 1;
-      const int m = tile * 128 + q * 32 + lane;
-      const bool row_ok = m < g.M;
-      long long opix = 0;
-      if (row_ok) {
-        const int n = m / rows_per_frame; const int rem = m - n * rows_per_frame;
-        const int a = rem / g.RB, b = rem - a * g.RB;
-        opix = ((long long)n * g.OH + (a * g.oys + g.oy0)) * g.OW + (b * g.oxs + g.ox0);
-      }
+      const int n = tile / tiles_per_frame, rem = tile - n * tiles_per_frame;
+      const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
+      const int a = ty * g.BH + a_l, b = tx * g.BW + b_l;
+      const bool row_ok = a_l < g.BH && a < g.RA && b < g.RB;
+      const long long opix = row_ok ? ((long long)n * g.OH + (a * g.oys + g.oy0)) * g.OW + (b * g.oxs + g.ox0) : 0;
       // prefetch the ReLU gate of this row (global latency) before blocking on the accumulator
       uint4 gate[BN / 8];
       if (ep.gate && row_ok) {
@@ -265,12 +244,12 @@ conv_tc_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ CUten
       cv_fence_after();
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 16) {
-        uint32_t r[16];
-        cv_ld16(tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16) + c0, r);
+        uint32_t rr[16];
+        cv_ld16(tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16) + c0, rr);
         if (!row_ok) continue;
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j];
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]) + s_bias[c0 + j];
         if (ep.relu) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -312,7 +291,7 @@ conv_tc_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ CUten
   }
   cv_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 1) {
     cv_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
@@ -350,11 +329,48 @@ static int cv_weight_tmap(CUtensorMap* tm, const void* wp, int ntaps, int BN) {
   return 0;
 }
 
+// 5-D view of an NHWC bf16 activation for the patch boxes: (64 channels, x, p, y, n); strides in bytes.
+struct ActView {
+  const void* base;
+  long long nx, np, ny, nn;
+  long long sx, sp, sy, sn;
+};
+static int cv_act_tmap(CUtensorMap* tm, const ActView& v, int BW, int BH) {
+  CvEncodeFn fn = cv_encode_fn();
+  TACORL_REQUIRE(fn, "conv_tc: cuTensorMapEncodeTiled is not available");
+  TACORL_REQUIRE(((uintptr_t)v.base & 15) == 0 && v.sx % 16 == 0 && v.sp % 16 == 0 && v.sy % 16 == 0 && v.sn % 16 == 0,
+                 "conv_tc: activation view must be 16-byte aligned (strides %lld %lld %lld %lld)", v.sx, v.sp, v.sy, v.sn);
+  cuuint64_t dims[5] = {64, (cuuint64_t)v.nx, (cuuint64_t)v.np, (cuuint64_t)v.ny, (cuuint64_t)v.nn};
+  cuuint64_t strides[4] = {(cuuint64_t)v.sx, (cuuint64_t)v.sp, (cuuint64_t)v.sy, (cuuint64_t)v.sn};
+  cuuint32_t box[5] = {64, (cuuint32_t)BW, 1, (cuuint32_t)BH, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(v.base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TACORL_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(activation) failed (%d): dims %lld %lld %lld %lld box %dx%d",
+                 (int)r, v.nx, v.np, v.ny, v.nn, BW, BH);
+  return 0;
+}
+
+// patch shape with the fewest wasted accumulator rows: maximise RA*RB / (tiles * 128)
+static void cv_choose_patch(int RA, int RB, int* BW, int* BH) {
+  long long best = -1;
+  *BW = 1; *BH = 1;
+  for (int bw = 1; bw <= 128 && bw <= RB; ++bw)
+    for (int bh = 1; bh * bw <= 128 && bh <= RA; ++bh) {
+      const long long tiles = (long long)cdiv(RB, bw) * cdiv(RA, bh);
+      // fewer tiles first; among equals prefer the wider patch (longer contiguous runs)
+      const long long score = -tiles * 1024 + bw;
+      if (best == -1 || score > best) { best = score; *BW = bw; *BH = bh; }
+    }
+}
+
 template <int BN>
-static int cv_launch(const ConvGeom& g, const void* wpacked, const ConvEpi& ep, cudaStream_t st) {
-  CUtensorMap tm;
-  int rc = cv_weight_tmap(&tm, wpacked, g.ntaps, BN);
+static int cv_launch(const ConvGeom& g, const ActView& view, const void* wpacked, const ConvEpi& ep, cudaStream_t st) {
+  CUtensorMap tw, ta;
+  int rc = cv_weight_tmap(&tw, wpacked, g.ntaps, BN);
   if (rc) return rc;
+  if ((rc = cv_act_tmap(&ta, view, g.BW, g.BH))) return rc;
   const size_t smem = (size_t)g.ntaps * BN * 128 + CV_STAGES * 128 * 128 + (2 * CV_STAGES + 5) * 8 + 16 + 1024;
   static size_t configured = 0;
   auto kern = conv_tc_kernel<BN>;
@@ -362,19 +378,22 @@ static int cv_launch(const ConvGeom& g, const void* wpacked, const ConvEpi& ep, 
     TACORL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  const int tiles = (g.M + 127) / 128;
-  const int ctas = tiles < 148 ? tiles : 148;
-  kern<<<ctas, CV_THREADS, smem, st>>>(g, tm, ep);
+  const int ctas = g.num_tiles < 148 ? g.num_tiles : 148;
+  kern<<<ctas, CV_THREADS, smem, st>>>(g, ta, tw, ep);
   TACORL_LAUNCH_CHECK();
   return 0;
 }
 
-int conv_tc_run(const ConvGeom& g, int BN, const void* wpacked, const ConvEpi& ep, cudaStream_t st) {
-  if (g.M == 0) return 0;
+// g: taps / output mapping / RA, RB filled in by the layer driver; the patch tiling is chosen here
+static int conv_tc_run(ConvGeom g, int N, const ActView& view, int BN, const void* wpacked, const ConvEpi& ep,
+                       cudaStream_t st) {
+  if (N == 0 || g.RA <= 0 || g.RB <= 0) return 0;
   TACORL_REQUIRE(g.ntaps >= 1 && g.ntaps <= CV_MAXT, "conv_tc: bad tap count %d", g.ntaps);
-  TACORL_REQUIRE(((uintptr_t)g.src & 15) == 0 && (g.SC * 2) % 16 == 0, "conv_tc: source must be 16-byte aligned");
-  if (BN == 32) return cv_launch<32>(g, wpacked, ep, st);
-  if (BN == 64) return cv_launch<64>(g, wpacked, ep, st);
+  cv_choose_patch(g.RA, g.RB, &g.BW, &g.BH);
+  g.tiles_x = cdiv(g.RB, g.BW); g.tiles_y = cdiv(g.RA, g.BH);
+  g.num_tiles = N * g.tiles_x * g.tiles_y;
+  if (BN == 32) return cv_launch<32>(g, view, wpacked, ep, st);
+  if (BN == 64) return cv_launch<64>(g, view, wpacked, ep, st);
   set_last_error("conv_tc: unsupported output width %d", BN);
   return -1;
 }
@@ -420,8 +439,8 @@ int conv_tc_pack(int mode, const float* W, void* Wp, cudaStream_t st) {
   return 0;
 }
 
-// fp32 NCHW image (N,3,H,W) -> bf16 space-to-depth(4) (N, SH, SW, 48), channel q = (py*4+px)*3 + c.
-// One thread per (n, Y, X, py): three float4 loads, 12 bf16 out (24 contiguous bytes).
+// fp32 NCHW image (N,3,H,W) -> bf16 space-to-depth(4) (N, SH, SW, 64), channel q = (py*4+px)*3 + c for q < 48, zero pad
+// above (128-byte pixels = one TMA / UMMA swizzle row).  One thread per (n, Y, X, py): three float4 loads, 12 bf16 out.
 __global__ void cv_s2d_kernel(const float* __restrict__ x, int H, int W, int SH, int SW, long long total,
                               __nv_bfloat16* __restrict__ xs) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -439,7 +458,11 @@ __global__ void cv_s2d_kernel(const float* __restrict__ x, int H, int W, int SH,
       c1 = __ldg(reinterpret_cast<const float4*>(p + (long long)H * W));
       c2 = __ldg(reinterpret_cast<const float4*>(p + 2LL * H * W));
     }
-    __nv_bfloat16* o = xs + ((n * SH + Y) * (long long)SW + X) * 48 + py * 12;
+    __nv_bfloat16* o = xs + ((n * SH + Y) * (long long)SW + X) * 64 + py * 12;
+    if (py == 0) {                                      // channels 48..63 of the pixel
+      reinterpret_cast<uint4*>(o + 48)[0] = make_uint4(0, 0, 0, 0);
+      reinterpret_cast<uint4*>(o + 48)[1] = make_uint4(0, 0, 0, 0);
+    }
     const float v[12] = {c0.x, c1.x, c2.x, c0.y, c1.y, c2.y, c0.z, c1.z, c2.z, c0.w, c1.w, c2.w};
     uint32_t pk[6];
 #pragma unroll
@@ -447,7 +470,7 @@ __global__ void cv_s2d_kernel(const float* __restrict__ x, int H, int W, int SH,
       __nv_bfloat162 t2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
       pk[j] = *reinterpret_cast<uint32_t*>(&t2);
     }
-    uint2* op = reinterpret_cast<uint2*>(o);          // 24-byte run, 8-byte aligned (96 B pixel pitch)
+    uint2* op = reinterpret_cast<uint2*>(o);          // 24-byte run, 8-byte aligned
     op[0] = make_uint2(pk[0], pk[1]); op[1] = make_uint2(pk[2], pk[3]); op[2] = make_uint2(pk[4], pk[5]);
   }
 }
@@ -476,7 +499,11 @@ __global__ void cv_s2d_u8_kernel(const unsigned char* __restrict__ x, int H, int
         v[6 + c] = fmaf((float)u.z, scale, shift); v[9 + c] = fmaf((float)u.w, scale, shift);
       }
     }
-    __nv_bfloat16* o = xs + ((n * SH + Y) * (long long)SW + X) * 48 + py * 12;
+    __nv_bfloat16* o = xs + ((n * SH + Y) * (long long)SW + X) * 64 + py * 12;
+    if (py == 0) {
+      reinterpret_cast<uint4*>(o + 48)[0] = make_uint4(0, 0, 0, 0);
+      reinterpret_cast<uint4*>(o + 48)[1] = make_uint4(0, 0, 0, 0);
+    }
     uint32_t pk[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
@@ -523,49 +550,50 @@ int conv_tc_s2d(const float* x, int N, int H, int W, int SH, int SW, void* xs, c
 }
 
 // ------------------------------------------------------------------------------------------ layer drivers
-// conv1 forward on the s2d image: 2x2 taps, stride 1, C = 48 (6 chunks), BN = 32
+static ActView cv_plain_view(const void* base, int N, int H, int W) {      // NHWC, 64 channels (128-byte pixels)
+  return ActView{base, W, 1, H, N, 128, 128, (long long)W * 128, (long long)H * W * 128};
+}
+// conv1 forward on the s2d image (N, H1+1, W1+1, 64: 48 real channels + zero pad): 2x2 taps, stride 1, BN = 32
 int conv_tc_conv1_fwd(const void* xs, int N, int H1, int W1, const void* wp, const float* bias, void* y1b,
                       cudaStream_t st) {
   ConvGeom g = {};
-  g.src = (const __nv_bfloat16*)xs; g.SH = H1 + 1; g.SW = W1 + 1; g.SC = 48; g.kchunks = 6;
-  g.RA = H1; g.RB = W1; g.M = N * H1 * W1; g.sy = 1; g.sx = 1; g.ntaps = 4;
-  for (int t = 0; t < 4; ++t) { g.dy[t] = t >> 1; g.dx[t] = t & 1; g.coff[t] = 0; }
+  g.RA = H1; g.RB = W1; g.ntaps = 4;
+  for (int t = 0; t < 4; ++t) { g.tap_y[t] = t >> 1; g.tap_x[t] = t & 1; }
   g.OH = H1; g.OW = W1; g.oys = 1; g.oxs = 1;
   ConvEpi e = {bias, 1, nullptr, (__nv_bfloat16*)y1b, nullptr};
-  return conv_tc_run(g, 32, wp, e, st);
+  return conv_tc_run(g, N, cv_plain_view(xs, N, H1 + 1, W1 + 1), 32, wp, e, st);
 }
-// conv2 forward: 4x4 stride 2 over y1 (C = 32): 8 tap pairs
+// conv2 forward: 4x4 stride 2 over y1 (N, H1, W1, 32).  Source pixel (2a+ky, 2b+kx): y1 is viewed as
+// (64 = pixel pair x 32 channels, pair index, row parity, row pair, frame), tap (ky, p) = box at pair b+p, row 2(a + ky/2) + ky%2.
 int conv_tc_conv2_fwd(const void* y1b, int N, int H1, int W1, int H2, int W2, const void* wp, const float* bias,
                       void* y2b, cudaStream_t st) {
   ConvGeom g = {};
-  g.src = (const __nv_bfloat16*)y1b; g.SH = H1; g.SW = W1; g.SC = 32; g.kchunks = 8;
-  g.RA = H2; g.RB = W2; g.M = N * H2 * W2; g.sy = 2; g.sx = 2; g.ntaps = 8;
-  for (int t = 0; t < 8; ++t) { g.dy[t] = t >> 1; g.dx[t] = 2 * (t & 1); g.coff[t] = 0; }
+  g.RA = H2; g.RB = W2; g.ntaps = 8;
+  for (int t = 0; t < 8; ++t) { const int ky = t >> 1; g.tap_x[t] = t & 1; g.tap_p[t] = ky & 1; g.tap_y[t] = ky >> 1; }
   g.OH = H2; g.OW = W2; g.oys = 1; g.oxs = 1;
   ConvEpi e = {bias, 1, nullptr, (__nv_bfloat16*)y2b, nullptr};
-  return conv_tc_run(g, 64, wp, e, st);
+  const ActView v{y1b, W2 + 1, 2, H2 + 1, N, 128, (long long)W1 * 64, (long long)W1 * 128, (long long)H1 * W1 * 64};
+  return conv_tc_run(g, N, v, 64, wp, e, st);
 }
 // conv3 forward: 3x3 stride 1 over y2 (C = 64): 9 taps; fp32 output for the soft-argmax
 int conv_tc_conv3_fwd(const void* y2b, int N, int H2, int W2, int H3, int W3, const void* wp, const float* bias,
                       float* y3, cudaStream_t st) {
   ConvGeom g = {};
-  g.src = (const __nv_bfloat16*)y2b; g.SH = H2; g.SW = W2; g.SC = 64; g.kchunks = 8;
-  g.RA = H3; g.RB = W3; g.M = N * H3 * W3; g.sy = 1; g.sx = 1; g.ntaps = 9;
-  for (int t = 0; t < 9; ++t) { g.dy[t] = t / 3; g.dx[t] = t % 3; g.coff[t] = 0; }
+  g.RA = H3; g.RB = W3; g.ntaps = 9;
+  for (int t = 0; t < 9; ++t) { g.tap_y[t] = t / 3; g.tap_x[t] = t % 3; }
   g.OH = H3; g.OW = W3; g.oys = 1; g.oxs = 1;
   ConvEpi e = {bias, 1, nullptr, nullptr, y3};
-  return conv_tc_run(g, 64, wp, e, st);
+  return conv_tc_run(g, N, cv_plain_view(y2b, N, H2, W2), 64, wp, e, st);
 }
-// conv3 dgrad: dy2[iy][ix][c] = [y2>0] * sum_{ky,kx,oc} dy3[iy-ky][ix-kx][oc] W3[oc][c][ky][kx]
+// conv3 dgrad: dy2[iy][ix][c] = [y2>0] * sum_{ky,kx,oc} dy3[iy-ky][ix-kx][oc] W3[oc][c][ky][kx]   (TMA zero-fills iy-ky < 0 ...)
 int conv_tc_conv3_dgrad(const void* dy3b, int N, int H2, int W2, int H3, int W3, const void* wp, const void* y2b,
                         void* dy2b, cudaStream_t st) {
   ConvGeom g = {};
-  g.src = (const __nv_bfloat16*)dy3b; g.SH = H3; g.SW = W3; g.SC = 64; g.kchunks = 8;
-  g.RA = H2; g.RB = W2; g.M = N * H2 * W2; g.sy = 1; g.sx = 1; g.ntaps = 9; g.check_bounds = 1;
-  for (int t = 0; t < 9; ++t) { g.dy[t] = -(t / 3); g.dx[t] = -(t % 3); g.coff[t] = 0; }
+  g.RA = H2; g.RB = W2; g.ntaps = 9;
+  for (int t = 0; t < 9; ++t) { g.tap_y[t] = -(t / 3); g.tap_x[t] = -(t % 3); }
   g.OH = H2; g.OW = W2; g.oys = 1; g.oxs = 1;
   ConvEpi e = {nullptr, 0, (const __nv_bfloat16*)y2b, (__nv_bfloat16*)dy2b, nullptr};
-  return conv_tc_run(g, 64, wp, e, st);
+  return conv_tc_run(g, N, cv_plain_view(dy3b, N, H3, W3), 64, wp, e, st);
 }
 // conv2 dgrad: four stride-parity classes (py,px); class rows (a,b) -> dy1 pixel (2a+py, 2b+px),
 //   dy1 = [y1>0] * sum_{j,i in {0,1}, oc} dy2[a-j][b-i][oc] W2[oc][c][py+2j][px+2i]
@@ -574,13 +602,12 @@ int conv_tc_conv2_dgrad(const void* dy2b, int N, int H1, int W1, int H2, int W2,
   for (int cls = 0; cls < 4; ++cls) {
     const int py = cls >> 1, px = cls & 1;
     ConvGeom g = {};
-    g.src = (const __nv_bfloat16*)dy2b; g.SH = H2; g.SW = W2; g.SC = 64; g.kchunks = 8;
-    g.RA = (H1 - py + 1) / 2; g.RB = (W1 - px + 1) / 2; g.M = N * g.RA * g.RB; g.sy = 1; g.sx = 1; g.ntaps = 4;
-    g.check_bounds = 1;
-    for (int t = 0; t < 4; ++t) { g.dy[t] = -(t >> 1); g.dx[t] = -(t & 1); g.coff[t] = 0; }
+    g.RA = (H1 - py + 1) / 2; g.RB = (W1 - px + 1) / 2; g.ntaps = 4;
+    for (int t = 0; t < 4; ++t) { g.tap_y[t] = -(t >> 1); g.tap_x[t] = -(t & 1); }
     g.OH = H1; g.OW = W1; g.oys = 2; g.oy0 = py; g.oxs = 2; g.ox0 = px;
     ConvEpi e = {nullptr, 0, (const __nv_bfloat16*)y1b, (__nv_bfloat16*)dy1b, nullptr};
-    int rc = conv_tc_run(g, 32, (const __nv_bfloat16*)wp_classes + (size_t)cls * 4 * 32 * 64, e, st);
+    int rc = conv_tc_run(g, N, cv_plain_view(dy2b, N, H2, W2), 32,
+                         (const __nv_bfloat16*)wp_classes + (size_t)cls * 4 * 32 * 64, e, st);
     if (rc) return rc;
   }
   return 0;
@@ -815,7 +842,7 @@ int conv_tc_wgrad(int layer, const void* dyb, const void* src, int N, int SH, in
     g.OC = 64; g.SC = 32; g.kchunks = 8; g.sy = g.sx = 2; g.NT = 4; g.groups = 2;
     for (int t = 0; t < 8; ++t) { g.dy_t[t] = t >> 1; g.dx_t[t] = 2 * (t & 1); g.coff[t] = 0; }
   } else {
-    g.OC = 32; g.SC = 48; g.kchunks = 6; g.sy = g.sx = 1; g.NT = 4; g.groups = 1;
+    g.OC = 32; g.SC = 64; g.kchunks = 6; g.sy = g.sx = 1; g.NT = 4; g.groups = 1;
     for (int t = 0; t < 4; ++t) { g.dy_t[t] = t >> 1; g.dx_t[t] = t & 1; g.coff[t] = 0; }
   }
   g.dy_chunks = g.OC / 8;
@@ -871,8 +898,8 @@ extern "C" int tacorl_conv_tc_debug(int op, const float* in0, const float* in1, 
   const long long P1 = (long long)H1 * W1, P2 = (long long)H2 * W2, P3 = (long long)H3 * W3;
   Arena ar(ws, ws_bytes);
   __nv_bfloat16* wp = ar.take<__nv_bfloat16>(16 * 64 * 64);
-  __nv_bfloat16* a0 = ar.take<__nv_bfloat16>((size_t)N * (H1 + 1) * (W1 + 1) * 48 + (size_t)N * P1 * 64);
-  __nv_bfloat16* a1 = ar.take<__nv_bfloat16>((size_t)N * (H1 + 1) * (W1 + 1) * 48 + (size_t)N * P1 * 64);
+  __nv_bfloat16* a0 = ar.take<__nv_bfloat16>((size_t)N * (H1 + 1) * (W1 + 1) * 64 + (size_t)N * P1 * 64);
+  __nv_bfloat16* a1 = ar.take<__nv_bfloat16>((size_t)N * (H1 + 1) * (W1 + 1) * 64 + (size_t)N * P1 * 64);
   __nv_bfloat16* ob = ar.take<__nv_bfloat16>((size_t)N * P1 * 64);
   float* wsf = ar.take<float>((32 << 20) / 4);
   TACORL_REQUIRE(wp && a0 && a1 && ob && wsf, "conv_tc_debug: workspace too small");

@@ -56,7 +56,7 @@ size_t tacorl_lmp_encoder_ws_bytes(int N, int H, int W, int hidden, int latent, 
   if (backward) fixed += (size_t)N * (hidden + 128 + g.P3 * 64 + 1) * 4 + 4 * (64 * 576) * 4 + (1 << 20);
   (void)latent;
   // implicit-GEMM tensor-core path: no col matrix, whole-batch bf16 gradient / s2d buffers instead
-  size_t tc = (size_t)N * ((size_t)(g.H1 + 1) * (g.W1 + 1) * 96 + g.P1 * 64 + g.P2 * 128 + g.P3 * 64 * 6 +
+  size_t tc = (size_t)N * ((size_t)(g.H1 + 1) * (g.W1 + 1) * 128 + g.P1 * 64 + g.P2 * 128 + g.P3 * 64 * 6 +
                            (g.P1 * 64 + g.P2 * 128) + (128 + 64 + 64 + hidden + 128 + hidden) * 4 + 4096) +
               kSplitKWs + (32 << 20);
   size_t legacy = fixed + per_frame * chunk + (size_t)N * 3 * H * W * 4 + 4096;   // (+ fp32 copy of uint8 frames)
@@ -75,7 +75,7 @@ static int enc_fwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
   __nv_bfloat16* wp2 = ar.take<__nv_bfloat16>(8 * 64 * 64);
   __nv_bfloat16* wp3 = ar.take<__nv_bfloat16>(9 * 64 * 64);
   float* fcws = ar.take<float>((8 << 20) / 4);
-  __nv_bfloat16* xs = ar.take<__nv_bfloat16>((size_t)N * (g.H1 + 1) * (g.W1 + 1) * 48);
+  __nv_bfloat16* xs = ar.take<__nv_bfloat16>((size_t)N * (g.H1 + 1) * (g.W1 + 1) * 64);
   __nv_bfloat16* y1b = y1 ? (__nv_bfloat16*)y1 : ar.take<__nv_bfloat16>((size_t)N * g.P1 * 32);
   __nv_bfloat16* y2b = y2 ? (__nv_bfloat16*)y2 : ar.take<__nv_bfloat16>((size_t)N * g.P2 * 64);
   if (!y3) y3 = ar.take<float>((size_t)N * g.P3 * 64);
@@ -121,7 +121,7 @@ static int enc_bwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
   __nv_bfloat16* dy3b = ar.take<__nv_bfloat16>((size_t)N * g.P3 * 64);
   __nv_bfloat16* dy2b = ar.take<__nv_bfloat16>((size_t)N * g.P2 * 64);
   __nv_bfloat16* dy1b = ar.take<__nv_bfloat16>((size_t)N * g.P1 * 32);
-  __nv_bfloat16* xs = ar.take<__nv_bfloat16>((size_t)N * (g.H1 + 1) * (g.W1 + 1) * 48);
+  __nv_bfloat16* xs = ar.take<__nv_bfloat16>((size_t)N * (g.H1 + 1) * (g.W1 + 1) * 64);
   TACORL_REQUIRE(wd3 && wd2 && dh4 && dfeat && dtau && csws && skws && dy3b && dy2b && dy1b && xs,
                  "lmp_encoder_bwd(bf16): workspace too small (%zu bytes)", ws_bytes);
   int rc;
