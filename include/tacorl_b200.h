@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TACORL_B200_ABI_VERSION 2
+#define TACORL_B200_ABI_VERSION 3
 
 #define TACORL_PREC_F32 0
 #define TACORL_PREC_BF16 1
@@ -69,18 +69,20 @@ int tacorl_rowscale(long long rows, int L, const float* x, const float* row_scal
  * Saved for backward (caller-owned; pass NULL for y1,y2[,y3,feat,smax,ssum,h4] in inference):
  *   y1 (N,H1,W1,32), y2 (N,H2,W2,64) post-ReLU NHWC (fp32 for PREC_F32, bf16 for PREC_BF16),
  *   y3 (N,H3,W3,64) post-ReLU NHWC fp32; feat (N,128);
- *   smax, ssum (N,64) softmax statistics; h4 (N,hidden).   emb: (N,latent). */
+ *   smax, ssum (N,64) softmax statistics; h4 (N,hidden).   emb: (N,latent).
+ *   xs (PREC_BF16 only, optional): the (N,H1+1,W1+1,64) bf16 space-to-depth copy of the normalised image that conv1
+ *   consumes; when the forward call stores it and the backward call receives it, the backward pass does not touch x. */
 size_t tacorl_lmp_encoder_ws_bytes(int N, int H, int W, int hidden, int latent, int backward);
 int tacorl_lmp_encoder_fwd(const void* x, int x_dtype, float x_scale, float x_shift, int N, int H, int W,
                            const float* const* params, int hidden,
                            int latent, float* y1, float* y2, float* y3, float* feat, float* smax,
-                           float* ssum, float* h4, float* emb, void* ws, size_t ws_bytes, int prec,
+                           float* ssum, float* h4, float* emb, void* xs, void* ws, size_t ws_bytes, int prec,
                            void* stream);
 int tacorl_lmp_encoder_bwd(const void* x, int x_dtype, float x_scale, float x_shift, int N, int H, int W,
                            const float* const* params, int hidden,
                            int latent, const float* y1, const float* y2, const float* y3,
                            const float* feat, const float* smax, const float* ssum, const float* h4,
-                           const float* d_emb, float* const* grads, int accumulate, void* ws,
+                           const float* d_emb, float* const* grads, int accumulate, const void* xs, void* ws,
                            size_t ws_bytes, int prec, void* stream);
 
 /* Diagnostic hook for the implicit-GEMM convolution kernels behind tacorl_lmp_encoder_* (PREC_BF16):

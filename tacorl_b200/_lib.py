@@ -27,9 +27,9 @@ _SIGS = {
     "tacorl_scale": [_ll, _vp, _vp, _f, _vp, _vp],
     "tacorl_rowscale": [_ll, _i, _vp, _vp, _f, _vp, _i, _vp],
     "tacorl_lmp_encoder_ws_bytes": [_i, _i, _i, _i, _i, _i],
-    "tacorl_lmp_encoder_fwd": [_vp, _i, _f, _f, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp],
+    "tacorl_lmp_encoder_fwd": [_vp, _i, _f, _f, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp],
     "tacorl_lmp_encoder_bwd": [_vp, _i, _f, _f, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i,
-                               _vp, _sz, _i, _vp],
+                               _vp, _vp, _sz, _i, _vp],
     "tacorl_conv_tc_debug": [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp],
     "tacorl_rnn_layer_ws_bytes": [_i, _i, _i, _i],
     "tacorl_rnn_layer_fwd": [_i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _ll, _vp, _sz, _i, _vp],

@@ -124,15 +124,28 @@ __global__ void softargmax_fwd_kernel(const float* __restrict__ y, int P, int OW
   const float inv_t = 1.f / __ldg(temperature);
   const float* yp = y + n * (long long)P * C;
   float m = -INFINITY, s = 0.f, sx = 0.f, sy = 0.f;
-  for (int p = g; p < P; p += G) {
-    const float v = yp[(long long)p * C + c] * inv_t;
-    const float col = (float)(p % OW), row = (float)(p / OW);
-    if (v > m) {
-      const float sc = expf(m - v);
-      s = s * sc + 1.f; sx = sx * sc + col; sy = sy * sc + row; m = v;
-    } else {
-      const float e = expf(v - m);
-      s += e; sx += e * col; sy += e * row;
+  // batches of 8 positions: all loads in flight first, one max, then the exponentials (merged into the running
+  // online-softmax state), instead of a load -> compare -> exp chain per position
+  constexpr int UB = 8;
+  for (int p0 = g; p0 < P; p0 += G * UB) {
+    float v[UB];
+#pragma unroll
+    for (int j = 0; j < UB; ++j) {
+      const int p = p0 + j * G;
+      v[j] = p < P ? yp[(long long)p * C + c] * inv_t : -INFINITY;
+    }
+    float bm = v[0];
+#pragma unroll
+    for (int j = 1; j < UB; ++j) bm = fmaxf(bm, v[j]);
+    if (bm > m) {
+      const float sc = expf(m - bm);       // exp(-inf) = 0 on the first batch
+      s *= sc; sx *= sc; sy *= sc; m = bm;
+    }
+#pragma unroll
+    for (int j = 0; j < UB; ++j) {
+      const int p = p0 + j * G;
+      const float e = expf(v[j] - m);      // 0 for the padded tail
+      s += e; sx += e * (float)(p % OW); sy += e * (float)(p / OW);
     }
   }
   float* q = sm + (g * C + c) * 4;
@@ -189,12 +202,23 @@ __global__ void softargmax_bwd_kernel(const float* __restrict__ y, int P, int OW
   const float M = smax[n * C + c], invS = 1.f / ssum[n * C + c];
   const float dotg = gx * fx + gy * fy;
   float dt = 0.f;
-  for (int p = g; p < P; p += G) {
-    const float yv = yp[(long long)p * C + c];
-    const float pr = expf(yv * inv_t - M) * invS;
-    const float dz = pr * (gx * (float)(p % OW) + gy * (float)(p / OW) - dotg);
-    dt += dz * yv;
-    sa_store(dyp + (long long)p * C + c, yv > 0.f ? dz * inv_t : 0.f);
+  constexpr int UB = 8;
+  for (int p0 = g; p0 < P; p0 += G * UB) {
+    float yv[UB];
+#pragma unroll
+    for (int j = 0; j < UB; ++j) {
+      const int p = p0 + j * G;
+      yv[j] = p < P ? yp[(long long)p * C + c] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < UB; ++j) {
+      const int p = p0 + j * G;
+      if (p >= P) break;
+      const float pr = expf(yv[j] * inv_t - M) * invS;
+      const float dz = pr * (gx * (float)(p % OW) + gy * (float)(p / OW) - dotg);
+      dt += dz * yv[j];
+      sa_store(dyp + (long long)p * C + c, yv[j] > 0.f ? dz * inv_t : 0.f);
+    }
   }
   dt = warp_sum(dt);
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;

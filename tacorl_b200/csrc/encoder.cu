@@ -68,14 +68,14 @@ size_t tacorl_lmp_encoder_ws_bytes(int N, int H, int W, int hidden, int latent, 
 // activations, packed bf16 weights resident in shared memory, no im2col buffers.
 static int enc_fwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, int N, int H, int W, const float* const* params, int hidden, int latent,
                       void* y1, void* y2, float* y3, float* feat, float* smax, float* ssum, float* h4, float* emb,
-                      void* ws, size_t ws_bytes, cudaStream_t st) {
+                      void* xs_save, void* ws, size_t ws_bytes, cudaStream_t st) {
   EncGeom g(N, H, W);
   Arena ar(ws, ws_bytes);
   __nv_bfloat16* wp1 = ar.take<__nv_bfloat16>(4 * 32 * 64);
   __nv_bfloat16* wp2 = ar.take<__nv_bfloat16>(8 * 64 * 64);
   __nv_bfloat16* wp3 = ar.take<__nv_bfloat16>(9 * 64 * 64);
   float* fcws = ar.take<float>((8 << 20) / 4);
-  __nv_bfloat16* xs = ar.take<__nv_bfloat16>((size_t)N * (g.H1 + 1) * (g.W1 + 1) * 64);
+  __nv_bfloat16* xs = xs_save ? (__nv_bfloat16*)xs_save : ar.take<__nv_bfloat16>((size_t)N * (g.H1 + 1) * (g.W1 + 1) * 64);
   __nv_bfloat16* y1b = y1 ? (__nv_bfloat16*)y1 : ar.take<__nv_bfloat16>((size_t)N * g.P1 * 32);
   __nv_bfloat16* y2b = y2 ? (__nv_bfloat16*)y2 : ar.take<__nv_bfloat16>((size_t)N * g.P2 * 64);
   if (!y3) y3 = ar.take<float>((size_t)N * g.P3 * 64);
@@ -107,7 +107,7 @@ static int enc_fwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
 static int enc_bwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, int N, int H, int W, const float* const* params, int hidden, int latent,
                       const void* y1, const void* y2, const float* y3, const float* feat, const float* smax,
                       const float* ssum, const float* h4, const float* d_emb, float* const* grads, int accumulate,
-                      void* ws, size_t ws_bytes, cudaStream_t st) {
+                      const void* xs_saved, void* ws, size_t ws_bytes, cudaStream_t st) {
   EncGeom g(N, H, W);
   const float beta0 = accumulate ? 1.f : 0.f;
   Arena ar(ws, ws_bytes);
@@ -121,7 +121,7 @@ static int enc_bwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
   __nv_bfloat16* dy3b = ar.take<__nv_bfloat16>((size_t)N * g.P3 * 64);
   __nv_bfloat16* dy2b = ar.take<__nv_bfloat16>((size_t)N * g.P2 * 64);
   __nv_bfloat16* dy1b = ar.take<__nv_bfloat16>((size_t)N * g.P1 * 32);
-  __nv_bfloat16* xs = ar.take<__nv_bfloat16>((size_t)N * (g.H1 + 1) * (g.W1 + 1) * 64);
+  __nv_bfloat16* xs = xs_saved ? (__nv_bfloat16*)xs_saved : ar.take<__nv_bfloat16>((size_t)N * (g.H1 + 1) * (g.W1 + 1) * 64);
   TACORL_REQUIRE(wd3 && wd2 && dh4 && dfeat && dtau && csws && skws && dy3b && dy2b && dy1b && xs,
                  "lmp_encoder_bwd(bf16): workspace too small (%zu bytes)", ws_bytes);
   int rc;
@@ -153,6 +153,7 @@ static int enc_bwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
   if ((rc = conv_tc_wgrad(2, dy2b, y1, N, g.H1, g.W1, g.H2, g.W2, beta0, grads[P_W2], grads[P_B2], skws, kSplitKWs, st))) return rc;
   if ((rc = conv_tc_conv2_dgrad(dy2b, N, g.H1, g.W1, g.H2, g.W2, wd2, y1, dy1b, st))) return rc;
   // ---- conv1 (weight gradient only; images receive no gradient)
+  if (!xs_saved)
   if ((rc = x_u8 ? conv_tc_s2d_u8((const unsigned char*)xv, N, H, W, g.H1 + 1, g.W1 + 1, x_scale, x_shift, xs, st)
                  : conv_tc_s2d((const float*)xv, N, H, W, g.H1 + 1, g.W1 + 1, xs, st))) return rc;
   return conv_tc_wgrad(1, dy1b, xs, N, g.H1 + 1, g.W1 + 1, g.H1, g.W1, beta0, grads[P_W1], grads[P_B1], skws, kSplitKWs, st);
@@ -161,7 +162,7 @@ static int enc_bwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
 static int enc_fwd(const void* xv, int x_u8, float x_scale, float x_shift, int N, int H, int W,
                    const float* const* params, int hidden,
                    int latent, float* y1, float* y2, float* y3, float* feat, float* smax,
-                   float* ssum, float* h4, float* emb, void* ws, size_t ws_bytes, int prec,
+                   float* ssum, float* h4, float* emb, void* xs_save, void* ws, size_t ws_bytes, int prec,
                    cudaStream_t st) {
   EncGeom g(N, H, W);
   const float* x = (const float*)xv;
@@ -172,7 +173,7 @@ static int enc_fwd(const void* xv, int x_u8, float x_scale, float x_shift, int N
   if (prec == PREC_BF16) {
     TACORL_REQUIRE(W % 4 == 0, "lmp_encoder_fwd(bf16): image width must be a multiple of 4 (got %d)", W);
     return enc_fwd_tc(xv, x_u8, x_scale, x_shift, N, H, W, params, hidden, latent, (void*)y1, (void*)y2, y3, feat,
-                      smax, ssum, h4, emb, ws, ws_bytes, st);
+                      smax, ssum, h4, emb, xs_save, ws, ws_bytes, st);
   }
   Arena ar(ws, ws_bytes);
   if (x_u8) {   // fp32 parity path: materialise the normalised fp32 image once
@@ -245,18 +246,18 @@ static int enc_fwd(const void* xv, int x_u8, float x_scale, float x_shift, int N
 int tacorl_lmp_encoder_fwd(const void* x, int x_dtype, float x_scale, float x_shift, int N, int H, int W,
                            const float* const* params, int hidden,
                            int latent, float* y1, float* y2, float* y3, float* feat, float* smax,
-                           float* ssum, float* h4, float* emb, void* ws, size_t ws_bytes, int prec,
+                           float* ssum, float* h4, float* emb, void* xs, void* ws, size_t ws_bytes, int prec,
                            void* stream) {
   TACORL_REQUIRE(x_dtype == 0 || x_dtype == 1, "lmp_encoder_fwd: x_dtype must be 0 (fp32) or 1 (uint8)");
   return enc_fwd(x, x_dtype, x_scale, x_shift, N, H, W, params, hidden, latent, y1, y2, y3, feat, smax, ssum, h4, emb,
-                 ws, ws_bytes, prec, (cudaStream_t)stream);
+                 xs, ws, ws_bytes, prec, (cudaStream_t)stream);
 }
 
 int tacorl_lmp_encoder_bwd(const void* xv, int x_dtype, float x_scale, float x_shift, int N, int H, int W,
                            const float* const* params, int hidden,
                            int latent, const float* y1, const float* y2, const float* y3,
                            const float* feat, const float* smax, const float* ssum, const float* h4,
-                           const float* d_emb, float* const* grads, int accumulate, void* ws,
+                           const float* d_emb, float* const* grads, int accumulate, const void* xs, void* ws,
                            size_t ws_bytes, int prec, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   EncGeom g(N, H, W);
@@ -269,7 +270,7 @@ int tacorl_lmp_encoder_bwd(const void* xv, int x_dtype, float x_scale, float x_s
   if (N == 0) return 0;
   if (prec == PREC_BF16)
     return enc_bwd_tc(xv, x_dtype, x_scale, x_shift, N, H, W, params, hidden, latent, (const void*)y1, (const void*)y2,
-                      y3, feat, smax, ssum, h4, d_emb, grads, accumulate, ws, ws_bytes, st);
+                      y3, feat, smax, ssum, h4, d_emb, grads, accumulate, xs, ws, ws_bytes, st);
   const float beta0 = accumulate ? 1.f : 0.f;
   Arena ar(ws, ws_bytes);
   if (x_dtype == 1) {   // fp32 parity path: normalised fp32 copy of the uint8 frames (conv1 weight gradient)

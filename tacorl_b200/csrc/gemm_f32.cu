@@ -183,21 +183,39 @@ int gemm_f32(const GemmArgs& g, float* ws, size_t ws_bytes, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------
-// column sums (bias gradients): out[n] (+)= sum_m X[m][n].  One CTA per 32 columns.
+// column sums (bias gradients): out[n] (+)= sum_m X[m][n].  One CTA of 32 x R threads per 32 columns.
+template <int R>
 __global__ void colsum_kernel(int M, int N, const float* __restrict__ X, long long ldx,
                               float* __restrict__ out, int accumulate) {
-  __shared__ float red[8][33];
+  __shared__ float red[R][33];
   const int n = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
   if (n < N)
-    for (int m = threadIdx.y; m < M; m += 8) s += X[(long long)m * ldx + n];
+    for (int m = threadIdx.y; m < M; m += R) s += X[(long long)m * ldx + n];
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && n < N) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    for (int i = 0; i < R; ++i) t += red[i][threadIdx.x];
     out[n] = accumulate ? out[n] + t : t;
+  }
+}
+
+// N == 1: plain deterministic sum of a strided vector by one 1024-thread CTA (loss reductions)
+__global__ void vecsum_kernel(int M, const float* __restrict__ X, long long ldx, float* __restrict__ out, int accumulate) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int m = threadIdx.x; m < M; m += 1024) s += X[(long long)m * ldx];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = red[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) out[0] = accumulate ? out[0] + t : t;
   }
 }
 
@@ -222,7 +240,9 @@ __global__ void colsum_slab_kernel(int M, int N, const float* __restrict__ X, lo
 
 int colsum_f32(int M, int N, const float* X, long long ldx, float* out, int accumulate, cudaStream_t st) {
   if (N == 0) return 0;
-  colsum_kernel<<<cdiv(N, 32), dim3(32, 8), 0, st>>>(M, N, X, ldx, out, accumulate);
+  if (N == 1) vecsum_kernel<<<1, 1024, 0, st>>>(M, X, ldx, out, accumulate);
+  else if (M >= 256) colsum_kernel<32><<<cdiv(N, 32), dim3(32, 32), 0, st>>>(M, N, X, ldx, out, accumulate);
+  else colsum_kernel<8><<<cdiv(N, 32), dim3(32, 8), 0, st>>>(M, N, X, ldx, out, accumulate);
   TACORL_LAUNCH_CHECK();
   return 0;
 }

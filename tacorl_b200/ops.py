@@ -150,22 +150,27 @@ class LMPEncoderFn(Function):
             smax = torch.empty(N, 64, device=dev)
             ssum = torch.empty(N, 64, device=dev)
             h4 = torch.empty(N, hidden, device=dev)
+            # bf16 path: keep conv1's space-to-depth input so the backward pass does not rebuild it from the frames
+            xs = (torch.empty(N, H1 + 1, W1 + 1, 64, device=dev, dtype=torch.bfloat16)
+                  if _STATE["prec"] == L.PREC_BF16 else None)
         else:
-            y1 = y2 = y3 = feat = smax = ssum = h4 = None
+            y1 = y2 = y3 = feat = smax = ssum = h4 = xs = None
         nbytes = L.query("tacorl_lmp_encoder_ws_bytes", N, H, W, hidden, latent, 0)
         ws = L.workspace(nbytes, dev)
         ctx.prec = _STATE["prec"]
         L.call("tacorl_lmp_encoder_fwd", L.ptr_any(x), *ctx.xnorm, N, H, W, L.ptr_array(params), hidden, latent, L.ptr_any(y1),
-               L.ptr_any(y2), L.ptr(y3), L.ptr(feat), L.ptr(smax), L.ptr(ssum), L.ptr(h4), L.ptr(emb),
+               L.ptr_any(y2), L.ptr(y3), L.ptr(feat), L.ptr(smax), L.ptr(ssum), L.ptr(h4), L.ptr(emb), L.ptr_any(xs),
                ctypes.c_void_p(ws.data_ptr()), ws.numel(), _STATE["prec"], L.stream())
         if save:
-            ctx.save_for_backward(x, y1, y2, y3, feat, smax, ssum, h4, *params)
+            ctx.has_xs = xs is not None
+            ctx.save_for_backward(x, y1, y2, y3, feat, smax, ssum, h4, *((xs,) if xs is not None else ()), *params)
         ctx.dims = (N, H, W, hidden, latent)
         return emb
 
     @staticmethod
     def backward(ctx, d_emb):
         x, y1, y2, y3, feat, smax, ssum, h4, *params = ctx.saved_tensors
+        xs = params.pop(0) if ctx.has_xs else None
         N, H, W, hidden, latent = ctx.dims
         grads = [torch.empty_like(p) for p in params]
         nbytes = L.query("tacorl_lmp_encoder_ws_bytes", N, H, W, hidden, latent, 1)
@@ -173,7 +178,7 @@ class LMPEncoderFn(Function):
         d_emb = _c(d_emb)
         L.call("tacorl_lmp_encoder_bwd", L.ptr_any(x), *ctx.xnorm, N, H, W, L.ptr_array(params), hidden, latent, L.ptr_any(y1),
                L.ptr_any(y2), L.ptr(y3), L.ptr(feat), L.ptr(smax), L.ptr(ssum), L.ptr(h4), L.ptr(d_emb),
-               L.ptr_array(grads), 0, ctypes.c_void_p(ws.data_ptr()), ws.numel(), ctx.prec, L.stream())
+               L.ptr_array(grads), 0, L.ptr_any(xs), ctypes.c_void_p(ws.data_ptr()), ws.numel(), ctx.prec, L.stream())
         return (None, None, None, *grads)
 
 
