@@ -50,6 +50,13 @@ unsigned long long tacorl_launch_count(void);
 int tacorl_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, long long lda,
                 const float* B, long long ldb, float beta, float* C, long long ldc, const float* bias, int act,
                 float* Cpre, long long ldpre, void* ws, size_t ws_bytes, int prec, void* stream);
+/* Same, with optional dense bf16 copies of the operands as stored (A_bf16: rows x cols of A with pitch = cols, likewise
+ * B_bf16).  PREC_BF16 uses them instead of staging a cast of the fp32 operand each call: the weights' copies are kept
+ * current by tacorl_adam_step (shadow_bf16).  Ignored for PREC_F32 or when the pitch is not a multiple of 8. */
+int tacorl_gemm_ex(int transA, int transB, int M, int N, int K, float alpha, const float* A, long long lda,
+                   const float* B, long long ldb, float beta, float* C, long long ldc, const float* bias, int act,
+                   float* Cpre, long long ldpre, const void* A_bf16, const void* B_bf16, void* ws, size_t ws_bytes,
+                   int prec, void* stream);
 /* out[n] (+)= sum_m X[m*ldx+n]  (bias gradients) */
 int tacorl_colsum(int M, int N, const float* X, long long ldx, float* out, int accumulate, void* stream);
 /* dZ = dY * act'(.)   relu: pass the post-activation, silu: pass the pre-activation */
@@ -101,14 +108,14 @@ int tacorl_conv_tc_debug(int op, const float* in0, const float* in1, const float
 size_t tacorl_rnn_layer_ws_bytes(int T, int B, int I, int H);
 int tacorl_rnn_layer_fwd(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
                          const float* w_hh, const float* b_ih, const float* b_hh, const float* h0,
-                         int reverse, int n_steps, float* out, long long ldo, void* ws, size_t ws_bytes,
-                         int prec, void* stream);
+                         int reverse, int n_steps, float* out, long long ldo, const void* w_ih_bf16,
+                         const void* w_hh_bf16, void* ws, size_t ws_bytes, int prec, void* stream);
 int tacorl_rnn_layer_bwd(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
                          const float* w_hh, const float* h0, int reverse, int n_steps, const float* out,
                          long long ldo, float* dout, long long lddo, const float* dhn, float* dx,
                          long long lddx, int dx_accumulate, float* dw_ih, float* dw_hh, float* db_ih,
-                         float* db_hh, int accumulate, float* dh0, void* ws, size_t ws_bytes, int prec,
-                         void* stream);
+                         float* db_hh, int accumulate, float* dh0, const void* w_ih_bf16, void* ws, size_t ws_bytes,
+                         int prec, void* stream);
 
 /* ---- action decoder losses: action_decoder_logistic.py:184-235 (_logistic_loss), :114-133 (_loss),
  * :238-266 (_sample).  logits row = [prob A*10 | mean A*10 | log_scale A*10 | gripper 2].
@@ -188,7 +195,7 @@ int tacorl_cql_actor_loss(int mode, int B, const float* log_pi, const float* a, 
  * call increments and reads (so a captured CUDA graph replays with the right bias correction). */
 int tacorl_adam_step(long long n, float* p, const float* g, float* m, float* v, float lr, float beta1,
                      float beta2, float eps, int step, int* step_dev, float grad_scale, const float* sqnorm,
-                     float max_norm, void* stream);
+                     float max_norm, void* shadow_bf16, void* stream);
 int tacorl_polyak_update(long long n, float* target, const float* source, float tau, void* stream);
 int tacorl_sqnorm(long long n, const float* x, float* out, float* ws, void* stream);
 

@@ -22,6 +22,8 @@ _vp, _i, _ll, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes
 # name -> argtypes (restype int unless listed in _RESTYPES)
 _SIGS = {
     "tacorl_gemm": [_i, _i, _i, _i, _i, _f, _vp, _ll, _vp, _ll, _f, _vp, _ll, _vp, _i, _vp, _ll, _vp, _sz, _i, _vp],
+    "tacorl_gemm_ex": [_i, _i, _i, _i, _i, _f, _vp, _ll, _vp, _ll, _f, _vp, _ll, _vp, _i, _vp, _ll, _vp, _vp, _vp, _sz, _i,
+                       _vp],
     "tacorl_colsum": [_i, _i, _vp, _ll, _vp, _i, _vp],
     "tacorl_act_bwd": [_i, _ll, _vp, _vp, _vp, _vp],
     "tacorl_scale": [_ll, _vp, _vp, _f, _vp, _vp],
@@ -32,9 +34,10 @@ _SIGS = {
                                _vp, _vp, _sz, _i, _vp],
     "tacorl_conv_tc_debug": [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp],
     "tacorl_rnn_layer_ws_bytes": [_i, _i, _i, _i],
-    "tacorl_rnn_layer_fwd": [_i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _ll, _vp, _sz, _i, _vp],
+    "tacorl_rnn_layer_fwd": [_i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _ll, _vp, _vp, _vp, _sz, _i,
+                             _vp],
     "tacorl_rnn_layer_bwd": [_i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp, _i, _i, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _i,
-                             _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _i, _vp],
+                             _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _vp],
     "tacorl_dlm_nll": [_i, _i, _vp, _ll, _vp, _ll, _i, _f, _f, _f, _vp, _vp, _vp, _ll, _vp],
     "tacorl_dlm_sample": [_i, _i, _vp, _ll, _vp, _vp, _vp, _ll, _f, _f, _vp, _vp, _vp, _vp],
     "tacorl_gauss_head_fwd": [_i, _i, _vp, _vp, _vp, _vp],
@@ -57,7 +60,7 @@ _SIGS = {
     "tacorl_cql_critic_loss": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _i,
                                _vp, _vp, _vp, _vp, _vp],
     "tacorl_cql_actor_loss": [_i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp],
-    "tacorl_adam_step": [_ll, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _vp, _f, _vp, _f, _vp],
+    "tacorl_adam_step": [_ll, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _vp, _f, _vp, _f, _vp, _vp],
     "tacorl_polyak_update": [_ll, _vp, _vp, _f, _vp],
     "tacorl_sqnorm": [_ll, _vp, _vp, _vp, _vp],
     "tacorl_last_error": [],

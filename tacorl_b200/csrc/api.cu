@@ -13,15 +13,23 @@ int tacorl_abi_version(void) { return TACORL_B200_ABI_VERSION; }
 
 unsigned long long tacorl_launch_count(void) { return launch_count(); }
 
-int tacorl_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, long long lda,
-                const float* B, long long ldb, float beta, float* C, long long ldc, const float* bias, int act,
-                float* Cpre, long long ldpre, void* ws, size_t ws_bytes, int prec, void* stream) {
+int tacorl_gemm_ex(int transA, int transB, int M, int N, int K, float alpha, const float* A, long long lda,
+                   const float* B, long long ldb, float beta, float* C, long long ldc, const float* bias, int act,
+                   float* Cpre, long long ldpre, const void* A_bf16, const void* B_bf16, void* ws, size_t ws_bytes,
+                   int prec, void* stream) {
   TACORL_REQUIRE(prec == PREC_F32 || prec == PREC_BF16, "gemm: unknown precision %d", prec);
   GemmArgs g;
   g.transA = transA; g.transB = transB; g.M = M; g.N = N; g.K = K; g.alpha = alpha;
   g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.beta = beta; g.C = C; g.ldc = ldc; g.bias = bias;
-  g.act = act; g.Cpre = Cpre; g.ldpre = ldpre; g.split_k = 0;
+  g.act = act; g.Cpre = Cpre; g.ldpre = ldpre; g.split_k = 0; g.A_bf16 = A_bf16; g.B_bf16 = B_bf16;
   return gemm_any(prec, g, (float*)ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int tacorl_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, long long lda,
+                const float* B, long long ldb, float beta, float* C, long long ldc, const float* bias, int act,
+                float* Cpre, long long ldpre, void* ws, size_t ws_bytes, int prec, void* stream) {
+  return tacorl_gemm_ex(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, act, Cpre, ldpre, nullptr,
+                        nullptr, ws, ws_bytes, prec, stream);
 }
 
 int tacorl_colsum(int M, int N, const float* X, long long ldx, float* out, int accumulate, void* stream) {

@@ -52,6 +52,8 @@ struct GemmArgs {
   int act = ACT_NONE;
   float* Cpre = nullptr; long long ldpre = 0;   // optional pre-activation output
   int split_k = 1;              // >1: partials in ws, deterministic reduce
+  // optional dense bf16 copies of A / B as stored (pitch = stored column count); used by the tensor-core path
+  const void* A_bf16 = nullptr; const void* B_bf16 = nullptr;
 };
 
 // fp32 SIMT GEMM (parity path).  ws is only needed when split_k > 1 (split_k*M*N floats).

@@ -807,14 +807,17 @@ int gemm_tc_from_f32(const GemmArgs& g, float* ws, size_t ws_bytes, cudaStream_t
   const long long a_rows = g.transA ? g.K : g.M, a_cols = g.transA ? g.M : g.K;
   const long long b_rows = g.transB ? g.N : g.K, b_cols = g.transB ? g.K : g.N;
   const long long lda = (a_cols + 7) & ~7LL, ldb = (b_cols + 7) & ~7LL;
+  // caller-maintained bf16 copies (dense, pitch = column count) replace the staging cast when TMA can read them
+  const bool a_ready = g.A_bf16 && lda == a_cols && ((uintptr_t)g.A_bf16 & 15) == 0;
+  const bool b_ready = g.B_bf16 && ldb == b_cols && ((uintptr_t)g.B_bf16 & 15) == 0;
   Arena ar(ws, ws_bytes);
-  __nv_bfloat16* Ab = ar.take<__nv_bfloat16>((size_t)a_rows * lda);
-  __nv_bfloat16* Bb = ar.take<__nv_bfloat16>((size_t)b_rows * ldb);
+  const __nv_bfloat16* Ab = a_ready ? (const __nv_bfloat16*)g.A_bf16 : ar.take<__nv_bfloat16>((size_t)a_rows * lda);
+  const __nv_bfloat16* Bb = b_ready ? (const __nv_bfloat16*)g.B_bf16 : ar.take<__nv_bfloat16>((size_t)b_rows * ldb);
   TACORL_REQUIRE(Ab && Bb, "gemm_tc: workspace too small for bf16 staging (%lld + %lld elements)", a_rows * lda,
                  b_rows * ldb);
   int rc;
-  if ((rc = cast_bf16_2d(g.A, g.lda, a_rows, (int)a_cols, Ab, lda, st))) return rc;
-  if ((rc = cast_bf16_2d(g.B, g.ldb, b_rows, (int)b_cols, Bb, ldb, st))) return rc;
+  if (!a_ready && (rc = cast_bf16_2d(g.A, g.lda, a_rows, (int)a_cols, (void*)Ab, lda, st))) return rc;
+  if (!b_ready && (rc = cast_bf16_2d(g.B, g.ldb, b_rows, (int)b_cols, (void*)Bb, ldb, st))) return rc;
   TcArgs e;
   e.alpha = g.alpha; e.beta = g.beta; e.C = g.C; e.ldc = g.ldc; e.bias = g.bias; e.act = g.act; e.Cpre = g.Cpre;
   e.ldpre = g.ldpre; e.split_k = g.split_k;

@@ -5,6 +5,7 @@
 // modules/cql/cql_offline_lightning.py:553-574; clip_grad_norm_ at :522-537;
 // soft_update_from_to at :229-232.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include "internal.h"
 #include "../../include/tacorl_b200.h"
 
@@ -19,7 +20,8 @@ constexpr int kOptBlocks = 148 * 4;
 __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g,
                             float* __restrict__ m, float* __restrict__ v, float lr, float b1, float b2,
                             float eps, float bc1, float bc2_sqrt, float grad_scale,
-                            const float* __restrict__ sqnorm, float max_norm, const int* __restrict__ step_dev) {
+                            const float* __restrict__ sqnorm, float max_norm, const int* __restrict__ step_dev,
+                            __nv_bfloat16* __restrict__ shadow) {
   if (step_dev) {   // CUDA-graph friendly: bias corrections from a device-resident step counter
     const float t = (float)(*step_dev);
     bc1 = 1.f - powf(b1, t);
@@ -44,13 +46,20 @@ __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __r
     ADAMC(x) ADAMC(y) ADAMC(z) ADAMC(w)
 #undef ADAMC
     p4[i] = pp; m4[i] = mm; v4[i] = vv;
+    if (shadow) {     // bf16 copy of the updated parameters: the tensor-core operands of the next step
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
+      reinterpret_cast<uint2*>(shadow)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo),
+                                                        *reinterpret_cast<const uint32_t*>(&hi));
+    }
   }
   for (long long i = (n4 << 2) + tid; i < n; i += nth) {
     const float gx = g[i] * gs;
     const float mm = b1 * m[i] + (1.f - b1) * gx;
     const float vv = b2 * v[i] + (1.f - b2) * gx * gx;
     m[i] = mm; v[i] = vv;
-    p[i] -= step * mm / (sqrtf(vv) / bc2_sqrt + eps);
+    const float pn = p[i] - step * mm / (sqrtf(vv) / bc2_sqrt + eps);
+    p[i] = pn;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pn);
   }
 }
 
@@ -106,7 +115,7 @@ extern "C" {
 
 int tacorl_adam_step(long long n, float* p, const float* g, float* m, float* v, float lr, float beta1,
                      float beta2, float eps, int step, int* step_dev, float grad_scale, const float* sqnorm,
-                     float max_norm, void* stream) {
+                     float max_norm, void* shadow_bf16, void* stream) {
   if (n == 0) return 0;
   TACORL_REQUIRE(p && g && m && v && (step >= 1 || step_dev), "adam_step: bad arguments");
   if (step_dev) {
@@ -115,12 +124,14 @@ int tacorl_adam_step(long long n, float* p, const float* g, float* m, float* v, 
     if (step < 1) step = 1;
   }
   TACORL_REQUIRE(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
-                     ((uintptr_t)v % 16 == 0), "adam_step: buffers must be 16-byte aligned");
+                     ((uintptr_t)v % 16 == 0) && ((uintptr_t)shadow_bf16 % 8 == 0),
+                 "adam_step: buffers must be 16-byte aligned");
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
   int blocks = (int)min((long long)kOptBlocks, (n / 4 + 255) / 256 + 1);
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(n, p, g, m, v, lr, beta1, beta2, eps, bc1, sqrtf(bc2),
-                                                       grad_scale, sqnorm, max_norm, step_dev);
+                                                       grad_scale, sqnorm, max_norm, step_dev,
+                                                       (__nv_bfloat16*)shadow_bf16);
   TACORL_LAUNCH_CHECK();
   return 0;
 }

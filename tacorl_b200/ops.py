@@ -47,16 +47,62 @@ def _ld(t):
     return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
 
 
-def gemm(A, B, C, transA=False, transB=False, alpha=1.0, beta=0.0, bias=None, act=L.ACT_NONE, Cpre=None):
-    """C = act(alpha * op(A) op(B) + beta*C + bias); A, B, C are row-major 2-D (possibly strided rows)."""
+# ---- bf16 shadow copies of optimiser-owned parameters.  tacorl_b200.optim.FlatAdam keeps a bf16 twin of its flat fp32
+# parameter buffer (written by the Adam kernel itself); the tensor-core ops read weights from it instead of casting the
+# fp32 weights on every call.  A parameter's slice of the twin is (re)cast lazily when the parameter's or the flat
+# buffer's torch version counter moved (load_state_dict, broadcast, manual init): raw kernel writes do not bump them.
+_SHADOW_OWNERS = []
+
+
+def register_shadow_owner(owner):
+    """owner: object with .pbuf.flat (fp32), .shadow (bf16, same numel), ._pver (dict) and ._flat_version."""
+    _SHADOW_OWNERS.append(owner)
+
+
+def refresh_shadows():
+    """Re-validate every registered parameter (used before replaying a captured step)."""
+    for o in _SHADOW_OWNERS:
+        for p in o.param_groups[0]["params"]:
+            shadow_of(p)
+
+
+def shadow_of(t):
+    """bf16 twin (flat view) of a whole fp32 parameter that lives inside a registered flat buffer, else None."""
+    if _STATE["prec"] != L.PREC_BF16 or t is None or not t.is_cuda or not t.is_contiguous():
+        return None
+    ptr = t.data_ptr()
+    for o in _SHADOW_OWNERS:
+        flat = o.pbuf.flat
+        base = flat.data_ptr()
+        if base <= ptr < base + flat.numel() * 4 and flat.device == t.device:
+            n = o._pnumel.get(ptr)
+            if n != t.numel():
+                return None                       # not a whole registered parameter
+            if o._flat_version != flat._version:  # the flat buffer itself was edited (e.g. broadcast): all stale
+                o._pver.clear()
+                o._flat_version = flat._version
+            off = (ptr - base) // 4
+            sh = o.shadow[off:off + n]
+            if o._pver.get(ptr) != t._version:
+                with torch.no_grad():
+                    sh.copy_(t.detach().reshape(-1))
+                o._pver[ptr] = t._version
+            return sh
+    return None
+
+
+def gemm(A, B, C, transA=False, transB=False, alpha=1.0, beta=0.0, bias=None, act=L.ACT_NONE, Cpre=None, A_bf16=None,
+         B_bf16=None):
+    """C = act(alpha * op(A) op(B) + beta*C + bias); A, B, C are row-major 2-D (possibly strided rows).
+    A_bf16 / B_bf16: optional dense bf16 copies of A / B (see shadow_of)."""
     M, N = C.shape
     K = A.shape[0] if transA else A.shape[1]
     assert (A.shape[1] if transA else A.shape[0]) == M, (A.shape, C.shape, transA)
     assert (B.shape[0] if transB else B.shape[1]) == N and (B.shape[1] if transB else B.shape[0]) == K
     ws = L.workspace(_GEMM_WS, C.device)
-    L.call("tacorl_gemm", int(transA), int(transB), M, N, K, float(alpha), L.ptr(A), _ld(A), L.ptr(B), _ld(B),
+    L.call("tacorl_gemm_ex", int(transA), int(transB), M, N, K, float(alpha), L.ptr(A), _ld(A), L.ptr(B), _ld(B),
            float(beta), L.ptr(C), _ld(C), L.ptr(bias), int(act), L.ptr(Cpre), _ld(Cpre) if Cpre is not None else 0,
-           ctypes.c_void_p(ws.data_ptr()), ws.numel(),
+           L.ptr_any(A_bf16), L.ptr_any(B_bf16), ctypes.c_void_p(ws.data_ptr()), ws.numel(),
            _STATE["prec"], L.stream())
     return C
 
@@ -86,7 +132,7 @@ class LinearFn(Function):
         Wc = _c(W)
         out = torch.empty(x2.shape[0], W.shape[0], device=x.device, dtype=torch.float32)
         pre = torch.empty_like(out) if act == L.ACT_SILU else None
-        gemm(x2, Wc, out, transB=True, bias=b, act=act, Cpre=pre)
+        gemm(x2, Wc, out, transB=True, bias=b, act=act, Cpre=pre, B_bf16=shadow_of(Wc))
         ctx.act = act
         ctx.has_bias = b is not None
         ctx.xshape = x.shape
@@ -105,7 +151,7 @@ class LinearFn(Function):
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x2)
-            gemm(dz, W, dx)
+            gemm(dz, W, dx, B_bf16=shadow_of(W))
             dx = dx.view(ctx.xshape)
         if ctx.needs_input_grad[1]:
             dW = torch.empty_like(W)
@@ -218,6 +264,7 @@ class ReluRNNFn(Function):
                 ws = L.workspace(nbytes, dev, tag)
                 L.call("tacorl_rnn_layer_fwd", T, B, Il, H, L.ptr(inp), Il, L.ptr(w_ih), L.ptr(w_hh), L.ptr(b_ih),
                        L.ptr(b_hh), L.ptr(h0_ld), d, n_steps, _off(out, d * H), D * H,
+                       L.ptr_any(shadow_of(w_ih)), L.ptr_any(shadow_of(w_hh)),
                        ctypes.c_void_p(ws.data_ptr()), ws.numel(), _STATE["prec"], L.stream())
 
             if D == 2:
@@ -278,7 +325,8 @@ class ReluRNNFn(Function):
                 L.call("tacorl_rnn_layer_bwd", T, B, Il, H, L.ptr(inp), Il, L.ptr(w_ih), L.ptr(w_hh), L.ptr(h0_ld),
                        d, n_steps, _off(outs[l], d * H), D * H, _off(dbuf, d * H), D * H, L.ptr(dhn_ld),
                        L.ptr(dx_buf), Il, 0, L.ptr(g[0]), L.ptr(g[1]), L.ptr(g[2]), L.ptr(g[3]), 0,
-                       L.ptr(dh0_ld), ctypes.c_void_p(ws.data_ptr()), ws.numel(), _STATE["prec"], L.stream())
+                       L.ptr(dh0_ld), L.ptr_any(shadow_of(w_ih)), ctypes.c_void_p(ws.data_ptr()), ws.numel(),
+                       _STATE["prec"], L.stream())
                 wgrads[k:k + 4] = g
 
             if D == 2:
@@ -583,11 +631,13 @@ def cql_alpha_loss(log_pi, log_alpha, target_entropy):
 
 # --------------------------------------------------------------------------------------- optimiser kernels
 def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, sqnorm=None, max_norm=0.0,
-              step_dev=None):
-    """step_dev: optional int32 device tensor holding the step count (incremented by the call)."""
+              step_dev=None, shadow=None):
+    """step_dev: optional int32 device tensor holding the step count (incremented by the call).
+    shadow: optional bf16 tensor of p.numel() elements that receives a bf16 copy of the updated parameters."""
     sd = ctypes.c_void_p(step_dev.data_ptr()) if step_dev is not None else None
     L.call("tacorl_adam_step", p.numel(), L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), float(lr), float(beta1),
-           float(beta2), float(eps), int(step), sd, float(grad_scale), L.ptr(sqnorm), float(max_norm), L.stream())
+           float(beta2), float(eps), int(step), sd, float(grad_scale), L.ptr(sqnorm), float(max_norm),
+           L.ptr_any(shadow), L.stream())
 
 
 def polyak_update(target, source, tau):

@@ -56,6 +56,16 @@ class FlatAdam(torch.optim.Optimizer):
         # device-resident step counter: the bias correction stays right when the step is replayed from a CUDA graph
         self._step_dev = (torch.zeros(1, dtype=torch.int32, device=self.pbuf.flat.device)
                           if self.pbuf.flat.is_cuda else None)
+        # bf16 twin of the parameters for the tensor-core operands: written by the Adam kernel; ops.shadow_of() re-casts a
+        # parameter's slice lazily when a torch-side in-place edit (load_state_dict, broadcast, manual init) moved the
+        # parameter's or the flat buffer's version counter
+        self.shadow = None
+        self._pver = {}
+        self._pnumel = {p.data_ptr(): p.numel() for p in ps}
+        self._flat_version = self.pbuf.flat._version
+        if self.pbuf.flat.is_cuda:
+            self.shadow = torch.zeros(self.pbuf.numel, device=self.pbuf.flat.device, dtype=torch.bfloat16)
+            ops.register_shadow_owner(self)
 
     @property
     def flat_params(self):
@@ -131,7 +141,8 @@ class FlatAdam(torch.optim.Optimizer):
             sq = ops.sqnorm(self.flat_grad, self._sqnorm)
         ops.adam_step(self.pbuf.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], self.step_count,
                       g["betas"][0], g["betas"][1], g["eps"], self.grad_scale, sq,
-                      float(self.max_grad_norm) if self.max_grad_norm is not None else 0.0, self._step_dev)
+                      float(self.max_grad_norm) if self.max_grad_norm is not None else 0.0, self._step_dev,
+                      self.shadow)
         return loss
 
     def set_grad(self, flat_values):

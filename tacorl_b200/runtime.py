@@ -70,6 +70,8 @@ class GraphedTrainStep:
             _copy_into(self.static, self._staging)
             self._consumed.record(main)
             self._staged = False
+        from . import ops
+        ops.refresh_shadows()      # parameters edited through torch since the last replay (checkpoint load, ...)
         self.graph.replay()
         self.replays += 1
         return self.out

@@ -3,7 +3,7 @@ import pytest
 import torch
 
 from oracle import synth as S
-from tests.gpu_util import DEV, build_play_lmp, to_dev
+from tests.gpu_util import DEV, build_play_lmp, rel_err, to_dev
 
 pytestmark = pytest.mark.gpu
 
@@ -38,3 +38,35 @@ def test_graphed_step_trains_and_counts_adam_steps():
     torch.cuda.synchronize()
     assert torch.equal(g.static["actions"].cpu(), host["actions"])
     assert torch.isfinite(torch.tensor(l1))
+
+
+def test_bf16_shadow_weights_follow_torch_side_edits():
+    """The Adam kernel keeps a bf16 twin of the parameters; an in-place torch edit of a parameter (what load_state_dict
+    does) must be picked up by the next tensor-core op instead of reading the stale twin."""
+    import torch
+    from tacorl_b200 import ops
+    from tacorl_b200.optim import FlatAdam
+    ops.set_precision("bf16")
+    try:
+        g = torch.Generator().manual_seed(0)
+        W = torch.nn.Parameter(torch.randn(512, 1024, generator=g).to(DEV))
+        x = torch.randn(256, 1024, generator=g).to(DEV)
+        opt = FlatAdam([W], lr=1e-2)
+        sh = ops.shadow_of(W)
+        assert sh is not None and sh.dtype == torch.bfloat16
+        assert torch.equal(sh.view(512, 1024).float(), W.data.bfloat16().float())
+        y0 = ops.linear(x, W)
+        with torch.no_grad():
+            W.mul_(2.0)                                   # torch-side edit: bumps the flat buffer's version
+        y1 = ops.linear(x, W)
+        assert rel_err(y1, 2.0 * y0) < 1e-6
+        y1.sum().backward()
+        opt.step()                                        # kernel rewrites parameters and twin together
+        assert torch.equal(ops.shadow_of(W).view(512, 1024).float(), W.data.bfloat16().float())
+        want = x.bfloat16().double() @ W.data.bfloat16().double().t()
+        assert rel_err(ops.linear(x, W), want) < 1e-5
+        with torch.no_grad():
+            opt.flat_params.mul_(0.5)                     # edit through the flat buffer (what a broadcast does)
+        assert rel_err(ops.linear(x, W), 0.5 * want) < 1e-5
+    finally:
+        ops.set_precision("fp32")
