@@ -45,24 +45,44 @@ sgemm_kernel(GemmArgs g, int k_chunk, float* __restrict__ partial) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
+  constexpr int LA = (BM * BK + NT - 1) / NT, LB = (BN * BK + NT - 1) / NT;
   for (int k0 = kbeg; k0 < kend; k0 += BK) {
-    for (int e = tid; e < BM * BK; e += NT) {
+    // all global loads of the K tile are issued before the first shared-memory store (one memory latency per
+    // tile instead of one per element)
+    float ra[LA], rb[LB];
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      const int e = tid + i * NT;
       int m, k;
       if (g.transA) { m = e % BM; k = e / BM; } else { k = e % BK; m = e / BK; }
       const int gm = m0 + m, gk = k0 + k;
-      float v = 0.f;
-      if (gm < g.M && gk < kend)
-        v = g.transA ? __ldg(g.A + (long long)gk * g.lda + gm) : __ldg(g.A + (long long)gm * g.lda + gk);
-      As[k][m] = v;
+      const bool ok = e < BM * BK && gm < g.M && gk < kend;
+      const long long off = g.transA ? (long long)gk * g.lda + gm : (long long)gm * g.lda + gk;
+      ra[i] = ok ? __ldg(g.A + off) : 0.f;
     }
-    for (int e = tid; e < BN * BK; e += NT) {
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      const int e = tid + i * NT;
       int n, k;
       if (g.transB) { k = e % BK; n = e / BK; } else { n = e % BN; k = e / BN; }
       const int gn = n0 + n, gk = k0 + k;
-      float v = 0.f;
-      if (gn < g.N && gk < kend)
-        v = g.transB ? __ldg(g.B + (long long)gn * g.ldb + gk) : __ldg(g.B + (long long)gk * g.ldb + gn);
-      Bs[k][n] = v;
+      const bool ok = e < BN * BK && gn < g.N && gk < kend;
+      const long long off = g.transB ? (long long)gn * g.ldb + gk : (long long)gk * g.ldb + gn;
+      rb[i] = ok ? __ldg(g.B + off) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      const int e = tid + i * NT;
+      int m, k;
+      if (g.transA) { m = e % BM; k = e / BM; } else { k = e % BK; m = e / BK; }
+      if (e < BM * BK) As[k][m] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      const int e = tid + i * NT;
+      int n, k;
+      if (g.transB) { k = e % BK; n = e / BK; } else { n = e % BN; k = e / BN; }
+      if (e < BN * BK) Bs[k][n] = rb[i];
     }
     __syncthreads();
 #pragma unroll
@@ -152,15 +172,17 @@ int gemm_f32(const GemmArgs& g, float* ws, size_t ws_bytes, cudaStream_t st) {
   else if (g.N <= 64) { BM = 128; BN = 64; }
   else { BM = 128; BN = 128; }
   long long ctas = (long long)cdiv(g.M, BM) * cdiv(g.N, BN);
+  bool small = false;
   if (ctas < 148) {
     BM = 64; BN = 64;
     ctas = (long long)cdiv(g.M, BM) * cdiv(g.N, BN);
+    small = true;   // latency-bound: deep K tiles (64 per iteration, every load of a tile in flight at once)
   }
   int splits = g.split_k;
   if (splits <= 0) {  // auto: fill ~2 waves of the 148 SMs when the output grid is small
     splits = 1;
-    if (ws && ctas < 148 && g.K >= 8 * BK) {
-      splits = (int)min((long long)cdiv(296, ctas), (long long)(g.K / (4 * BK)));
+    if (ws && small && g.K >= 128) {          // one or two 64-deep iterations per CTA
+      splits = (int)min((long long)cdiv(296, ctas), (long long)cdiv(g.K, 64));
       if (splits < 1) splits = 1;
     }
   }
@@ -179,6 +201,7 @@ int gemm_f32(const GemmArgs& g, float* ws, size_t ws_bytes, cudaStream_t st) {
   if (BM == 256) return launch_sgemm<256, 32, BK, 8, 4>(g, splits, ws, st);
   if (BM == 128 && BN == 64) return launch_sgemm<128, 64, BK, 8, 4>(g, splits, ws, st);
   if (BM == 128) return launch_sgemm<128, 128, BK, 8, 8>(g, splits, ws, st);
+  if (small) return launch_sgemm<64, 64, 64, 4, 4>(g, splits, ws, st);
   return launch_sgemm<64, 64, BK, 4, 4>(g, splits, ws, st);
 }
 
