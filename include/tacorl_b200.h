@@ -106,6 +106,14 @@ int tacorl_conv_tc_debug(int op, const float* in0, const float* in1, const float
  * bwd: `dout` (dL/dout) is overwritten with dL/dpre; dx rows outside the active range are zeroed
  * unless dx_accumulate.  Any of dx/dw_ih/dw_hh/db_ih/db_hh/dh0/dhn may be NULL. */
 size_t tacorl_rnn_layer_ws_bytes(int T, int B, int I, int H);
+/* bf16 path: steps 1..n_steps-1 of a layer run in ONE persistent launch (weights resident in shared memory, steps
+ * chained by device-side arrival counters); set TACORL_RNN_SEQ=0 to launch step by step instead (bit-identical
+ * results).  A persistent launch occupies 120 of the 148 SMs and spin-waits on its peer clusters; the library chains
+ * such launches through an event so that two of them never run concurrently, whatever streams they are on.  Returns how many spin-waits ever gave up (0 in a healthy process;
+ * synchronises the device). */
+unsigned tacorl_rnn_seq_timeouts(void);
+/* switch the persistent launch on/off at run time; returns the previous setting */
+int tacorl_rnn_seq_enable(int on);
 int tacorl_rnn_layer_fwd(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
                          const float* w_hh, const float* b_ih, const float* b_hh, const float* h0,
                          int reverse, int n_steps, float* out, long long ldo, const void* w_ih_bf16,

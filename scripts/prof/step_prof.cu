@@ -88,5 +88,32 @@ int main(int argc, char** argv) {
     }
 #endif
   }
+  {  // persistent recurrence: STEPS dependent steps in one launch
+    const int T = STEPS + 1;
+    __nv_bfloat16* hb; float* Cs; unsigned* flags;
+    cudaMalloc(&hb, (size_t)T * M * N * 2); cudaMalloc(&Cs, (size_t)T * M * N * 4); cudaMalloc(&flags, 256);
+    cudaMemset(hb, 0, (size_t)T * M * N * 2); cudaMemset(Cs, 0, (size_t)T * M * N * 4);
+    auto run = [&]() {
+      int rc = rnn_seq_tc(hb, T, W, K, M, N, K, 1, 1, STEPS, 1.f, Cs, N, (long long)M * N, nullptr, 0, 0, hb, ACT_RELU, flags, st);
+      if (rc) { printf("rnn_seq_tc rc=%d %s\n", rc, tacorl_last_error()); exit(1); }
+    };
+    run(); cudaStreamSynchronize(st);
+    for (int i = 0; i < 3; ++i) run();
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < 10; ++i) run();
+    cudaEventRecord(e1, st);
+    cudaStreamSynchronize(st);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    printf("persistent (M=%d): %.2f us per dependent step (%d steps per launch), timeouts %u\n", M, ms * 1000 / (10 * STEPS), STEPS,
+           rnn_seq_timeouts());
+#ifdef TACORL_STEP_PROFILE
+    long long h[16];
+    cudaMemcpyFromSymbol(h, g_seq_prof, sizeof(h));
+    const char* nm[] = {"issuer: step start", "flags ok", "tma issued", "first A stage landed", "mma issued+commit",
+                        "epi: mma done", "S stored", "cluster sync A", "dsmem summed + arrive B", "bf16 stored + fence",
+                        "bar + flag released"};
+    for (int i = 0; i < 11; ++i) printf("  %-26s t=%6lld cyc (+%lld)\n", nm[i], h[i] - h[0], i ? h[i] - h[i - 1] : 0);
+#endif
+  }
   return 0;
 }

@@ -66,10 +66,13 @@ _SIGS = {
     "tacorl_last_error": [],
     "tacorl_abi_version": [],
     "tacorl_launch_count": [],
+    "tacorl_rnn_seq_timeouts": [],
+    "tacorl_rnn_seq_enable": [_i],
 }
 _RESTYPES = {
     "tacorl_lmp_encoder_ws_bytes": _sz, "tacorl_rnn_layer_ws_bytes": _sz,
     "tacorl_last_error": ctypes.c_char_p, "tacorl_launch_count": ctypes.c_ulonglong,
+    "tacorl_rnn_seq_timeouts": ctypes.c_uint,
 }
 EXPORTED = tuple(_SIGS)
 

@@ -13,6 +13,10 @@ int tacorl_abi_version(void) { return TACORL_B200_ABI_VERSION; }
 
 unsigned long long tacorl_launch_count(void) { return launch_count(); }
 
+unsigned tacorl_rnn_seq_timeouts(void) { return rnn_seq_timeouts(); }
+
+int tacorl_rnn_seq_enable(int on) { const int was = rnn_seq_enabled() ? 1 : 0; rnn_seq_set_enabled(on); return was; }
+
 int tacorl_gemm_ex(int transA, int transB, int M, int N, int K, float alpha, const float* A, long long lda,
                    const float* B, long long ldb, float beta, float* C, long long ldc, const float* bias, int act,
                    float* Cpre, long long ldpre, const void* A_bf16, const void* B_bf16, void* ws, size_t ws_bytes,

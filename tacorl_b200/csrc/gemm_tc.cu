@@ -69,6 +69,15 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // SM100 shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -527,7 +536,7 @@ skinny_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int bi = e / NT4, n = (e - bi * NT4) * 4;
       const uint32_t addr = smem_u32(S + ((int)rank * per + (e < elems ? bi : 0)) * SP + (e < elems ? n : 0));
 #pragma unroll
-      for (int q = 0; q < RS_KS; ++q) part[i][q] = ld_dsmem_v4(addr, q);
+      for (int q = 0; q < RS_KS; ++q) part[i][q] = ld_dsmem_v4(addr, (q + rank) & (RS_KS - 1));   // staggered: 8 CTAs read 8 different peers
     }
 #pragma unroll
     for (int i = 0; i < RS_MAXE; ++i) {
@@ -581,6 +590,259 @@ skinny_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   RS_STAMP(10)
   RS_STAMP(11)
   RS_CTA_STAMP(1)
+}
+
+// ------------------------------------------------------------------------------------------ persistent recurrence
+// A whole sequence of dependent recurrent steps  C[tau] = epilogue(C[tau] + A[tau - dtau] . W^T)  in ONE launch of the
+// cluster split-K layout above: the CTA's weight slab (NT columns x K/RS_KS, <= 72 KB) is loaded once and stays in
+// shared memory, TMEM and the barriers are set up once, and a step only moves the (batch x K/RS_KS) slab of the
+// previous hidden state.  Steps are chained by per-tile arrival counters in global memory: the CTAs of N tile j bump
+// flags[j] (release, gpu scope) after their rows of step s are stored; a CTA starts step s + 1 once the tiles covering
+// ITS K slab have all RS_KS arrivals for step s (acquire) - no grid-wide barrier, no host involvement.
+// All clusters must be co-resident (checked on the host with cudaOccupancyMaxActiveClusters); a bounded spin marks
+// g_rnn_seq_timeouts instead of hanging if that assumption is ever violated.  Per-step arithmetic (operand tiles, summation
+// order, epilogue) is exactly skinny_cluster_kernel's, so both paths produce bit-identical results.
+struct SeqArgs {
+  int n_steps;                            // steps of this launch: s = 0 .. n_steps-1, output time tau = tau0 + s*dtau
+  int tau0, dtau;                         // A operand of step s = bf16 rows of time tau - dtau (3-D tensor map, z = time)
+  float beta;
+  float* C; long long ldc, c_ts;          // fp32 in (pre-activation / upstream gradient) and out; row pitch, time stride
+  const float* gate; long long ldgate, gate_ts;
+  __nv_bfloat16* Cb; long long cb_ts;     // dense bf16 copy of the output (row pitch N): the next step's A operand
+  int act;
+  unsigned* flags;                        // [tiles] arrival counters, zero before the launch
+};
+__device__ unsigned g_rnn_seq_timeouts = 0;
+#ifdef TACORL_STEP_PROFILE
+__device__ long long g_seq_prof[16];
+#define SQ_STAMP(i) if (step == 8 && blockIdx.x == 1 && blockIdx.y == 3) g_seq_prof[i] = clock64();
+#else
+#define SQ_STAMP(i)
+#endif
+//   // flag waits that gave up (never expected; read by tacorl_rnn_seq_timeouts)
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __cluster_dims__(RS_KS, 1, 1) __launch_bounds__(RS_THREADS, 1)
+rnn_seq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const SeqArgs sa,
+               int M, int Mpad, int N, int NT, int kb_per_cta) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t A_TILE = 128 * 128, W_BYTES = (uint32_t)NT * 128, W_STAGE = (W_BYTES + 1023) & ~1023u;
+  const int SP = NT + 4;
+  const int per = Mpad / RS_KS;
+  uint8_t* w_smem = smem;                                              // resident weight slab: kb x [NT][64] bf16
+  uint8_t* a_smem = smem + (size_t)kb_per_cta * W_STAGE;               // hidden-state slab of the current step
+  float* S = (float*)(a_smem + (size_t)kb_per_cta * A_TILE);           // partial accumulators, read by the peers
+  uint64_t* bars = (uint64_t*)((uint8_t*)S + (((size_t)((Mpad + 31) & ~31) * SP * 4 + 1023) & ~(size_t)1023));
+  uint32_t* tmem_slot = (uint32_t*)(bars + 10);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = blockIdx.x;
+  const int tile = blockIdx.y, n0 = tile * NT, tiles = gridDim.y;
+  const uint32_t tmem_cols = NT <= 32 ? 32 : (NT <= 64 ? 64 : (NT <= 128 ? 128 : 256));
+  const uint32_t done_bar = smem_u32(bars + 8), w_bar = smem_u32(bars + 9);
+
+  if (tid == RS_EPI) {
+    for (int s = 0; s < kb_per_cta; ++s) mbar_init(smem_u32(bars + s), 1);
+    mbar_init(done_bar, 1);
+    mbar_init(w_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == RS_EPI / 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int k_begin = (int)rank * kb_per_cta * TC_BK;
+
+  if (tid == RS_EPI) {                                                  // the weight slab, once
+    mbar_expect_tx(w_bar, (uint32_t)kb_per_cta * W_BYTES);
+    for (int s = 0; s < kb_per_cta; ++s)
+      tma_load_2d(smem_u32(w_smem + (size_t)s * W_STAGE), &tmW, k_begin + s * TC_BK, n0, w_bar);
+  }
+  // tiles whose columns intersect my K slab [k_begin, k_begin + kb*64)
+  const int j_lo = k_begin / NT, j_hi = min(tiles - 1, (k_begin + kb_per_cta * TC_BK - 1) / NT);
+  const int NT4 = NT >> 2, elems = per * NT4;
+  bool dead = false;                                                    // a flag wait timed out: stop waiting
+
+  for (int step = 0; step < sa.n_steps; ++step) {
+    const int tau = sa.tau0 + step * sa.dtau;
+    const uint32_t ph = (uint32_t)step & 1u;
+    float4 cold[RS_MAXE], gt[RS_MAXE];
+    if (warp == RS_EPI / 32) {
+      if (lane == 0) {
+        SQ_STAMP(0)
+        if (step == 0) mbar_wait(w_bar, 0);
+        else if (!dead) {
+          const unsigned want = (unsigned)(RS_KS * step);
+          for (int j = j_lo; j <= j_hi && !dead; ++j) {
+            unsigned spins = 0;
+            while (ld_acquire_gpu(sa.flags + j) < want) {
+              if (++spins > (1u << 21)) { dead = true; atomicAdd(&g_rnn_seq_timeouts, 1u); break; }
+            }
+          }
+        }
+        SQ_STAMP(1)
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        for (int s = 0; s < kb_per_cta; ++s) {
+          const uint32_t bar = smem_u32(bars + s);
+          mbar_expect_tx(bar, (uint32_t)Mpad * 128);
+          tma_load_3d(smem_u32(a_smem + (size_t)s * A_TILE), &tmA, k_begin + s * TC_BK, 0, tau - sa.dtau, bar);
+        }
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        SQ_STAMP(2)
+        for (int s = 0; s < kb_per_cta; ++s) {
+          mbar_wait(smem_u32(bars + s), ph);
+          tc_fence_after();
+          if (s == 0) { SQ_STAMP(3) }
+          const uint32_t a_src = smem_u32(a_smem + (size_t)s * A_TILE), w_src = smem_u32(w_smem + (size_t)s * W_STAGE);
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+            tc_mma_bf16(tmem_base, make_smem_desc(a_src + k * 32, 16, 1024), make_smem_desc(w_src + k * 32, 16, 1024), idesc,
+                        (s > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(done_bar);
+        SQ_STAMP(4)
+      }
+      __syncwarp();
+    } else {
+      // epilogue operands of this step do not depend on the recurrence: fetch them while the MMAs run
+      const float* Ct = sa.C + (long long)tau * sa.c_ts;
+      const float* Gt = sa.gate ? sa.gate + (long long)tau * sa.gate_ts : nullptr;
+      long long offc[RS_MAXE], offg[RS_MAXE];
+#pragma unroll
+      for (int i = 0; i < RS_MAXE; ++i) {
+        const int e = tid + i * RS_EPI;
+        const int bi = e / NT4, n = (e - bi * NT4) * 4, b = (int)rank * per + bi, col = n0 + n;
+        const bool ok = e < elems && b < M && col < N;
+        offc[i] = ok ? (long long)b * sa.ldc + col : 0;
+        offg[i] = ok ? (long long)b * sa.ldgate + col : 0;
+      }
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f), one = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+      for (int i = 0; i < RS_MAXE; ++i) cold[i] = sa.beta != 0.f ? *reinterpret_cast<const float4*>(Ct + offc[i]) : zero;
+#pragma unroll
+      for (int i = 0; i < RS_MAXE; ++i) gt[i] = Gt ? *reinterpret_cast<const float4*>(Gt + offg[i]) : one;
+      mbar_wait(done_bar, ph);
+      tc_fence_after();
+      if (tid == 0) { SQ_STAMP(5) }
+    }
+    if (step > 0) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");   // peers finished reading my previous S
+    if (warp < RS_EPI / 32) {
+      const int q = warp & 3;
+      if (q * 32 < Mpad) {
+        float* Srow = S + (q * 32 + lane) * SP;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {         // two TMEM loads in flight per wait
+          uint32_t r[2][16];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int c0 = (warp >> 2) * 16 + 64 * (2 * h + i);
+            if (c0 < NT) tc_ld16_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r[i]);
+          }
+          tc_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int c0 = (warp >> 2) * 16 + 64 * (2 * h + i);
+            if (c0 < NT) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                reinterpret_cast<float4*>(Srow + c0)[j] = make_float4(__uint_as_float(r[i][4 * j]), __uint_as_float(r[i][4 * j + 1]),
+                                                                      __uint_as_float(r[i][4 * j + 2]), __uint_as_float(r[i][4 * j + 3]));
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    if (tid == 0) { SQ_STAMP(6) }
+    cluster_sync_all();
+    tc_fence_after();
+    if (tid == 0) { SQ_STAMP(7) }
+    float4 acc[RS_MAXE];
+    if (warp < RS_EPI / 32) {
+      float4 part[RS_MAXE][RS_KS];
+#pragma unroll
+      for (int i = 0; i < RS_MAXE; ++i) {
+        const int e = tid + i * RS_EPI;
+        const int bi = e / NT4, n = (e - bi * NT4) * 4;
+        const uint32_t addr = smem_u32(S + ((int)rank * per + (e < elems ? bi : 0)) * SP + (e < elems ? n : 0));
+#pragma unroll
+        for (int q = 0; q < RS_KS; ++q) part[i][q] = ld_dsmem_v4(addr, (q + rank) & (RS_KS - 1));   // staggered: 8 CTAs read 8 different peers
+      }
+#pragma unroll
+      for (int i = 0; i < RS_MAXE; ++i) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < RS_KS; ++q) { v.x += part[i][q].x; v.y += part[i][q].y; v.z += part[i][q].z; v.w += part[i][q].w; }
+        acc[i] = v;
+      }
+      float dep = 0.f;
+#pragma unroll
+      for (int i = 0; i < RS_MAXE; ++i) dep += acc[i].x + acc[i].y + acc[i].z + acc[i].w;
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::"f"(dep) : "memory");
+      if (tid == 0) { SQ_STAMP(8) }
+      // epilogue: the bf16 copy (the next step's operand) first, then the arrival, then the fp32 store
+      float* Ct = sa.C + (long long)tau * sa.c_ts;
+      __nv_bfloat16* Bt = sa.Cb + (long long)tau * sa.cb_ts;
+      float4 outv[RS_MAXE];
+      bool okv[RS_MAXE];
+#pragma unroll
+      for (int i = 0; i < RS_MAXE; ++i) {
+        const int e = tid + i * RS_EPI;
+        const int bi = e / NT4, n = (e - bi * NT4) * 4, b = (int)rank * per + bi, col = n0 + n;
+        okv[i] = e < elems && b < M && col < N;
+        float v[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
+        const float c4[4] = {cold[i].x, cold[i].y, cold[i].z, cold[i].w};
+        const float g4[4] = {gt[i].x, gt[i].y, gt[i].z, gt[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[j] = fmaf(sa.beta, c4[j], v[j]);
+          if (sa.act == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+          if (g4[j] <= 0.f) v[j] = 0.f;
+        }
+        outv[i] = make_float4(v[0], v[1], v[2], v[3]);
+        if (okv[i]) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+          *reinterpret_cast<uint2*>(Bt + (long long)b * N + col) =
+              make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        }
+      }
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      if (tid == 0) { SQ_STAMP(9) }
+      asm volatile("bar.sync 1, %0;" ::"n"(RS_EPI) : "memory");
+      if (tid == 0) { __threadfence(); red_release_gpu_add(sa.flags + tile, 1u); SQ_STAMP(10) }
+#pragma unroll
+      for (int i = 0; i < RS_MAXE; ++i) {
+        const int e = tid + i * RS_EPI;
+        const int bi = e / NT4, n = (e - bi * NT4) * 4, b = (int)rank * per + bi, col = n0 + n;
+        if (okv[i]) *reinterpret_cast<float4*>(Ct + (long long)b * sa.ldc + col) = outv[i];
+      }
+    } else {
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    }
+  }
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+  if (warp == RS_EPI / 32) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -688,6 +950,103 @@ static int launch_skinny_cluster(const void* A, long long lda, const void* W, lo
   skinny_cluster_kernel<<<dim3(RS_KS, tiles), RS_THREADS, smem, st>>>(ta, tw, ep, M, Mpad, N, NT, kb);
   TACORL_LAUNCH_CHECK();
   return 0;
+}
+
+static int g_rnn_seq_enabled = -1;
+bool rnn_seq_enabled() {
+  if (g_rnn_seq_enabled < 0) { const char* e = getenv("TACORL_RNN_SEQ"); g_rnn_seq_enabled = !(e && e[0] == '0'); }
+  return g_rnn_seq_enabled != 0;
+}
+void rnn_seq_set_enabled(int on) { g_rnn_seq_enabled = on ? 1 : 0; }
+
+// Runs n_steps dependent steps C[tau] = epi(beta*C[tau] + A[tau - dtau] . W^T), tau = tau0 + s*dtau, in one launch of
+// rnn_seq_kernel.  Ab: dense bf16 [T][M][K] (K == N: the recurrence feeds its own output back), W: bf16 [N][K].
+// Returns 1 when the shape / device cannot run the persistent kernel (the caller then launches step by step).
+int rnn_seq_tc(const void* Ab, int T, const void* W, long long ldw, int M, int N, int K, int tau0, int dtau, int n_steps,
+               float beta, float* C, long long ldc, long long c_ts, const float* gate, long long ldgate, long long gate_ts,
+               void* Cb, int act, unsigned* flags, cudaStream_t st) {
+  if (!rnn_seq_enabled() || n_steps < 2) return 1;
+  if (M < 1 || M > 128 || K != N || K % (TC_BK * RS_KS) != 0 || N % 4 != 0 || !Cb || !C || !flags) return 1;
+  auto al16 = [](const void* p, long long ld) { return p == nullptr || (((uintptr_t)p & 15) == 0 && (ld * 4) % 16 == 0); };
+  if (!al16(C, ldc) || !al16(C, c_ts) || !al16(gate, ldgate) || !al16(gate, gate_ts) || ((uintptr_t)Cb & 15) != 0) return 1;
+  const int Mpad = (M + 15) & ~15, kb = K / (TC_BK * RS_KS);
+  const int NT = 16 * cdiv(N, 16 * RS_MAX_TILES), tiles = cdiv(N, NT);
+  if (NT > 256 || kb > 8 || (Mpad / RS_KS) * (NT / 4) > RS_MAXE * RS_EPI) return 1;
+  const size_t w_stage = ((size_t)NT * 128 + 1023) & ~(size_t)1023;
+  const size_t s_bytes = ((size_t)((Mpad + 31) & ~31) * (NT + 4) * 4 + 1023) & ~(size_t)1023;
+  const size_t smem = (size_t)kb * (w_stage + 128 * 128) + s_bytes + 10 * 8 + 16 + 1024;
+  if (smem > 227 * 1024) return 1;
+  static size_t configured = 0;
+  if (smem > configured) {
+    TACORL_CHECK_CUDA(cudaFuncSetAttribute(rnn_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  {   // every cluster of the grid must be resident at once: the steps are chained by spin-waits on peers
+    static size_t checked_smem = 0;
+    static int max_clusters = 0;
+    if (checked_smem != smem) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(RS_KS, tiles); cfg.blockDim = dim3(RS_THREADS); cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = RS_KS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, rnn_seq_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+      max_clusters = n; checked_smem = smem;
+    }
+    if (max_clusters < tiles) return 1;
+  }
+  CUtensorMap ta, tw;
+  int rc;
+  {
+    EncodeTiledFn fn = get_encode_fn();
+    TACORL_REQUIRE(fn, "rnn_seq: cuTensorMapEncodeTiled is not available from the driver");
+    TACORL_REQUIRE(((uintptr_t)Ab & 15) == 0, "rnn_seq: hidden-state buffer must be 16-byte aligned");
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)M, (cuuint64_t)T};
+    cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)M * K * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)Mpad, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(Ab), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TACORL_REQUIRE(r == CUDA_SUCCESS, "rnn_seq: cuTensorMapEncodeTiled failed (%d) K=%d M=%d T=%d", (int)r, K, M, T);
+  }
+  if ((rc = make_tmap(&tw, W, K, N, ldw, 64, NT))) return rc;
+  TACORL_CHECK_CUDA(cudaMemsetAsync(flags, 0, (size_t)tiles * sizeof(unsigned), st));
+  SeqArgs sa;
+  sa.n_steps = n_steps; sa.tau0 = tau0; sa.dtau = dtau; sa.beta = beta; sa.C = C; sa.ldc = ldc; sa.c_ts = c_ts;
+  sa.gate = gate; sa.ldgate = ldgate; sa.gate_ts = gate_ts; sa.Cb = (__nv_bfloat16*)Cb; sa.cb_ts = (long long)M * N;
+  sa.act = act; sa.flags = flags;
+  // Two persistent launches must never be co-scheduled (each spin-waits on its own clusters being resident): chain
+  // them through an event, whatever streams they are issued on.  Inside a stream capture the chain only links
+  // launches of the same capture (an event recorded elsewhere cannot be waited on there; the graph launch itself is
+  // stream-ordered after earlier work).
+  {
+    static cudaEvent_t ev[64] = {};
+    static unsigned long long ev_capture[64] = {};
+    static bool ev_recorded[64] = {};
+    int dev = 0;
+    TACORL_CHECK_CUDA(cudaGetDevice(&dev));
+    TACORL_REQUIRE(dev >= 0 && dev < 64, "rnn_seq: device index %d out of range", dev);
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    unsigned long long cid = 0;
+    TACORL_CHECK_CUDA(cudaStreamGetCaptureInfo(st, &cs, &cid));
+    if (cs != cudaStreamCaptureStatusActive) cid = 0;
+    if (!ev[dev]) TACORL_CHECK_CUDA(cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming));
+    if (ev_recorded[dev] && ev_capture[dev] == cid) TACORL_CHECK_CUDA(cudaStreamWaitEvent(st, ev[dev], 0));
+    rnn_seq_kernel<<<dim3(RS_KS, tiles), RS_THREADS, smem, st>>>(ta, tw, sa, M, Mpad, N, NT, kb);
+    TACORL_LAUNCH_CHECK();
+    TACORL_CHECK_CUDA(cudaEventRecord(ev[dev], st));
+    ev_recorded[dev] = true; ev_capture[dev] = cid;
+  }
+  return 0;
+}
+
+unsigned rnn_seq_timeouts() {
+  unsigned v = 0;
+  cudaMemcpyFromSymbol(&v, g_rnn_seq_timeouts, sizeof(v));
+  return v;
 }
 
 // Core entry: bf16 operands already in global memory.

@@ -38,6 +38,13 @@ struct TcArgs {
 // bf16 operands in place: a_mn/b_mn = operand stored [K][rows] (rows contiguous) instead of [rows][K]
 int gemm_tc_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, int M, int N,
                  int K, const TcArgs& e, float* ws, size_t ws_bytes, cudaStream_t st);
+// persistent recurrence (gemm_tc.cu): returns 1 if unsupported (caller launches step by step); flags: >= 16 unsigned
+int rnn_seq_tc(const void* Ab, int T, const void* W, long long ldw, int M, int N, int K, int tau0, int dtau, int n_steps,
+               float beta, float* C, long long ldc, long long c_ts, const float* gate, long long ldgate, long long gate_ts,
+               void* Cb, int act, unsigned* flags, cudaStream_t st);
+unsigned rnn_seq_timeouts();
+bool rnn_seq_enabled();
+void rnn_seq_set_enabled(int on);
 int cast_bf16_2d(const float* src, long long lds, long long rows, int cols, void* dst, long long ldd, cudaStream_t st);
 int cast_transpose_bf16(const float* src, long long lds, int rows, int cols, void* dst, long long ldd, cudaStream_t st);
 int gemm_tc_from_f32(const GemmArgs& g, float* ws, size_t ws_bytes, cudaStream_t st);

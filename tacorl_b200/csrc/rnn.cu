@@ -217,7 +217,8 @@ static int rnn_fwd_bf16(int T, int B, int I, int H, const float* x, long long ld
   __nv_bfloat16* xb = ar.take<__nv_bfloat16>((size_t)n_steps * B * Ip);
   __nv_bfloat16* hb = ar.take<__nv_bfloat16>((size_t)T * B * H);
   __nv_bfloat16* h0b = h0 ? ar.take<__nv_bfloat16>((size_t)B * H) : nullptr;
-  TACORL_REQUIRE(bsum && wih && whh && xb && hb && (!h0 || h0b), "rnn_layer_fwd(bf16): workspace too small");
+  unsigned* flags = ar.take<unsigned>(64);
+  TACORL_REQUIRE(bsum && wih && whh && xb && hb && (!h0 || h0b) && flags, "rnn_layer_fwd(bf16): workspace too small");
   TACORL_REQUIRE(H % 8 == 0, "rnn_layer_fwd(bf16): hidden size must be a multiple of 8");
   float* sk = (float*)(ar.base + ar.off);
   size_t sk_bytes = ar.left();
@@ -242,6 +243,12 @@ static int rnn_fwd_bf16(int T, int B, int I, int H, const float* x, long long ld
       TACORL_LAUNCH_CHECK();
       continue;
     }
+    if (s == 1 && flags) {   // steps 1 .. n_steps-1 in one persistent launch (weights resident in shared memory)
+      rc = rnn_seq_tc(hb, T, whh, H, B, H, H, t, reverse ? -1 : 1, n_steps - 1, 1.f, out, ldo, (long long)B * ldo, nullptr, 0,
+                      0, hb, ACT_RELU, flags, st);
+      if (rc < 0) return rc;
+      if (rc == 0) break;
+    }
     TcArgs r;
     r.C = ot; r.ldc = ldo; r.beta = 1.f; r.act = ACT_RELU; r.Cb = hbt; r.ldcb = H; r.split_k = 0;
     if ((rc = gemm_tc_bf16(hp, H, 0, whh, H, 0, B, H, H, r, sk, sk_bytes, st))) return rc;
@@ -264,7 +271,8 @@ static int rnn_bwd_bf16(int T, int B, int I, int H, const float* x, long long ld
   __nv_bfloat16* hb = ar.take<__nv_bfloat16>((size_t)T * B * H);
   __nv_bfloat16* db = ar.take<__nv_bfloat16>((size_t)T * B * H);
   __nv_bfloat16* h0b = h0 ? ar.take<__nv_bfloat16>((size_t)B * H) : nullptr;
-  TACORL_REQUIRE(wih && whh && xb && hb && db && (!h0 || h0b), "rnn_layer_bwd(bf16): workspace too small");
+  unsigned* flags = ar.take<unsigned>(64);
+  TACORL_REQUIRE(wih && whh && xb && hb && db && (!h0 || h0b) && flags, "rnn_layer_bwd(bf16): workspace too small");
   float* sk = (float*)(ar.base + ar.off);
   size_t sk_bytes = ar.left();
   const float beta0 = accumulate ? 1.f : 0.f;
@@ -285,6 +293,13 @@ static int rnn_bwd_bf16(int T, int B, int I, int H, const float* x, long long ld
   for (int s = n_steps - 1; s >= 0; --s) {
     const int t = reverse ? T - 1 - s : s;
     __nv_bfloat16* dbt = db + (long long)t * B * H;
+    if (s == n_steps - 1 && s > 0) {   // the whole BPTT chain s = n_steps-1 .. 1 in one persistent launch
+      const int tp = reverse ? t + 1 : t - 1;
+      rc = rnn_seq_tc(db, T, whh, H, B, H, H, tp, reverse ? 1 : -1, n_steps - 1, 1.f, dout, lddo, (long long)B * lddo, out, ldo,
+                      (long long)B * ldo, db, ACT_NONE, flags, st);
+      if (rc < 0) return rc;
+      if (rc == 0) { s = 1; continue; }   // resume at s = 0 (dh0)
+    }
     if (s > 0) {   // dpre[t_prev] = (dout[t_prev] + dpre[t] W_hh) * [h[t_prev] > 0], one fused GEMM (+ bf16 copy)
       const int tp = reverse ? t + 1 : t - 1;
       TcArgs c;

@@ -269,12 +269,19 @@ class ReluRNNFn(Function):
 
             if D == 2:
                 # the two directions of a layer are independent: the reverse one runs on a side stream
-                # (own workspace), joined before the next layer reads the concatenated output
+                # (own workspace), joined before the next layer reads the concatenated output.  Step-by-step
+                # launches here: two persistent launches would be chained one after the other (they may never
+                # be co-scheduled), which measured slower than letting the per-step kernels of the two
+                # directions interleave (BiRNN fwd+bwd 1.16 ms vs 1.12 ms).
                 main, side = torch.cuda.current_stream(dev), _side_stream(dev)
                 side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    run_dir(1, "rnn_side")
-                run_dir(0, "main")
+                was = L.lib().tacorl_rnn_seq_enable(0)
+                try:
+                    with torch.cuda.stream(side):
+                        run_dir(1, "rnn_side")
+                    run_dir(0, "main")
+                finally:
+                    L.lib().tacorl_rnn_seq_enable(was)
                 main.wait_stream(side)
             else:
                 run_dir(0, "main")
@@ -332,9 +339,13 @@ class ReluRNNFn(Function):
             if D == 2:
                 main, side = torch.cuda.current_stream(dev), _side_stream(dev)
                 side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    run_dir(1, "rnn_side", dx_rev)
-                run_dir(0, "main", dx)
+                was = L.lib().tacorl_rnn_seq_enable(0)
+                try:
+                    with torch.cuda.stream(side):
+                        run_dir(1, "rnn_side", dx_rev)
+                    run_dir(0, "main", dx)
+                finally:
+                    L.lib().tacorl_rnn_seq_enable(was)
                 main.wait_stream(side)
                 if need_dx:
                     dx.add_(dx_rev)

@@ -163,3 +163,39 @@ def test_play_lmp_bf16_loss_curve_tracks_fp32_oracle(bf16_ops):
         last = want
     assert last < first - 2.0, (first, last)          # the model actually trained
     assert worst <= 1e-2, worst
+
+
+@pytest.mark.parametrize("B,H,bidir,with_h0", [(64, 2048, False, False), (128, 2048, False, True), (64, 2048, True, False),
+                                               (24, 512, True, False), (100, 1024, False, True)])
+def test_persistent_recurrence_bit_identical_to_stepwise(bf16_ops, B, H, bidir, with_h0):
+    """The persistent launch (weights resident in shared memory, steps chained by device-side arrival counters)
+    performs exactly the per-step kernel's arithmetic: outputs and every gradient must be bit-identical."""
+    from tacorl_b200 import _lib
+    g = torch.Generator().manual_seed(B + H)
+    T, I, D = 16, 48, 2 if bidir else 1
+    bound = 1.0 / H ** 0.5
+    shapes = []
+    for l in range(2):
+        for _ in range(D):
+            shapes += [(H, I if l == 0 else H * D), (H, H), (H,), (H,)]
+    w0 = [(torch.rand(s, generator=g) * 2 - 1) * bound for s in shapes]
+    x = torch.randn(T, B, I, generator=g)
+    h0 = torch.rand(2 * D, B, H, generator=g) if with_h0 else None
+    cot = torch.randn(T, B, D * H, generator=g).to(DEV)
+    res = {}
+    for mode in (1, 0):
+        was = _lib.lib().tacorl_rnn_seq_enable(mode)
+        try:
+            ws = [w.clone().to(DEV).requires_grad_(True) for w in w0]
+            xd = x.to(DEV).requires_grad_(True)
+            h0d = h0.to(DEV).requires_grad_(True) if with_h0 else None
+            out, _ = bf16_ops.relu_rnn(xd, ws, 2, bidir, False, h0d)
+            (out * cot).sum().backward()
+            torch.cuda.synchronize()
+            res[mode] = [out.detach(), xd.grad] + [w.grad for w in ws] + ([h0d.grad] if with_h0 else [])
+        finally:
+            _lib.lib().tacorl_rnn_seq_enable(was)
+    assert _lib.lib().tacorl_rnn_seq_timeouts() == 0
+    for i, (a, b) in enumerate(zip(res[1], res[0])):
+        assert torch.isfinite(a).all()
+        assert torch.equal(a, b), (i, float((a - b).abs().max()))
