@@ -118,11 +118,14 @@ template <int G>
 __global__ void softargmax_fwd_kernel(const float* __restrict__ y, int P, int OW, int C,
                                       const float* __restrict__ temperature, float* __restrict__ feat,
                                       float* __restrict__ smax, float* __restrict__ ssum) {
-  extern __shared__ float sm[];  // 4 * G * C
+  extern __shared__ float sm[];  // 4 * G * C partials, then the (col, row) coordinate of every position
   const int c = threadIdx.x, g = threadIdx.y;
   const long long n = blockIdx.x;
   const float inv_t = 1.f / __ldg(temperature);
   const float* yp = y + n * (long long)P * C;
+  float2* xy = reinterpret_cast<float2*>(sm + 4 * G * C);   // replaces an integer divide per element
+  for (int p = g * C + c; p < P; p += G * C) xy[p] = make_float2((float)(p % OW), (float)(p / OW));
+  __syncthreads();
   float m = -INFINITY, s = 0.f, sx = 0.f, sy = 0.f;
   // batches of 8 positions: all loads in flight first, one max, then the exponentials (merged into the running
   // online-softmax state), instead of a load -> compare -> exp chain per position
@@ -138,14 +141,15 @@ __global__ void softargmax_fwd_kernel(const float* __restrict__ y, int P, int OW
 #pragma unroll
     for (int j = 1; j < UB; ++j) bm = fmaxf(bm, v[j]);
     if (bm > m) {
-      const float sc = expf(m - bm);       // exp(-inf) = 0 on the first batch
+      const float sc = __expf(m - bm);     // exp(-inf) = 0 on the first batch
       s *= sc; sx *= sc; sy *= sc; m = bm;
     }
 #pragma unroll
     for (int j = 0; j < UB; ++j) {
       const int p = p0 + j * G;
-      const float e = expf(v[j] - m);      // 0 for the padded tail
-      s += e; sx += e * (float)(p % OW); sy += e * (float)(p / OW);
+      const float e = __expf(v[j] - m);    // 0 for the padded tail
+      const float2 q = xy[p < P ? p : 0];
+      s += e; sx += e * q.x; sy += e * q.y;
     }
   }
   float* q = sm + (g * C + c) * 4;
@@ -174,8 +178,9 @@ int softargmax_fwd_f32(const float* y, int N, int OH, int OW, int C, const float
   if (N == 0) return 0;
   constexpr int G = 16;
   TACORL_REQUIRE(C * G <= 1024, "softargmax: too many channels");
-  softargmax_fwd_kernel<G><<<N, dim3(C, G), 4 * G * C * sizeof(float), st>>>(y, OH * OW, OW, C, temperature,
-                                                                            feat, smax, ssum);
+  const size_t smem = (4 * (size_t)G * C + 2 * (size_t)OH * OW) * sizeof(float);
+  TACORL_REQUIRE(smem <= 48 * 1024, "softargmax: feature map of %d x %d positions is too large", OH, OW);
+  softargmax_fwd_kernel<G><<<N, dim3(C, G), smem, st>>>(y, OH * OW, OW, C, temperature, feat, smax, ssum);
   TACORL_LAUNCH_CHECK();
   return 0;
 }
@@ -192,11 +197,15 @@ __global__ void softargmax_bwd_kernel(const float* __restrict__ y, int P, int OW
                                       const float* __restrict__ ssum, const float* __restrict__ dfeat,
                                       OutT* __restrict__ dy, float* __restrict__ dtau_part) {
   __shared__ float red[32];
+  extern __shared__ float sm[];   // (col, row) coordinate of every position
   const int c = threadIdx.x, g = threadIdx.y;
   const long long n = blockIdx.x;
   const float tau = __ldg(temperature), inv_t = 1.f / tau;
   const float* yp = y + n * (long long)P * C;
   OutT* dyp = dy + n * (long long)P * C;
+  float2* xy = reinterpret_cast<float2*>(sm);
+  for (int p = g * C + c; p < P; p += G * C) xy[p] = make_float2((float)(p % OW), (float)(p / OW));
+  __syncthreads();
   const float gx = dfeat[n * 2 * C + 2 * c], gy = dfeat[n * 2 * C + 2 * c + 1];
   const float fx = feat[n * 2 * C + 2 * c], fy = feat[n * 2 * C + 2 * c + 1];
   const float M = smax[n * C + c], invS = 1.f / ssum[n * C + c];
@@ -214,8 +223,9 @@ __global__ void softargmax_bwd_kernel(const float* __restrict__ y, int P, int OW
     for (int j = 0; j < UB; ++j) {
       const int p = p0 + j * G;
       if (p >= P) break;
-      const float pr = expf(yv[j] * inv_t - M) * invS;
-      const float dz = pr * (gx * (float)(p % OW) + gy * (float)(p / OW) - dotg);
+      const float pr = __expf(yv[j] * inv_t - M) * invS;
+      const float2 q = xy[p];
+      const float dz = pr * (gx * q.x + gy * q.y - dotg);
       dt += dz * yv[j];
       sa_store(dyp + (long long)p * C + c, yv[j] > 0.f ? dz * inv_t : 0.f);
     }
@@ -238,8 +248,9 @@ int softargmax_bwd_f32(const float* y, int N, int OH, int OW, int C, const float
   if (N == 0) return 0;
   constexpr int G = 4;
   TACORL_REQUIRE(C * G <= 1024 && (C * G) % 32 == 0, "softargmax bwd: unsupported channel count");
-  softargmax_bwd_kernel<G, float><<<N, dim3(C, G), 0, st>>>(y, OH * OW, OW, C, temperature, feat, smax, ssum,
-                                                          dfeat, dy, dtau_part);
+  TACORL_REQUIRE((size_t)OH * OW * 8 <= 40 * 1024, "softargmax bwd: feature map of %d x %d positions is too large", OH, OW);
+  softargmax_bwd_kernel<G, float><<<N, dim3(C, G), (size_t)OH * OW * 8, st>>>(y, OH * OW, OW, C, temperature, feat, smax,
+                                                                            ssum, dfeat, dy, dtau_part);
   TACORL_LAUNCH_CHECK();
   return 0;
 }
@@ -251,8 +262,9 @@ int softargmax_bwd_bf16out(const float* y, int N, int OH, int OW, int C, const f
   if (N == 0) return 0;
   constexpr int G = 16;
   TACORL_REQUIRE(C * G <= 1024 && (C * G) % 32 == 0, "softargmax bwd: unsupported channel count");
-  softargmax_bwd_kernel<G, __nv_bfloat16><<<N, dim3(C, G), 0, st>>>(y, OH * OW, OW, C, temperature, feat, smax, ssum,
-                                                                  dfeat, (__nv_bfloat16*)dy_bf16, dtau_part);
+  TACORL_REQUIRE((size_t)OH * OW * 8 <= 40 * 1024, "softargmax bwd: feature map of %d x %d positions is too large", OH, OW);
+  softargmax_bwd_kernel<G, __nv_bfloat16><<<N, dim3(C, G), (size_t)OH * OW * 8, st>>>(
+      y, OH * OW, OW, C, temperature, feat, smax, ssum, dfeat, (__nv_bfloat16*)dy_bf16, dtau_part);
   TACORL_LAUNCH_CHECK();
   return 0;
 }

@@ -17,6 +17,7 @@
 #include "internal.h"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <algorithm>
 
 namespace tacorl {
 
@@ -136,7 +137,7 @@ __device__ __forceinline__ uint64_t cv_desc(uint32_t saddr, uint32_t lbo, uint32
 // (64 channels x BW x 1 x BH x 1 frame) written straight into a 128B-swizzled stage.  Out-of-image taps (data
 // gradients) and the ragged patch edges are zero-filled by TMA; stride-2 layers address the source through a
 // (pixel pair, row parity) view so no element strides are needed.
-template <int BN>
+template <int BN, int NTAPS>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ CUtensorMap tmA,
                const __grid_constant__ CUtensorMap tmW, const ConvEpi ep) {
@@ -200,21 +201,26 @@ conv_tc_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ CUten
     if (lane == 0) {
       cv_mbar_wait(w_bar, 0);
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // one thread of scalar code issues every MMA: descriptors are precomputed (weights: per tap and K step; stages:
+      // base + stage * size), leaving one 64-bit add per operand per instruction
+      uint64_t bdesc[NTAPS * 4];
+#pragma unroll
+      for (int i = 0; i < NTAPS * 4; ++i) bdesc[i] = cv_desc(w_base + (i >> 2) * W_TAP_BYTES + (i & 3) * 32, 16, 1024);
+      const uint64_t adesc0 = cv_desc(a_base, 16, 1024);
       uint32_t it = 0, lt = 0;
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++lt) {
         const uint32_t acc = lt & 1;
         cv_mbar_wait(tempty_bar(acc), ((lt >> 1) & 1) ^ 1);
         cv_fence_after();
         const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
-        for (int t = 0; t < g.ntaps; ++t, ++it) {
+#pragma unroll
+        for (int t = 0; t < NTAPS; ++t, ++it) {
           const int s = it % CV_STAGES;
           cv_mbar_wait(full_bar(s), (it / CV_STAGES) & 1);
           cv_fence_after();
-          const uint32_t a_src = a_base + s * A_BYTES, b_src = w_base + t * W_TAP_BYTES;
+          const uint64_t adesc = adesc0 + (uint64_t)(s * (A_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            cv_mma(tmem_d, cv_desc(a_src + k * 32, 16, 1024), cv_desc(b_src + k * 32, 16, 1024), idesc,
-                   (t > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) cv_mma(tmem_d, adesc + 2 * k, bdesc[t * 4 + k], idesc, (t > 0 || k > 0) ? 1u : 0u);
           cv_commit(empty_bar(s));
         }
         cv_commit(tfull_bar(acc));
@@ -241,6 +247,189 @@ conv_tc_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ CUten
         for (int j = 0; j < BN / 8; ++j) gate[j] = __ldg(gp + j);
       }
       cv_mbar_wait(tfull_bar(acc), (lt >> 1) & 1);
+      cv_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t rr[16];
+        cv_ld16(tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16) + c0, rr);
+        if (!row_ok) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]) + s_bias[c0 + j];
+        if (ep.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (ep.gate) {
+          const uint4 g0 = gate[c0 / 8], g1 = gate[c0 / 8 + 1];
+          const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&g0);
+          const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&g1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f0 = __bfloat1622float2(h0[j]), f1 = __bfloat1622float2(h1[j]);
+            if (f0.x <= 0.f) v[2 * j] = 0.f;
+            if (f0.y <= 0.f) v[2 * j + 1] = 0.f;
+            if (f1.x <= 0.f) v[8 + 2 * j] = 0.f;
+            if (f1.y <= 0.f) v[8 + 2 * j + 1] = 0.f;
+          }
+        }
+        if (ep.out_bf16) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            pk[j] = *reinterpret_cast<uint32_t*>(&t2);
+          }
+          cv_st32(ep.out_bf16 + opix * BN + c0, pk);
+        }
+        if (ep.out_f32) {
+          uint32_t lo[8], hi[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { lo[j] = __float_as_uint(v[j]); hi[j] = __float_as_uint(v[8 + j]); }
+          cv_st32(ep.out_f32 + opix * BN + c0, lo);
+          cv_st32(ep.out_f32 + opix * BN + c0 + 8, hi);
+        }
+      }
+      cv_fence_before();
+      __syncwarp();
+      if (lane == 0) cv_mbar_arrive(tempty_bar(acc));
+    }
+  }
+  cv_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    cv_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ linear-shift variant
+// Stride-1 layers whose input and output share one row pitch W: output pixel with linear index p = a*W + b reads, for
+// filter tap (ky, kx), input pixel p + ky*W + kx - the SAME linear pixel array shifted by a constant.  A tile is 128
+// consecutive linear pixels of one frame; its whole input window (128 + max shift pixel rows of 128 bytes) is loaded
+// ONCE by a single 2-D TMA box, and every tap's A operand is that stage addressed at a shifted start: the UMMA
+// descriptor's start address simply advances by shift*128 bytes.  The tensor core applies the 128-byte swizzle to the
+// absolute shared-memory address bits (the same bits TMA used when it wrote the stage), so a start address that is
+// not aligned to the 1024-byte swizzle atom needs no further adjustment - measured: results are exact with the
+// descriptor's base-offset field left 0 and wrong with it set to (shift & 7); tests/test_gpu_conv_tc.py.  L2->SM
+// traffic per tile drops from ntaps x 16 KB to (128 + max shift) x 128 B; the columns b >= OW of each output row are
+// computed and discarded (conv3: 21 of 23 kept).
+struct ConvLinGeom {
+  int W, OH, OW;                    // shared row pitch (input pixels per row), valid output grid
+  int frame_rows;                   // input pixel rows per frame in the 2-D view (H*W)
+  int tiles_per_frame, num_tiles;
+  int ntaps, load_rows;             // load_rows = 128 + max shift, rounded up to 8
+  int stages;
+  int shift[CV_MAXT];
+  // output pixel (a, b) -> (a*oys + oy0, b*oxs + ox0) of an (N, OHt, OWt, BN) tensor
+  int OHt, OWt, oys, oy0, oxs, ox0;
+};
+constexpr int CL_MAX_STAGES = 8;    // ring depth g.stages <= 8: as many input windows in flight as shared memory holds
+
+template <int BN, int NTAPS, int KSTEPS>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv_lin_kernel(const __grid_constant__ ConvLinGeom g, const __grid_constant__ CUtensorMap tmA,
+                const __grid_constant__ CUtensorMap tmW, const ConvEpi ep) {
+  constexpr uint32_t W_TAP_BYTES = BN * 128;
+  constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;
+  constexpr int NACC = 4;                       // accumulator ring: the epilogue may lag the MMAs by up to 3 tiles
+  constexpr uint32_t TMEM_COLS = NACC * ACC_COLS;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t stage_bytes = ((uint32_t)g.load_rows * 128 + 1023) & ~1023u;
+  const uint32_t w_base = cv_smem(smem);
+  const uint32_t a_base = w_base + g.ntaps * W_TAP_BYTES;
+  uint64_t* bars = (uint64_t*)(smem + g.ntaps * W_TAP_BYTES + g.stages * stage_bytes);
+  const int CL_STAGES = g.stages;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * CL_MAX_STAGES + 2 * NACC + 1);
+  auto full_bar = [&](int s) { return cv_smem(bars + s); };
+  auto empty_bar = [&](int s) { return cv_smem(bars + CL_MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return cv_smem(bars + 2 * CL_MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return cv_smem(bars + 2 * CL_MAX_STAGES + NACC + a); };
+  const uint32_t w_bar = cv_smem(bars + 2 * CL_MAX_STAGES + 2 * NACC);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float s_bias[BN];
+  if (threadIdx.x < BN) s_bias[threadIdx.x] = ep.bias ? ep.bias[threadIdx.x] : 0.f;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < CL_STAGES; ++s) { cv_mbar_init(full_bar(s), 1); cv_mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < NACC; ++a) { cv_mbar_init(tfull_bar(a), 1); cv_mbar_init(tempty_bar(a), 4); }
+    cv_mbar_init(w_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(cv_smem(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  cv_fence_before();
+  __syncthreads();
+  cv_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      cv_mbar_expect_tx(w_bar, g.ntaps * W_TAP_BYTES);
+      for (int t = 0; t < g.ntaps; ++t) cv_tma_2d(w_base + t * W_TAP_BYTES, &tmW, 0, t * BN, w_bar);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+        const int n = tile / g.tiles_per_frame, k = tile - n * g.tiles_per_frame;
+        const int s = it % CL_STAGES;
+        cv_mbar_wait(empty_bar(s), ((it / CL_STAGES) & 1) ^ 1);
+        cv_mbar_expect_tx(full_bar(s), (uint32_t)g.load_rows * 128);
+        cv_tma_2d(a_base + s * stage_bytes, &tmA, 0, n * g.frame_rows + k * 128, full_bar(s));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      cv_mbar_wait(w_bar, 0);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // The issue loop is one thread of scalar code: keep it to one 64-bit add per operand per MMA.  Descriptor =
+      // (constant high word, start address >> 4 in the low 14 bits); offsets below never carry out of that field
+      // (shared memory is < 256 KB = 2^14 x 16 B).
+      uint32_t aoff[NTAPS * KSTEPS];
+      uint64_t bdesc[NTAPS * KSTEPS];
+#pragma unroll
+      for (int t = 0; t < NTAPS; ++t)
+#pragma unroll
+        for (int k = 0; k < KSTEPS; ++k) {
+          aoff[t * KSTEPS + k] = ((uint32_t)g.shift[t] * 128 + k * 32) >> 4;
+          bdesc[t * KSTEPS + k] = cv_desc(w_base + t * W_TAP_BYTES + k * 32, 16, 1024);
+        }
+      const uint64_t adesc0 = cv_desc(a_base, 16, 1024);
+      const uint32_t stage16 = stage_bytes >> 4;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it % NACC;
+        const int s = it % CL_STAGES;
+        cv_mbar_wait(tempty_bar(acc), ((it / NACC) & 1) ^ 1);
+        cv_mbar_wait(full_bar(s), (it / CL_STAGES) & 1);
+        cv_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
+        const uint64_t adesc = adesc0 + (uint64_t)(s * stage16);
+#pragma unroll
+        for (int i = 0; i < NTAPS * KSTEPS; ++i) cv_mma(tmem_d, adesc + aoff[i], bdesc[i], idesc, i > 0 ? 1u : 0u);
+        cv_commit(empty_bar(s));
+        cv_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t acc = lt % NACC;
+      const int n = tile / g.tiles_per_frame, k = tile - n * g.tiles_per_frame;
+      const int p = k * 128 + r, a = p / g.W, b = p - a * g.W;
+      const bool row_ok = a < g.OH && b < g.OW;
+      const long long opix = row_ok ? ((long long)n * g.OHt + (a * g.oys + g.oy0)) * g.OWt + (b * g.oxs + g.ox0) : 0;
+      uint4 gate[BN / 8];
+      if (ep.gate && row_ok) {
+        const uint4* gp = reinterpret_cast<const uint4*>(ep.gate + opix * BN);
+#pragma unroll
+        for (int j = 0; j < BN / 8; ++j) gate[j] = __ldg(gp + j);
+      }
+      cv_mbar_wait(tfull_bar(acc), (lt / NACC) & 1);
       cv_fence_after();
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -365,7 +554,7 @@ static void cv_choose_patch(int RA, int RB, int* BW, int* BH) {
     }
 }
 
-template <int BN>
+template <int BN, int NTAPS>
 static int cv_launch(const ConvGeom& g, const ActView& view, const void* wpacked, const ConvEpi& ep, cudaStream_t st) {
   CUtensorMap tw, ta;
   int rc = cv_weight_tmap(&tw, wpacked, g.ntaps, BN);
@@ -373,7 +562,7 @@ static int cv_launch(const ConvGeom& g, const ActView& view, const void* wpacked
   if ((rc = cv_act_tmap(&ta, view, g.BW, g.BH))) return rc;
   const size_t smem = (size_t)g.ntaps * BN * 128 + CV_STAGES * 128 * 128 + (2 * CV_STAGES + 5) * 8 + 16 + 1024;
   static size_t configured = 0;
-  auto kern = conv_tc_kernel<BN>;
+  auto kern = conv_tc_kernel<BN, NTAPS>;
   if (smem > configured) {
     TACORL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
@@ -392,10 +581,76 @@ static int conv_tc_run(ConvGeom g, int N, const ActView& view, int BN, const voi
   cv_choose_patch(g.RA, g.RB, &g.BW, &g.BH);
   g.tiles_x = cdiv(g.RB, g.BW); g.tiles_y = cdiv(g.RA, g.BH);
   g.num_tiles = N * g.tiles_x * g.tiles_y;
-  if (BN == 32) return cv_launch<32>(g, view, wpacked, ep, st);
-  if (BN == 64) return cv_launch<64>(g, view, wpacked, ep, st);
-  set_last_error("conv_tc: unsupported output width %d", BN);
+  if (BN == 32 && g.ntaps == 4) return cv_launch<32, 4>(g, view, wpacked, ep, st);
+  if (BN == 64 && g.ntaps == 8) return cv_launch<64, 8>(g, view, wpacked, ep, st);
+  if (BN == 64 && g.ntaps == 9) return cv_launch<64, 9>(g, view, wpacked, ep, st);
+  set_last_error("conv_tc: unsupported output width %d / tap count %d", BN, g.ntaps);
   return -1;
+}
+
+// Linear-shift launch: src is an NHWC bf16 activation with 128-byte pixels, frame_rows pixel rows per frame.
+template <int BN, int NTAPS, int KSTEPS>
+static int cl_launch(ConvLinGeom g, int N, const void* src, const void* wpacked, const ConvEpi& ep, cudaStream_t st) {
+  CvEncodeFn fn = cv_encode_fn();
+  TACORL_REQUIRE(fn, "conv_lin: cuTensorMapEncodeTiled is not available");
+  int max_shift = 0;
+  for (int t = 0; t < g.ntaps; ++t) max_shift = g.shift[t] > max_shift ? g.shift[t] : max_shift;
+  g.load_rows = (128 + max_shift + 7) & ~7;
+  TACORL_REQUIRE(g.load_rows <= 256, "conv_lin: input window of %d pixel rows exceeds one TMA box", g.load_rows);
+  const int lin = (g.OH - 1) * g.W + g.OW;            // linear extent of the valid outputs of one frame
+  g.tiles_per_frame = cdiv(lin, 128);
+  g.num_tiles = N * g.tiles_per_frame;
+  CUtensorMap tw, ta;
+  int rc = cv_weight_tmap(&tw, wpacked, g.ntaps, BN);
+  if (rc) return rc;
+  {
+    TACORL_REQUIRE(((uintptr_t)src & 15) == 0, "conv_lin: activation must be 16-byte aligned");
+    cuuint64_t dims[2] = {64, (cuuint64_t)N * g.frame_rows};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, (cuuint32_t)g.load_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(src), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TACORL_REQUIRE(r == CUDA_SUCCESS, "conv_lin: cuTensorMapEncodeTiled(activation) failed (%d)", (int)r);
+  }
+  const size_t stage = ((size_t)g.load_rows * 128 + 1023) & ~(size_t)1023;
+  const size_t fixed = (size_t)g.ntaps * BN * 128 + (2 * CL_MAX_STAGES + 12) * 8 + 16 + 1024 + 256;
+  g.stages = (int)std::min<size_t>(CL_MAX_STAGES, (227 * 1024 - fixed) / stage);
+  TACORL_REQUIRE(g.stages >= 2, "conv_lin: input window of %zu bytes leaves no room for a stage ring", stage);
+  const size_t smem = fixed - 256 + g.stages * stage;
+  static size_t configured = 0;
+  TACORL_REQUIRE(g.ntaps == NTAPS, "conv_lin: tap count mismatch");
+  auto kern = conv_lin_kernel<BN, NTAPS, KSTEPS>;
+  if (smem > configured) {
+    TACORL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int ctas = g.num_tiles < 148 ? g.num_tiles : 148;
+  kern<<<ctas, CV_THREADS, smem, st>>>(g, ta, tw, ep);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
+// conv3 forward, linear-shift form: y2 (N, H2, W2, 64) -> y3 fp32 (N, H3, W3, 64)
+int conv_lin_conv3_fwd(const void* y2b, int N, int H2, int W2, int H3, int W3, const void* wp, const float* bias,
+                       float* y3, cudaStream_t st) {
+  ConvLinGeom g = {};
+  g.W = W2; g.OH = H3; g.OW = W3; g.frame_rows = H2 * W2; g.ntaps = 9;
+  for (int t = 0; t < 9; ++t) g.shift[t] = (t / 3) * W2 + (t % 3);
+  g.OHt = H3; g.OWt = W3; g.oys = 1; g.oxs = 1;
+  ConvEpi e = {bias, 1, nullptr, nullptr, y3};
+  return cl_launch<64, 9, 4>(g, N, y2b, wp, e, st);
+}
+// conv1 forward on the s2d image (N, H1+1, W1+1, 64): 2x2 taps
+int conv_lin_conv1_fwd(const void* xs, int N, int H1, int W1, const void* wp, const float* bias, void* y1b,
+                       cudaStream_t st) {
+  ConvLinGeom g = {};
+  g.W = W1 + 1; g.OH = H1; g.OW = W1; g.frame_rows = (H1 + 1) * (W1 + 1); g.ntaps = 4;
+  for (int t = 0; t < 4; ++t) g.shift[t] = (t >> 1) * (W1 + 1) + (t & 1);
+  g.OHt = H1; g.OWt = W1; g.oys = 1; g.oxs = 1;
+  ConvEpi e = {bias, 1, nullptr, (__nv_bfloat16*)y1b, nullptr};
+  return cl_launch<32, 4, 3>(g, N, xs, wp, e, st);
 }
 
 // ------------------------------------------------------------------------------------------ packing kernels
@@ -626,7 +881,9 @@ namespace tacorl {
 
 constexpr int WG_STAGES = 5;
 constexpr int WG_LAG = 3;
-constexpr int WG_THREADS = 224;       // 2 producer warps (64 pixel rows), 1 MMA warp, 4 epilogue warps
+constexpr int WG_PL = 4;              // producer lanes per pixel row (chunks j = c*WG_PL + h: whole 32-byte sectors per warp instruction)
+constexpr int WG_PROD = 64 * WG_PL;   // producer threads; warps 0..3 also drain TMEM at the end
+constexpr int WG_THREADS = WG_PROD + 32;   // + the MMA warp
 
 struct WgradGeom {
   const __nv_bfloat16* dy;            // (M, OC) output gradient, NHWC rows
@@ -675,11 +932,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_tc_wgrad_kernel(const __gr
         make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);          // bf16 1.0 pairs
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < WG_STAGES; ++s) { cv_mbar_init(full_bar(s), 64); cv_mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < WG_STAGES; ++s) { cv_mbar_init(full_bar(s), WG_PROD); cv_mbar_init(empty_bar(s), 1); }
     cv_mbar_init(done_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == WG_PROD / 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(cv_smem(tmem_slot)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -690,43 +947,39 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_tc_wgrad_kernel(const __gr
   cv_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 2) {
-    // a lane pair gathers pixel rows p and p+32 of the K block; lane h takes the chunks 2i+h (whole sectors per warp)
-    const int h = threadIdx.x & 1, p = threadIdx.x >> 1;
+  if (warp < WG_PROD / 32) {
+    // WG_PL lanes gather pixel row p of the K block; lane h takes the 16-byte chunks c*WG_PL + h
+    const int h = threadIdx.x % WG_PL, p = threadIdx.x / WG_PL;
+    const uint32_t row_off = (uint32_t)p * 128, sw = (uint32_t)(p & 7);
     for (int i = 0; i < nkb; ++i) {
       const int s = i % WG_STAGES;
       const uint32_t ph = (i / WG_STAGES) & 1;
       cv_mbar_wait(empty_bar(s), ph ^ 1);
       const uint32_t st = base + s * stage_bytes;
+      const int m = m_begin + i * 64 + p;
+      const bool ok = m < m_end;
+      int n = 0, a = 0, b = 0;
+      if (ok) { n = m / rows_per_frame; const int rem = m - n * rows_per_frame; a = rem / g.RB; b = rem - a * g.RB; }
+      const __nv_bfloat16* dyp = g.dy + (long long)(ok ? m : 0) * g.OC;
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int r = p + 32 * u;
-        const uint32_t row_off = (uint32_t)r * 128, sw = (uint32_t)(r & 7);
-        const int m = m_begin + i * 64 + r;
-        const bool ok = m < m_end;
-        int n = 0, a = 0, b = 0;
-        if (ok) { n = m / rows_per_frame; const int rem = m - n * rows_per_frame; a = rem / g.RB; b = rem - a * g.RB; }
-        const __nv_bfloat16* dyp = g.dy + (long long)(ok ? m : 0) * g.OC;
+      for (int c = 0; c < 8 / WG_PL; ++c) {
+        const int j = WG_PL * c + h;
+        cv_cp16(st + row_off + ((j ^ sw) << 4), dyp + j * 8, (ok && j < g.dy_chunks) ? 16u : 0u);
+      }
+      const __nv_bfloat16* frame = g.src + (long long)n * g.SH * g.SW * g.SC;
+      for (int t = 0; t < g.NT; ++t) {
+        const int tt = grp * g.NT + t;
+        const __nv_bfloat16* sp = frame + ((long long)(a * g.sy + g.dy_t[tt]) * g.SW + (b * g.sx + g.dx_t[tt])) * g.SC + g.coff[tt];
+        const uint32_t dst = st + (1 + t) * TILE + row_off;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int j = 2 * c + h;
-          cv_cp16(st + row_off + ((j ^ sw) << 4), dyp + j * 8, (ok && j < g.dy_chunks) ? 16u : 0u);
-        }
-        const __nv_bfloat16* frame = g.src + (long long)n * g.SH * g.SW * g.SC;
-        for (int t = 0; t < g.NT; ++t) {
-          const int tt = grp * g.NT + t;
-          const __nv_bfloat16* sp = frame + ((long long)(a * g.sy + g.dy_t[tt]) * g.SW + (b * g.sx + g.dx_t[tt])) * g.SC + g.coff[tt];
-          const uint32_t dst = st + (1 + t) * TILE + row_off;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int j = 2 * c + h;
-            cv_cp16(dst + ((j ^ sw) << 4), sp + j * 8, (ok && j < g.kchunks) ? 16u : 0u);
-          }
+        for (int c = 0; c < 8 / WG_PL; ++c) {
+          const int j = WG_PL * c + h;
+          cv_cp16(dst + ((j ^ sw) << 4), sp + j * 8, (ok && j < g.kchunks) ? 16u : 0u);
         }
       }
       cv_cp_async_arrive(full_bar(s));
     }
-  } else if (warp == 2) {
+  } else if (warp == WG_PROD / 32) {
     if (lane == 0 && nkb > 0) {
       // A and B MN-major (bits 15, 16), D = f32, bf16 inputs, M = 128, N = NT*64
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
@@ -754,8 +1007,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_tc_wgrad_kernel(const __gr
       }
       cv_commit(done_bar);
     }
-  } else {
-    const int q = warp & 3;                     // warps 3..6 -> quarters 3,0,1,2
+  }
+  if (warp < 4) {   // the producer warps drain the accumulator: TMEM lane quarter = warp index
+    const int q = warp;
     const int oc = q * 32 + lane;
     if (nkb > 0) { cv_mbar_wait(done_bar, 0); cv_fence_after(); }
     float* P = g.partial + (((long long)blockIdx.x * g.groups + grp) * g.OC + oc) * NCOLS;
@@ -784,7 +1038,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_tc_wgrad_kernel(const __gr
   }
   cv_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == WG_PROD / 32) {
     cv_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
@@ -943,6 +1197,15 @@ extern "C" int tacorl_conv_tc_debug(int op, const float* in0, const float* in1, 
       if ((rc = cast_bf16_2d(in0, 32, N * P1, 32, a0, 32, st))) return rc;
       if ((rc = conv_tc_s2d(in1, N, H, W, H1 + 1, W1 + 1, a1, st))) return rc;
       return conv_tc_wgrad(1, a0, a1, N, H1 + 1, W1 + 1, H1, W1, 0.f, out, out + 32 * 3 * 64, wsf, 32 << 20, st);
+    case 11:     // conv1 forward, linear-shift kernel
+      if ((rc = conv_tc_pack(2, Wt, wp, st))) return rc;
+      if ((rc = conv_tc_s2d(in0, N, H, W, H1 + 1, W1 + 1, a0, st))) return rc;
+      if ((rc = conv_lin_conv1_fwd(a0, N, H1, W1, wp, bias, ob, st))) return rc;
+      return cv_to_f32(N * P1 * 32, ob, out, st);
+    case 13:     // conv3 forward, linear-shift kernel
+      if ((rc = conv_tc_pack(0, Wt, wp, st))) return rc;
+      if ((rc = cast_bf16_2d(in0, 64, N * P2, 64, a0, 64, st))) return rc;
+      return conv_lin_conv3_fwd(a0, N, H2, W2, H3, W3, wp, bias, out, st);
     default:
       set_last_error("conv_tc_debug: unknown op %d", op);
       return -1;

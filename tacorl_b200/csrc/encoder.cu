@@ -91,9 +91,9 @@ static int enc_fwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
   if ((rc = conv_tc_pack(0, params[P_W3], wp3, st))) return rc;
   if ((rc = x_u8 ? conv_tc_s2d_u8((const unsigned char*)xv, N, H, W, g.H1 + 1, g.W1 + 1, x_scale, x_shift, xs, st)
                  : conv_tc_s2d((const float*)xv, N, H, W, g.H1 + 1, g.W1 + 1, xs, st))) return rc;
-  if ((rc = conv_tc_conv1_fwd(xs, N, g.H1, g.W1, wp1, params[P_B1], y1b, st))) return rc;
+  if ((rc = conv_lin_conv1_fwd(xs, N, g.H1, g.W1, wp1, params[P_B1], y1b, st))) return rc;
   if ((rc = conv_tc_conv2_fwd(y1b, N, g.H1, g.W1, g.H2, g.W2, wp2, params[P_B2], y2b, st))) return rc;
-  if ((rc = conv_tc_conv3_fwd(y2b, N, g.H2, g.W2, g.H3, g.W3, wp3, params[P_B3], y3, st))) return rc;
+  if ((rc = conv_lin_conv3_fwd(y2b, N, g.H2, g.W2, g.H3, g.W3, wp3, params[P_B3], y3, st))) return rc;
   if ((rc = softargmax_fwd_f32(y3, N, g.H3, g.W3, 64, params[P_TEMP], feat, smax, ssum, st))) return rc;
   GemmArgs f;
   f.transB = 1; f.M = N; f.N = hidden; f.K = 128; f.A = feat; f.lda = 128; f.B = params[P_W4]; f.ldb = 128;

@@ -55,6 +55,11 @@ def test_implicit_gemm_convs_match_torch(N, H, W):
     y1 = F.relu(F.conv2d(xd, W1t.double(), b1.double(), stride=4))
     got = _run(1, x, None, W1t, b1, N, H, W, (N, H1, W1, 32))
     assert_close("conv1 fwd", got, nhwc(y1), 6e-3)
+    # linear-shift form (one input window per tile, taps = UMMA descriptors with shifted start addresses): what the
+    # encoder runs; must agree with the per-tap-box kernel to the last bit (same products, same accumulation order)
+    got_lin = _run(11, x, None, W1t, b1, N, H, W, (N, H1, W1, 32))
+    assert_close("conv1 fwd (linear-shift)", got_lin, nhwc(y1), 6e-3)
+    assert torch.equal(got_lin, got)
     y1b = _bf(nhwc(y1).float())                         # what the next layer actually consumes
     y1n = y1b.permute(0, 3, 1, 2).double()
     y2 = F.relu(F.conv2d(y1n, W2t.double(), b2.double(), stride=2))
@@ -65,6 +70,9 @@ def test_implicit_gemm_convs_match_torch(N, H, W):
     y3 = F.relu(F.conv2d(y2n, W3t.double(), b3.double(), stride=1))
     got = _run(3, y2b, None, W3t, b3, N, H, W, (N, H3, W3, 64))
     assert_close("conv3 fwd", got, nhwc(y3), 1e-4)
+    got_lin = _run(13, y2b, None, W3t, b3, N, H, W, (N, H3, W3, 64))
+    assert_close("conv3 fwd (linear-shift)", got_lin, nhwc(y3), 1e-4)
+    assert torch.equal(got_lin, got)
     # ---- data gradients
     dy3 = _bf(torch.randn(N, H3, W3, 64, generator=g))
     dy3n = dy3.permute(0, 3, 1, 2).double()
