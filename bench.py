@@ -28,14 +28,21 @@ import torch  # noqa: E402
 T_FRAMES, IMG = 16, 200
 # algorithmic FLOPs (2/MAC, fwd+bwd, de-duplicated)
 ENC_FLOP_PER_FRAME = 260.8e6
+# Algorithmic HBM bytes of the encoder fwd+bwd per 200x200 frame with bf16 stored activations:
+# uint8 image 2 x 120000 (conv1 forward, conv1 weight gradient), y1/dy1 153664 (bf16, 49x49x32), y2/dy2 67712 (23x23x64),
+# y3 112896 (fp32, 21x21x64), dy3 56448:  forward 788544 + backward 1355456.
+ENC_BYTES_PER_FRAME = 2_144_000
+# dram__bytes_read.sum + dram__bytes_write.sum over the encoder's kernels in one `ncu --set full` capture of
+# scripts/profile_encoder.py (1024 frames; profiles/r01_encoder_kernels_ncu.md), uint8-input equivalent
+ENC_NCU_TRAFFIC_BYTES = 3.216e9
 PLAYLMP_FLOP_PER_WINDOW = 8.97e9
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("TACORL_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=64, help="windows per GPU")
@@ -109,46 +116,60 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle-reason samples DURING the timed region: an NVML polling thread (a sample every few ms; the
+    timed region of a default run is only tens of ms long, too short for `nvidia-smi -lms`)."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.proc = None
+        self.samples, self.reasons, self.power = [], set(), []
+        self._stop = None
+        self._thread = None
+        self.max_mhz = None
+        self.err = None
+
+    def _run(self, nv, h):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1e3)
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
+                return
+            time.sleep(0.002)
 
     def start(self):
+        import threading
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].isdigit() else self.idx
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self._stop = threading.Event()
+            self._thread = threading.Thread(target=self._run, args=(nv, h), daemon=True)
+            self._thread.start()
+        except Exception as e:
+            self.err = repr(e)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ""
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in out.strip().splitlines():
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for nme, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nme)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable: " + str(self.err)], "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_min_mhz": min(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "power_w_max": max(self.power) if self.power else None, "source": "nvml, sampled during the timed region"}
 
 
 # ----------------------------------------------------------------------------------- TACO-RL (secondary line item)
@@ -313,12 +334,20 @@ def run_ours(args):
     enc_fb(0)
     enc_ms = timed(enc_fb, 5) / 5
     pk, pk_kind = peaks()
-    achieved_tf = B * T_FRAMES * ENC_FLOP_PER_FRAME / (enc_ms / 1e3) / 1e12
-    roof = {"kernel": "lmp_encoder fwd+bwd (conv implicit GEMMs + soft-argmax + FC)", "bound": "tensor",
-            "achieved": achieved_tf, "peak": pk["bf16_tflops"], "peak_kind": pk_kind + " burst (cuBLAS bf16)",
-            "unit": "TFLOP/s", "frac": achieved_tf / pk["bf16_tflops"], "traffic": None,
-            "ms_per_launch": enc_ms, "algorithmic_flops_per_launch": B * T_FRAMES * ENC_FLOP_PER_FRAME,
-            "share_of_step": enc_ms / ms_per_step}
+    n_frames = B * T_FRAMES
+    achieved_tf = n_frames * ENC_FLOP_PER_FRAME / (enc_ms / 1e3) / 1e12
+    achieved_gbs = n_frames * ENC_BYTES_PER_FRAME / (enc_ms / 1e3) / 1e9
+    # 260.8 MFLOP over 2.144 MB per frame = 122 FLOP/B, below the ridge of the measured peaks (1623 TF/s / 6.54 TB/s =
+    # 248 FLOP/B): with stored activations the encoder pass is bounded by HBM, not by the tensor pipe
+    roof = {"kernel": "lmp_encoder fwd+bwd pass (s2d + implicit-GEMM convs fwd/dgrad/wgrad + soft-argmax + FC), timed alone",
+            "bound": "hbm", "achieved": achieved_gbs, "peak": pk["hbm_gbs"], "peak_kind": pk_kind + " burst (copy)",
+            "unit": "GB/s", "frac": achieved_gbs / pk["hbm_gbs"],
+            "traffic": ENC_NCU_TRAFFIC_BYTES * n_frames / 1024 if args.input == "u8" else None,
+            "algorithmic_bytes_per_launch": n_frames * ENC_BYTES_PER_FRAME,
+            "ms_per_launch": enc_ms, "share_of_step": enc_ms / ms_per_step,
+            "tensor": {"achieved": achieved_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                       "frac": achieved_tf / pk["bf16_tflops"],
+                       "algorithmic_flops_per_launch": n_frames * ENC_FLOP_PER_FRAME}}
 
     tac = None
     if not args.no_tacorl:
