@@ -216,6 +216,12 @@ def measure_tacorl(args, dev, world, rank, timed):
 
 
 # ----------------------------------------------------------------------------------- our arm
+def trace(msg):
+    if os.environ.get("BENCH_TRACE"):
+        sys.stderr.write(f"[bench rank {os.environ.get('RANK', '0')} +{time.perf_counter():.1f}s] {msg}\n")
+        sys.stderr.flush()
+
+
 def run_ours(args):
     import torch.distributed as dist
     from tacorl_b200 import _lib, configs, ops, parallel, runtime
@@ -228,10 +234,18 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
+        # the gradient all-reduce runs under the encoder backward: 16 NCCL channels on the 16 SMs the persistent
+        # convolution kernels leave free (parallel.attach_data_parallel).  N=2 sweep, ms/step: default channels / no
+        # reserve 4.05, 8/8 4.30, 16/16 3.96, 24/24 4.01, 32/32 4.07 (scripts/n2_reserve_sweep.sh)
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "16")
+        os.environ.setdefault("NCCL_MIN_NCHANNELS", "16")
         dist.init_process_group("nccl", device_id=dev)
     ops.set_precision(args.precision)
     B = args.batch
 
+    trace("process group up")
     torch.manual_seed(0)
     m = instantiate(configs.play_lmp_for_rl("tanh_net"))
     synthetic.init_like_reference(m, seed=0)              # identical random-init weights on every rank
@@ -286,6 +300,7 @@ def run_ours(args):
         return float(ms)
 
     used_graph = graphed is not None
+    trace(f"graph captured: {used_graph}")
     for s in range(args.warmup):
         step(None, None, s)
     clocks = ClockSampler(local)
@@ -299,6 +314,7 @@ def run_ours(args):
         launches += graphed.launches_per_replay * (graphed.replays - r0)
     clk = clocks.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
+    trace(f"timed region done: {ms_per_step:.3f} ms/step")
     fps = world * B * T_FRAMES / (ms_per_step / 1e3)
 
     # end-to-end: pinned host batch -> H2D every step, loss read back every step.  With the graph runner the copy
@@ -320,6 +336,7 @@ def run_ours(args):
     e2e_step(0)
     e2e_ms = timed(e2e_step, args.steps) / args.steps
     e2e_fps = world * B * T_FRAMES / (e2e_ms / 1e3)
+    trace(f"e2e done: {e2e_ms:.3f} ms/step")
 
     # dominant op, timed alone with CUDA events on the launch stream: the vision encoder fwd+bwd
     enc = m.perceptual_encoder.networks["rgb_static"]
@@ -333,6 +350,7 @@ def run_ours(args):
 
     enc_fb(0)
     enc_ms = timed(enc_fb, 5) / 5
+    trace(f"encoder pass timed: {enc_ms:.3f} ms")
     pk, pk_kind = peaks()
     n_frames = B * T_FRAMES
     achieved_tf = n_frames * ENC_FLOP_PER_FRAME / (enc_ms / 1e3) / 1e12
@@ -394,11 +412,23 @@ def run_ours(args):
                                               "oracle port of the reference step on torch CPU fp32"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # destroy_process_group() can block for minutes while captured CUDA graphs still reference the communicator
+        # (seen at N=2: the JSON line was out, the process never exited).  Everything is measured and printed:
+        # leave together and skip the teardown.
+        trace("leaving")
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
     args = parse()
+    if os.environ.get("BENCH_TRACE"):       # where is each rank when a wrapper's timeout sends SIGTERM?
+        import faulthandler
+        import signal
+        faulthandler.register(signal.SIGTERM, all_threads=False, chain=True)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -41,6 +41,11 @@ int tacorl_abi_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py reports the delta) */
 unsigned long long tacorl_launch_count(void);
 
+/* Leave n SMs out of the grids of the persistent one-CTA-per-SM kernels (convolutions, weight gradients) so that a
+ * concurrently running collective (NCCL all-reduce of the previous gradient slice) finds free SMs; returns the CTA count
+ * those kernels now launch.  Default 0 (env TACORL_SM_RESERVE). */
+int tacorl_set_sm_reserve(int n);
+
 /* ---- dense layers -------------------------------------------------------------------------
  * C[M,N] = act(alpha * op(A)[M,K] op(B)[K,N] + beta * C + bias[N]); row-major with leading dims.
  * transA: A stored [K,M]; transB: B stored [N,K] (a torch Linear weight).  Cpre (optional) receives

@@ -68,6 +68,7 @@ _SIGS = {
     "tacorl_launch_count": [],
     "tacorl_rnn_seq_timeouts": [],
     "tacorl_rnn_seq_enable": [_i],
+    "tacorl_set_sm_reserve": [_i],
 }
 _RESTYPES = {
     "tacorl_lmp_encoder_ws_bytes": _sz, "tacorl_rnn_layer_ws_bytes": _sz,

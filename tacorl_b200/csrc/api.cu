@@ -5,6 +5,16 @@
 
 using namespace tacorl;
 
+namespace tacorl {
+static int g_sm_reserve = -1;
+int persistent_ctas() {
+  if (g_sm_reserve < 0) { const char* e = getenv("TACORL_SM_RESERVE"); g_sm_reserve = e ? atoi(e) : 0; }
+  const int n = 148 - g_sm_reserve;
+  return n < 8 ? 8 : n;
+}
+void set_sm_reserve(int n) { g_sm_reserve = n < 0 ? 0 : (n > 140 ? 140 : n); }
+}  // namespace tacorl
+
 extern "C" {
 
 const char* tacorl_last_error(void) { return last_error(); }
@@ -14,6 +24,8 @@ int tacorl_abi_version(void) { return TACORL_B200_ABI_VERSION; }
 unsigned long long tacorl_launch_count(void) { return launch_count(); }
 
 unsigned tacorl_rnn_seq_timeouts(void) { return rnn_seq_timeouts(); }
+
+int tacorl_set_sm_reserve(int n) { set_sm_reserve(n); return persistent_ctas(); }
 
 int tacorl_rnn_seq_enable(int on) { const int was = rnn_seq_enabled() ? 1 : 0; rnn_seq_set_enabled(on); return was; }
 

@@ -567,7 +567,7 @@ static int cv_launch(const ConvGeom& g, const ActView& view, const void* wpacked
     TACORL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  const int ctas = g.num_tiles < 148 ? g.num_tiles : 148;
+  const int ctas = g.num_tiles < persistent_ctas() ? g.num_tiles : persistent_ctas();
   kern<<<ctas, CV_THREADS, smem, st>>>(g, ta, tw, ep);
   TACORL_LAUNCH_CHECK();
   return 0;
@@ -626,7 +626,7 @@ static int cl_launch(ConvLinGeom g, int N, const void* src, const void* wpacked,
     TACORL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  const int ctas = g.num_tiles < 148 ? g.num_tiles : 148;
+  const int ctas = g.num_tiles < persistent_ctas() ? g.num_tiles : persistent_ctas();
   kern<<<ctas, CV_THREADS, smem, st>>>(g, ta, tw, ep);
   TACORL_LAUNCH_CHECK();
   return 0;
@@ -1102,7 +1102,7 @@ int conv_tc_wgrad(int layer, const void* dyb, const void* src, int N, int SH, in
   g.dy_chunks = g.OC / 8;
   if (g.M == 0) return 0;
   const int NCOLS = g.NT * 64;
-  int splits = 148 / g.groups;
+  int splits = persistent_ctas() / g.groups;
   const int kblocks = (g.M + 63) / 64;
   if (splits > kblocks) splits = kblocks;
   const size_t per_split = ((size_t)g.groups * g.OC * NCOLS + g.OC) * sizeof(float);

@@ -24,6 +24,12 @@ int softargmax_bwd_f32(const float* y, int N, int OH, int OW, int C, const float
                        const float* feat, const float* smax, const float* ssum, const float* dfeat,
                        float* dy, float* dtau_part, cudaStream_t st);
 
+// CTAs a persistent one-CTA-per-SM kernel launches: 148 minus the SMs left free for concurrently running collectives
+// (tacorl_set_sm_reserve / TACORL_SM_RESERVE).  A statically scheduled 148-CTA kernel whose last CTAs cannot be placed
+// because NCCL holds their SMs takes up to twice as long; leaving those SMs out of the grid costs only their share.
+int persistent_ctas();
+void set_sm_reserve(int n);
+
 // ---- bf16 tcgen05 GEMM (gemm_tc.cu)
 struct TcArgs {
   float alpha = 1.f, beta = 0.f;

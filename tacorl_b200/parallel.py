@@ -2,8 +2,12 @@
 buffer over NVLink/NVSwitch, 1/world folded into the fused Adam kernel.  Replaces Lightning's DDP-over-gloo
 (/root/reference/config/trainer/default.yaml:1-3, scripts/train.py:73-75).  Works on CPU tensors with the
 gloo backend (tests/test_parallel_gloo.py)."""
+import os
+
 import torch
 import torch.distributed as dist
+
+SM_RESERVE_FOR_COLLECTIVES = 16   # SMs left out of the persistent conv grids when gradients are exchanged (one per NCCL channel)
 
 
 class BucketedAllReduce:
@@ -49,6 +53,10 @@ def attach_data_parallel(optimizer, world_size, group=None, bucket_elems=16 << 2
     mean of local-mean gradients; clip-by-norm acts on the reduced gradient, cql_offline_lightning.py:521-537)."""
     optimizer.grad_sync = BucketedAllReduce(world_size, bucket_elems, group)
     optimizer.grad_scale = 1.0 / world_size
+    if world_size > 1 and optimizer.flat_params.is_cuda and "TACORL_SM_RESERVE" not in os.environ:
+        # the all-reduce of the non-encoder slice overlaps the encoder backward: keep SMs free for its channels
+        from . import _lib
+        _lib.lib().tacorl_set_sm_reserve(SM_RESERVE_FOR_COLLECTIVES)
     return optimizer
 
 
