@@ -53,7 +53,8 @@ def attach_data_parallel(optimizer, world_size, group=None, bucket_elems=16 << 2
     mean of local-mean gradients; clip-by-norm acts on the reduced gradient, cql_offline_lightning.py:521-537)."""
     optimizer.grad_sync = BucketedAllReduce(world_size, bucket_elems, group)
     optimizer.grad_scale = 1.0 / world_size
-    if world_size > 1 and optimizer.flat_params.is_cuda and "TACORL_SM_RESERVE" not in os.environ:
+    flat = getattr(optimizer, "flat_params", None)
+    if world_size > 1 and flat is not None and flat.is_cuda and "TACORL_SM_RESERVE" not in os.environ:
         # the all-reduce of the non-encoder slice overlaps the encoder backward: keep SMs free for its channels
         from . import _lib
         _lib.lib().tacorl_set_sm_reserve(SM_RESERVE_FOR_COLLECTIVES)
