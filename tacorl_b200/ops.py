@@ -91,6 +91,37 @@ def shadow_of(t):
     return None
 
 
+# ---- gradient slots.  FlatAdam owns one flat gradient buffer; a backward kernel that produces the whole gradient of a
+# registered parameter can write it straight into that parameter's slice (and hand autograd the view) instead of into
+# a temporary that step() would then copy (189 MB read + write per PlayLMP step).  A slot is handed out at most once
+# between two step()/zero_grad() calls: a second backward through the same weight gets a temporary, and autograd
+# accumulates it into the first result as usual.
+_GRAD_OWNERS = []
+
+
+def register_grad_owner(owner):
+    """owner: object with .pbuf.flat, .flat_grad (same numel), ._pnumel (data_ptr -> numel) and ._slots_taken (set)."""
+    _GRAD_OWNERS.append(owner)
+
+
+def grad_slot_of(t):
+    """View of the owning optimiser's flat gradient for the whole parameter `t` (first request since the last
+    step()/zero_grad()), else None."""
+    if t is None or not t.is_cuda or not t.is_contiguous():
+        return None
+    ptr = t.data_ptr()
+    for o in _GRAD_OWNERS:
+        flat = o.pbuf.flat
+        base = flat.data_ptr()
+        if base <= ptr < base + flat.numel() * 4 and flat.device == t.device:
+            if o._pnumel.get(ptr) != t.numel() or ptr in o._slots_taken:
+                return None
+            o._slots_taken.add(ptr)
+            off = (ptr - base) // 4
+            return o.flat_grad[off:off + t.numel()].view(t.shape)
+    return None
+
+
 def gemm(A, B, C, transA=False, transB=False, alpha=1.0, beta=0.0, bias=None, act=L.ACT_NONE, Cpre=None, A_bf16=None,
          B_bf16=None):
     """C = act(alpha * op(A) op(B) + beta*C + bias); A, B, C are row-major 2-D (possibly strided rows).
@@ -323,7 +354,10 @@ class ReluRNNFn(Function):
             def run_dir(d, tag, dx_buf):
                 k = (l * D + d) * 4
                 w_ih, w_hh = weights[k], weights[k + 1]
-                g = [torch.empty_like(weights[k + j]) for j in range(4)]
+                g = []
+                for j in range(4):     # straight into the optimiser's flat gradient when this is the parameter's first use
+                    slot = grad_slot_of(weights[k + j])
+                    g.append(slot if slot is not None else torch.empty_like(weights[k + j]))
                 n_steps = 1 if (last_only and l == num_layers - 1 and d == 1) else T
                 h0_ld = None if h0 is None else _c(h0[l * D + d])
                 dhn_ld = None if d_hn is None else _c(d_hn[l * D + d])

@@ -63,9 +63,11 @@ class FlatAdam(torch.optim.Optimizer):
         self._pver = {}
         self._pnumel = {p.data_ptr(): p.numel() for p in ps}
         self._flat_version = self.pbuf.flat._version
+        self._slots_taken = set()
         if self.pbuf.flat.is_cuda:
             self.shadow = torch.zeros(self.pbuf.numel, device=self.pbuf.flat.device, dtype=torch.bfloat16)
             ops.register_shadow_owner(self)
+            ops.register_grad_owner(self)
 
     @property
     def flat_params(self):
@@ -103,8 +105,9 @@ class FlatAdam(torch.optim.Optimizer):
         dst, src, missing = [], [], []
         for p, gv in zip(ps, self.grad_views[lo:hi]):
             if p.grad is None:
-                missing.append(gv)
-            else:
+                if p.data_ptr() not in self._slots_taken:   # (a taken slot already holds this pass's gradient)
+                    missing.append(gv)
+            elif p.grad.data_ptr() != gv.data_ptr():      # else: the backward kernel wrote the slot itself (ops.grad_slot_of)
                 dst.append(gv)
                 src.append(p.grad)
         if dst:
@@ -112,9 +115,14 @@ class FlatAdam(torch.optim.Optimizer):
         for gv in missing:
             gv.zero_()
 
+    def zero_grad(self, set_to_none=True):
+        self._slots_taken.clear()
+        return super().zero_grad(set_to_none=set_to_none)
+
     @torch.no_grad()
     def step(self, closure=None, gathered=False):
         loss = closure() if closure is not None else None
+        self._slots_taken.clear()
         if self._synced is not None and self.grad_sync is not None:
             lo, hi, e0, e1 = self._synced          # [lo,hi) already gathered and in flight on the side stream
             n = len(self.param_groups[0]["params"])

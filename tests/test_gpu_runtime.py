@@ -70,3 +70,38 @@ def test_bf16_shadow_weights_follow_torch_side_edits():
         assert rel_err(ops.linear(x, W), 0.5 * want) < 1e-5
     finally:
         ops.set_precision("fp32")
+
+
+def test_rnn_weight_gradients_land_in_the_flat_gradient_buffer():
+    """ReluRNN's backward writes dW straight into FlatAdam's flat gradient (ops.grad_slot_of): after backward the
+    parameter's .grad aliases its slice, step() copies nothing for it, and the update equals the copy path's."""
+    import copy
+    from tacorl_b200 import ops
+    from tacorl_b200.networks.layers import ReluRNN
+    from tacorl_b200.optim import FlatAdam
+    ops.set_precision("fp32")
+    torch.manual_seed(3)
+    rnn_a = ReluRNN(12, 64, 2, True).to(DEV)
+    rnn_b = copy.deepcopy(rnn_a)
+    x = torch.randn(5, 7, 12, device=DEV)
+    opt_a = FlatAdam(rnn_a.parameters(), lr=1e-2)
+    for step in range(2):
+        opt_a.zero_grad()
+        out, _ = rnn_a(x)
+        out.square().mean().backward()
+        for p, gv in zip(opt_a.param_groups[0]["params"], opt_a.grad_views):
+            assert p.grad is not None and p.grad.data_ptr() == gv.data_ptr()
+        opt_a.step()
+    # reference: same two steps with the gradients produced in temporaries (slots exhausted -> copy path)
+    opt_b = FlatAdam(rnn_b.parameters(), lr=1e-2)
+    for step in range(2):
+        opt_b.zero_grad()
+        for p in opt_b.param_groups[0]["params"]:
+            opt_b._slots_taken.add(p.data_ptr())
+        out, _ = rnn_b(x)
+        out.square().mean().backward()
+        for p, gv in zip(opt_b.param_groups[0]["params"], opt_b.grad_views):
+            assert p.grad.data_ptr() != gv.data_ptr()
+        opt_b.step()
+    for pa, pb in zip(rnn_a.parameters(), rnn_b.parameters()):
+        assert torch.equal(pa, pb)
