@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TACORL_B200_ABI_VERSION 3
+#define TACORL_B200_ABI_VERSION 5
 
 #define TACORL_PREC_F32 0
 #define TACORL_PREC_BF16 1
@@ -119,16 +119,22 @@ size_t tacorl_rnn_layer_ws_bytes(int T, int B, int I, int H);
 unsigned tacorl_rnn_seq_timeouts(void);
 /* switch the persistent launch on/off at run time; returns the previous setting */
 int tacorl_rnn_seq_enable(int on);
+/* bf16 path, optional (NULL = stage internally): w_*_bf16 dense bf16 copies of the weights (tacorl_adam_step keeps
+ * them current); h_bf16_out: (T, B, H) bf16 buffer that receives the hidden states the tensor cores consumed — hand
+ * it back to the backward call as h_bf16 and BPTT skips re-casting the saved fp32 activations; w_hh_t_bf16: W_hh^T
+ * as bf16 (tacorl_cast_transpose_bf16), which the caller can prepare off the critical path. */
 int tacorl_rnn_layer_fwd(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
                          const float* w_hh, const float* b_ih, const float* b_hh, const float* h0,
                          int reverse, int n_steps, float* out, long long ldo, const void* w_ih_bf16,
-                         const void* w_hh_bf16, void* ws, size_t ws_bytes, int prec, void* stream);
+                         const void* w_hh_bf16, void* h_bf16_out, void* ws, size_t ws_bytes, int prec, void* stream);
 int tacorl_rnn_layer_bwd(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
                          const float* w_hh, const float* h0, int reverse, int n_steps, const float* out,
                          long long ldo, float* dout, long long lddo, const float* dhn, float* dx,
                          long long lddx, int dx_accumulate, float* dw_ih, float* dw_hh, float* db_ih,
-                         float* db_hh, int accumulate, float* dh0, const void* w_ih_bf16, void* ws, size_t ws_bytes,
-                         int prec, void* stream);
+                         float* db_hh, int accumulate, float* dh0, const void* w_ih_bf16, const void* w_hh_t_bf16,
+                         const void* h_bf16, void* ws, size_t ws_bytes, int prec, void* stream);
+/* dst (cols x rows, bf16, dense) = transpose of src (rows x cols, fp32, dense) */
+int tacorl_cast_transpose_bf16(const float* src, int rows, int cols, void* dst, void* stream);
 
 /* ---- action decoder losses: action_decoder_logistic.py:184-235 (_logistic_loss), :114-133 (_loss),
  * :238-266 (_sample).  logits row = [prob A*10 | mean A*10 | log_scale A*10 | gripper 2].

@@ -34,10 +34,11 @@ _SIGS = {
                                _vp, _vp, _sz, _i, _vp],
     "tacorl_conv_tc_debug": [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp],
     "tacorl_rnn_layer_ws_bytes": [_i, _i, _i, _i],
-    "tacorl_rnn_layer_fwd": [_i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _ll, _vp, _vp, _vp, _sz, _i,
-                             _vp],
+    "tacorl_rnn_layer_fwd": [_i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _ll, _vp, _vp, _vp, _vp, _sz,
+                             _i, _vp],
     "tacorl_rnn_layer_bwd": [_i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp, _i, _i, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _i,
-                             _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _vp],
+                             _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp],
+    "tacorl_cast_transpose_bf16": [_vp, _i, _i, _vp, _vp],
     "tacorl_dlm_nll": [_i, _i, _vp, _ll, _vp, _ll, _i, _f, _f, _f, _vp, _vp, _vp, _ll, _vp],
     "tacorl_dlm_sample": [_i, _i, _vp, _ll, _vp, _vp, _vp, _ll, _f, _f, _vp, _vp, _vp, _vp],
     "tacorl_gauss_head_fwd": [_i, _i, _vp, _vp, _vp, _vp],

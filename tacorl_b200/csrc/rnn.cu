@@ -67,7 +67,7 @@ size_t tacorl_rnn_layer_ws_bytes(int T, int B, int I, int H) {
 
 static int rnn_fwd_f32(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
                        const float* w_hh, const float* b_ih, const float* b_hh, const float* h0,
-                       int reverse, int n_steps, float* out, long long ldo, const void*, const void*, void* ws,
+                       int reverse, int n_steps, float* out, long long ldo, const void*, const void*, void*, void* ws,
                        size_t ws_bytes, cudaStream_t st) {
   TACORL_REQUIRE(x && w_ih && w_hh && b_ih && b_hh && out && ws, "rnn_layer_fwd: null pointer");
   TACORL_REQUIRE(n_steps >= 1 && n_steps <= T, "rnn_layer_fwd: n_steps %d out of range (T=%d)", n_steps, T);
@@ -109,8 +109,8 @@ static int rnn_bwd_f32(int T, int B, int I, int H, const float* x, long long ldx
                        const float* w_hh, const float* h0, int reverse, int n_steps, const float* out,
                        long long ldo, float* dout, long long lddo, const float* dhn, float* dx,
                        long long lddx, int dx_accumulate, float* dw_ih, float* dw_hh, float* db_ih,
-                       float* db_hh, int accumulate, float* dh0, const void*, void* ws, size_t ws_bytes,
-                       cudaStream_t st) {
+                       float* db_hh, int accumulate, float* dh0, const void*, const void*, const void*, void* ws,
+                       size_t ws_bytes, cudaStream_t st) {
   TACORL_REQUIRE(x && w_ih && w_hh && out && dout && ws, "rnn_layer_bwd: null pointer");
   TACORL_REQUIRE(n_steps >= 1 && n_steps <= T, "rnn_layer_bwd: n_steps out of range");
   if (B == 0) return 0;
@@ -205,7 +205,7 @@ static int rnn_bwd_f32(int T, int B, int I, int H, const float* x, long long ldx
 static int rnn_fwd_bf16(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
                         const float* w_hh, const float* b_ih, const float* b_hh, const float* h0,
                         int reverse, int n_steps, float* out, long long ldo, const void* w_ih_bf16,
-                        const void* w_hh_bf16, void* ws, size_t ws_bytes, cudaStream_t st) {
+                        const void* w_hh_bf16, void* h_bf16_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   const long long Ip = (I + 7) & ~7LL;
   // caller-maintained bf16 weight copies (tacorl_adam_step shadow) replace the per-call staging casts
   const bool wih_ready = w_ih_bf16 && Ip == I && ((uintptr_t)w_ih_bf16 & 15) == 0;
@@ -215,7 +215,10 @@ static int rnn_fwd_bf16(int T, int B, int I, int H, const float* x, long long ld
   const __nv_bfloat16* wih = wih_ready ? (const __nv_bfloat16*)w_ih_bf16 : ar.take<__nv_bfloat16>((size_t)H * Ip);
   const __nv_bfloat16* whh = whh_ready ? (const __nv_bfloat16*)w_hh_bf16 : ar.take<__nv_bfloat16>((size_t)H * H);
   __nv_bfloat16* xb = ar.take<__nv_bfloat16>((size_t)n_steps * B * Ip);
-  __nv_bfloat16* hb = ar.take<__nv_bfloat16>((size_t)T * B * H);
+  // the bf16 hidden states are the next step's operand; a caller that will run the backward pass keeps them
+  // (h_bf16_out, dense [T][B][H]) so that BPTT does not have to re-cast the saved fp32 activations
+  const bool hb_ext = h_bf16_out && ((uintptr_t)h_bf16_out & 15) == 0;
+  __nv_bfloat16* hb = hb_ext ? (__nv_bfloat16*)h_bf16_out : ar.take<__nv_bfloat16>((size_t)T * B * H);
   __nv_bfloat16* h0b = h0 ? ar.take<__nv_bfloat16>((size_t)B * H) : nullptr;
   unsigned* flags = ar.take<unsigned>(64);
   TACORL_REQUIRE(bsum && wih && whh && xb && hb && (!h0 || h0b) && flags, "rnn_layer_fwd(bf16): workspace too small");
@@ -260,15 +263,17 @@ static int rnn_bwd_bf16(int T, int B, int I, int H, const float* x, long long ld
                         const float* w_hh, const float* h0, int reverse, int n_steps, const float* out,
                         long long ldo, float* dout, long long lddo, const float* dhn, float* dx,
                         long long lddx, int dx_accumulate, float* dw_ih, float* dw_hh, float* db_ih,
-                        float* db_hh, int accumulate, float* dh0, const void* w_ih_bf16, void* ws, size_t ws_bytes,
-                        cudaStream_t st) {
+                        float* db_hh, int accumulate, float* dh0, const void* w_ih_bf16, const void* w_hh_t_bf16,
+                        const void* h_bf16, void* ws, size_t ws_bytes, cudaStream_t st) {
   const long long Ip = (I + 7) & ~7LL;
   const bool wih_ready = w_ih_bf16 && Ip == I && ((uintptr_t)w_ih_bf16 & 15) == 0;
+  const bool whht_ready = w_hh_t_bf16 && ((uintptr_t)w_hh_t_bf16 & 15) == 0;   // W_hh^T, prepared off the critical path
+  const bool hb_ready = h_bf16 && ((uintptr_t)h_bf16 & 15) == 0;               // bf16 hidden states kept by the forward
   Arena ar(ws, ws_bytes);
   const __nv_bfloat16* wih = wih_ready ? (const __nv_bfloat16*)w_ih_bf16 : ar.take<__nv_bfloat16>((size_t)H * Ip);
-  __nv_bfloat16* whh = ar.take<__nv_bfloat16>((size_t)H * H);
+  __nv_bfloat16* whh = whht_ready ? (__nv_bfloat16*)w_hh_t_bf16 : ar.take<__nv_bfloat16>((size_t)H * H);
   __nv_bfloat16* xb = ar.take<__nv_bfloat16>((size_t)n_steps * B * Ip);
-  __nv_bfloat16* hb = ar.take<__nv_bfloat16>((size_t)T * B * H);
+  __nv_bfloat16* hb = hb_ready ? (__nv_bfloat16*)h_bf16 : ar.take<__nv_bfloat16>((size_t)T * B * H);
   __nv_bfloat16* db = ar.take<__nv_bfloat16>((size_t)T * B * H);
   __nv_bfloat16* h0b = h0 ? ar.take<__nv_bfloat16>((size_t)B * H) : nullptr;
   unsigned* flags = ar.take<unsigned>(64);
@@ -280,9 +285,9 @@ static int rnn_bwd_bf16(int T, int B, int I, int H, const float* x, long long ld
   const long long rows = (long long)n_steps * B;
   int rc;
   if (!wih_ready && (rc = cast_bf16_2d(w_ih, I, H, I, (void*)wih, Ip, st))) return rc;
-  if ((rc = cast_transpose_bf16(w_hh, H, H, H, whh, H, st))) return rc;     // whh = W_hh^T: K-major B for the carry GEMM
+  if (!whht_ready && (rc = cast_transpose_bf16(w_hh, H, H, H, whh, H, st))) return rc;   // W_hh^T: K-major B for the carry GEMM
   if ((rc = cast_bf16_2d(x + (long long)t_lo * B * ldx, ldx, rows, I, xb, Ip, st))) return rc;
-  if ((rc = cast_bf16_2d(out + (long long)t_lo * B * ldo, ldo, rows, H, hb + (long long)t_lo * B * H, H, st))) return rc;
+  if (!hb_ready && (rc = cast_bf16_2d(out + (long long)t_lo * B * ldo, ldo, rows, H, hb + (long long)t_lo * B * H, H, st))) return rc;
   if (h0 && (rc = cast_bf16_2d(h0, H, B, H, h0b, H, st))) return rc;
   {  // last step of the recurrence: dpre = (dout (+ dhn)) * [h > 0]
     const int t = reverse ? T - n_steps : n_steps - 1;
@@ -368,23 +373,29 @@ static int rnn_bwd_bf16(int T, int B, int I, int H, const float* x, long long ld
 int tacorl_rnn_layer_fwd(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
                          const float* w_hh, const float* b_ih, const float* b_hh, const float* h0,
                          int reverse, int n_steps, float* out, long long ldo, const void* w_ih_bf16,
-                         const void* w_hh_bf16, void* ws, size_t ws_bytes, int prec, void* stream) {
+                         const void* w_hh_bf16, void* h_bf16_out, void* ws, size_t ws_bytes, int prec, void* stream) {
   TACORL_REQUIRE(prec == PREC_F32 || prec == PREC_BF16, "rnn_layer_fwd: unknown precision %d", prec);
   auto fn = prec == PREC_BF16 ? rnn_fwd_bf16 : rnn_fwd_f32;
-  return fn(T, B, I, H, x, ldx, w_ih, w_hh, b_ih, b_hh, h0, reverse, n_steps, out, ldo, w_ih_bf16, w_hh_bf16, ws,
-            ws_bytes, (cudaStream_t)stream);
+  return fn(T, B, I, H, x, ldx, w_ih, w_hh, b_ih, b_hh, h0, reverse, n_steps, out, ldo, w_ih_bf16, w_hh_bf16, h_bf16_out,
+            ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int tacorl_rnn_layer_bwd(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
                          const float* w_hh, const float* h0, int reverse, int n_steps, const float* out,
                          long long ldo, float* dout, long long lddo, const float* dhn, float* dx,
                          long long lddx, int dx_accumulate, float* dw_ih, float* dw_hh, float* db_ih,
-                         float* db_hh, int accumulate, float* dh0, const void* w_ih_bf16, void* ws, size_t ws_bytes,
-                         int prec, void* stream) {
+                         float* db_hh, int accumulate, float* dh0, const void* w_ih_bf16, const void* w_hh_t_bf16,
+                         const void* h_bf16, void* ws, size_t ws_bytes, int prec, void* stream) {
   TACORL_REQUIRE(prec == PREC_F32 || prec == PREC_BF16, "rnn_layer_bwd: unknown precision %d", prec);
   auto fn = prec == PREC_BF16 ? rnn_bwd_bf16 : rnn_bwd_f32;
   return fn(T, B, I, H, x, ldx, w_ih, w_hh, h0, reverse, n_steps, out, ldo, dout, lddo, dhn, dx, lddx,
-            dx_accumulate, dw_ih, dw_hh, db_ih, db_hh, accumulate, dh0, w_ih_bf16, ws, ws_bytes, (cudaStream_t)stream);
+            dx_accumulate, dw_ih, dw_hh, db_ih, db_hh, accumulate, dh0, w_ih_bf16, w_hh_t_bf16, h_bf16, ws, ws_bytes,
+            (cudaStream_t)stream);
+}
+
+int tacorl_cast_transpose_bf16(const float* src, int rows, int cols, void* dst, void* stream) {
+  TACORL_REQUIRE(src && dst, "cast_transpose_bf16: null pointer");
+  return cast_transpose_bf16(src, cols, rows, cols, dst, rows, (cudaStream_t)stream);
 }
 
 }  // extern "C"

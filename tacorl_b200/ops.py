@@ -34,6 +34,13 @@ def _side_stream(dev):
     return _SIDE[key]
 
 
+def _prep_stream(dev):
+    key = ("prep", dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
 def _off(t, elems):
     return ctypes.c_void_p(t.data_ptr() + 4 * elems)
 
@@ -283,6 +290,20 @@ class ReluRNNFn(Function):
         outs = []
         inp = x
         hn = [] if not last_only else None
+        # bf16 training: keep the bf16 hidden states for BPTT, and transpose W_hh (the carry GEMM's operand) on the
+        # side stream now, where it overlaps the latency-bound recurrence, instead of on the backward's critical path
+        train = _STATE["prec"] == L.PREC_BF16 and any(ctx.needs_input_grad)   # (grad mode itself is off inside forward)
+        hbs = [torch.empty(T, B, H, device=dev, dtype=torch.bfloat16) if train else None for _ in range(num_layers * D)]
+        whts, prep_done = [None] * (num_layers * D), None
+        if train:
+            main, prep = torch.cuda.current_stream(dev), _prep_stream(dev)
+            whts = [torch.empty(H, H, device=dev, dtype=torch.bfloat16) for _ in range(num_layers * D)]   # main-stream pool
+            prep.wait_stream(main)
+            with torch.cuda.stream(prep):
+                for k in range(num_layers * D):
+                    L.call("tacorl_cast_transpose_bf16", L.ptr(weights[k * 4 + 1]), H, H, L.ptr_any(whts[k]), L.stream())
+                prep_done = torch.cuda.Event()
+                prep_done.record(prep)
         for l in range(num_layers):
             Il = inp.shape[2]
             out = torch.empty(T, B, D * H, device=dev, dtype=torch.float32)
@@ -295,7 +316,7 @@ class ReluRNNFn(Function):
                 ws = L.workspace(nbytes, dev, tag)
                 L.call("tacorl_rnn_layer_fwd", T, B, Il, H, L.ptr(inp), Il, L.ptr(w_ih), L.ptr(w_hh), L.ptr(b_ih),
                        L.ptr(b_hh), L.ptr(h0_ld), d, n_steps, _off(out, d * H), D * H,
-                       L.ptr_any(shadow_of(w_ih)), L.ptr_any(shadow_of(w_hh)),
+                       L.ptr_any(shadow_of(w_ih)), L.ptr_any(shadow_of(w_hh)), L.ptr_any(hbs[l * D + d]),
                        ctypes.c_void_p(ws.data_ptr()), ws.numel(), _STATE["prec"], L.stream())
 
             if D == 2:
@@ -323,6 +344,7 @@ class ReluRNNFn(Function):
             inp = out
         ctx.cfg = (T, B, I, H, D, num_layers, last_only)
         ctx.has_h0 = h0 is not None
+        ctx.bf16_aux = (hbs, whts, prep_done) if train else None
         ctx.save_for_backward(x, h0, *outs, *weights)
         if last_only:
             return inp[T - 1], None
@@ -343,6 +365,10 @@ class ReluRNNFn(Function):
             dbuf = d_out.contiguous().clone() if d_out is not None else torch.zeros(T, B, D * H, device=dev)
         wgrads = [None] * len(weights)
         dh0 = torch.empty_like(h0) if (ctx.has_h0 and ctx.needs_input_grad[1]) else None
+        aux = ctx.bf16_aux if _STATE["prec"] == L.PREC_BF16 else None
+        hbs, whts = (aux[0], aux[1]) if aux is not None else ([None] * (num_layers * D),) * 2
+        if aux is not None:
+            torch.cuda.current_stream(dev).wait_event(aux[2])
         for l in range(num_layers - 1, -1, -1):
             inp = x if l == 0 else outs[l - 1]
             Il = inp.shape[2]
@@ -366,8 +392,8 @@ class ReluRNNFn(Function):
                 L.call("tacorl_rnn_layer_bwd", T, B, Il, H, L.ptr(inp), Il, L.ptr(w_ih), L.ptr(w_hh), L.ptr(h0_ld),
                        d, n_steps, _off(outs[l], d * H), D * H, _off(dbuf, d * H), D * H, L.ptr(dhn_ld),
                        L.ptr(dx_buf), Il, 0, L.ptr(g[0]), L.ptr(g[1]), L.ptr(g[2]), L.ptr(g[3]), 0,
-                       L.ptr(dh0_ld), L.ptr_any(shadow_of(w_ih)), ctypes.c_void_p(ws.data_ptr()), ws.numel(),
-                       _STATE["prec"], L.stream())
+                       L.ptr(dh0_ld), L.ptr_any(shadow_of(w_ih)), L.ptr_any(whts[l * D + d]), L.ptr_any(hbs[l * D + d]),
+                       ctypes.c_void_p(ws.data_ptr()), ws.numel(), _STATE["prec"], L.stream())
                 wgrads[k:k + 4] = g
 
             if D == 2:
