@@ -69,6 +69,11 @@ __device__ __forceinline__ void cv_tma_2d(uint32_t dst, const CUtensorMap* tm, i
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void cv_tma_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void cv_tma_5d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4,
                                           uint32_t bar) {
   asm volatile(
@@ -486,6 +491,173 @@ conv_lin_kernel(const __grid_constant__ ConvLinGeom g, const __grid_constant__ C
   }
 }
 
+// ------------------------------------------------------------------------------------------ fused conv2 data gradient
+// dy1[2a+py][2b+px][c] = [y1 > 0] * sum_{j,i in {0,1}} sum_oc dy2[a-j][b-i][oc] * W2[oc][c][py+2j][px+2i].
+// All four stride-parity classes (py, px) of output pixel pair-block (a, b) read the SAME four dy2 pixels, so one MMA
+// per tap with N = 4 classes x 32 channels = 128 replaces four N = 32 launches that each re-read dy2.  A tile is a
+// PW x PH = 16 x 8 patch of dy2 pixels loaded ONCE by a 4-D TMA box whose origin lies one pixel above / left of the
+// tile's first output (out-of-image pixels are zero-filled: they are exactly the taps that fall off the gradient map);
+// tap (j, i) is the stage read through a UMMA descriptor shifted by ((1-j)*PW + (1-i)) pixel rows, and the patch's
+// last row and column only serve as halo (15 x 7 outputs (a, b) per tile, each producing a 2 x 2 block of dy1).
+constexpr int DG_PW = 16, DG_PH = 8;
+constexpr int DG_STAGES = 8;
+struct Dgrad2Geom {
+  int H1, W1, H2, W2;               // dy1 / y1 grid, dy2 grid
+  int RA, RB;                       // pair-block grid: RA = ceil(H1 / 2), RB = ceil(W1 / 2)
+  int tiles_x, tiles_y, num_tiles;
+};
+
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv_dgrad2_kernel(const __grid_constant__ Dgrad2Geom g, const __grid_constant__ CUtensorMap tmA,
+                   const __grid_constant__ CUtensorMap tmW, const __nv_bfloat16* __restrict__ y1,
+                   __nv_bfloat16* __restrict__ dy1) {
+  constexpr uint32_t A_BYTES = 128 * 128, W_TAP_BYTES = 128 * 128, ACC_COLS = 128, TMEM_COLS = 256;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t w_base = cv_smem(smem);
+  const uint32_t a_base = w_base + 4 * W_TAP_BYTES;
+  // (one spare tile after the ring: the shifted reads of the halo rows run up to 17 rows past the last stage)
+  uint64_t* bars = (uint64_t*)(smem + 4 * W_TAP_BYTES + (DG_STAGES + 1) * A_BYTES);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * DG_STAGES + 5);
+  auto full_bar = [&](int s) { return cv_smem(bars + s); };
+  auto empty_bar = [&](int s) { return cv_smem(bars + DG_STAGES + s); };
+  auto tfull_bar = [&](int a) { return cv_smem(bars + 2 * DG_STAGES + a); };
+  auto tempty_bar = [&](int a) { return cv_smem(bars + 2 * DG_STAGES + 2 + a); };
+  const uint32_t w_bar = cv_smem(bars + 2 * DG_STAGES + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_frame = g.tiles_x * g.tiles_y;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < DG_STAGES; ++s) { cv_mbar_init(full_bar(s), 1); cv_mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { cv_mbar_init(tfull_bar(a), 1); cv_mbar_init(tempty_bar(a), 4); }
+    cv_mbar_init(w_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(cv_smem(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  cv_fence_before();
+  __syncthreads();
+  cv_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      cv_mbar_expect_tx(w_bar, 4 * W_TAP_BYTES);
+      for (int t = 0; t < 4; ++t) cv_tma_2d(w_base + t * W_TAP_BYTES, &tmW, 0, t * 128, w_bar);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+        const int n = tile / tiles_per_frame, rem = tile - n * tiles_per_frame;
+        const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
+        const int s = it % DG_STAGES;
+        cv_mbar_wait(empty_bar(s), ((it / DG_STAGES) & 1) ^ 1);
+        cv_mbar_expect_tx(full_bar(s), A_BYTES);
+        cv_tma_4d(a_base + s * A_BYTES, &tmA, 0, tx * (DG_PW - 1) - 1, ty * (DG_PH - 1) - 1, n, full_bar(s));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      cv_mbar_wait(w_bar, 0);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      uint32_t aoff[16];
+      uint64_t bdesc[16];
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int j = t >> 1, i = t & 1;
+          aoff[t * 4 + k] = (uint32_t)(((1 - j) * DG_PW + (1 - i)) * 128 + k * 32) >> 4;
+          bdesc[t * 4 + k] = cv_desc(w_base + t * W_TAP_BYTES + k * 32, 16, 1024);
+        }
+      const uint64_t adesc0 = cv_desc(a_base, 16, 1024);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1;
+        const int s = it % DG_STAGES;
+        cv_mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
+        cv_mbar_wait(full_bar(s), (it / DG_STAGES) & 1);
+        cv_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
+        const uint64_t adesc = adesc0 + (uint64_t)(s * (A_BYTES >> 4));
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cv_mma(tmem_d, adesc + aoff[i], bdesc[i], idesc, i > 0 ? 1u : 0u);
+        cv_commit(empty_bar(s));
+        cv_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int al = r / DG_PW, bl = r - al * DG_PW;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t acc = lt & 1;
+      const int n = tile / tiles_per_frame, rem = tile - n * tiles_per_frame;
+      const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
+      const int a = ty * (DG_PH - 1) + al, b = tx * (DG_PW - 1) + bl;
+      const bool row_ok = al < DG_PH - 1 && bl < DG_PW - 1 && a < g.RA && b < g.RB;
+      // ReLU gates of the 2 x 2 output block (global latency): all in flight before blocking on the accumulator
+      bool okc[4];
+      long long opixc[4];
+      uint4 gate[4][4];
+#pragma unroll
+      for (int cls = 0; cls < 4; ++cls) {
+        const int oy = 2 * a + (cls >> 1), ox = 2 * b + (cls & 1);
+        okc[cls] = row_ok && oy < g.H1 && ox < g.W1;
+        opixc[cls] = okc[cls] ? ((long long)n * g.H1 + oy) * g.W1 + ox : 0;
+        const uint4* gp = reinterpret_cast<const uint4*>(y1 + opixc[cls] * 32);   // (pixel 0 of the tensor when masked)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gate[cls][j] = __ldg(gp + j);
+      }
+      cv_mbar_wait(tfull_bar(acc), (lt >> 1) & 1);
+      cv_fence_after();
+#pragma unroll
+      for (int cls = 0; cls < 4; ++cls) {
+        const bool ok = okc[cls];
+        const long long opix = opixc[cls];
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 16) {
+          uint32_t rr[16];
+          cv_ld16(tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16) + cls * 32 + c0, rr);
+          if (!ok) continue;
+          const uint4 g0 = gate[cls][c0 / 8], g1 = gate[cls][c0 / 8 + 1];
+          const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&g0);
+          const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&g1);
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f0 = __bfloat1622float2(h0[j]), f1 = __bfloat1622float2(h1[j]);
+            if (f0.x <= 0.f) v[2 * j] = 0.f;
+            if (f0.y <= 0.f) v[2 * j + 1] = 0.f;
+            if (f1.x <= 0.f) v[8 + 2 * j] = 0.f;
+            if (f1.y <= 0.f) v[8 + 2 * j + 1] = 0.f;
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            pk[j] = *reinterpret_cast<uint32_t*>(&t2);
+          }
+          cv_st32(dy1 + opix * 32 + c0, pk);
+        }
+      }
+      cv_fence_before();
+      __syncwarp();
+      if (lane == 0) cv_mbar_arrive(tempty_bar(acc));
+    }
+  }
+  cv_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    cv_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*CvEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -653,12 +825,49 @@ int conv_lin_conv1_fwd(const void* xs, int N, int H1, int W1, const void* wp, co
   return cl_launch<32, 4, 3>(g, N, xs, wp, e, st);
 }
 
+// conv2 data gradient, all four stride-parity classes in one kernel (weights packed with mode 5)
+int conv_dgrad2_fused(const void* dy2b, int N, int H1, int W1, int H2, int W2, const void* wp5, const void* y1b, void* dy1b,
+                      cudaStream_t st) {
+  if (N == 0) return 0;
+  CvEncodeFn fn = cv_encode_fn();
+  TACORL_REQUIRE(fn, "conv_dgrad2: cuTensorMapEncodeTiled is not available");
+  Dgrad2Geom g = {};
+  g.H1 = H1; g.W1 = W1; g.H2 = H2; g.W2 = W2; g.RA = (H1 + 1) / 2; g.RB = (W1 + 1) / 2;
+  g.tiles_x = cdiv(g.RB, DG_PW - 1); g.tiles_y = cdiv(g.RA, DG_PH - 1);
+  g.num_tiles = N * g.tiles_x * g.tiles_y;
+  CUtensorMap tw, ta;
+  int rc = cv_weight_tmap(&tw, wp5, 4, 128);
+  if (rc) return rc;
+  {
+    TACORL_REQUIRE(((uintptr_t)dy2b & 15) == 0, "conv_dgrad2: dy2 must be 16-byte aligned");
+    cuuint64_t dims[4] = {64, (cuuint64_t)W2, (cuuint64_t)H2, (cuuint64_t)N};
+    cuuint64_t strides[3] = {128, (cuuint64_t)W2 * 128, (cuuint64_t)H2 * W2 * 128};
+    cuuint32_t box[4] = {64, DG_PW, DG_PH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy2b), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TACORL_REQUIRE(r == CUDA_SUCCESS, "conv_dgrad2: cuTensorMapEncodeTiled(dy2) failed (%d)", (int)r);
+  }
+  const size_t smem = 4 * 128 * 128 + (size_t)(DG_STAGES + 1) * 128 * 128 + (2 * DG_STAGES + 5) * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    TACORL_CHECK_CUDA(cudaFuncSetAttribute(conv_dgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int ctas = g.num_tiles < persistent_ctas() ? g.num_tiles : persistent_ctas();
+  conv_dgrad2_kernel<<<ctas, CV_THREADS, smem, st>>>(g, ta, tw, (const __nv_bfloat16*)y1b, (__nv_bfloat16*)dy1b);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------ packing kernels
 // mode 0: conv3 fwd   Wp[t=(ky,kx)][oc][c]            = W3[oc][c][ky][kx]            (9 taps, BN=64)
 // mode 1: conv2 fwd   Wp[t=(ky,p)][oc][(kx-2p)*32+c]  = W2[oc][c][ky][kx]            (8 tap pairs, BN=64)
 // mode 2: conv1 fwd   Wp[t=(dy,dx)][oc][q]            = W1[oc][c][4dy+py][4dx+px], q=(py*4+px)*3+c (<48, else 0)  (4 taps, BN=32)
 // mode 3: conv3 dgrad Wp[t=(ky,kx)][c][oc]            = W3[oc][c][ky][kx]            (9 taps, BN=64)
 // mode 4: conv2 dgrad Wp[cls=(py,px)][t=(j,i)][c][oc] = W2[oc][c][py+2j][px+2i]      (4 classes x 4 taps, BN=32)
+// mode 5: conv2 dgrad Wp[t=(j,i)][cls*32 + c][oc]     = W2[oc][c][py+2j][px+2i]      (4 taps, BN=128: all classes fused)
 __global__ void cv_pack_kernel(int mode, const float* __restrict__ W, __nv_bfloat16* __restrict__ Wp, int total) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -679,16 +888,19 @@ __global__ void cv_pack_kernel(int mode, const float* __restrict__ W, __nv_bfloa
   } else if (mode == 3) {
     const int c = (i >> 6) & 63, t = i >> 12, ky = t / 3, kx = t % 3;
     v = W[((k * 64 + c) * 3 + ky) * 3 + kx];
-  } else {
+  } else if (mode == 4) {
     const int c = (i >> 6) & 31, t = (i >> 11) & 3, cls = i >> 13, py = cls >> 1, px = cls & 1, j = t >> 1, ii = t & 1;
+    v = W[((k * 32 + c) * 4 + (py + 2 * j)) * 4 + (px + 2 * ii)];
+  } else {
+    const int nn = (i >> 6) & 127, t = i >> 13, cls = nn >> 5, c = nn & 31, py = cls >> 1, px = cls & 1, j = t >> 1, ii = t & 1;
     v = W[((k * 32 + c) * 4 + (py + 2 * j)) * 4 + (px + 2 * ii)];
   }
   Wp[i] = __float2bfloat16(v);
 }
 
 int conv_tc_pack(int mode, const float* W, void* Wp, cudaStream_t st) {
-  static const int totals[5] = {9 * 64 * 64, 8 * 64 * 64, 4 * 32 * 64, 9 * 64 * 64, 16 * 32 * 64};
-  TACORL_REQUIRE(mode >= 0 && mode < 5, "conv_tc_pack: bad mode");
+  static const int totals[6] = {9 * 64 * 64, 8 * 64 * 64, 4 * 32 * 64, 9 * 64 * 64, 16 * 32 * 64, 4 * 128 * 64};
+  TACORL_REQUIRE(mode >= 0 && mode < 6, "conv_tc_pack: bad mode");
   cv_pack_kernel<<<cdiv(totals[mode], 256), 256, 0, st>>>(mode, W, (__nv_bfloat16*)Wp, totals[mode]);
   TACORL_LAUNCH_CHECK();
   return 0;
@@ -1201,6 +1413,12 @@ extern "C" int tacorl_conv_tc_debug(int op, const float* in0, const float* in1, 
       if ((rc = conv_tc_pack(2, Wt, wp, st))) return rc;
       if ((rc = conv_tc_s2d(in0, N, H, W, H1 + 1, W1 + 1, a0, st))) return rc;
       if ((rc = conv_lin_conv1_fwd(a0, N, H1, W1, wp, bias, ob, st))) return rc;
+      return cv_to_f32(N * P1 * 32, ob, out, st);
+    case 15:     // conv2 data gradient, four parity classes fused into one kernel
+      if ((rc = conv_tc_pack(5, Wt, wp, st))) return rc;
+      if ((rc = cast_bf16_2d(in0, 64, N * P2, 64, a0, 64, st))) return rc;
+      if ((rc = cast_bf16_2d(in1, 32, N * P1, 32, a1, 32, st))) return rc;
+      if ((rc = conv_dgrad2_fused(a0, N, H1, W1, H2, W2, wp, a1, ob, st))) return rc;
       return cv_to_f32(N * P1 * 32, ob, out, st);
     case 13:     // conv3 forward, linear-shift kernel
       if ((rc = conv_tc_pack(0, Wt, wp, st))) return rc;

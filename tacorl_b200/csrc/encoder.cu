@@ -147,11 +147,11 @@ static int enc_bwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
   if ((rc = colsum_f32(N, 1, dtau, 1, grads[P_TEMP], accumulate, st))) return rc;
   // ---- per layer: weight + bias gradient (one kernel), then the data gradient gated by the input's ReLU
   if ((rc = conv_tc_pack(3, params[P_W3], wd3, st))) return rc;
-  if ((rc = conv_tc_pack(4, params[P_W2], wd2, st))) return rc;
+  if ((rc = conv_tc_pack(5, params[P_W2], wd2, st))) return rc;
   if ((rc = conv_tc_wgrad(3, dy3b, y2, N, g.H2, g.W2, g.H3, g.W3, beta0, grads[P_W3], grads[P_B3], skws, kSplitKWs, st))) return rc;
   if ((rc = conv_tc_conv3_dgrad(dy3b, N, g.H2, g.W2, g.H3, g.W3, wd3, y2, dy2b, st))) return rc;
   if ((rc = conv_tc_wgrad(2, dy2b, y1, N, g.H1, g.W1, g.H2, g.W2, beta0, grads[P_W2], grads[P_B2], skws, kSplitKWs, st))) return rc;
-  if ((rc = conv_tc_conv2_dgrad(dy2b, N, g.H1, g.W1, g.H2, g.W2, wd2, y1, dy1b, st))) return rc;
+  if ((rc = conv_dgrad2_fused(dy2b, N, g.H1, g.W1, g.H2, g.W2, wd2, y1, dy1b, st))) return rc;
   // ---- conv1 (weight gradient only; images receive no gradient)
   if (!xs_saved)
   if ((rc = x_u8 ? conv_tc_s2d_u8((const unsigned char*)xv, N, H, W, g.H1 + 1, g.W1 + 1, x_scale, x_shift, xs, st)

@@ -87,6 +87,10 @@ def test_implicit_gemm_convs_match_torch(N, H, W):
     dy1 = full * (y1n > 0)
     got = _run(5, dy2b, y1b, W2t, None, N, H, W, (N, H1, W1, 32))
     assert_close("conv2 dgrad", got, nhwc(dy1), 6e-3)
+    # the encoder's form: all four stride-parity classes in one kernel (one haloed dy2 patch per tile, N = 128)
+    got_fused = _run(15, dy2b, y1b, W2t, None, N, H, W, (N, H1, W1, 32))
+    assert_close("conv2 dgrad (fused classes)", got_fused, nhwc(dy1), 6e-3)
+    assert_close("conv2 dgrad fused vs per-class", got_fused, got, 1e-6)
     # ---- weight gradients (fp32 accumulation, fp32 output)
     w = W3t.double().requires_grad_(True)
     (F.conv2d(y2n, w, stride=1) * dy3n).sum().backward()
