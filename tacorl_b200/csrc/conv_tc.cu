@@ -126,6 +126,14 @@ __device__ __forceinline__ void cv_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cv_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void cv_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint64_t cv_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
@@ -617,10 +625,13 @@ conv_dgrad2_kernel(const __grid_constant__ Dgrad2Geom g, const __grid_constant__
       for (int cls = 0; cls < 4; ++cls) {
         const bool ok = okc[cls];
         const long long opix = opixc[cls];
+        uint32_t r2[2][16];                  // both 16-column halves of the class in flight before the one wait
+        cv_ld16_nowait(tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16) + cls * 32, r2[0]);
+        cv_ld16_nowait(tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16) + cls * 32 + 16, r2[1]);
+        cv_ld_wait();
 #pragma unroll
         for (int c0 = 0; c0 < 32; c0 += 16) {
-          uint32_t rr[16];
-          cv_ld16(tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16) + cls * 32 + c0, rr);
+          const uint32_t (&rr)[16] = r2[c0 / 16];
           if (!ok) continue;
           const uint4 g0 = gate[cls][c0 / 8], g1 = gate[cls][c0 / 8 + 1];
           const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&g0);
