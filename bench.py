@@ -32,9 +32,9 @@ ENC_FLOP_PER_FRAME = 260.8e6
 # uint8 image 2 x 120000 (conv1 forward, conv1 weight gradient), y1/dy1 153664 (bf16, 49x49x32), y2/dy2 67712 (23x23x64),
 # y3 112896 (fp32, 21x21x64), dy3 56448:  forward 788544 + backward 1355456.
 ENC_BYTES_PER_FRAME = 2_144_000
-# dram__bytes_read.sum + dram__bytes_write.sum over the encoder's kernels in one `ncu --set full` capture of
-# scripts/profile_encoder.py (1024 frames; profiles/r01_encoder_kernels_ncu.md), uint8-input equivalent
-ENC_NCU_TRAFFIC_BYTES = 3.216e9
+# dram__bytes_read.sum + dram__bytes_write.sum summed over every launch of one encoder forward+backward pass under ncu
+# (scripts/profile_encoder.py, 1024 frames; profiles/r01_encoder_kernels_ncu.md "final state"), uint8-input equivalent
+ENC_NCU_TRAFFIC_BYTES = 2.837e9
 PLAYLMP_FLOP_PER_WINDOW = 8.97e9
 
 
