@@ -133,3 +133,23 @@ def test_data_parallel_mean_gradient_equals_global_batch_gradient_gloo(tmp_path)
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "DP_OK" in outs[0]
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the driver's reference arm) runs the CPU oracle port and prints exactly one JSON
+    line with the contract's keys; under torchrun every rank but 0 leaves silently with exit code 0."""
+    import json
+    import subprocess
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--batch", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "play_lmp_train_frames_per_sec" and d["unit"] == "frames/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(env, RANK="1", WORLD_SIZE="2"))
+    assert other.returncode == 0 and other.stdout.strip() == ""
