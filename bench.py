@@ -241,7 +241,19 @@ def run_ours(args):
         # reserve 4.05, 8/8 4.30, 16/16 3.96, 24/24 4.01, 32/32 4.07 (scripts/n2_reserve_sweep.sh)
         os.environ.setdefault("NCCL_MAX_NCHANNELS", "16")
         os.environ.setdefault("NCCL_MIN_NCHANNELS", "16")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL announces its version on stdout when the image sets NCCL_DEBUG: send its log to stderr, and route
+        # fd 1 to stderr while the communicator comes up, so that stdout carries the JSON line and nothing else
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     ops.set_precision(args.precision)
     B = args.batch
 
