@@ -818,6 +818,8 @@ static int cl_launch(ConvLinGeom g, int N, const void* src, const void* wpacked,
 // conv3 forward, linear-shift form: y2 (N, H2, W2, 64) -> y3 fp32 (N, H3, W3, 64)
 int conv_lin_conv3_fwd(const void* y2b, int N, int H2, int W2, int H3, int W3, const void* wp, const float* bias,
                        float* y3, cudaStream_t st) {
+  if (128 + 2 * W2 + 2 > 256)      // input window larger than one TMA box (images wider than ~500 px): per-tap boxes
+    return conv_tc_conv3_fwd(y2b, N, H2, W2, H3, W3, wp, bias, y3, st);
   ConvLinGeom g = {};
   g.W = W2; g.OH = H3; g.OW = W3; g.frame_rows = H2 * W2; g.ntaps = 9;
   for (int t = 0; t < 9; ++t) g.shift[t] = (t / 3) * W2 + (t % 3);
@@ -828,6 +830,8 @@ int conv_lin_conv3_fwd(const void* y2b, int N, int H2, int W2, int H3, int W3, c
 // conv1 forward on the s2d image (N, H1+1, W1+1, 64): 2x2 taps
 int conv_lin_conv1_fwd(const void* xs, int N, int H1, int W1, const void* wp, const float* bias, void* y1b,
                        cudaStream_t st) {
+  if (128 + (W1 + 1) + 1 > 256)    // images wider than ~510 px
+    return conv_tc_conv1_fwd(xs, N, H1, W1, wp, bias, y1b, st);
   ConvLinGeom g = {};
   g.W = W1 + 1; g.OH = H1; g.OW = W1; g.frame_rows = (H1 + 1) * (W1 + 1); g.ntaps = 4;
   for (int t = 0; t < 4; ++t) g.shift[t] = (t >> 1) * (W1 + 1) + (t & 1);
