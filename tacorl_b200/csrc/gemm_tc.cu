@@ -612,14 +612,13 @@ struct SeqArgs {
   int act;
   unsigned* flags;                        // [tiles] arrival counters, zero before the launch
 };
-__device__ unsigned g_rnn_seq_timeouts = 0;
-#ifdef TACORL_STEP_PROFILE
+__device__ unsigned g_rnn_seq_timeouts = 0;   // flag waits that gave up (never expected; read by tacorl_rnn_seq_timeouts)
+#ifdef TACORL_STEP_PROFILE                    // stage stamps of one CTA at step 8 (scripts/prof/step_prof.cu)
 __device__ long long g_seq_prof[16];
 #define SQ_STAMP(i) if (step == 8 && blockIdx.x == 1 && blockIdx.y == 3) g_seq_prof[i] = clock64();
 #else
 #define SQ_STAMP(i)
 #endif
-//   // flag waits that gave up (never expected; read by tacorl_rnn_seq_timeouts)
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
   asm volatile(
