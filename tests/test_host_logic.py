@@ -153,3 +153,46 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(env, RANK="1", WORLD_SIZE="2"))
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_reference_class_paths_are_remapped_to_the_b200_mirrors():
+    """A reference config (`_target_: tacorl....`) selects the B200 class unchanged."""
+    from tacorl_b200.utils import config as C
+    assert C.remap_target("tacorl.networks.visual_encoders.goal_encoder.VisualGoalEncoder") == \
+        "tacorl_b200.networks.visual_encoders.goal_encoder.VisualGoalEncoder"
+    assert C.remap_target("tacorl_b200.networks.x.Y") == "tacorl_b200.networks.x.Y"
+    assert C.remap_target("torch.nn.Linear") == "torch.nn.Linear"
+    ref_cfg = {"_target_": "tacorl.networks.visual_encoders.goal_encoder.VisualGoalEncoder", "in_features": 32,
+               "hidden_size": 256, "latent_goal_features": 32, "l2_normalize_goal_embeddings": False,
+               "activation_function": "ReLU"}
+    import inspect
+    from tacorl_b200.networks.visual_encoders.goal_encoder import VisualGoalEncoder
+    accepted = set(inspect.signature(VisualGoalEncoder.__init__).parameters)
+    m = C.instantiate({k: v for k, v in ref_cfg.items() if k == "_target_" or k in accepted})
+    assert type(m) is VisualGoalEncoder
+    assert C.instantiate(None) is None and C.instantiate({}) is None
+
+
+def test_shard_batch_splits_every_leaf_contiguously():
+    from tacorl_b200.parallel import shard_batch
+    batch = {"states": {"rgb_static": torch.arange(8 * 3).view(8, 3)}, "actions": torch.arange(8), "disp": torch.arange(8) * 10}
+    parts = [shard_batch(batch, r, 4) for r in range(4)]
+    assert all(p["actions"].numel() == 2 for p in parts)
+    assert torch.equal(torch.cat([p["actions"] for p in parts]), batch["actions"])
+    assert torch.equal(torch.cat([p["states"]["rgb_static"] for p in parts]), batch["states"]["rgb_static"])
+    assert torch.equal(parts[3]["disp"], torch.tensor([60, 70]))
+
+
+def test_committed_ncu_launch_lists_parse_and_carry_our_kernels():
+    """profiles/*.csv are the ncu launch lists the DESIGN / profile summaries quote: they must parse with the committed
+    summariser and contain the library's kernels (tcgen05 convolutions, recurrent kernels, Adam)."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from ncu_summary import rows
+    step = list(rows(os.path.join(ROOT, "profiles", "r01_step_launches.csv")))
+    names = " ".join(n for _, n, _ in step)
+    assert len(step) >= 1000 and all(us > 0 for _, _, us in step)
+    for k in ("tacorl::conv_lin_kernel", "tacorl::conv_tc_wgrad_kernel", "tacorl::skinny_cluster_kernel",
+              "tacorl::rnn_seq_kernel", "tacorl::adam_kernel", "tacorl::gemm_tc_kernel"):
+        assert k in names, k
+    enc = list(rows(os.path.join(ROOT, "profiles", "r01_encoder_launches_final.csv")))
+    assert any("conv_dgrad2_kernel" in n for _, n, _ in enc)
