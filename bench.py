@@ -343,10 +343,53 @@ def run_ours(args):
             loss = step(host_img.to(dev, non_blocking=True), host_act.to(dev, non_blocking=True), s)
         losses.append(float(loss))   # .item(): D2H read of the step's loss + sync
 
-    if graphed is not None:
+    def time_e2e_sync():
+        if graphed is not None:
+            graphed.prefetch(host_batch)
+        e2e_step(0)
+        return timed(e2e_step, args.steps) / args.steps
+
+    def time_e2e_pipelined():
+        """Same work per step (one full-batch H2D, one D2H read of the step's loss), but the loss travels through an
+        asynchronous copy into pinned memory and is read on the host one launch later, so the next step is already
+        enqueued when the host blocks: the ~0.2 ms launch latency of a 290-node graph no longer sits between steps.
+        The last step's loss is read before the closing event, so K steps = K H2D copies + K loss reads."""
+        pinned = [torch.empty((), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        n = args.steps
+
+        def read(i):
+            done[i % 2].synchronize()
+            losses.append(float(pinned[i % 2]))
+
+        def fn(s):
+            loss = graphed()
+            pinned[s % 2].copy_(loss, non_blocking=True)
+            done[s % 2].record(torch.cuda.current_stream(dev))
+            graphed.prefetch(host_batch)
+            if s > 0:
+                read(s - 1)
+            if s == n - 1:
+                read(s)
+
         graphed.prefetch(host_batch)
-    e2e_step(0)
-    e2e_ms = timed(e2e_step, args.steps) / args.steps
+        graphed()                                # warm the staging path; leaves the next batch prefetched
+        graphed.prefetch(host_batch)
+        torch.cuda.synchronize()
+        return timed(fn, n) / n
+
+    e2e_mode = "synchronous loss read every step"
+    e2e_ms = None
+    if graphed is not None and os.environ.get("BENCH_E2E_SYNC", "") != "1":
+        try:
+            e2e_ms = time_e2e_pipelined()
+            e2e_mode = "loss copied D2H asynchronously every step, read on the host one launch later"
+        except Exception as e:  # pragma: no cover - fall back to the plain loop, say so
+            sys.stderr.write(f"[bench] pipelined e2e loop failed ({e!r}); using the synchronous loop\n")
+            torch.cuda.synchronize()
+            e2e_ms = None
+    if e2e_ms is None:
+        e2e_ms = time_e2e_sync()
     e2e_fps = world * B * T_FRAMES / (e2e_ms / 1e3)
     trace(f"e2e done: {e2e_ms:.3f} ms/step")
 
@@ -404,7 +447,7 @@ def run_ours(args):
                        "l2_policy": f"inputs ({host_img.numel() * host_img.element_size() / 1e6:.0f} MB images/step) + "
                                     "activations (> 1 GB/step) exceed the 126 MB L2"},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": 4},
+                    "d2h_bytes_per_step": 4, "loss_read": e2e_mode},
             "gpu_launches": launches,
             "launches_per_step": launches / args.steps,
             "clocks": clk,
