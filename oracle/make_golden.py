@@ -65,23 +65,30 @@ def golden_play_lmp(name, pr_kind, modalities, B, T, H, W, rnn_hidden, steps=3, 
     print("wrote", name, rec["steps"][0]["scalars"])
 
 
-def golden_tacorl(name, pr_kind, B, T, H, W, rnn_hidden, epoch, steps=2, seed=13):
+def golden_tacorl(name, pr_kind, B, T, H, W, rnn_hidden, epoch, steps=2, seed=13, modalities=("rgb_static",),
+                  goal_modalities=None, latent_plan_dim=16, dropout_p=0.0):
+    """dropout_p > 0 with the transformer recogniser pins the eval-mode call of the frozen LMP (tacorl.py:237-238):
+    the reference must NOT draw dropout masks inside get_pr_latent_plan."""
     torch.manual_seed(0)
-    lmp = R.build_reference_play_lmp(pr_kind=pr_kind, rnn_hidden=rnn_hidden, dropout_p=0.0,
-                                     max_window=T)
+    lmp = R.build_reference_play_lmp(pr_kind=pr_kind, rnn_hidden=rnn_hidden, dropout_p=dropout_p,
+                                     max_window=T, modalities=modalities, goal_modalities=goal_modalities,
+                                     latent_plan_dim=latent_plan_dim)
     t = R.build_reference_tacorl(lmp)
+    t.train()
     t.current_epoch = epoch
     shapes = _shapes(t)
     _load_synth(t, seed)
     # targets start as copies of q1/q2 in the reference (tacorl.py:121-122); synthetic params
     # are independent per key, which exercises Polyak more strongly — keep them independent.
-    batch = S.synth_play_batch(B, T, H, W, seed, with_goal=True)
+    goal_mods = list(goal_modalities) if goal_modalities is not None else list(modalities)[:1]
+    batch = S.synth_play_batch(B, T, H, W, seed, modalities=modalities, with_goal=True, goal_modalities=goal_mods)
     batch["disp"][0] = 1
     batch["disp"][1] = -1
     rec = {"kind": "tacorl", "pr_kind": pr_kind, "B": B, "T": T, "H": H, "W": W,
            "rnn_hidden": rnn_hidden, "seed": seed, "epoch": epoch, "shapes": shapes,
            "disp": batch["disp"].tolist(), "noise_seed_base": 2000,
-           "target_entropy": float(t.target_entropy), "steps": []}
+           "modalities": list(modalities), "goal_modalities": goal_mods, "latent_plan_dim": latent_plan_dim,
+           "dropout_p": dropout_p, "target_entropy": float(t.target_entropy), "steps": []}
     for s in range(steps):
         torch.manual_seed(2000 + s)
         t.training_step(S.clone_batch(batch))
@@ -169,20 +176,38 @@ def golden_ops(name, seed=19):
     print("wrote", name, rec["dlm_loss"])
 
 
+FIXTURES = {
+    "ops_kat": lambda: golden_ops("ops_kat"),
+    "encoder_shapes": lambda: golden_encoder("encoder_shapes", [(2, 84, 84), (2, 128, 128), (1, 150, 200), (1, 200, 200)]),
+    "playlmp_birnn_84": lambda: golden_play_lmp("playlmp_birnn_84", "tanh_net", ("rgb_static",), 3, 8, 84, 84, 64),
+    "playlmp_birnn_pad_128": lambda: golden_play_lmp("playlmp_birnn_pad_128", "tanh_net", ("rgb_static",), 2, 16, 128,
+                                                     128, 96, steps=2, pad=True),
+    "playlmp_multiview": lambda: golden_play_lmp("playlmp_multiview", "tanh_net", ("rgb_static", "rgb_gripper"), 2, 8,
+                                                 96, 128, 64, steps=2),
+    "playlmp_transformer_84": lambda: golden_play_lmp("playlmp_transformer_84", "transformer", ("rgb_static",), 3, 8,
+                                                      84, 84, 64, steps=2, dropout_p=0.0),
+    "tacorl_bc_84": lambda: golden_tacorl("tacorl_bc_84", "tanh_net", 4, 8, 84, 84, 64, epoch=0),
+    "tacorl_q_84": lambda: golden_tacorl("tacorl_q_84", "tanh_net", 4, 8, 84, 84, 64, epoch=7),
+    "tacorl_defaultpr_84": lambda: golden_tacorl("tacorl_defaultpr_84", "default", 3, 8, 84, 84, 64, epoch=7),
+    # round 2: the shipped plan recogniser (transformer, dropout 0.1) under TACORL: the frozen LMP runs in eval mode
+    "tacorl_transformer_84": lambda: golden_tacorl("tacorl_transformer_84", "transformer", 3, 8, 84, 84, 64, epoch=7,
+                                                   dropout_p=0.1),
+    # round 2: BASELINE configs[3] (tacorl_real_world on a play_lmp_gripper_real_world LMP): static + gripper views
+    # for observation AND goal, latent plan 32 (experiment/play_lmp_real_world.yaml:10)
+    "tacorl_multiview_bc": lambda: golden_tacorl("tacorl_multiview_bc", "tanh_net", 3, 8, 96, 128, 64, epoch=0,
+                                                 modalities=("rgb_static", "rgb_gripper"),
+                                                 goal_modalities=("rgb_static", "rgb_gripper"), latent_plan_dim=32),
+    "tacorl_multiview_q": lambda: golden_tacorl("tacorl_multiview_q", "tanh_net", 3, 8, 96, 128, 64, epoch=7,
+                                                modalities=("rgb_static", "rgb_gripper"),
+                                                goal_modalities=("rgb_static", "rgb_gripper"), latent_plan_dim=32),
+}
+
+
 def main():
+    """python -m oracle.make_golden [name ...]   (no names: every fixture)"""
     os.makedirs(OUT, exist_ok=True)
-    golden_ops("ops_kat")
-    golden_encoder("encoder_shapes", [(2, 84, 84), (2, 128, 128), (1, 150, 200), (1, 200, 200)])
-    golden_play_lmp("playlmp_birnn_84", "tanh_net", ("rgb_static",), 3, 8, 84, 84, 64)
-    golden_play_lmp("playlmp_birnn_pad_128", "tanh_net", ("rgb_static",), 2, 16, 128, 128, 96,
-                    steps=2, pad=True)
-    golden_play_lmp("playlmp_multiview", "tanh_net", ("rgb_static", "rgb_gripper"), 2, 8, 96, 128,
-                    64, steps=2)
-    golden_play_lmp("playlmp_transformer_84", "transformer", ("rgb_static",), 3, 8, 84, 84, 64,
-                    steps=2, dropout_p=0.0)
-    golden_tacorl("tacorl_bc_84", "tanh_net", 4, 8, 84, 84, 64, epoch=0)
-    golden_tacorl("tacorl_q_84", "tanh_net", 4, 8, 84, 84, 64, epoch=7)
-    golden_tacorl("tacorl_defaultpr_84", "default", 3, 8, 84, 84, 64, epoch=7)
+    for name in (sys.argv[1:] or list(FIXTURES)):
+        FIXTURES[name]()
 
 
 if __name__ == "__main__":

@@ -101,8 +101,9 @@ def action_decoder_cfg(latent_plan_dim=16, hidden_size=2048):
 
 
 def play_lmp_cfg(pr_kind="tanh_net", modalities=("rgb_static",), latent_plan_dim=16,
-                 rnn_hidden=2048, max_window=16, dropout_p=0.1):
+                 rnn_hidden=2048, max_window=16, dropout_p=0.1, goal_modalities=None):
     mods = list(modalities)
+    goal_mods = list(goal_modalities) if goal_modalities is not None else mods[:1]
     return {
         "plan_proposal": actor_cfg(),
         "plan_recognition": plan_recognition_cfg(pr_kind, latent_plan_dim, rnn_hidden, max_window,
@@ -114,7 +115,7 @@ def play_lmp_cfg(pr_kind="tanh_net", modalities=("rgb_static",), latent_plan_dim
         "lr": 1e-4,
         "kl_beta": 1e-3,
         "plan_proposal_obs_modalities": mods,
-        "plan_proposal_goal_modalities": mods[:1],
+        "plan_proposal_goal_modalities": goal_mods,
         "plan_recognition_modalities": mods,
         "action_decoder_modalities": mods,
         "real_world": True,

@@ -65,7 +65,7 @@ def synth_images(shape, seed, name="img"):
 
 
 def synth_play_batch(B, T, H, W, seed, modalities=("rgb_static",), gripper_hw=(84, 84),
-                     with_goal=False, pad=False):
+                     with_goal=False, pad=False, goal_modalities=("rgb_static",)):
     """CALVIN-shaped PlayLMP / TACO-RL batch.  actions U(-1,1) with gripper channel ±1;
     `pad=True` mimics pad_sequence: window w~U{T/2..T}, frames repeat the last valid one and
     relative actions are zero after w (gripper kept)."""
@@ -88,7 +88,8 @@ def synth_play_batch(B, T, H, W, seed, modalities=("rgb_static",), gripper_hw=(8
             actions[b, w_:, 6] = actions[b, w_ - 1, 6]
         batch["window_size"] = ws
     if with_goal:
-        batch["goal"] = {"rgb_static": synth_images((B, 3, H, W), seed, "goal")}
+        batch["goal"] = {m: synth_images((B, 3) + ((H, W) if m == "rgb_static" else tuple(gripper_hw)), seed,
+                                         "goal" if m == "rgb_static" else "goal_" + m) for m in goal_modalities}
         # disp ~ Geometric(0.3) with 10% = -1 (config/datamodule/dataset/tacorl.yaml:11-14)
         u = torch.rand(B, generator=g)
         disp = torch.floor(torch.log(1 - u) / torch.log(torch.tensor(0.7))).long() + 1

@@ -422,12 +422,15 @@ def polyak_update(target, source, tau):
 
 
 # ----------------------------------------------------------------------------- CQL / TACO-RL
-def visual_emb(P, pre, obs_img, goal_img, mod="rgb_static"):
+def visual_emb(P, pre, obs, goal, obs_mods=("rgb_static",), goal_mods=("rgb_static",)):
     """Visual{Actor,Critic}Wrapper.get_emb_representation,
-    networks/actor_critic/visual_actor_wrapper.py:41-62 / visual_critic_wrapper.py:50-71."""
-    e = lmp_encoder(P, pre + f"encoder.networks.{mod}.", obs_img)
-    g = goal_encoder(P, pre + "goal_encoder.", lmp_encoder(P, pre + f"encoder.networks.{mod}.", goal_img))
-    return torch.cat([e, g], dim=-1)
+    networks/actor_critic/visual_actor_wrapper.py:41-62 / visual_critic_wrapper.py:50-71:
+    LateFusion concatenates the per-modality embeddings in the order of the modality list
+    (representation_network.py:36-65); the goal embedding goes through the goal encoder.
+    obs / goal: dicts modality -> image batch."""
+    e = torch.cat([lmp_encoder(P, pre + f"encoder.networks.{m}.", obs[m]) for m in obs_mods], dim=-1)
+    g = torch.cat([lmp_encoder(P, pre + f"encoder.networks.{m}.", goal[m]) for m in goal_mods], dim=-1)
+    return torch.cat([e, goal_encoder(P, pre + "goal_encoder.", g)], dim=-1)
 
 
 def q_value(P, pre, emb, action):
@@ -442,8 +445,8 @@ def tacorl_losses(P, batch, noise, cfg, epoch=0, alpha_override=None):
     :451-456).  Returns the individual losses as autograd-carrying scalars plus logged
     values; the update ordering is restated in `tacorl_training_step`.
 
-    batch: states.rgb_static (B,T,3,H,W), goal.rgb_static (B,3,H,W), actions (B,T,7),
-           disp (B,) int64.
+    batch: states[mod] (B,T,3,H,W), goal[mod] (B,3,H,W), actions (B,T,7), disp (B,) int64;
+           cfg['modalities'] / cfg['goal_modalities'] name the views (default: rgb_static only).
     noise: plan_noise (B,L) [z = mu + std*noise for pr_dist.sample()],
            eps_actor (B,L), eps_next (B,L), rand_actions (n*B,L) in (-1,1),
            eps_curr (n,B,L), eps_nextn (n,B,L).
@@ -454,13 +457,19 @@ def tacorl_losses(P, batch, noise, cfg, epoch=0, alpha_override=None):
     target_entropy = cfg.get("target_entropy", -7.0)
     gap = cfg.get("lagrange_thresh", 5.0)
     bc_epochs = cfg.get("bc_epochs", 5)
-    mod = "rgb_static"
-    x = batch["states"][mod]
-    B, T = x.shape[:2]
+    # modality lists inherited from the PlayLMP module (tacorl.py:56-75): all four lists of the shipped experiment
+    # configs are equal (experiment/play_lmp_for_rl.yaml, play_lmp_gripper_real_world.yaml:8-15) except that the
+    # goal may use fewer views
+    mods = list(cfg.get("modalities", ["rgb_static"]))
+    goal_mods = list(cfg.get("goal_modalities", mods[:1]))
+    x0 = batch["states"][mods[0]]
+    B, T = x0.shape[:2]
     out = {}
     # --- get_pr_latent_plan, tacorl.py:235-252 (frozen, eval, no_grad)
     with torch.no_grad():
-        emb = lmp_encoder(P, f"perceptual_encoder.networks.{mod}.", x.reshape(B * T, *x.shape[2:])).view(B, T, -1)
+        emb = torch.cat([lmp_encoder(P, f"perceptual_encoder.networks.{m}.",
+                                     batch["states"][m].reshape(B * T, *batch["states"][m].shape[2:])).view(B, T, -1)
+                         for m in mods], dim=-1)
         mu_q, std_q = plan_recognition_birnn(P, "plan_recognition.", emb) \
             if cfg.get("pr_kind", "default") != "transformer" else \
             plan_recognition_transformer(P, "plan_recognition.", emb)
@@ -472,11 +481,15 @@ def tacorl_losses(P, batch, noise, cfg, epoch=0, alpha_override=None):
     lp, ls, mu, grip, _ = action_decoder_forward(P, "action_decoder.", plan, emb[:, :-1])
     out["action_loss"] = dlm_loss(lp, ls, mu, grip, batch["actions"][:, :-1])
     # --- get_rl_batch, tacorl.py:142-179
-    obs, nxt, goal = x[:, 0], x[:, -1], batch["goal"][mod]
-    rew = (batch["disp"] == 1).to(x.dtype).unsqueeze(-1)
+    obs = {m: batch["states"][m][:, 0] for m in mods}
+    nxt = {m: batch["states"][m][:, -1] for m in mods}
+    goal = batch["goal"]
+    rew = (batch["disp"] == 1).to(x0.dtype).unsqueeze(-1)
     done = rew
+    _ve = visual_emb
+    visual_emb_ = lambda P_, pre_, o_, g_: _ve(P_, pre_, o_, g_, mods, goal_mods)
     # --- actor & alpha, cql_offline_lightning.py:439-468
-    a_emb = visual_emb(P, "actor.", obs, goal)
+    a_emb = visual_emb_(P, "actor.", obs, goal)
     mu_a, std_a = mlp_policy(P, "actor.actor.policy.", a_emb)
     z = mu_a + std_a * noise["eps_actor"]
     curr_actions = torch.tanh(z)
@@ -484,8 +497,8 @@ def tacorl_losses(P, batch, noise, cfg, epoch=0, alpha_override=None):
     out["alpha_loss"] = -(P["log_alpha"][0] * (curr_log_pi + target_entropy).detach()).mean()
     alpha = P["log_alpha"][0].exp() if alpha_override is None else alpha_override
     out["alpha"] = alpha
-    q1_emb = visual_emb(P, "q1.", obs, goal)
-    q2_emb = visual_emb(P, "q2.", obs, goal)
+    q1_emb = visual_emb_(P, "q1.", obs, goal)
+    q2_emb = visual_emb_(P, "q2.", obs, goal)
     if epoch < bc_epochs:
         plp = tanh_normal_log_prob(mu_a, std_a, value=plan)
         out["actor_loss"] = (alpha * curr_log_pi - plp).mean()
@@ -494,11 +507,11 @@ def tacorl_losses(P, batch, noise, cfg, epoch=0, alpha_override=None):
         out["actor_loss"] = (alpha * curr_log_pi - qv).mean()
     # --- Bellman, :284-314 (deterministic_backup=True)
     with torch.no_grad():
-        an_emb = visual_emb(P, "actor.", nxt, goal)
+        an_emb = visual_emb_(P, "actor.", nxt, goal)
         mu_n, std_n = mlp_policy(P, "actor.actor.policy.", an_emb)
         next_actions = torch.tanh(mu_n + std_n * noise["eps_next"])
-        tq = torch.min(q_value(P, "target_q1.", visual_emb(P, "target_q1.", nxt, goal), next_actions),
-                       q_value(P, "target_q2.", visual_emb(P, "target_q2.", nxt, goal), next_actions))
+        tq = torch.min(q_value(P, "target_q1.", visual_emb_(P, "target_q1.", nxt, goal), next_actions),
+                       q_value(P, "target_q2.", visual_emb_(P, "target_q2.", nxt, goal), next_actions))
         q_target = reward_scale * rew + (1 - done) * discount * tq
     q1_data = q_value(P, "q1.", q1_emb, plan)
     q2_data = q_value(P, "q2.", q2_emb, plan)

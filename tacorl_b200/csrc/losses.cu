@@ -21,7 +21,7 @@ __device__ __forceinline__ float softplus_acc(float x) { return x > 20.f ? x : l
 // One thread per (row, action dim); the dim-0 thread of a row also does the gripper CE.
 // row_loss: (rows, A+1) per-term losses (already divided by rows); dlogits same layout as logits.
 __global__ void dlm_nll_kernel(int rows, int A, const float* __restrict__ logits, long long ld,
-                               const float* __restrict__ actions, long long lda, float half_bin,
+                               const float* __restrict__ actions, long long lda, float half_bin, float log_half_classes,
                                float act_min, float act_max, float gripper_alpha,
                                float* __restrict__ row_loss, float* __restrict__ dlogits, long long ldd) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,7 +60,7 @@ __global__ void dlm_nll_kernel(int rows, int A, const float* __restrict__ logits
         lp = logf(fmaxf(delta, 1e-12f));
         gP = sP * (1.f - sP) / delta; gM = -sM * (1.f - sM) / delta;
       } else {
-        lp = mid - s - 2.f * softplus_acc(mid) - 1.5040773967762742f;   // log(4.5)
+        lp = mid - s - 2.f * softplus_acc(mid) - log_half_classes;   // log((num_classes - 1) / 2), :231
         gm = 1.f - 2.f * sigmoid_acc(mid); gs_direct = -1.f;
       }
     }
@@ -285,9 +285,11 @@ int tacorl_dlm_nll(int rows, int act_dims, const float* logits, long long ld, co
   cudaStream_t st = (cudaStream_t)stream;
   TACORL_REQUIRE(logits && actions && row_loss && loss_out, "dlm_nll: null pointer");
   TACORL_REQUIRE(rows > 0 && act_dims > 0, "dlm_nll: empty input");
+  TACORL_REQUIRE(num_classes >= 2, "dlm_nll: num_classes must be >= 2 (got %d)", num_classes);
   const float half_bin = (act_max - act_min) / 2.f / (float)(num_classes - 1);
+  const float log_half_classes = logf((float)(num_classes - 1) / 2.f);
   dlm_nll_kernel<<<nb((long long)rows * act_dims, 128), 128, 0, st>>>(rows, act_dims, logits, ld, actions, lda,
-                                                                     half_bin, act_min, act_max, gripper_alpha,
+                                                                     half_bin, log_half_classes, act_min, act_max, gripper_alpha,
                                                                      row_loss, dlogits, ldd);
   TACORL_LAUNCH_CHECK();
   return colsum_f32(rows * (act_dims + 1), 1, row_loss, 1, loss_out, 0, st);

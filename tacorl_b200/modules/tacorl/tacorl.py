@@ -161,6 +161,9 @@ class TACORL(LightningModule):
 
     def get_pr_latent_plan(self, batch, return_emb_states=True):
         with torch.no_grad():
+            # the frozen LMP runs in eval mode (tacorl.py:237-238): no dropout in the transformer plan recogniser
+            self.perceptual_encoder.eval()
+            self.plan_recognition.eval()
             emb_states = self.get_emb_states(batch["states"], modalities=self.all_modalities)
             pr_states = self._cat([emb_states[k] for k in self.plan_recognition_modalities])
             latent_plan = self.plan_recognition(pr_states).sample()

@@ -5,6 +5,7 @@ contraction / reduction / loss below runs in libtacorl_b200.so.  No CPU path exi
 """
 import ctypes
 import math
+import weakref
 
 import torch
 from torch.autograd import Function
@@ -58,17 +59,17 @@ def _ld(t):
 # parameter buffer (written by the Adam kernel itself); the tensor-core ops read weights from it instead of casting the
 # fp32 weights on every call.  A parameter's slice of the twin is (re)cast lazily when the parameter's or the flat
 # buffer's torch version counter moved (load_state_dict, broadcast, manual init): raw kernel writes do not bump them.
-_SHADOW_OWNERS = []
+_SHADOW_OWNERS = weakref.WeakSet()      # optimisers come and go (tests, re-configured modules): no strong references
 
 
 def register_shadow_owner(owner):
     """owner: object with .pbuf.flat (fp32), .shadow (bf16, same numel), ._pver (dict) and ._flat_version."""
-    _SHADOW_OWNERS.append(owner)
+    _SHADOW_OWNERS.add(owner)
 
 
 def refresh_shadows():
     """Re-validate every registered parameter (used before replaying a captured step)."""
-    for o in _SHADOW_OWNERS:
+    for o in list(_SHADOW_OWNERS):
         for p in o.param_groups[0]["params"]:
             shadow_of(p)
 
@@ -78,7 +79,7 @@ def shadow_of(t):
     if _STATE["prec"] != L.PREC_BF16 or t is None or not t.is_cuda or not t.is_contiguous():
         return None
     ptr = t.data_ptr()
-    for o in _SHADOW_OWNERS:
+    for o in list(_SHADOW_OWNERS):
         flat = o.pbuf.flat
         base = flat.data_ptr()
         if base <= ptr < base + flat.numel() * 4 and flat.device == t.device:
@@ -101,14 +102,16 @@ def shadow_of(t):
 # ---- gradient slots.  FlatAdam owns one flat gradient buffer; a backward kernel that produces the whole gradient of a
 # registered parameter can write it straight into that parameter's slice (and hand autograd the view) instead of into
 # a temporary that step() would then copy (189 MB read + write per PlayLMP step).  A slot is handed out at most once
-# between two step()/zero_grad() calls: a second backward through the same weight gets a temporary, and autograd
-# accumulates it into the first result as usual.
-_GRAD_OWNERS = []
+# between two step()/zero_grad() calls, and only while the owning parameter's .grad is None: a second backward through
+# the same weight (shared weight, gradient accumulation, zero_grad(set_to_none=False), no zero_grad at all) gets a
+# temporary, and autograd accumulates it into the existing .grad as usual -- never a kernel write over a live .grad.
+_GRAD_OWNERS = weakref.WeakSet()
 
 
 def register_grad_owner(owner):
-    """owner: object with .pbuf.flat, .flat_grad (same numel), ._pnumel (data_ptr -> numel) and ._slots_taken (set)."""
-    _GRAD_OWNERS.append(owner)
+    """owner: object with .pbuf.flat, .flat_grad (same numel), ._pnumel (data_ptr -> numel), ._pparam (data_ptr ->
+    parameter) and ._slots_taken (set)."""
+    _GRAD_OWNERS.add(owner)
 
 
 def grad_slot_of(t):
@@ -117,11 +120,14 @@ def grad_slot_of(t):
     if t is None or not t.is_cuda or not t.is_contiguous():
         return None
     ptr = t.data_ptr()
-    for o in _GRAD_OWNERS:
+    for o in list(_GRAD_OWNERS):
         flat = o.pbuf.flat
         base = flat.data_ptr()
         if base <= ptr < base + flat.numel() * 4 and flat.device == t.device:
             if o._pnumel.get(ptr) != t.numel() or ptr in o._slots_taken:
+                return None
+            owner_param = o._pparam.get(ptr)
+            if owner_param is None or owner_param.grad is not None:
                 return None
             o._slots_taken.add(ptr)
             off = (ptr - base) // 4

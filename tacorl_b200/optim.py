@@ -62,6 +62,7 @@ class FlatAdam(torch.optim.Optimizer):
         self.shadow = None
         self._pver = {}
         self._pnumel = {p.data_ptr(): p.numel() for p in ps}
+        self._pparam = {p.data_ptr(): p for p in ps}       # slot hand-out checks the owning parameter's .grad
         self._flat_version = self.pbuf.flat._version
         self._slots_taken = set()
         if self.pbuf.flat.is_cuda:
@@ -119,6 +120,67 @@ class FlatAdam(torch.optim.Optimizer):
         self._slots_taken.clear()
         return super().zero_grad(set_to_none=set_to_none)
 
+    # ---- checkpointing: torch.optim.Adam's layout ({"state": {i: {step, exp_avg, exp_avg_sq}}, "param_groups": [...]}),
+    # so that a Lightning checkpoint written with the reference's Adam resumes here and vice versa
+    def invalidate_shadow(self):
+        """Call after editing parameters through `p.data` (which does not move the version counters ops.shadow_of
+        watches): every bf16 twin slice is re-cast on its next use."""
+        self._pver.clear()
+
+    def state_dict(self):
+        ps = self.param_groups[0]["params"]
+        state = {}
+        if self.step_count > 0:
+            for i, (p, o) in enumerate(zip(ps, self.pbuf.offsets)):
+                n = p.numel()
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.exp_avg[o:o + n].view(p.shape).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).clone()}
+        groups = [{**{k: v for k, v in g.items() if k != "params"}, "params": list(range(len(ps)))}
+                  for g in self.param_groups]
+        return {"state": state, "param_groups": groups}
+
+    @torch.no_grad()
+    def load_state_dict(self, sd):
+        ps = self.param_groups[0]["params"]
+        saved = sd["param_groups"][0]
+        assert len(saved["params"]) == len(ps), "optimizer state_dict holds a different number of parameters"
+        for k in ("lr", "betas", "eps"):
+            if k in saved:
+                self.param_groups[0][k] = tuple(saved[k]) if k == "betas" else saved[k]
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        steps = set()
+        for i, (p, o) in enumerate(zip(ps, self.pbuf.offsets)):
+            st = sd["state"].get(i, sd["state"].get(str(i)))
+            if st is None:
+                continue
+            n = p.numel()
+            self.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(st["step"])))
+        assert len(steps) <= 1, f"per-parameter step counts differ ({sorted(steps)}): not one flat Adam group"
+        self.step_count = steps.pop() if steps else 0
+        if self._step_dev is not None:
+            self._step_dev.fill_(self.step_count)
+        self.invalidate_shadow()
+
+    def snapshot(self):
+        """Everything a step mutates (parameters, moments, step counters): see runtime.GraphedTrainStep."""
+        return {"p": self.pbuf.flat.clone(), "m": self.exp_avg.clone(), "v": self.exp_avg_sq.clone(),
+                "step": self.step_count, "shadow": None if self.shadow is None else self.shadow.clone()}
+
+    @torch.no_grad()
+    def restore(self, snap):
+        self.pbuf.flat.copy_(snap["p"])
+        self.exp_avg.copy_(snap["m"])
+        self.exp_avg_sq.copy_(snap["v"])
+        self.step_count = snap["step"]
+        if self._step_dev is not None:
+            self._step_dev.fill_(self.step_count)
+        if self.shadow is not None:
+            self.shadow.copy_(snap["shadow"])
+
     @torch.no_grad()
     def step(self, closure=None, gathered=False):
         loss = closure() if closure is not None else None
@@ -159,4 +221,9 @@ class FlatAdam(torch.optim.Optimizer):
 
 
 def polyak_update(target_buf: FlatBuffer, source_flat: torch.Tensor, tau: float):
+    """target <- (1 - tau) target + tau source over two flat buffers with the SAME layout (every source parameter
+    trainable, cql_offline_lightning.py:229-232 pairs .parameters() by position)."""
+    assert target_buf.flat.numel() == source_flat.numel(), (
+        f"Polyak: target buffer ({target_buf.flat.numel()}) and source buffer ({source_flat.numel()}) differ: a frozen "
+        "q-network parameter changes the flat layout")
     ops.polyak_update(target_buf.flat, source_flat, tau)

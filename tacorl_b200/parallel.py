@@ -65,6 +65,7 @@ def shard_batch(batch, rank, world_size):
     """Contiguous split of a replay batch over ranks."""
     def sl(t):
         n = t.shape[0]
+        assert n % world_size == 0, f"batch of {n} windows does not split evenly over {world_size} ranks"
         per = n // world_size
         return t[rank * per:(rank + 1) * per]
     return {k: ({kk: sl(vv) for kk, vv in v.items()} if isinstance(v, dict) else sl(v)) for k, v in batch.items()}

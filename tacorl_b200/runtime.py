@@ -35,32 +35,81 @@ def _copy_into(static, batch):
             static[k].copy_(v, non_blocking=True)
 
 
+def _snapshot(objs):
+    return [(o, o.snapshot() if hasattr(o, "snapshot") else o.clone()) for o in objs]
+
+
+@torch.no_grad()
+def _restore(snaps):
+    for o, s in snaps:
+        if hasattr(o, "restore"):
+            o.restore(s)
+        else:
+            o.copy_(s)
+
+
 class GraphedTrainStep:
     """step_fn(static_batch) must run one full optimisation step and return a scalar device tensor (or None).
-    Usage:  g = GraphedTrainStep(step_fn, example_batch); loss = g(next_batch)"""
+    Usage:  g = GraphedTrainStep(step_fn, example_batch); loss = g(next_batch)
 
-    def __init__(self, step_fn, example_batch, device=None, warmup=3):
+    A captured graph freezes everything the HOST decided while it was recorded: Python branches (TACO-RL's
+    `current_epoch < bc_epochs` actor loss, `finetune_action_decoder`) and scalars passed by value (`kl_beta`, learning
+    rates).  `mode_key` (default: `step_fn.mode_key`) returns a hashable summary of that host state; one graph is kept
+    per distinct key and a new one is captured the first time a key is seen, so crossing `bc_epochs` or calling
+    `set_kl_beta` takes effect on the next call.  `preserve` (default: `step_fn.preserve`) lists the optimisers /
+    tensors a step mutates: they are saved before the warm-up steps a capture needs and restored afterwards, so
+    building a graph does not train on the example batch."""
+
+    def __init__(self, step_fn, example_batch, device=None, warmup=3, mode_key=None, preserve=None):
         device = device or torch.device("cuda", torch.cuda.current_device())
+        self.device = device
         self.static = _clone_to_static(example_batch, device)
         self.step_fn = step_fn
+        self.warmup = warmup
+        self.mode_key = mode_key if mode_key is not None else getattr(step_fn, "mode_key", None)
+        self.preserve = preserve if preserve is not None else getattr(step_fn, "preserve", None)
+        self._graphs = {}
+        self.replays = 0
+        self.captures = 0
+        self._select(self._key())
+
+    def _key(self):
+        return self.mode_key() if self.mode_key is not None else None
+
+    def _capture(self):
+        from . import _lib
+        device = self.device
+        snaps = _snapshot(self.preserve()) if self.preserve is not None else None
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
-            for _ in range(warmup):
-                step_fn(self.static)
+            for _ in range(self.warmup):
+                self.step_fn(self.static)
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
-        from . import _lib
-        self.graph = torch.cuda.CUDAGraph()
+        graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
-        with torch.cuda.graph(self.graph):
-            out = step_fn(self.static)
-            self.out = out.detach() if torch.is_tensor(out) else None
+        with torch.cuda.graph(graph):
+            out = self.step_fn(self.static)
+            out = out.detach() if torch.is_tensor(out) else None
         # kernels of libtacorl_b200.so recorded in the graph = launched again by every replay
-        self.launches_per_replay = _lib.launch_count() - n0
-        self.replays = 0
+        launches = _lib.launch_count() - n0
+        if snaps is not None:
+            _restore(snaps)
+            torch.cuda.synchronize(device)
+        self.captures += 1
+        return graph, out, launches
+
+    def _select(self, key):
+        if key not in self._graphs:
+            self._graphs[key] = self._capture()
+        self.graph, self.out, self.launches_per_replay = self._graphs[key]
+        self._active_key = key
 
     def __call__(self, batch=None):
+        key = self._key()
+        if key != self._active_key:
+            self._select(key)
         if batch is not None:
             _copy_into(self.static, batch)
         elif self._staged:
@@ -103,6 +152,8 @@ def play_lmp_step_fn(module, optimizer):
         loss.backward()
         optimizer.step()
         return loss
+    step.mode_key = lambda: (float(module.kl_beta), float(optimizer.param_groups[0]["lr"]), bool(module.training))
+    step.preserve = lambda: [optimizer]
     return step
 
 
@@ -110,4 +161,8 @@ def tacorl_step_fn(module):
     def step(batch):
         module.training_step(batch)
         return module.logged.get("train/q1_loss")
+    opts = module.optimizers()
+    step.mode_key = lambda: (module.current_epoch < module.bc_epochs, bool(module.finetune_action_decoder),
+                             tuple(float(o.param_groups[0]["lr"]) for o in opts), bool(module.training))
+    step.preserve = lambda: list(opts) + [b.flat for b in (module._target_bufs or ())]
     return step

@@ -32,10 +32,10 @@ def load_golden(name):
 
 
 def build_play_lmp(pr_kind="tanh_net", modalities=("rgb_static",), rnn_hidden=2048, latent=16, max_window=16,
-                   dropout_p=0.0):
+                   dropout_p=0.0, goal_modalities=None):
     from tacorl_b200.utils.config import instantiate
     cfg = RC.play_lmp_cfg(pr_kind=pr_kind, modalities=modalities, rnn_hidden=rnn_hidden, latent_plan_dim=latent,
-                          max_window=max_window, dropout_p=dropout_p)
+                          max_window=max_window, dropout_p=dropout_p, goal_modalities=goal_modalities)
     cfg["_target_"] = "tacorl.modules.play_lmp.play_lmp_for_rl.PlayLMP"   # reference path, remapped
     cfg["_recursive_"] = False
     return instantiate(cfg)
@@ -55,3 +55,35 @@ def play_lmp_tape(noise, B, goal_dim=32):
 
 def double_params(sd, frozen=()):
     return O.params_from({k: (v.double() if v.dtype.is_floating_point else v) for k, v in sd.items()}, frozen)
+
+
+def build_tacorl(lmp, precision="fp32", **overrides):
+    from tacorl_b200 import ops
+    from tacorl_b200.utils.config import instantiate
+    ops.set_precision(precision)
+    cfg = RC.tacorl_cfg()
+    cfg.update(overrides)
+    cfg["_target_"] = "tacorl.modules.tacorl.tacorl.TACORL"                # reference path, remapped
+    cfg["_recursive_"] = False
+    return instantiate(cfg, play_lmp=lmp)
+
+
+def tacorl_tape(noise):
+    return [noise[k] for k in ("plan_noise", "eps_actor", "eps_next", "rand_actions", "eps_curr", "eps_nextn")]
+
+
+TACORL_KEYS = ["action_loss", "alpha", "alpha_loss", "actor_loss", "q1_loss", "q2_loss", "bellman_q1_loss",
+               "bellman_q2_loss", "conservative_q1_loss", "conservative_q2_loss", "alpha_prime", "alpha_prime_loss",
+               "q1_data", "q1_random", "q1_policy", "q2_data", "q2_random", "q2_policy"]
+
+
+def parity_report(name, rows):
+    """Per-tensor / per-scalar numbers of a parity test, written to gpurun_out/parity/<name>.json (gpurun brings the
+    directory back; the round's copy is committed under profiles/)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "gpurun_out", "parity")
+    try:
+        os.makedirs(out, exist_ok=True)
+        json.dump({"test": name, "rows": rows}, open(os.path.join(out, name + ".json"), "w"), indent=1)
+    except OSError:      # read-only checkout: the assertions still run
+        pass

@@ -20,16 +20,28 @@ def test_graphed_step_trains_and_counts_adam_steps():
     batch = to_dev(S.synth_play_batch(B, T, H, W, 4))
     batch = {"states": batch["states"], "actions": batch["actions"]}
     torch.manual_seed(0)
+    initial = opt.flat_params.clone()
     g = runtime.GraphedTrainStep(runtime.play_lmp_step_fn(m, opt), batch, warmup=2)
     assert g.launches_per_replay > 100                  # the graph holds our kernels, not a fallback
     before = opt.flat_params.clone()
+    assert torch.equal(before, initial)                 # the warm-up steps of the capture were rolled back
+    assert int(opt._step_dev) == 0 and opt.step_count == 0 and float(opt.exp_avg.abs().sum()) == 0.0
     n0 = _lib.launch_count()
     losses = [float(g()) for _ in range(6)]
     assert _lib.launch_count() == n0                    # replays issue no host-side launches
     assert all(torch.isfinite(torch.tensor(losses)))
     assert losses[-1] < losses[0]
     assert not torch.equal(before, opt.flat_params)
-    assert int(opt._step_dev) == 2 + 6                  # warm-up + replays (capture records, it does not run)
+    assert int(opt._step_dev) == 6                      # replays only (warm-up rolled back; capture records, it does not run)
+    # host-side scalars are baked into a graph: a new kl_beta must select a newly captured graph
+    m.set_kl_beta(0.5)
+    l_new = float(g())
+    assert g.captures == 2 and int(opt._step_dev) == 7
+    kl, act = float(m.logged["train/kl_loss"]), float(m.logged["train/action_loss"])
+    assert abs(l_new - (0.5 * kl + act)) <= 1e-5 * abs(l_new)
+    m.set_kl_beta(1e-3)
+    g()
+    assert g.captures == 2                              # the first graph is re-used
     # host-fed path: pinned batch prefetched on the copy stream, consumed by the next call
     host = S.synth_play_batch(B, T, H, W, 5)
     host = {"states": {k: v.pin_memory() for k, v in host["states"].items()}, "actions": host["actions"].pin_memory()}
@@ -105,3 +117,113 @@ def test_rnn_weight_gradients_land_in_the_flat_gradient_buffer():
         opt_b.step()
     for pa, pb in zip(rnn_a.parameters(), rnn_b.parameters()):
         assert torch.equal(pa, pb)
+
+
+def test_graphed_tacorl_step_switches_actor_loss_at_bc_epochs():
+    """TACORL's actor loss is a host-side branch on current_epoch < bc_epochs (cql_offline_lightning.py:459-466): the
+    graph runner must not keep replaying the BC loss after the switch."""
+    from tacorl_b200 import runtime
+    from tests.gpu_util import build_tacorl
+    lmp = build_play_lmp("tanh_net", ("rgb_static",), 64, 16, 8)
+    t = build_tacorl(lmp)
+    shapes = {k: list(v.shape) for k, v in t.state_dict().items()}
+    t.load_state_dict(S.synth_state_dict(shapes, 6))
+    t.to(DEV)
+    t.optimizers()
+    batch = to_dev(S.synth_play_batch(3, 8, 84, 84, 6, with_goal=True))
+    batch = {k: batch[k] for k in ("states", "actions", "goal", "disp")}
+    g = runtime.GraphedTrainStep(runtime.tacorl_step_fn(t), batch, warmup=2)
+    t.current_epoch = 0
+    g()
+    bc_loss = float(t.logged["train/actor_loss"])
+    assert g.captures == 1
+    t.current_epoch = t.bc_epochs
+    g()
+    q_loss = float(t.logged["train/actor_loss"])
+    assert g.captures == 2
+    assert abs(bc_loss - q_loss) > 1.0        # BC: alpha*log_pi - log_pi(plan) (positive, large); Q: alpha*log_pi - min Q
+
+
+def test_flat_adam_state_dict_round_trip_and_resume():
+    """Adam moments / step survive state_dict() -> load_state_dict() in torch.optim.Adam's layout; resuming continues the
+    trajectory bit for bit (the optimiser used to checkpoint an empty state)."""
+    from tacorl_b200.optim import FlatAdam
+    g = torch.Generator().manual_seed(1)
+    mk = lambda: [torch.nn.Parameter(torch.randn(33, 7, generator=g).to(DEV)), torch.nn.Parameter(torch.randn(130, generator=g).to(DEV))]
+    ps = mk()
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    o1, oref = FlatAdam(ps, lr=1e-2), torch.optim.Adam(ref, lr=1e-2)
+    grads = [[torch.randn(p.shape, generator=g).to(DEV) for p in ps] for _ in range(5)]
+    for gs in grads[:3]:
+        for p, r, gr in zip(ps, ref, gs):
+            p.grad, r.grad = gr.clone(), gr.clone()
+        o1.step()
+        oref.step()
+    sd = o1.state_dict()
+    assert set(sd["state"]) == {0, 1} and float(sd["state"][0]["step"]) == 3.0
+    assert sd["state"][0]["exp_avg"].shape == ps[0].shape
+    for i, r in enumerate(ref):            # same moments as torch.optim.Adam keeps
+        assert rel_err(sd["state"][i]["exp_avg"], oref.state[r]["exp_avg"]) < 1e-6
+        assert rel_err(sd["state"][i]["exp_avg_sq"], oref.state[r]["exp_avg_sq"]) < 1e-6
+    ps2 = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    o2 = FlatAdam(ps2, lr=1e-2)
+    o2.load_state_dict(sd)
+    assert o2.step_count == 3 and int(o2._step_dev) == 3
+    for gs in grads[3:]:
+        for p, p2, gr in zip(ps, ps2, gs):
+            p.grad, p2.grad = gr.clone(), gr.clone()
+        o1.step()
+        o2.step()
+    for p, p2 in zip(ps, ps2):
+        assert torch.equal(p.data, p2.data)
+    # and a torch.optim.Adam checkpoint loads too (reference -> B200 resume)
+    o3 = FlatAdam([torch.nn.Parameter(r.detach().clone()) for r in ref], lr=1e-2)
+    o3.load_state_dict(oref.state_dict())
+    assert o3.step_count == 3 and rel_err(o3.exp_avg[:33 * 7], oref.state[ref[0]]["exp_avg"].reshape(-1)) == 0.0
+
+
+def test_rnn_gradient_slots_survive_accumulation_and_kept_grads():
+    """The RNN backward writes weight gradients straight into FlatAdam's flat gradient (ops.grad_slot_of).  With
+    gradient accumulation, zero_grad(set_to_none=False) or no zero_grad at all, p.grad is still alive at the next
+    backward: the kernel must then write a temporary and let autograd accumulate."""
+    from tacorl_b200 import ops
+    from tacorl_b200.networks.layers import ReluRNN
+    from tacorl_b200.optim import FlatAdam
+    ops.set_precision("fp32")
+    torch.manual_seed(0)
+    rnn = ReluRNN(12, 32, num_layers=2, bidirectional=True).to(DEV)
+    opt = FlatAdam(list(rnn.parameters()), lr=1e-3)
+    xs = [torch.randn(3, 5, 12, device=DEV) for _ in range(2)]
+
+    def grads_of(x):
+        for p in rnn.parameters():
+            p.grad = None
+        opt._slots_taken.clear()
+        out, _ = rnn(x)
+        out.square().sum().backward()
+        return [p.grad.clone() for p in rnn.parameters()]
+
+    g0, g1 = grads_of(xs[0]), grads_of(xs[1])
+    # (a) accumulation over two micro-batches without zero_grad in between
+    opt.zero_grad(set_to_none=True)
+    for x in xs:
+        out, _ = rnn(x)
+        out.square().sum().backward()
+    for p, a, b in zip(rnn.parameters(), g0, g1):
+        assert rel_err(p.grad, a + b) < 1e-6
+    # (b) step() without zero_grad, then another backward: grads accumulate like torch (not 2x the last one)
+    opt.step()
+    out, _ = rnn(xs[0])
+    out.square().sum().backward()
+    # (the parameters moved by one Adam step of lr 1e-3: compare against a fresh evaluation at the new weights)
+    kept = [p.grad.clone() for p in rnn.parameters()]
+    fresh = grads_of(xs[0])
+    for k, a, b, f in zip(kept, g0, g1, fresh):
+        assert rel_err(k, a + b + f) < 1e-5
+    # (c) zero_grad(set_to_none=False) keeps zeroed .grad tensors alive (some of them ARE the flat-gradient slots)
+    fresh1 = grads_of(xs[1])
+    opt.zero_grad(set_to_none=False)
+    out, _ = rnn(xs[1])
+    out.square().sum().backward()
+    for p, f in zip(rnn.parameters(), fresh1):
+        assert rel_err(p.grad, f) < 1e-6

@@ -50,7 +50,8 @@ def _build(kind, rec):
     from tacorl_b200.utils.config import instantiate
     latent = rec["shapes"]["plan_recognition.mean_fc.weight"][0]
     cfg = RC.play_lmp_cfg(pr_kind=rec["pr_kind"], modalities=tuple(rec.get("modalities", ["rgb_static"])),
-                          rnn_hidden=rec["rnn_hidden"], latent_plan_dim=latent, max_window=rec["T"], dropout_p=0.0)
+                          rnn_hidden=rec["rnn_hidden"], latent_plan_dim=latent, max_window=rec["T"],
+                          dropout_p=rec.get("dropout_p", 0.0), goal_modalities=rec.get("goal_modalities"))
     cfg["_target_"] = "tacorl.modules.play_lmp.play_lmp_for_rl.PlayLMP"     # the REFERENCE class path
     cfg["_recursive_"] = False
     lmp = instantiate(cfg)
@@ -63,7 +64,8 @@ def _build(kind, rec):
 
 
 @pytest.mark.parametrize("name,kind", [("playlmp_birnn_84", "play_lmp"), ("playlmp_multiview", "play_lmp"),
-                                       ("tacorl_bc_84", "tacorl"), ("tacorl_defaultpr_84", "tacorl")])
+                                       ("tacorl_bc_84", "tacorl"), ("tacorl_defaultpr_84", "tacorl"),
+                                       ("tacorl_transformer_84", "tacorl"), ("tacorl_multiview_bc", "tacorl")])
 def test_state_dict_layout_equals_reference(name, kind):
     """Keys, order and shapes of the mirrors' state_dict == the reference's (recorded in the goldens)."""
     rec = json.load(open(os.path.join(GOLD, name + ".json")))
@@ -76,6 +78,44 @@ def test_state_dict_layout_equals_reference(name, kind):
         frozen = [n for n, p in m.named_parameters() if not p.requires_grad]
         assert frozen and all(n.startswith(("perceptual_encoder.", "plan_recognition.")) for n in frozen)
         assert m.target_entropy == rec["target_entropy"]
+
+
+def test_frozen_lmp_runs_in_eval_mode_inside_get_pr_latent_plan():
+    """tacorl.py:237-238: the frozen encoder / plan recogniser are put in eval mode on every call (no dropout in the
+    transformer recogniser), whatever train() did to the whole module before."""
+    rec = json.load(open(os.path.join(GOLD, "tacorl_transformer_84.json")))
+    t = _build("tacorl", rec)
+    t.train()
+    assert t.plan_recognition.training and t.plan_recognition.dropout_p == 0.1
+    src = open(os.path.join(ROOT, "tacorl_b200", "modules", "tacorl", "tacorl.py")).read()
+    body = src[src.index("def get_pr_latent_plan"):src.index("def get_rl_batch")]
+    assert "self.perceptual_encoder.eval()" in body and "self.plan_recognition.eval()" in body
+
+
+def test_flat_adam_checkpoint_layout_is_torch_adam_compatible():
+    """state_dict() / load_state_dict() carry the Adam moments and step in torch.optim.Adam's layout (CPU: no kernels)."""
+    from tacorl_b200.optim import FlatAdam
+    g = torch.Generator().manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(3, 4, generator=g)), torch.nn.Parameter(torch.randn(5, generator=g))]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    oref = torch.optim.Adam(ref, lr=1e-2)
+    for _ in range(2):
+        for r in ref:
+            r.grad = torch.randn(r.shape, generator=g)
+        oref.step()
+    o = FlatAdam(ps, lr=1e-3)
+    assert o.state_dict()["state"] == {}                       # nothing stepped yet
+    o.load_state_dict(oref.state_dict())
+    assert o.step_count == 2 and o.param_groups[0]["lr"] == 1e-2
+    sd = o.state_dict()
+    assert sd["param_groups"][0]["params"] == [0, 1] and set(sd["state"]) == {0, 1}
+    for i, r in enumerate(ref):
+        assert torch.equal(sd["state"][i]["exp_avg"], oref.state[r]["exp_avg"])
+        assert torch.equal(sd["state"][i]["exp_avg_sq"], oref.state[r]["exp_avg_sq"])
+        assert float(sd["state"][i]["step"]) == 2.0
+    back = torch.optim.Adam([torch.nn.Parameter(p.detach().clone()) for p in ps], lr=1.0)
+    back.load_state_dict(sd)                                   # and torch reads ours
+    assert back.param_groups[0]["lr"] == 1e-2
 
 
 def test_native_configs_build_the_same_modules():
@@ -181,6 +221,8 @@ def test_shard_batch_splits_every_leaf_contiguously():
     assert torch.equal(torch.cat([p["actions"] for p in parts]), batch["actions"])
     assert torch.equal(torch.cat([p["states"]["rgb_static"] for p in parts]), batch["states"]["rgb_static"])
     assert torch.equal(parts[3]["disp"], torch.tensor([60, 70]))
+    with pytest.raises(AssertionError):
+        shard_batch(batch, 0, 3)
 
 
 def test_committed_ncu_launch_lists_parse_and_carry_our_kernels():

@@ -52,20 +52,29 @@ def test_play_lmp_steps_match_reference(name):
             _check_fp(f"{name}/step{s}/param/{k}", P[k], fp)
 
 
-@pytest.mark.parametrize("name", ["tacorl_bc_84", "tacorl_q_84", "tacorl_defaultpr_84"])
+TACORL_FIXTURES = ["tacorl_bc_84", "tacorl_q_84", "tacorl_defaultpr_84", "tacorl_transformer_84",
+                   "tacorl_multiview_bc", "tacorl_multiview_q"]
+
+
+@pytest.mark.parametrize("name", TACORL_FIXTURES)
 def test_tacorl_steps_match_reference(name):
     rec = _load(name)
+    mods = rec.get("modalities", ["rgb_static"])
+    goal_mods = rec.get("goal_modalities", mods[:1])
+    latent = rec.get("latent_plan_dim", 16)
     P = O.params_from(S.synth_state_dict(rec["shapes"], rec["seed"]), O.TACORL_FROZEN)
-    batch = S.synth_play_batch(rec["B"], rec["T"], rec["H"], rec["W"], rec["seed"], with_goal=True)
+    batch = S.synth_play_batch(rec["B"], rec["T"], rec["H"], rec["W"], rec["seed"], modalities=mods, with_goal=True,
+                               goal_modalities=goal_mods)
     batch["disp"] = torch.tensor(rec["disp"])
     opt = O.new_tacorl_opt_state(P)
-    cfg = {"pr_kind": rec["pr_kind"], "target_entropy": rec["target_entropy"]}
+    cfg = {"pr_kind": rec["pr_kind"], "target_entropy": rec["target_entropy"], "modalities": mods,
+           "goal_modalities": goal_mods}
     keys = ["action_loss", "alpha", "alpha_loss", "actor_loss", "q1_loss", "q2_loss", "bellman_q1_loss",
             "bellman_q2_loss", "conservative_q1_loss", "conservative_q2_loss", "alpha_prime",
             "alpha_prime_loss", "q1_data", "q1_random", "q1_policy", "q2_data", "q2_random", "q2_policy"]
     for s, step in enumerate(rec["steps"]):
         torch.manual_seed(rec["noise_seed_base"] + s)
-        noise = O.draw_tacorl_noise(rec["B"])
+        noise = O.draw_tacorl_noise(rec["B"], latent=latent)
         logged, _ = O.tacorl_training_step(P, opt, S.clone_batch(batch), noise, cfg, rec["epoch"])
         _check_scalars(logged, step["scalars"], keys)
         for k, fp in step["params"].items():
