@@ -1,9 +1,10 @@
 """TEST INFRASTRUCTURE — loads the UNMODIFIED reference (ErickRosete/tacorl) from
 /root/reference/src through the dependency stubs in oracle/stubs.
 
-Only usable in the build container (the reference does not travel to the GPU box).
-Used by oracle/make_golden.py and tests/test_oracle_vs_reference.py to pin the
-restatement in oracle/tacorl_oracle.py against the real reference code.
+Usable where the reference is present: /root/reference in the build container, or the copy
+oracle/vendor_reference.py makes under oracle/_ref (git-ignored; it travels to the GPU box with
+the gpurun snapshot).  Used by oracle/make_golden.py to pin the restatement in
+oracle/tacorl_oracle.py against the real reference code, and by bench.py's reference arm.
 
 Nothing in the product package (tacorl_b200/) imports this file.
 """
@@ -12,19 +13,34 @@ import os
 import sys
 import types
 
-REF_SRC = "/root/reference/src"
-_STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stubs")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STUBS = os.path.join(_HERE, "stubs")
+
+
+def _ref_src():
+    """The reference package root: /root/reference/src in the build container, else the tree vendored by
+    oracle/vendor_reference.py (oracle/_ref, git-ignored, travels to the GPU box)."""
+    roots = ("/root/reference/src", os.path.join(_HERE, "_ref"))
+    if os.environ.get("TACORL_REF_VENDORED_ONLY"):      # tests: behave like the GPU box
+        roots = roots[1:]
+    for p in roots:
+        if os.path.isdir(os.path.join(p, "tacorl")):
+            return p
+    return None
+
+
+REF_SRC = _ref_src()
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REF_SRC, "tacorl"))
+    return _ref_src() is not None
 
 
 def import_reference():
     """Put stubs + reference on sys.path and return the `tacorl` package."""
     if not reference_available():
-        raise RuntimeError("reference not present at /root/reference")
-    for p in (REF_SRC, _STUBS):
+        raise RuntimeError("reference not present (neither /root/reference nor oracle/_ref)")
+    for p in (_ref_src(), _STUBS):
         if p not in sys.path:
             sys.path.insert(0, p)
     # plan_recognition_net.py:11 imports a module that does not exist in the reference.

@@ -59,15 +59,18 @@ def action_decoder(latent_plan_dim=16, hidden_size=2048):         # networks/act
 
 
 def play_lmp_for_rl(pr_kind="tanh_net", modalities=("rgb_static",), latent_plan_dim=16, rnn_hidden=2048,
-                    max_window_size=16):
-    """config/module/play_lmp_for_rl.yaml + experiment/play_lmp_for_rl.yaml (static camera)."""
+                    max_window_size=16, goal_modalities=None):
+    """config/module/play_lmp_for_rl.yaml + experiment/play_lmp_for_rl.yaml (static camera);
+    modalities=(rgb_static, rgb_gripper), goal_modalities=(rgb_static, rgb_gripper), latent_plan_dim=32 =
+    experiment/play_lmp_gripper_real_world.yaml:8-15 + play_lmp_real_world.yaml:10."""
     mods = list(modalities)
+    goal_mods = list(goal_modalities) if goal_modalities is not None else mods[:1]
     return {"_target_": "tacorl_b200.modules.play_lmp.play_lmp_for_rl.PlayLMP", "_recursive_": False,
             "plan_proposal": actor(), "plan_recognition": plan_recognition(pr_kind, latent_plan_dim, rnn_hidden,
                                                                            max_window_size),
             "goal_encoder": goal_encoder(), "perceptual_encoder": lmp_encoder(),
             "action_decoder": action_decoder(latent_plan_dim, rnn_hidden), "lr": 1e-4, "kl_beta": 1e-3,
-            "plan_proposal_obs_modalities": mods, "plan_proposal_goal_modalities": mods[:1],
+            "plan_proposal_obs_modalities": mods, "plan_proposal_goal_modalities": goal_mods,
             "plan_recognition_modalities": mods, "action_decoder_modalities": mods, "real_world": True}
 
 

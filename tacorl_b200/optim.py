@@ -127,9 +127,16 @@ class FlatAdam(torch.optim.Optimizer):
         watches): every bf16 twin slice is re-cast on its next use."""
         self._pver.clear()
 
+    @property
+    def steps_done(self):
+        """Optimiser steps taken so far.  The device-resident counter is the truth: CUDA-graph replays advance it without
+        running this object's Python."""
+        return int(self._step_dev.item()) if self._step_dev is not None else self.step_count
+
     def state_dict(self):
         ps = self.param_groups[0]["params"]
         state = {}
+        self.step_count = self.steps_done
         if self.step_count > 0:
             for i, (p, o) in enumerate(zip(ps, self.pbuf.offsets)):
                 n = p.numel()
@@ -168,7 +175,7 @@ class FlatAdam(torch.optim.Optimizer):
     def snapshot(self):
         """Everything a step mutates (parameters, moments, step counters): see runtime.GraphedTrainStep."""
         return {"p": self.pbuf.flat.clone(), "m": self.exp_avg.clone(), "v": self.exp_avg_sq.clone(),
-                "step": self.step_count, "shadow": None if self.shadow is None else self.shadow.clone()}
+                "step": self.steps_done, "shadow": None if self.shadow is None else self.shadow.clone()}
 
     @torch.no_grad()
     def restore(self, snap):

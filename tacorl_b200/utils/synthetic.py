@@ -3,7 +3,8 @@
 import torch
 
 
-def play_batch(B, T=16, H=200, W=200, seed=0, modalities=("rgb_static",), gripper_hw=(84, 84), with_goal=False):
+def play_batch(B, T=16, H=200, W=200, seed=0, modalities=("rgb_static",), gripper_hw=(84, 84), with_goal=False,
+               goal_modalities=("rgb_static",)):
     g = torch.Generator().manual_seed(seed)
     actions = torch.rand(B, T, 7, generator=g) * 2 - 1
     actions[..., -1] = torch.where(actions[..., -1] > 0, 1.0, -1.0)
@@ -13,8 +14,8 @@ def play_batch(B, T=16, H=200, W=200, seed=0, modalities=("rgb_static",), grippe
         states[m] = torch.randint(0, 256, (B, T, 3, h, w), generator=g, dtype=torch.uint8).float() / 127.5 - 1.0
     batch = {"states": states, "actions": actions}
     if with_goal:
-        batch["goal"] = {"rgb_static": torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8).float()
-                         / 127.5 - 1.0}
+        batch["goal"] = {m: torch.randint(0, 256, (B, 3) + ((H, W) if m == "rgb_static" else tuple(gripper_hw)),
+                                          generator=g, dtype=torch.uint8).float() / 127.5 - 1.0 for m in goal_modalities}
         u = torch.rand(B, generator=g)
         disp = torch.floor(torch.log(1 - u) / torch.log(torch.tensor(0.7))).long() + 1
         disp[torch.rand(B, generator=g) < 0.1] = -1

@@ -176,23 +176,45 @@ def test_data_parallel_mean_gradient_equals_global_batch_gradient_gloo(tmp_path)
 
 
 def test_bench_reference_arm_prints_one_contract_line():
-    """`bench.py --impl reference` (the driver's reference arm) runs the CPU oracle port and prints exactly one JSON
-    line with the contract's keys; under torchrun every rank but 0 leaves silently with exit code 0."""
+    """`bench.py --impl reference` (the driver's reference arm) runs the unmodified reference modules (oracle/_ref; the
+    oracle port when that tree is absent) on the host cores and prints exactly one JSON line with the contract's keys,
+    the TACO-RL step riding in `tacorl`; under torchrun every rank but 0 leaves silently with exit code 0."""
     import json
     import subprocess
     env = dict(os.environ, OMP_NUM_THREADS="4")
     cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--batch", "1"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, lines
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "play_lmp_train_frames_per_sec" and d["unit"] == "frames/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import ref_loader
+    want_kind = "reference" if ref_loader.reference_available() else "port"
+    assert d["cpu_baseline"]["kind"] == want_kind and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["windows_per_step"] == 1          # the batch asked for, whatever the step count
+    assert d["tacorl"]["metric"] == "tacorl_train_frames_per_sec" and d["tacorl"]["value"] > 0
+    assert d["tacorl"]["cpu_baseline"]["kind"] == want_kind
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(env, RANK="1", WORLD_SIZE="2"))
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_vendored_reference_tree_is_importable_without_the_source_checkout():
+    """oracle/vendor_reference.py copies the pure-Python reference package to oracle/_ref (git-ignored, travels to the
+    GPU box); the loader must work from that tree alone, as it has to on the box."""
+    import subprocess
+    if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "tacorl")):
+        pytest.skip("oracle/_ref not built (run python -m oracle.vendor_reference in the build container)")
+    code = ("from oracle import ref_loader as R; "
+            "assert R.REF_SRC.endswith('oracle/_ref'), R.REF_SRC; "
+            "m = R.build_reference_play_lmp(pr_kind='tanh_net', rnn_hidden=32, dropout_p=0.0, max_window=8); "
+            "import tacorl; print('VENDORED_OK', tacorl.__file__)")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT,
+                         env=dict(os.environ, TACORL_REF_VENDORED_ONLY="1"))
+    assert out.returncode == 0 and "VENDORED_OK" in out.stdout, out.stderr[-1500:]
+    assert "oracle/_ref/tacorl" in out.stdout
 
 
 def test_reference_class_paths_are_remapped_to_the_b200_mirrors():
