@@ -844,6 +844,232 @@ rnn_seq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------ two-lane persistent recurrence
+// rnn_seq_kernel with the K split over 4-CTA clusters and up to TWO independent recurrences ("lanes": the forward and
+// the reverse direction of a bidirectional layer, each with its own weights, buffers and arrival counters) running
+// side by side in one launch: grid (4, tiles, lanes), 16 tiles of NT = 128 columns per lane for a 2048-wide layer
+// = 64 CTAs per lane, 128 of the 148 SMs for both.  Per CTA: W slab NT x K/4 (128 KB bf16 at K = 2048) resident,
+// the (batch x K/4) slab of h_{t-1} at a Mpad x 128 B pitch per 64-wide K block (64 KB at batch 64), partials S.
+// Against the 8-way split: the DSMEM reduce-scatter moves half the bytes (4 partials of 16 rows x 128 columns per
+// CTA instead of 8 x 8 rows x 144), the MMA count per CTA doubles (32 x 128x128x16, still ~1 us), and two lanes no
+// longer time-share the SMs launch by launch (the BiRNN issued 2 x 16 per-step launches per layer, each holding 120
+// SMs).  A single lane leaves 84 SMs to whatever else is in flight (weight-gradient GEMMs on a side stream).
+// Batch rows <= 64 (above that the h slab does not fit next to the weights: rnn_seq_kernel).  Per-step arithmetic is
+// deterministic and independent of the number of lanes (bit-identical results 1-lane vs 2-lane).
+constexpr int RW_KS = 4;
+constexpr int RW_MAX_TILES = 16;
+struct WaveLane {
+  int n_steps, tau0, dtau, act;           // steps s = 0 .. n_steps-1 write time tau0 + s*dtau from A[time tau - dtau]
+  float beta;
+  float* C; long long ldc, c_ts;          // fp32 pre-activation / upstream gradient in, result out
+  const float* gate; long long ldgate, gate_ts;
+  __nv_bfloat16* Cb; long long ldcb, cb_ts;   // bf16 copy of the result = the next step's A operand (row pitch, time stride)
+  unsigned* flags;                        // [tiles] arrival counters, zero before the launch
+};
+struct WaveArgs { WaveLane lane[2]; };
+
+__global__ void __launch_bounds__(RS_THREADS, 1)
+rnn_wave_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmW0,
+                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW1,
+                const __grid_constant__ WaveArgs wa, int M, int Mpad, int N, int NT, int kb_per_cta) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t W_BYTES = (uint32_t)NT * 128, W_STAGE = (W_BYTES + 1023) & ~1023u, A_PITCH = (uint32_t)Mpad * 128;
+  const int SP = NT + 4;
+  const int per = Mpad / RW_KS;
+  uint8_t* w_smem = smem;                                              // resident weight slab: kb x [NT][64] bf16
+  uint8_t* a_smem = smem + (size_t)kb_per_cta * W_STAGE;               // h slab of the current step: kb x [Mpad][64] bf16
+  // (UMMA M = 128 reads 128 rows from each stage base: rows >= Mpad are the next stage / the head of S -- never drained)
+  float* S = (float*)(a_smem + (size_t)kb_per_cta * A_PITCH);          // partial accumulators, read by the peers
+  uint64_t* bars = (uint64_t*)((uint8_t*)S + (((size_t)((Mpad + 31) & ~31) * SP * 4 + 1023) & ~(size_t)1023));
+  uint32_t* tmem_slot = (uint32_t*)(bars + 10);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = blockIdx.x;                                    // == %cluster_ctarank (cluster dims (4,1,1))
+  const int tile = blockIdx.y, n0 = tile * NT, tiles = gridDim.y;
+  const WaveLane& sa = wa.lane[blockIdx.z];
+  const CUtensorMap* tmA = blockIdx.z ? &tmA1 : &tmA0;
+  const CUtensorMap* tmW = blockIdx.z ? &tmW1 : &tmW0;
+  const uint32_t tmem_cols = NT <= 32 ? 32 : (NT <= 64 ? 64 : 128);
+  const uint32_t done_bar = smem_u32(bars + 8), w_bar = smem_u32(bars + 9);
+
+  if (tid == RS_EPI) {
+    for (int s = 0; s < kb_per_cta; ++s) mbar_init(smem_u32(bars + s), 1);
+    mbar_init(done_bar, 1);
+    mbar_init(w_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == RS_EPI / 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int k_begin = (int)rank * kb_per_cta * TC_BK;
+
+  if (tid == RS_EPI) {                                                  // the weight slab, once
+    mbar_expect_tx(w_bar, (uint32_t)kb_per_cta * W_BYTES);
+    for (int s = 0; s < kb_per_cta; ++s)
+      tma_load_2d(smem_u32(w_smem + (size_t)s * W_STAGE), tmW, k_begin + s * TC_BK, n0, w_bar);
+  }
+  // tiles whose columns intersect my K slab [k_begin, k_begin + kb*64)
+  const int j_lo = k_begin / NT, j_hi = min(tiles - 1, (k_begin + kb_per_cta * TC_BK - 1) / NT);
+  const int NT4 = NT >> 2, elems = per * NT4;
+  bool dead = false;                                                    // a flag wait timed out: stop waiting
+
+  for (int step = 0; step < sa.n_steps; ++step) {
+    const int tau = sa.tau0 + step * sa.dtau;
+    const uint32_t ph = (uint32_t)step & 1u;
+    float4 cold[RS_MAXE], gt[RS_MAXE];
+    if (warp == RS_EPI / 32) {
+      if (lane == 0) {
+        if (step == 0) mbar_wait(w_bar, 0);
+        else if (!dead) {
+          const unsigned want = (unsigned)(RW_KS * step);
+          for (int j = j_lo; j <= j_hi && !dead; ++j) {
+            unsigned spins = 0;
+            while (ld_acquire_gpu(sa.flags + j) < want) {
+              if (++spins > (1u << 21)) { dead = true; atomicAdd(&g_rnn_seq_timeouts, 1u); break; }
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        for (int s = 0; s < kb_per_cta; ++s) {
+          const uint32_t bar = smem_u32(bars + s);
+          mbar_expect_tx(bar, A_PITCH);
+          tma_load_3d(smem_u32(a_smem + (size_t)s * A_PITCH), tmA, k_begin + s * TC_BK, 0, tau - sa.dtau, bar);
+        }
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        for (int s = 0; s < kb_per_cta; ++s) {
+          mbar_wait(smem_u32(bars + s), ph);
+          tc_fence_after();
+          const uint32_t a_src = smem_u32(a_smem + (size_t)s * A_PITCH), w_src = smem_u32(w_smem + (size_t)s * W_STAGE);
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+            tc_mma_bf16(tmem_base, make_smem_desc(a_src + k * 32, 16, 1024), make_smem_desc(w_src + k * 32, 16, 1024), idesc,
+                        (s > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(done_bar);
+      }
+      __syncwarp();
+    } else {
+      // epilogue operands of this step do not depend on the recurrence: fetch them while the MMAs run
+      const float* Ct = sa.C + (long long)tau * sa.c_ts;
+      const float* Gt = sa.gate ? sa.gate + (long long)tau * sa.gate_ts : nullptr;
+      long long offc[RS_MAXE], offg[RS_MAXE];
+#pragma unroll
+      for (int i = 0; i < RS_MAXE; ++i) {
+        const int e = tid + i * RS_EPI;
+        const int bi = e / NT4, n = (e - bi * NT4) * 4, b = (int)rank * per + bi, col = n0 + n;
+        const bool ok = e < elems && b < M && col < N;
+        offc[i] = ok ? (long long)b * sa.ldc + col : 0;
+        offg[i] = ok ? (long long)b * sa.ldgate + col : 0;
+      }
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f), one = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+      for (int i = 0; i < RS_MAXE; ++i) cold[i] = sa.beta != 0.f ? *reinterpret_cast<const float4*>(Ct + offc[i]) : zero;
+#pragma unroll
+      for (int i = 0; i < RS_MAXE; ++i) gt[i] = Gt ? *reinterpret_cast<const float4*>(Gt + offg[i]) : one;
+      mbar_wait(done_bar, ph);
+      tc_fence_after();
+    }
+    if (step > 0) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");   // peers finished reading my previous S
+    if (warp < RS_EPI / 32) {
+      const int q = warp & 3;
+      if (q * 32 < Mpad) {
+        float* Srow = S + (q * 32 + lane) * SP;
+        uint32_t r[2][16];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {           // two TMEM loads in flight per wait: column chunks w/4*16 + {0, 64}
+          const int c0 = (warp >> 2) * 16 + 64 * i;
+          if (c0 < NT) tc_ld16_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r[i]);
+        }
+        tc_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c0 = (warp >> 2) * 16 + 64 * i;
+          if (c0 < NT) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              reinterpret_cast<float4*>(Srow + c0)[j] = make_float4(__uint_as_float(r[i][4 * j]), __uint_as_float(r[i][4 * j + 1]),
+                                                                    __uint_as_float(r[i][4 * j + 2]), __uint_as_float(r[i][4 * j + 3]));
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    float4 acc[RS_MAXE];
+    if (warp < RS_EPI / 32) {
+      float4 part[RS_MAXE][RW_KS];
+#pragma unroll
+      for (int i = 0; i < RS_MAXE; ++i) {
+        const int e = tid + i * RS_EPI;
+        const int bi = e / NT4, n = (e - bi * NT4) * 4;
+        const uint32_t addr = smem_u32(S + ((int)rank * per + (e < elems ? bi : 0)) * SP + (e < elems ? n : 0));
+#pragma unroll
+        for (int q = 0; q < RW_KS; ++q) part[i][q] = ld_dsmem_v4(addr, (q + rank) & (RW_KS - 1));   // staggered peers
+      }
+#pragma unroll
+      for (int i = 0; i < RS_MAXE; ++i) {        // fixed order (K slab rank, rank+1, ...): deterministic
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < RW_KS; ++q) { v.x += part[i][q].x; v.y += part[i][q].y; v.z += part[i][q].z; v.w += part[i][q].w; }
+        acc[i] = v;
+      }
+      float dep = 0.f;
+#pragma unroll
+      for (int i = 0; i < RS_MAXE; ++i) dep += acc[i].x + acc[i].y + acc[i].z + acc[i].w;
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::"f"(dep) : "memory");
+      // epilogue: the bf16 copy (the next step's operand) first, then the arrival, then the fp32 store
+      float* Ct = sa.C + (long long)tau * sa.c_ts;
+      __nv_bfloat16* Bt = sa.Cb + (long long)tau * sa.cb_ts;
+      float4 outv[RS_MAXE];
+      bool okv[RS_MAXE];
+#pragma unroll
+      for (int i = 0; i < RS_MAXE; ++i) {
+        const int e = tid + i * RS_EPI;
+        const int bi = e / NT4, n = (e - bi * NT4) * 4, b = (int)rank * per + bi, col = n0 + n;
+        okv[i] = e < elems && b < M && col < N;
+        float v[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
+        const float c4[4] = {cold[i].x, cold[i].y, cold[i].z, cold[i].w};
+        const float g4[4] = {gt[i].x, gt[i].y, gt[i].z, gt[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[j] = fmaf(sa.beta, c4[j], v[j]);
+          if (sa.act == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+          if (g4[j] <= 0.f) v[j] = 0.f;
+        }
+        outv[i] = make_float4(v[0], v[1], v[2], v[3]);
+        if (okv[i]) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+          *reinterpret_cast<uint2*>(Bt + (long long)b * sa.ldcb + col) =
+              make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        }
+      }
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(RS_EPI) : "memory");
+      if (tid == 0) { __threadfence(); red_release_gpu_add(sa.flags + tile, 1u); }
+#pragma unroll
+      for (int i = 0; i < RS_MAXE; ++i) {
+        const int e = tid + i * RS_EPI;
+        const int bi = e / NT4, n = (e - bi * NT4) * 4, b = (int)rank * per + bi, col = n0 + n;
+        if (okv[i]) *reinterpret_cast<float4*>(Ct + (long long)b * sa.ldc + col) = outv[i];
+      }
+    } else {
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    }
+  }
+  if (sa.n_steps > 0) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+  if (warp == RS_EPI / 32) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -958,6 +1184,37 @@ bool rnn_seq_enabled() {
 }
 void rnn_seq_set_enabled(int on) { g_rnn_seq_enabled = on ? 1 : 0; }
 
+// Two persistent launches must never be co-scheduled (each spin-waits on its own clusters being resident): chain
+// them through an event, whatever streams they are issued on.  Inside a stream capture the chain only links
+// launches of the same capture (an event recorded elsewhere cannot be waited on there; the graph launch itself is
+// stream-ordered after earlier work).
+static cudaEvent_t g_chain_ev[64] = {};
+static unsigned long long g_chain_capture[64] = {};
+static bool g_chain_recorded[64] = {};
+static int chain_slot(cudaStream_t st, int* dev, unsigned long long* cid) {
+  TACORL_CHECK_CUDA(cudaGetDevice(dev));
+  TACORL_REQUIRE(*dev >= 0 && *dev < 64, "persistent launch: device index %d out of range", *dev);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  *cid = 0;
+  TACORL_CHECK_CUDA(cudaStreamGetCaptureInfo(st, &cs, cid));
+  if (cs != cudaStreamCaptureStatusActive) *cid = 0;
+  if (!g_chain_ev[*dev]) TACORL_CHECK_CUDA(cudaEventCreateWithFlags(&g_chain_ev[*dev], cudaEventDisableTiming));
+  return 0;
+}
+static int persistent_chain_enter(cudaStream_t st) {
+  int dev; unsigned long long cid; int rc;
+  if ((rc = chain_slot(st, &dev, &cid))) return rc;
+  if (g_chain_recorded[dev] && g_chain_capture[dev] == cid) TACORL_CHECK_CUDA(cudaStreamWaitEvent(st, g_chain_ev[dev], 0));
+  return 0;
+}
+static int persistent_chain_leave(cudaStream_t st) {
+  int dev; unsigned long long cid; int rc;
+  if ((rc = chain_slot(st, &dev, &cid))) return rc;
+  TACORL_CHECK_CUDA(cudaEventRecord(g_chain_ev[dev], st));
+  g_chain_recorded[dev] = true; g_chain_capture[dev] = cid;
+  return 0;
+}
+
 // Runs n_steps dependent steps C[tau] = epi(beta*C[tau] + A[tau - dtau] . W^T), tau = tau0 + s*dtau, in one launch of
 // rnn_seq_kernel.  Ab: dense bf16 [T][M][K] (K == N: the recurrence feeds its own output back), W: bf16 [N][K].
 // Returns 1 when the shape / device cannot run the persistent kernel (the caller then launches step by step).
@@ -1017,28 +1274,88 @@ int rnn_seq_tc(const void* Ab, int T, const void* W, long long ldw, int M, int N
   sa.n_steps = n_steps; sa.tau0 = tau0; sa.dtau = dtau; sa.beta = beta; sa.C = C; sa.ldc = ldc; sa.c_ts = c_ts;
   sa.gate = gate; sa.ldgate = ldgate; sa.gate_ts = gate_ts; sa.Cb = (__nv_bfloat16*)Cb; sa.cb_ts = (long long)M * N;
   sa.act = act; sa.flags = flags;
-  // Two persistent launches must never be co-scheduled (each spin-waits on its own clusters being resident): chain
-  // them through an event, whatever streams they are issued on.  Inside a stream capture the chain only links
-  // launches of the same capture (an event recorded elsewhere cannot be waited on there; the graph launch itself is
-  // stream-ordered after earlier work).
-  {
-    static cudaEvent_t ev[64] = {};
-    static unsigned long long ev_capture[64] = {};
-    static bool ev_recorded[64] = {};
-    int dev = 0;
-    TACORL_CHECK_CUDA(cudaGetDevice(&dev));
-    TACORL_REQUIRE(dev >= 0 && dev < 64, "rnn_seq: device index %d out of range", dev);
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    unsigned long long cid = 0;
-    TACORL_CHECK_CUDA(cudaStreamGetCaptureInfo(st, &cs, &cid));
-    if (cs != cudaStreamCaptureStatusActive) cid = 0;
-    if (!ev[dev]) TACORL_CHECK_CUDA(cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming));
-    if (ev_recorded[dev] && ev_capture[dev] == cid) TACORL_CHECK_CUDA(cudaStreamWaitEvent(st, ev[dev], 0));
-    rnn_seq_kernel<<<dim3(RS_KS, tiles), RS_THREADS, smem, st>>>(ta, tw, sa, M, Mpad, N, NT, kb);
-    TACORL_LAUNCH_CHECK();
-    TACORL_CHECK_CUDA(cudaEventRecord(ev[dev], st));
-    ev_recorded[dev] = true; ev_capture[dev] = cid;
+  int rc2;
+  if ((rc2 = persistent_chain_enter(st))) return rc2;
+  rnn_seq_kernel<<<dim3(RS_KS, tiles), RS_THREADS, smem, st>>>(ta, tw, sa, M, Mpad, N, NT, kb);
+  TACORL_LAUNCH_CHECK();
+  if ((rc2 = persistent_chain_leave(st))) return rc2;
+  return 0;
+}
+
+// Runs n_lanes (1 or 2) independent recurrences of n_steps dependent steps each in ONE launch of rnn_wave_kernel.
+// Returns 1 when the shape / device cannot run it (the caller falls back to rnn_seq_tc / step-by-step launches).
+int rnn_wave_tc(const WaveLaneHost* lanes, int n_lanes, int T, int M, int N, int K, cudaStream_t st) {
+  if (!rnn_seq_enabled() || n_lanes < 1 || n_lanes > 2) return 1;
+  if (M < 1 || M > 64 || K != N || K % (TC_BK * RW_KS) != 0 || N % 4 != 0) return 1;
+  const int Mpad = (M + 15) & ~15, kb = K / (TC_BK * RW_KS);
+  const int NT = 16 * cdiv(N, 16 * RW_MAX_TILES), tiles = cdiv(N, NT);
+  if (NT > 128 || kb > 8 || (Mpad / RW_KS) * (NT / 4) > RS_MAXE * RS_EPI) return 1;
+  auto al16 = [](const void* p, long long ld) { return p == nullptr || (((uintptr_t)p & 15) == 0 && (ld * 4) % 16 == 0); };
+  int max_steps = 0;
+  for (int l = 0; l < n_lanes; ++l) {
+    const WaveLaneHost& h = lanes[l];
+    if (!h.Ab || !h.W || !h.C || !h.Cb || !h.flags || h.n_steps < 0) return 1;
+    if (!al16(h.C, h.ldc) || !al16(h.C, h.c_ts) || !al16(h.gate, h.ldgate) || !al16(h.gate, h.gate_ts)) return 1;
+    if (((uintptr_t)h.Cb & 7) != 0 || h.ldcb % 4 != 0 || h.cb_ts % 4 != 0) return 1;
+    if (((uintptr_t)h.Ab & 15) != 0 || (h.lda * 2) % 16 != 0 || (h.a_ts * 2) % 16 != 0) return 1;
+    max_steps = std::max(max_steps, h.n_steps);
   }
+  if (max_steps < 2) return 1;
+  const size_t w_stage = ((size_t)NT * 128 + 1023) & ~(size_t)1023, a_pitch = (size_t)Mpad * 128;
+  const size_t s_bytes = ((size_t)((Mpad + 31) & ~31) * (NT + 4) * 4 + 1023) & ~(size_t)1023;
+  // the last h stage is read as a 128-row UMMA operand: keep 16 KB behind its base inside the allocation
+  const size_t tail = std::max(a_pitch + s_bytes + 256, (size_t)16384 + 256);
+  const size_t smem = (size_t)kb * w_stage + (size_t)(kb - 1) * a_pitch + tail + 1024;
+  if (smem > 227 * 1024) return 1;
+  static size_t configured = 0;
+  if (smem > configured) {
+    TACORL_CHECK_CUDA(cudaFuncSetAttribute(rnn_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TACORL_CHECK_CUDA(cudaFuncSetAttribute(rnn_wave_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
+    configured = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(RW_KS, tiles, n_lanes); cfg.blockDim = dim3(RS_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = RW_KS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  {   // every cluster of the grid must be resident at once: the steps are chained by spin-waits on peers
+    static size_t checked_smem = 0;
+    static int max_clusters = 0;
+    if (checked_smem != smem) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, rnn_wave_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+      max_clusters = n; checked_smem = smem;
+    }
+    if (max_clusters < tiles * n_lanes) return 1;
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  TACORL_REQUIRE(fn, "rnn_wave: cuTensorMapEncodeTiled is not available from the driver");
+  CUtensorMap ta[2], tw[2];
+  WaveArgs wa;
+  int rc;
+  for (int l = 0; l < 2; ++l) {
+    const WaveLaneHost& h = lanes[l < n_lanes ? l : 0];
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)M, (cuuint64_t)T};
+    cuuint64_t strides[2] = {(cuuint64_t)h.lda * 2, (cuuint64_t)h.a_ts * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)Mpad, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(&ta[l], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(h.Ab), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TACORL_REQUIRE(r == CUDA_SUCCESS, "rnn_wave: cuTensorMapEncodeTiled failed (%d) K=%d M=%d T=%d", (int)r, K, M, T);
+    if ((rc = make_tmap(&tw[l], h.W, K, N, h.ldw, 64, NT))) return rc;
+    WaveLane& d = wa.lane[l];
+    d.n_steps = l < n_lanes ? h.n_steps : 0; d.tau0 = h.tau0; d.dtau = h.dtau; d.act = h.act; d.beta = h.beta;
+    d.C = h.C; d.ldc = h.ldc; d.c_ts = h.c_ts; d.gate = h.gate; d.ldgate = h.ldgate; d.gate_ts = h.gate_ts;
+    d.Cb = (__nv_bfloat16*)h.Cb; d.ldcb = h.ldcb; d.cb_ts = h.cb_ts; d.flags = h.flags;
+    if (l < n_lanes) TACORL_CHECK_CUDA(cudaMemsetAsync(h.flags, 0, (size_t)tiles * sizeof(unsigned), st));
+  }
+  if ((rc = persistent_chain_enter(st))) return rc;
+  void* args[] = {&ta[0], &tw[0], &ta[1], &tw[1], &wa, (void*)&M, (void*)&Mpad, (void*)&N, (void*)&NT, (void*)&kb};
+  TACORL_CHECK_CUDA(cudaLaunchKernelExC(&cfg, (const void*)rnn_wave_kernel, args));
+  note_launch();
+  if ((rc = persistent_chain_leave(st))) return rc;
   return 0;
 }
 

@@ -48,6 +48,21 @@ int gemm_tc_bf16(const void* A, long long lda, int a_mn, const void* B, long lon
 int rnn_seq_tc(const void* Ab, int T, const void* W, long long ldw, int M, int N, int K, int tau0, int dtau, int n_steps,
                float beta, float* C, long long ldc, long long c_ts, const float* gate, long long ldgate, long long gate_ts,
                void* Cb, int act, unsigned* flags, cudaStream_t st);
+// two-lane persistent recurrence (gemm_tc.cu, rnn_wave_kernel): batch rows <= 64, 1 or 2 independent recurrences in one
+// launch.  Ab: bf16 [T][M][K] with row pitch lda and time stride a_ts (elements); Cb receives the bf16 results (row pitch
+// ldcb, time stride cb_ts) and is normally the same tensor as Ab.  flags: >= 16 unsigned per lane.
+struct WaveLaneHost {
+  const void* Ab = nullptr; long long lda = 0, a_ts = 0;
+  const void* W = nullptr; long long ldw = 0;
+  int tau0 = 0, dtau = 1, n_steps = 0;
+  float beta = 1.f;
+  float* C = nullptr; long long ldc = 0, c_ts = 0;
+  const float* gate = nullptr; long long ldgate = 0, gate_ts = 0;
+  void* Cb = nullptr; long long ldcb = 0, cb_ts = 0;
+  int act = ACT_NONE;
+  unsigned* flags = nullptr;
+};
+int rnn_wave_tc(const WaveLaneHost* lanes, int n_lanes, int T, int M, int N, int K, cudaStream_t st);
 unsigned rnn_seq_timeouts();
 bool rnn_seq_enabled();
 void rnn_seq_set_enabled(int on);
