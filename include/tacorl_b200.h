@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TACORL_B200_ABI_VERSION 5
+#define TACORL_B200_ABI_VERSION 6
 
 #define TACORL_PREC_F32 0
 #define TACORL_PREC_BF16 1
@@ -117,7 +117,8 @@ size_t tacorl_rnn_layer_ws_bytes(int T, int B, int I, int H);
  * such launches through an event so that two of them never run concurrently, whatever streams they are on.  Returns how many spin-waits ever gave up (0 in a healthy process;
  * synchronises the device). */
 unsigned tacorl_rnn_seq_timeouts(void);
-/* switch the persistent launch on/off at run time; returns the previous setting */
+/* persistent launches at run time: 0 = off (step-by-step launches), 1 = on, 2 = on with the two lanes of a
+ * bidirectional layer launched one after the other (diagnostic: bit-identical to 1); returns the previous setting */
 int tacorl_rnn_seq_enable(int on);
 /* bf16 path, optional (NULL = stage internally): w_*_bf16 dense bf16 copies of the weights (tacorl_adam_step keeps
  * them current); h_bf16_out: (T, B, H) bf16 buffer that receives the hidden states the tensor cores consumed — hand
@@ -133,6 +134,30 @@ int tacorl_rnn_layer_bwd(int T, int B, int I, int H, const float* x, long long l
                          long long lddx, int dx_accumulate, float* dw_ih, float* dw_hh, float* db_ih,
                          float* db_hh, int accumulate, float* dh0, const void* w_ih_bf16, const void* w_hh_t_bf16,
                          const void* h_bf16, void* ws, size_t ws_bytes, int prec, void* stream);
+/* ---- a whole (bi)directional layer in one call, bf16 tensor-core path (replaces nn.RNN's per-layer work at
+ * plan_recognition_tanh_net.py:23-46 (bidirectional, D = 2) and rnn_models.py:5-16 (decoder, D = 1), h_init = 0).
+ * The recurrences of the two directions run side by side in ONE persistent launch (rnn_wave_kernel: 4-CTA clusters split
+ * K, 64 CTAs per direction, weights resident in shared memory, steps chained by device-side arrival counters; batch
+ * <= 64; larger batches use the 8-way kernel above or per-step launches).  Layouts: out / dout fp32 (T, B, D*H),
+ * direction d owns columns [d*H, (d+1)*H); out_bf16 / dpre_bf16 are bf16 twins in the SAME layout, written by the
+ * recurrence kernels: the next layer's input projection (x_bf16 of the next call), BPTT and the weight-gradient GEMMs
+ * read them in place, so no staging cast is launched.
+ *   w      : fwd [4*D] = w_ih, w_hh, b_ih, b_hh of the forward direction, then of the reverse one;
+ *            bwd [2*D] = w_ih, w_hh per direction.
+ *   w_bf16 : [2*D] per direction: bf16 twin of w_ih, and of w_hh (fwd) / of W_hh^T (bwd); entries may be NULL.
+ *   n_steps: [D] steps each direction runs (reverse: t = T-1 .. T-n); bwd needs n_steps[0] == T.
+ *   dw     : [4*D] dw_ih, dw_hh, db_ih, db_hh per direction (entries may be NULL); dx: (T, B, I) or NULL.
+ *   grad_rows: 0 or B = every batch row; 0 < grad_rows < B: only the first grad_rows rows of each time step carry a
+ *            gradient (rows behind them in dout AND dpre_bf16 must be zero on entry): BPTT runs on those rows alone. */
+size_t tacorl_rnn_layer2_ws_bytes(int T, int B, int I, int H, int D);
+int tacorl_rnn_layer2_fwd(int T, int B, int I, int H, int D, const float* x, long long ldx, const void* x_bf16,
+                          long long ldxb, const float* const* w, const void* const* w_bf16, const int* n_steps,
+                          float* out, long long ldo, void* out_bf16, void* ws, size_t ws_bytes, void* stream);
+int tacorl_rnn_layer2_bwd(int T, int B, int grad_rows, int I, int H, int D, const float* x, long long ldx, const void* x_bf16,
+                          long long ldxb, const float* const* w, const void* const* w_bf16, const int* n_steps,
+                          const float* out, long long ldo, const void* out_bf16, float* dout, long long lddo,
+                          void* dpre_bf16, float* dx, long long lddx, float* const* dw, void* ws, size_t ws_bytes,
+                          void* stream);
 /* dst (cols x rows, bf16, dense) = transpose of src (rows x cols, fp32, dense) */
 int tacorl_cast_transpose_bf16(const float* src, int rows, int cols, void* dst, void* stream);
 

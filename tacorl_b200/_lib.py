@@ -38,6 +38,10 @@ _SIGS = {
                              _i, _vp],
     "tacorl_rnn_layer_bwd": [_i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp, _i, _i, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _i,
                              _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp],
+    "tacorl_rnn_layer2_ws_bytes": [_i, _i, _i, _i, _i],
+    "tacorl_rnn_layer2_fwd": [_i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _sz, _vp],
+    "tacorl_rnn_layer2_bwd": [_i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _ll,
+                              _vp, _vp, _sz, _vp],
     "tacorl_cast_transpose_bf16": [_vp, _i, _i, _vp, _vp],
     "tacorl_dlm_nll": [_i, _i, _vp, _ll, _vp, _ll, _i, _f, _f, _f, _vp, _vp, _vp, _ll, _vp],
     "tacorl_dlm_sample": [_i, _i, _vp, _ll, _vp, _vp, _vp, _ll, _f, _f, _vp, _vp, _vp, _vp],
@@ -72,7 +76,7 @@ _SIGS = {
     "tacorl_set_sm_reserve": [_i],
 }
 _RESTYPES = {
-    "tacorl_lmp_encoder_ws_bytes": _sz, "tacorl_rnn_layer_ws_bytes": _sz,
+    "tacorl_lmp_encoder_ws_bytes": _sz, "tacorl_rnn_layer_ws_bytes": _sz, "tacorl_rnn_layer2_ws_bytes": _sz,
     "tacorl_last_error": ctypes.c_char_p, "tacorl_launch_count": ctypes.c_ulonglong,
     "tacorl_rnn_seq_timeouts": ctypes.c_uint,
 }
@@ -143,10 +147,15 @@ def ptr_any(t):
 
 
 def ptr_array(tensors):
+    """void*[] of device pointers (None -> NULL)."""
     arr = (ctypes.c_void_p * len(tensors))()
     for i, t in enumerate(tensors):
-        arr[i] = t.data_ptr()
+        arr[i] = None if t is None else t.data_ptr()
     return arr
+
+
+def int_array(values):
+    return (ctypes.c_int * len(values))(*[int(v) for v in values])
 
 
 _WS = {}

@@ -27,7 +27,7 @@ unsigned tacorl_rnn_seq_timeouts(void) { return rnn_seq_timeouts(); }
 
 int tacorl_set_sm_reserve(int n) { set_sm_reserve(n); return persistent_ctas(); }
 
-int tacorl_rnn_seq_enable(int on) { const int was = rnn_seq_enabled() ? 1 : 0; rnn_seq_set_enabled(on); return was; }
+int tacorl_rnn_seq_enable(int on) { const int was = rnn_seq_mode(); rnn_seq_set_enabled(on); return was; }
 
 int tacorl_gemm_ex(int transA, int transB, int M, int N, int K, float alpha, const float* A, long long lda,
                    const float* B, long long ldb, float beta, float* C, long long ldc, const float* bias, int act,

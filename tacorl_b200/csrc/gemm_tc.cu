@@ -1182,7 +1182,8 @@ bool rnn_seq_enabled() {
   if (g_rnn_seq_enabled < 0) { const char* e = getenv("TACORL_RNN_SEQ"); g_rnn_seq_enabled = !(e && e[0] == '0'); }
   return g_rnn_seq_enabled != 0;
 }
-void rnn_seq_set_enabled(int on) { g_rnn_seq_enabled = on ? 1 : 0; }
+void rnn_seq_set_enabled(int on) { g_rnn_seq_enabled = on < 0 ? 0 : (on > 2 ? 2 : on); }   // 2: lanes launched one by one
+int rnn_seq_mode() { rnn_seq_enabled(); return g_rnn_seq_enabled; }
 
 // Two persistent launches must never be co-scheduled (each spin-waits on its own clusters being resident): chain
 // them through an event, whatever streams they are issued on.  Inside a stream capture the chain only links
@@ -1286,6 +1287,10 @@ int rnn_seq_tc(const void* Ab, int T, const void* W, long long ldw, int M, int N
 // Returns 1 when the shape / device cannot run it (the caller falls back to rnn_seq_tc / step-by-step launches).
 int rnn_wave_tc(const WaveLaneHost* lanes, int n_lanes, int T, int M, int N, int K, cudaStream_t st) {
   if (!rnn_seq_enabled() || n_lanes < 1 || n_lanes > 2) return 1;
+  if (n_lanes == 2 && rnn_seq_mode() == 2) {      // diagnostic mode: the same arithmetic, one lane per launch
+    int rc = rnn_wave_tc(lanes, 1, T, M, N, K, st);
+    return rc ? rc : rnn_wave_tc(lanes + 1, 1, T, M, N, K, st);
+  }
   if (M < 1 || M > 64 || K != N || K % (TC_BK * RW_KS) != 0 || N % 4 != 0) return 1;
   const int Mpad = (M + 15) & ~15, kb = K / (TC_BK * RW_KS);
   const int NT = 16 * cdiv(N, 16 * RW_MAX_TILES), tiles = cdiv(N, NT);

@@ -66,6 +66,7 @@ int rnn_wave_tc(const WaveLaneHost* lanes, int n_lanes, int T, int M, int N, int
 unsigned rnn_seq_timeouts();
 bool rnn_seq_enabled();
 void rnn_seq_set_enabled(int on);
+int rnn_seq_mode();
 int cast_bf16_2d(const float* src, long long lds, long long rows, int cols, void* dst, long long ldd, cudaStream_t st);
 int cast_transpose_bf16(const float* src, long long lds, int rows, int cols, void* dst, long long ldd, cudaStream_t st);
 int gemm_tc_from_f32(const GemmArgs& g, float* ws, size_t ws_bytes, cudaStream_t st);

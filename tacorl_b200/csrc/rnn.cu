@@ -20,21 +20,21 @@ __global__ void vec_add_kernel(int n, const float* a, const float* b, float* o) 
   if (i < n) o[i] = a[i] + b[i];
 }
 
-// rows x H block with row stride ld: p = relu(p)  (+ optional dense bf16 copy, pitch H)
-__global__ void relu_rows_kernel(long long rows, int H, float* p, long long ld, __nv_bfloat16* pb) {
+// rows x H block with row stride ld: p = relu(p)  (+ optional bf16 copy with row pitch ldb)
+__global__ void relu_rows_kernel(long long rows, int H, float* p, long long ld, __nv_bfloat16* pb, long long ldb) {
   const long long total = rows * H;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     float* q = p + (i / H) * ld + (i % H);
     const float v = fmaxf(*q, 0.f);
     *q = v;
-    if (pb) pb[i] = __float2bfloat16(v);
+    if (pb) pb[(i / H) * ldb + (i % H)] = __float2bfloat16(v);
   }
 }
 
-// d = (d + add?) * [out > 0]  (+ optional dense bf16 copy, pitch H)
+// d = (d + add?) * [out > 0]  (+ optional bf16 copy with row pitch lddb)
 __global__ void mask_rows_kernel(long long rows, int H, float* d, long long ldd, const float* out,
-                                 long long ldo, const float* add, long long lda, __nv_bfloat16* db) {
+                                 long long ldo, const float* add, long long lda, __nv_bfloat16* db, long long lddb) {
   const long long total = rows * H;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -43,7 +43,7 @@ __global__ void mask_rows_kernel(long long rows, int H, float* d, long long ldd,
     if (add) v += add[r * lda + c];
     v = out[r * ldo + c] > 0.f ? v : 0.f;
     d[r * ldd + c] = v;
-    if (db) db[i] = __float2bfloat16(v);
+    if (db) db[r * lddb + c] = __float2bfloat16(v);
   }
 }
 
@@ -93,7 +93,7 @@ static int rnn_fwd_f32(int T, int B, int I, int H, const float* x, long long ldx
     if (s == 0) { hp = h0; ldh = H; }
     else { hp = out + (long long)(reverse ? t + 1 : t - 1) * B * ldo; ldh = ldo; }
     if (!hp) {
-      relu_rows_kernel<<<ew_blocks((long long)B * H), 256, 0, st>>>(B, H, ot, ldo, nullptr);
+      relu_rows_kernel<<<ew_blocks((long long)B * H), 256, 0, st>>>(B, H, ot, ldo, nullptr, 0);
       TACORL_LAUNCH_CHECK();
       continue;
     }
@@ -125,7 +125,7 @@ static int rnn_bwd_f32(int T, int B, int I, int H, const float* x, long long ldx
     float* dt = dout + (long long)t * B * lddo;
     const float* ot = out + (long long)t * B * ldo;
     mask_rows_kernel<<<ew_blocks((long long)B * H), 256, 0, st>>>(
-        B, H, dt, lddo, ot, ldo, (s == n_steps - 1) ? dhn : nullptr, H, nullptr);
+        B, H, dt, lddo, ot, ldo, (s == n_steps - 1) ? dhn : nullptr, H, nullptr, 0);
     TACORL_LAUNCH_CHECK();
     if (s > 0) {  // dout[t_prev] += dpre[t] W_hh
       const int tp = reverse ? t + 1 : t - 1;
@@ -242,7 +242,7 @@ static int rnn_fwd_bf16(int T, int B, int I, int H, const float* x, long long ld
     __nv_bfloat16* hbt = hb + (long long)t * B * H;
     const __nv_bfloat16* hp = (s == 0) ? h0b : hb + (long long)(reverse ? t + 1 : t - 1) * B * H;
     if (!hp) {
-      relu_rows_kernel<<<ew_blocks((long long)B * H), 256, 0, st>>>(B, H, ot, ldo, hbt);
+      relu_rows_kernel<<<ew_blocks((long long)B * H), 256, 0, st>>>(B, H, ot, ldo, hbt, H);
       TACORL_LAUNCH_CHECK();
       continue;
     }
@@ -292,7 +292,7 @@ static int rnn_bwd_bf16(int T, int B, int I, int H, const float* x, long long ld
   {  // last step of the recurrence: dpre = (dout (+ dhn)) * [h > 0]
     const int t = reverse ? T - n_steps : n_steps - 1;
     mask_rows_kernel<<<ew_blocks((long long)B * H), 256, 0, st>>>(
-        B, H, dout + (long long)t * B * lddo, lddo, out + (long long)t * B * ldo, ldo, dhn, H, db + (long long)t * B * H);
+        B, H, dout + (long long)t * B * lddo, lddo, out + (long long)t * B * ldo, ldo, dhn, H, db + (long long)t * B * H, H);
     TACORL_LAUNCH_CHECK();
   }
   for (int s = n_steps - 1; s >= 0; --s) {
@@ -370,6 +370,239 @@ static int rnn_bwd_bf16(int T, int B, int I, int H, const float* x, long long ld
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------ whole layer, both directions
+// bf16 tensor-core path of one (bi)directional layer in one call: the two directions' recurrences run side by side in
+// ONE persistent launch (rnn_wave_kernel, batch <= 64), the hidden states / pre-activation gradients have bf16 twins in
+// the layer's own (T, B, D*H) layout (written by the recurrence kernels), so the next layer's input projection, the BPTT
+// and the weight-gradient GEMMs read them in place: no staging casts, no per-direction streams, no concat.
+struct Layer2Ws {
+  float* bsum[2] = {nullptr, nullptr};
+  const __nv_bfloat16* wih[2] = {nullptr, nullptr};
+  const __nv_bfloat16* whh[2] = {nullptr, nullptr};
+  const __nv_bfloat16* xb = nullptr; long long ldxb = 0;
+  unsigned* flags = nullptr;
+  float* sk = nullptr; size_t sk_bytes = 0;
+};
+
+static int layer2_fwd_bf16(int T, int B, int I, int H, int D, const float* x, long long ldx, const void* x_bf16,
+                           long long ldxb, const float* const* w, const void* const* w_bf16, const int* n_steps,
+                           float* out, long long ldo, void* out_bf16, void* ws, size_t ws_bytes, cudaStream_t st) {
+  TACORL_REQUIRE(x && w && n_steps && out && out_bf16 && ws, "rnn_layer2_fwd: null pointer");
+  TACORL_REQUIRE(D == 1 || D == 2, "rnn_layer2_fwd: D must be 1 or 2");
+  TACORL_REQUIRE(H % 8 == 0 && ldo % 8 == 0 && ((uintptr_t)out_bf16 & 15) == 0,
+                 "rnn_layer2_fwd: hidden size / output pitch must be multiples of 8 and the bf16 twin 16-byte aligned");
+  for (int d = 0; d < D; ++d)
+    TACORL_REQUIRE(n_steps[d] >= 1 && n_steps[d] <= T, "rnn_layer2_fwd: n_steps[%d] = %d out of range (T=%d)", d, n_steps[d], T);
+  if (B == 0) return 0;
+  const long long Ip = (I + 7) & ~7LL;
+  Arena ar(ws, ws_bytes);
+  Layer2Ws L;
+  int rc;
+  for (int d = 0; d < D; ++d) {
+    L.bsum[d] = ar.take<float>(H);
+    const void* tih = w_bf16 ? w_bf16[2 * d] : nullptr;
+    const void* thh = w_bf16 ? w_bf16[2 * d + 1] : nullptr;
+    const bool ih_ready = tih && Ip == I && ((uintptr_t)tih & 15) == 0, hh_ready = thh && ((uintptr_t)thh & 15) == 0;
+    __nv_bfloat16* cih = ih_ready ? nullptr : ar.take<__nv_bfloat16>((size_t)H * Ip);
+    __nv_bfloat16* chh = hh_ready ? nullptr : ar.take<__nv_bfloat16>((size_t)H * H);
+    TACORL_REQUIRE(L.bsum[d] && (ih_ready || cih) && (hh_ready || chh), "rnn_layer2_fwd: workspace too small");
+    if (!ih_ready && (rc = cast_bf16_2d(w[4 * d], I, H, I, cih, Ip, st))) return rc;
+    if (!hh_ready && (rc = cast_bf16_2d(w[4 * d + 1], H, H, H, chh, H, st))) return rc;
+    L.wih[d] = ih_ready ? (const __nv_bfloat16*)tih : cih;
+    L.whh[d] = hh_ready ? (const __nv_bfloat16*)thh : chh;
+    vec_add_kernel<<<cdiv(H, 256), 256, 0, st>>>(H, w[4 * d + 2], w[4 * d + 3], L.bsum[d]);
+    TACORL_LAUNCH_CHECK();
+  }
+  const bool x_ready = x_bf16 && ldxb % 8 == 0 && ldxb >= I && ((uintptr_t)x_bf16 & 15) == 0 && (I % 8 == 0);
+  if (x_ready) { L.xb = (const __nv_bfloat16*)x_bf16; L.ldxb = ldxb; }
+  else {
+    __nv_bfloat16* xc = ar.take<__nv_bfloat16>((size_t)T * B * Ip);
+    TACORL_REQUIRE(xc, "rnn_layer2_fwd: workspace too small");
+    if ((rc = cast_bf16_2d(x, ldx, (long long)T * B, I, xc, Ip, st))) return rc;
+    L.xb = xc; L.ldxb = Ip;
+  }
+  L.flags = ar.take<unsigned>(128);
+  TACORL_REQUIRE(L.flags, "rnn_layer2_fwd: workspace too small");
+  L.sk = (float*)(ar.base + ar.off); L.sk_bytes = ar.left();
+  __nv_bfloat16* outb = (__nv_bfloat16*)out_bf16;
+  WaveLaneHost lanes[2];
+  int n_lanes = 0;
+  for (int d = 0; d < D; ++d) {
+    const int n = n_steps[d], t_lo = d ? T - n : 0, t0 = d ? T - 1 : 0;
+    TcArgs in;   // pre-activations of the active steps: out[t, :, dH:(d+1)H] = x[t] W_ih^T + (b_ih + b_hh)
+    in.C = out + (long long)t_lo * B * ldo + (long long)d * H; in.ldc = ldo; in.bias = L.bsum[d]; in.split_k = 1;
+    if ((rc = gemm_tc_bf16(L.xb + (long long)t_lo * B * L.ldxb, L.ldxb, 0, L.wih[d], Ip, 0, n * B, H, I, in, L.sk, L.sk_bytes, st)))
+      return rc;
+    // first step: h_init = 0
+    relu_rows_kernel<<<ew_blocks((long long)B * H), 256, 0, st>>>(B, H, out + (long long)t0 * B * ldo + (long long)d * H, ldo,
+                                                                 outb + (long long)t0 * B * ldo + (long long)d * H, ldo);
+    TACORL_LAUNCH_CHECK();
+    if (n > 1) {
+      WaveLaneHost& h = lanes[n_lanes];
+      h.Ab = outb + (long long)d * H; h.lda = ldo; h.a_ts = (long long)B * ldo;
+      h.W = L.whh[d]; h.ldw = H;
+      h.tau0 = d ? T - 2 : 1; h.dtau = d ? -1 : 1; h.n_steps = n - 1; h.beta = 1.f;
+      h.C = out + (long long)d * H; h.ldc = ldo; h.c_ts = (long long)B * ldo;
+      h.Cb = outb + (long long)d * H; h.ldcb = ldo; h.cb_ts = (long long)B * ldo;
+      h.act = ACT_RELU; h.flags = L.flags + 64 * n_lanes;
+      ++n_lanes;
+    }
+  }
+  if (n_lanes == 0) return 0;
+  rc = rnn_wave_tc(lanes, n_lanes, T, B, H, H, st);
+  if (rc <= 0) return rc;
+  for (int l = 0; l < n_lanes; ++l) {          // shapes the two-lane kernel does not cover
+    const WaveLaneHost& h = lanes[l];
+    rc = 1;
+    if (h.lda == H)                              // dense hidden states (D == 1): the 8-way persistent kernel, batch <= 128
+      rc = rnn_seq_tc(h.Ab, T, h.W, H, B, H, H, h.tau0, h.dtau, h.n_steps, 1.f, h.C, h.ldc, h.c_ts, nullptr, 0, 0, h.Cb,
+                      ACT_RELU, h.flags, st);
+    if (rc < 0) return rc;
+    if (rc == 0) continue;
+    for (int s = 0; s < h.n_steps; ++s) {        // step by step
+      const int tau = h.tau0 + s * h.dtau;
+      TcArgs r;
+      r.C = h.C + (long long)tau * h.c_ts; r.ldc = h.ldc; r.beta = 1.f; r.act = ACT_RELU;
+      r.Cb = (__nv_bfloat16*)h.Cb + (long long)tau * h.cb_ts; r.ldcb = h.ldcb; r.split_k = 0;
+      if ((rc = gemm_tc_bf16((const __nv_bfloat16*)h.Ab + (long long)(tau - h.dtau) * h.a_ts, h.lda, 0, h.W, H, 0, B, H, H, r,
+                             L.sk, L.sk_bytes, st)))
+        return rc;
+    }
+  }
+  return 0;
+}
+
+static int layer2_bwd_bf16(int T, int B, int Bg, int I, int H, int D, const float* x, long long ldx, const void* x_bf16,
+                           long long ldxb, const float* const* w, const void* const* w_bf16, const int* n_steps,
+                           const float* out, long long ldo, const void* out_bf16, float* dout, long long lddo,
+                           void* dpre_bf16, float* dx, long long lddx, float* const* dw, void* ws, size_t ws_bytes,
+                           cudaStream_t st) {
+  TACORL_REQUIRE(x && w && n_steps && out && out_bf16 && dout && dpre_bf16 && dw && ws, "rnn_layer2_bwd: null pointer");
+  TACORL_REQUIRE(D == 1 || D == 2, "rnn_layer2_bwd: D must be 1 or 2");
+  TACORL_REQUIRE(H % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0 && ((uintptr_t)out_bf16 & 15) == 0 && ((uintptr_t)dpre_bf16 & 15) == 0,
+                 "rnn_layer2_bwd: pitches must be multiples of 8 and the bf16 twins 16-byte aligned");
+  TACORL_REQUIRE(n_steps[0] == T, "rnn_layer2_bwd: the forward direction must cover every step");
+  TACORL_REQUIRE(Bg >= 0 && Bg <= B, "rnn_layer2_bwd: grad_rows %d out of range (B=%d)", Bg, B);
+  if (B == 0) return 0;
+  if (Bg == 0) Bg = B;
+  const long long Ip = (I + 7) & ~7LL;
+  Arena ar(ws, ws_bytes);
+  int rc;
+  const __nv_bfloat16* wih[2] = {nullptr, nullptr};
+  const __nv_bfloat16* whht[2] = {nullptr, nullptr};
+  for (int d = 0; d < D; ++d) {
+    TACORL_REQUIRE(n_steps[d] >= 1 && n_steps[d] <= T, "rnn_layer2_bwd: n_steps out of range");
+    const void* tih = w_bf16 ? w_bf16[2 * d] : nullptr;
+    const void* tht = w_bf16 ? w_bf16[2 * d + 1] : nullptr;       // W_hh^T, prepared off the critical path
+    const bool ih_ready = tih && Ip == I && ((uintptr_t)tih & 15) == 0, ht_ready = tht && ((uintptr_t)tht & 15) == 0;
+    __nv_bfloat16* cih = ih_ready ? nullptr : ar.take<__nv_bfloat16>((size_t)H * Ip);
+    __nv_bfloat16* cht = ht_ready ? nullptr : ar.take<__nv_bfloat16>((size_t)H * H);
+    TACORL_REQUIRE((ih_ready || cih) && (ht_ready || cht), "rnn_layer2_bwd: workspace too small");
+    if (!ih_ready && (rc = cast_bf16_2d(w[2 * d], I, H, I, cih, Ip, st))) return rc;
+    if (!ht_ready && (rc = cast_transpose_bf16(w[2 * d + 1], H, H, H, cht, H, st))) return rc;
+    wih[d] = ih_ready ? (const __nv_bfloat16*)tih : cih;
+    whht[d] = ht_ready ? (const __nv_bfloat16*)tht : cht;
+  }
+  const bool x_ready = x_bf16 && ldxb % 8 == 0 && ldxb >= I && ((uintptr_t)x_bf16 & 15) == 0 && (I % 8 == 0);
+  const __nv_bfloat16* xb; long long ldb_x;
+  if (x_ready) { xb = (const __nv_bfloat16*)x_bf16; ldb_x = ldxb; }
+  else {
+    __nv_bfloat16* xc = ar.take<__nv_bfloat16>((size_t)T * B * Ip);
+    TACORL_REQUIRE(xc, "rnn_layer2_bwd: workspace too small");
+    if ((rc = cast_bf16_2d(x, ldx, (long long)T * B, I, xc, Ip, st))) return rc;
+    xb = xc; ldb_x = Ip;
+  }
+  unsigned* flags = ar.take<unsigned>(128);
+  TACORL_REQUIRE(flags, "rnn_layer2_bwd: workspace too small");
+  float* sk = (float*)(ar.base + ar.off);
+  const size_t sk_bytes = ar.left();
+  const __nv_bfloat16* hb = (const __nv_bfloat16*)out_bf16;
+  __nv_bfloat16* dpb = (__nv_bfloat16*)dpre_bf16;
+  WaveLaneHost lanes[2];
+  int n_lanes = 0;
+  for (int d = 0; d < D; ++d) {
+    const int n = n_steps[d];
+    const int t_last = d ? T - n : n - 1;     // last step of the recurrence: dpre = dout * [h > 0]
+    const long long col = (long long)d * H;
+    mask_rows_kernel<<<ew_blocks((long long)Bg * H), 256, 0, st>>>(
+        Bg, H, dout + (long long)t_last * B * lddo + col, lddo, out + (long long)t_last * B * ldo + col, ldo, nullptr, 0,
+        dpb + (long long)t_last * B * lddo + col, lddo);
+    TACORL_LAUNCH_CHECK();
+    if (n > 1) {   // dpre[t_prev] = (dout[t_prev] + dpre[t] W_hh) * [h[t_prev] > 0] down the whole chain
+      WaveLaneHost& h = lanes[n_lanes];
+      h.Ab = dpb + col; h.lda = lddo; h.a_ts = (long long)B * lddo;
+      h.W = whht[d]; h.ldw = H;
+      h.tau0 = d ? T - n + 1 : n - 2; h.dtau = d ? 1 : -1; h.n_steps = n - 1; h.beta = 1.f;
+      h.C = dout + col; h.ldc = lddo; h.c_ts = (long long)B * lddo;
+      h.gate = out + col; h.ldgate = ldo; h.gate_ts = (long long)B * ldo;
+      h.Cb = dpb + col; h.ldcb = lddo; h.cb_ts = (long long)B * lddo;
+      h.act = ACT_NONE; h.flags = flags + 64 * n_lanes;
+      ++n_lanes;
+    }
+  }
+  if (n_lanes > 0) {
+    rc = rnn_wave_tc(lanes, n_lanes, T, Bg, H, H, st);   // (rows >= Bg of a time step carry no gradient: they stay zero)
+    if (rc < 0) return rc;
+    if (rc > 0) {
+      for (int l = 0; l < n_lanes; ++l) {
+        const WaveLaneHost& h = lanes[l];
+        rc = 1;
+        if (h.lda == H && h.ldgate == H && Bg == B)
+          rc = rnn_seq_tc(h.Ab, T, h.W, H, B, H, H, h.tau0, h.dtau, h.n_steps, 1.f, h.C, h.ldc, h.c_ts, h.gate, h.ldgate,
+                          h.gate_ts, h.Cb, ACT_NONE, h.flags, st);
+        if (rc < 0) return rc;
+        if (rc == 0) continue;
+        for (int s = 0; s < h.n_steps; ++s) {
+          const int tau = h.tau0 + s * h.dtau;
+          TcArgs c;
+          c.C = h.C + (long long)tau * h.c_ts; c.ldc = h.ldc; c.beta = 1.f; c.split_k = 0;
+          c.gate = h.gate + (long long)tau * h.gate_ts; c.ldgate = h.ldgate;
+          c.Cb = (__nv_bfloat16*)h.Cb + (long long)tau * h.cb_ts; c.ldcb = h.ldcb;
+          if ((rc = gemm_tc_bf16((const __nv_bfloat16*)h.Ab + (long long)(tau - h.dtau) * h.a_ts, h.lda, 0, h.W, H, 0, Bg, H, H, c,
+                                 sk, sk_bytes, st)))
+            return rc;
+        }
+      }
+    }
+  }
+  for (int d = 0; d < D; ++d) {
+    const int n = n_steps[d], t_lo = d ? T - n : 0;
+    const long long col = (long long)d * H, rows = (long long)n * B;
+    float* dpre = dout + (long long)t_lo * B * lddo + col;
+    const __nv_bfloat16* dp = dpb + (long long)t_lo * B * lddo + col;
+    float *dw_ih = dw[4 * d], *dw_hh = dw[4 * d + 1], *db_ih = dw[4 * d + 2], *db_hh = dw[4 * d + 3];
+    if (dw_hh) {
+      if (n > 1) {   // dW_hh = dpre[pairs]^T h[prev]: both operands stored [K = rows][H]: MN-major
+        const __nv_bfloat16 *a, *b;
+        if (d == 0) { a = dp + (long long)B * lddo; b = hb + col; }
+        else { a = dp; b = hb + (long long)(t_lo + 1) * B * ldo + col; }
+        TcArgs g;
+        g.C = dw_hh; g.ldc = H; g.split_k = 0;
+        if ((rc = gemm_tc_bf16(a, lddo, 1, b, ldo, 1, H, H, (n - 1) * B, g, sk, sk_bytes, st))) return rc;
+      } else {
+        TACORL_CHECK_CUDA(cudaMemsetAsync(dw_hh, 0, (size_t)H * H * 4, st));
+      }
+    }
+    if (dw_ih) {
+      TcArgs g;
+      g.C = dw_ih; g.ldc = I; g.split_k = 0;
+      if ((rc = gemm_tc_bf16(dp, lddo, 1, xb + (long long)t_lo * B * ldb_x, ldb_x, 1, H, I, (int)rows, g, sk, sk_bytes, st))) return rc;
+    }
+    if (db_ih || db_hh) {   // db_ih == db_hh == column sums of dpre: reduce once, reuse
+      float* first = db_ih ? db_ih : db_hh;
+      if ((rc = colsum2_f32((int)rows, H, dpre, lddo, first, 0, sk, sk_bytes, st))) return rc;
+      if (db_ih && db_hh) TACORL_CHECK_CUDA(cudaMemcpyAsync(db_hh, db_ih, (size_t)H * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    if (dx) {   // dx (+)= dpre_d W_ih_d  (B operand = W_ih as stored [K = H][N = I]: MN-major)
+      TcArgs g;
+      g.C = dx + (long long)t_lo * B * lddx; g.ldc = lddx; g.beta = d ? 1.f : 0.f; g.split_k = 1;
+      if ((rc = gemm_tc_bf16(dp, lddo, 0, wih[d], Ip, 1, (int)rows, I, H, g, sk, sk_bytes, st))) return rc;
+    }
+  }
+  return 0;
+}
+
 int tacorl_rnn_layer_fwd(int T, int B, int I, int H, const float* x, long long ldx, const float* w_ih,
                          const float* w_hh, const float* b_ih, const float* b_hh, const float* h0,
                          int reverse, int n_steps, float* out, long long ldo, const void* w_ih_bf16,
@@ -391,6 +624,26 @@ int tacorl_rnn_layer_bwd(int T, int B, int I, int H, const float* x, long long l
   return fn(T, B, I, H, x, ldx, w_ih, w_hh, h0, reverse, n_steps, out, ldo, dout, lddo, dhn, dx, lddx,
             dx_accumulate, dw_ih, dw_hh, db_ih, db_hh, accumulate, dh0, w_ih_bf16, w_hh_t_bf16, h_bf16, ws, ws_bytes,
             (cudaStream_t)stream);
+}
+
+size_t tacorl_rnn_layer2_ws_bytes(int T, int B, int I, int H, int D) {
+  return (size_t)D * tacorl_rnn_layer_ws_bytes(T, B, I, H) + 8192;
+}
+
+int tacorl_rnn_layer2_fwd(int T, int B, int I, int H, int D, const float* x, long long ldx, const void* x_bf16,
+                          long long ldxb, const float* const* w, const void* const* w_bf16, const int* n_steps,
+                          float* out, long long ldo, void* out_bf16, void* ws, size_t ws_bytes, void* stream) {
+  return layer2_fwd_bf16(T, B, I, H, D, x, ldx, x_bf16, ldxb, w, w_bf16, n_steps, out, ldo, out_bf16, ws, ws_bytes,
+                         (cudaStream_t)stream);
+}
+
+int tacorl_rnn_layer2_bwd(int T, int B, int grad_rows, int I, int H, int D, const float* x, long long ldx, const void* x_bf16,
+                          long long ldxb, const float* const* w, const void* const* w_bf16, const int* n_steps,
+                          const float* out, long long ldo, const void* out_bf16, float* dout, long long lddo,
+                          void* dpre_bf16, float* dx, long long lddx, float* const* dw, void* ws, size_t ws_bytes,
+                          void* stream) {
+  return layer2_bwd_bf16(T, B, grad_rows, I, H, D, x, ldx, x_bf16, ldxb, w, w_bf16, n_steps, out, ldo, out_bf16, dout, lddo, dpre_bf16,
+                         dx, lddx, dw, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int tacorl_cast_transpose_bf16(const float* src, int rows, int cols, void* dst, void* stream) {

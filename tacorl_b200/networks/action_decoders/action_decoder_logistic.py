@@ -59,11 +59,11 @@ class ActionDecoderLogistic(ActionDecoder):
         b = torch.cat([self.prob_fc.bias, self.mean_fc.bias, self.log_scale_fc.bias, self.gripper_fc.bias], 0)
         return w, b
 
-    def _logits_time_major(self, latent_plan, perceptual_emb, h_0=None):
+    def _logits_time_major(self, latent_plan, perceptual_emb, h_0=None, grad_rows=None):
         """(T*B, 3*A*10+2) head outputs, rows ordered (t, b)."""
         B, T = perceptual_emb.shape[:2]
         x = torch.cat([latent_plan.unsqueeze(1).expand(-1, T, -1), perceptual_emb], dim=-1)
-        r, h_n = self.rnn.forward_time_major(x.transpose(0, 1), h_0)
+        r, h_n = self.rnn.forward_time_major(x.transpose(0, 1), h_0, grad_rows=grad_rows)
         w, b = self._head_params()
         return ops.linear(r.reshape(T * B, -1), w, b), h_n, (B, T)
 
@@ -100,7 +100,7 @@ class ActionDecoderLogistic(ActionDecoder):
         B = latent_plan.shape[0]
         plans = torch.cat([latent_plan, other_plan.detach()], dim=0)
         embs = torch.cat([perceptual_emb, perceptual_emb.detach()], dim=0)
-        logits, _, (B2, T) = self._logits_time_major(plans, embs)
+        logits, _, (B2, T) = self._logits_time_major(plans, embs, grad_rows=B)      # the second plan is logging-only
         lg = logits.view(T, B2, -1)
         la = lg[:, :B].reshape(T * B, -1)
         lb = lg[:, B:].reshape(T * B, -1).detach()

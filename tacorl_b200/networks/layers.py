@@ -89,5 +89,6 @@ class ReluRNN(nn.Module):
             return out, None
         return out.transpose(0, 1), hn
 
-    def forward_time_major(self, x_tm, h0=None, last_only=False):
-        return ops.relu_rnn(x_tm, self.weights(), self.num_layers, self.bidirectional, last_only, h0)
+    def forward_time_major(self, x_tm, h0=None, last_only=False, grad_rows=None):
+        """grad_rows: only the first `grad_rows` batch rows will ever receive a gradient (see ops.ReluRNN2Fn)."""
+        return ops.relu_rnn(x_tm, self.weights(), self.num_layers, self.bidirectional, last_only, h0, grad_rows)

@@ -421,7 +421,104 @@ class ReluRNNFn(Function):
         return (dbuf if ctx.needs_input_grad[0] else None, dh0, None, None, None, *wgrads)
 
 
-def relu_rnn(x_tm, weights, num_layers, bidirectional, last_only=False, h0=None):
+class ReluRNN2Fn(Function):
+    """bf16 tensor-core path of a multi-layer (bi)directional ReLU RNN with h_init = 0, one C call per layer
+    (tacorl_rnn_layer2_{fwd,bwd}): both directions of a layer in one persistent launch, bf16 twins of every layer
+    output / pre-activation gradient kept in the layer's own layout (no staging casts, no per-direction streams).
+    grad_rows: only the first `grad_rows` batch rows ever receive a gradient (the action decoder batches a
+    logging-only second plan behind the trained one): BPTT then runs on those rows alone."""
+
+    @staticmethod
+    def forward(ctx, x, num_layers, bidir, last_only, grad_rows, *weights):
+        T, B, I = x.shape
+        D = 2 if bidir else 1
+        H = weights[1].shape[0]
+        x = _c(x)
+        weights = [_c(w) for w in weights]
+        dev = x.device
+        train = any(ctx.needs_input_grad)            # (grad mode itself is off inside forward)
+        whts, prep_done = [None] * (num_layers * D), None
+        if train:   # W_hh^T (the BPTT operand) on a side stream, under the latency-bound recurrence
+            main, prep = torch.cuda.current_stream(dev), _prep_stream(dev)
+            whts = [torch.empty(H, H, device=dev, dtype=torch.bfloat16) for _ in range(num_layers * D)]
+            prep.wait_stream(main)
+            with torch.cuda.stream(prep):
+                for k in range(num_layers * D):
+                    L.call("tacorl_cast_transpose_bf16", L.ptr(weights[k * 4 + 1]), H, H, L.ptr_any(whts[k]), L.stream())
+                prep_done = torch.cuda.Event()
+                prep_done.record(prep)
+        outs, outbs = [], []
+        inp, inp_b = x, None
+        for l in range(num_layers):
+            Il = inp.shape[2]
+            out = torch.empty(T, B, D * H, device=dev, dtype=torch.float32)
+            outb = torch.empty(T, B, D * H, device=dev, dtype=torch.bfloat16)
+            wl = weights[l * D * 4:(l + 1) * D * 4]
+            tw = []
+            for d in range(D):
+                tw += [shadow_of(wl[4 * d]), shadow_of(wl[4 * d + 1])]
+            nst = [T] + ([1 if (last_only and l == num_layers - 1) else T] if D == 2 else [])
+            ws = L.workspace(L.query("tacorl_rnn_layer2_ws_bytes", T, B, Il, H, D), dev, "main")
+            L.call("tacorl_rnn_layer2_fwd", T, B, Il, H, D, L.ptr(inp), Il, L.ptr_any(inp_b), Il, L.ptr_array(wl),
+                   L.ptr_array(tw), L.int_array(nst), L.ptr(out), D * H, L.ptr_any(outb),
+                   ctypes.c_void_p(ws.data_ptr()), ws.numel(), L.stream())
+            outs.append(out)
+            outbs.append(outb)
+            inp, inp_b = out, outb
+        ctx.cfg = (T, B, I, H, D, num_layers, last_only, B if grad_rows is None else int(grad_rows))
+        ctx.aux = (outbs, whts, prep_done)
+        ctx.save_for_backward(x, *outs, *weights)
+        if last_only:
+            return inp[T - 1], None
+        hn = torch.stack([outs[l][0 if d == 1 else T - 1, :, d * H:(d + 1) * H] for l in range(num_layers) for d in range(D)], 0)
+        ctx.mark_non_differentiable(hn)
+        return inp, hn
+
+    @staticmethod
+    def backward(ctx, d_out, _d_hn):
+        T, B, I, H, D, num_layers, last_only, Bg = ctx.cfg
+        saved = ctx.saved_tensors
+        x = saved[0]
+        outs = saved[1:1 + num_layers]
+        weights = saved[1 + num_layers:]
+        outbs, whts, prep_done = ctx.aux
+        dev = x.device
+        if last_only:
+            dbuf = torch.zeros(T, B, D * H, device=dev, dtype=torch.float32)
+            dbuf[T - 1].copy_(d_out)
+        else:
+            dbuf = d_out.contiguous().clone()
+        if prep_done is not None:
+            torch.cuda.current_stream(dev).wait_event(prep_done)
+        wgrads = [None] * len(weights)
+        for l in range(num_layers - 1, -1, -1):
+            inp, inp_b = (x, None) if l == 0 else (outs[l - 1], outbs[l - 1])
+            Il = inp.shape[2]
+            need_dx = l > 0 or ctx.needs_input_grad[0]
+            dx = torch.empty(T, B, Il, device=dev, dtype=torch.float32) if need_dx else None
+            mk = torch.zeros if Bg < B else torch.empty       # rows without a gradient must read as zeros
+            dpb = mk(T, B, D * H, device=dev, dtype=torch.bfloat16)
+            wl = weights[l * D * 4:(l + 1) * D * 4]
+            w2, tw, g = [], [], []
+            for d in range(D):
+                w2 += [wl[4 * d], wl[4 * d + 1]]
+                tw += [shadow_of(wl[4 * d]), whts[l * D + d]]
+                for j in range(4):   # straight into the optimiser's flat gradient when this is the parameter's first use
+                    slot = grad_slot_of(wl[4 * d + j])
+                    g.append(slot if slot is not None else torch.empty_like(wl[4 * d + j]))
+            nst = [T] + ([1 if (last_only and l == num_layers - 1) else T] if D == 2 else [])
+            ws = L.workspace(L.query("tacorl_rnn_layer2_ws_bytes", T, B, Il, H, D), dev, "main")
+            L.call("tacorl_rnn_layer2_bwd", T, B, Bg, Il, H, D, L.ptr(inp), Il, L.ptr_any(inp_b), Il, L.ptr_array(w2),
+                   L.ptr_array(tw), L.int_array(nst), L.ptr(outs[l]), D * H, L.ptr_any(outbs[l]), L.ptr(dbuf), D * H,
+                   L.ptr_any(dpb), L.ptr(dx), Il, L.ptr_array(g), ctypes.c_void_p(ws.data_ptr()), ws.numel(), L.stream())
+            wgrads[l * D * 4:(l + 1) * D * 4] = g
+            dbuf = dx
+        return (dbuf if ctx.needs_input_grad[0] else None, None, None, None, None, *wgrads)
+
+
+def relu_rnn(x_tm, weights, num_layers, bidirectional, last_only=False, h0=None, grad_rows=None):
+    if h0 is None and _STATE["prec"] == L.PREC_BF16 and x_tm.is_cuda and weights[1].shape[0] % 8 == 0:
+        return ReluRNN2Fn.apply(x_tm, num_layers, bidirectional, last_only, grad_rows, *weights)
     return ReluRNNFn.apply(x_tm, h0, num_layers, bidirectional, last_only, *weights)
 
 

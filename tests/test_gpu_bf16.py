@@ -165,11 +165,13 @@ def test_play_lmp_bf16_loss_curve_tracks_fp32_oracle(bf16_ops):
     assert worst <= 1e-2, worst
 
 
-@pytest.mark.parametrize("B,H,bidir,with_h0", [(64, 2048, False, False), (128, 2048, False, True), (64, 2048, True, False),
-                                               (24, 512, True, False), (100, 1024, False, True)])
+@pytest.mark.parametrize("B,H,bidir,with_h0", [(64, 2048, False, True), (128, 2048, False, True), (64, 2048, True, True),
+                                               (24, 512, True, True), (100, 1024, False, True), (128, 2048, False, False)])
 def test_persistent_recurrence_bit_identical_to_stepwise(bf16_ops, B, H, bidir, with_h0):
-    """The persistent launch (weights resident in shared memory, steps chained by device-side arrival counters)
-    performs exactly the per-step kernel's arithmetic: outputs and every gradient must be bit-identical."""
+    """The 8-way persistent launch (weights resident in shared memory, steps chained by device-side arrival counters)
+    performs exactly the per-step kernel's arithmetic: outputs and every gradient must be bit-identical.  (With an
+    initial hidden state the per-direction path runs; without one and batch > 64 the whole-layer path falls back to the
+    same two kernels.)"""
     from tacorl_b200 import _lib
     g = torch.Generator().manual_seed(B + H)
     T, I, D = 16, 48, 2 if bidir else 1
@@ -199,3 +201,52 @@ def test_persistent_recurrence_bit_identical_to_stepwise(bf16_ops, B, H, bidir, 
     for i, (a, b) in enumerate(zip(res[1], res[0])):
         assert torch.isfinite(a).all()
         assert torch.equal(a, b), (i, float((a - b).abs().max()))
+
+
+@pytest.mark.parametrize("B,H,T,bidir,last_only,grad_rows", [(64, 2048, 16, True, True, None), (64, 2048, 16, True, False, None),
+                                                             (64, 2048, 15, False, False, None), (24, 512, 9, True, True, None),
+                                                             (3, 256, 5, True, False, None), (128, 2048, 15, False, False, 64),
+                                                             (40, 1024, 8, False, False, 16)])
+def test_two_lane_recurrence_deterministic_and_close_to_stepwise(bf16_ops, B, H, T, bidir, last_only, grad_rows):
+    """rnn_wave_kernel (4-CTA clusters split K; both directions of a layer side by side in one launch):
+    (a) bit-identical whether the two lanes share a launch or run one after the other;
+    (b) equal to the per-step kernels (8-way K split: another fp32 summation order, so a handful of bf16 roundings of
+        the hidden state differ) within 2e-3 on the outputs, 5e-2 on the gradients;  (c) grad_rows: BPTT over the leading rows only == BPTT over all rows
+        when the rest of the upstream gradient is zero."""
+    from tacorl_b200 import _lib
+    g = torch.Generator().manual_seed(B + H + T)
+    I, D = 48, 2 if bidir else 1
+    bound = 1.0 / H ** 0.5
+    shapes = []
+    for l in range(2):
+        for _ in range(D):
+            shapes += [(H, I if l == 0 else H * D), (H, H), (H,), (H,)]
+    w0 = [(torch.rand(s, generator=g) * 2 - 1) * bound for s in shapes]
+    x = torch.randn(T, B, I, generator=g)
+    cot = torch.randn((B, D * H) if last_only else (T, B, D * H), generator=g).to(DEV)
+    if grad_rows is not None:
+        cot[:, grad_rows:] = 0
+    res = {}
+    for mode, gr in ((1, grad_rows), (2, grad_rows), (0, grad_rows), (1, None)):
+        if (mode, gr) in res:
+            continue
+        was = _lib.lib().tacorl_rnn_seq_enable(mode)
+        try:
+            ws = [w.clone().to(DEV).requires_grad_(True) for w in w0]
+            xd = x.to(DEV).requires_grad_(True)
+            out, _ = bf16_ops.relu_rnn(xd, ws, 2, bidir, last_only, None, gr)
+            (out * cot).sum().backward()
+            torch.cuda.synchronize()
+            res[(mode, gr)] = [out.detach(), xd.grad] + [w.grad for w in ws]
+        finally:
+            _lib.lib().tacorl_rnn_seq_enable(was)
+    assert _lib.lib().tacorl_rnn_seq_timeouts() == 0
+    for i, (a, b) in enumerate(zip(res[(1, grad_rows)], res[(2, grad_rows)])):
+        assert torch.isfinite(a).all()
+        assert torch.equal(a, b), ("lanes", i, float((a - b).abs().max()))
+    # outputs: a handful of differing bf16 roundings; gradients: those roundings flip a few ReLU gates, and BPTT through
+    # 2 layers x T steps of random weights amplifies that (the bf16-vs-fp64 bar of test_rnn_bf16_close_to_fp64 is 0.1)
+    for i, (a, b) in enumerate(zip(res[(1, grad_rows)], res[(0, grad_rows)])):
+        assert rel_err(a, b) < (2e-3 if i == 0 else 5e-2), ("vs stepwise", i, rel_err(a, b))
+    for i, (a, b) in enumerate(zip(res[(1, grad_rows)], res[(1, None)])):
+        assert rel_err(a, b) < (2e-3 if i == 0 else 5e-2), ("grad_rows", i, rel_err(a, b))
