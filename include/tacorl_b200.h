@@ -240,6 +240,12 @@ int tacorl_cql_actor_loss(int mode, int B, const float* log_pi, const float* a, 
 int tacorl_adam_step(long long n, float* p, const float* g, float* m, float* v, float lr, float beta1,
                      float beta2, float eps, int step, int* step_dev, float grad_scale, const float* sqnorm,
                      float max_norm, void* shadow_bf16, void* stream);
+/* One optimiser step applied slice by slice (a slice whose gradient is final early -- everything behind the vision
+ * encoders -- is updated on a side stream while the encoder backward still runs): every slice of the step reads the same
+ * device step count; only the FIRST call of a step passes increment_step = 1. */
+int tacorl_adam_step_range(long long n, float* p, const float* g, float* m, float* v, float lr, float beta1,
+                           float beta2, float eps, int step, int* step_dev, int increment_step, float grad_scale,
+                           const float* sqnorm, float max_norm, void* shadow_bf16, void* stream);
 int tacorl_polyak_update(long long n, float* target, const float* source, float tau, void* stream);
 int tacorl_sqnorm(long long n, const float* x, float* out, float* ws, void* stream);
 

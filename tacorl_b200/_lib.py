@@ -66,6 +66,7 @@ _SIGS = {
                                _vp, _vp, _vp, _vp, _vp],
     "tacorl_cql_actor_loss": [_i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp],
     "tacorl_adam_step": [_ll, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _vp, _f, _vp, _f, _vp, _vp],
+    "tacorl_adam_step_range": [_ll, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _vp, _i, _f, _vp, _f, _vp, _vp],
     "tacorl_polyak_update": [_ll, _vp, _vp, _f, _vp],
     "tacorl_sqnorm": [_ll, _vp, _vp, _vp, _vp],
     "tacorl_last_error": [],

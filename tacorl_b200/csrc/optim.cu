@@ -113,16 +113,27 @@ using namespace tacorl;
 
 extern "C" {
 
+int tacorl_adam_step_range(long long n, float* p, const float* g, float* m, float* v, float lr, float beta1,
+                           float beta2, float eps, int step, int* step_dev, int increment_step, float grad_scale,
+                           const float* sqnorm, float max_norm, void* shadow_bf16, void* stream);
+
 int tacorl_adam_step(long long n, float* p, const float* g, float* m, float* v, float lr, float beta1,
                      float beta2, float eps, int step, int* step_dev, float grad_scale, const float* sqnorm,
                      float max_norm, void* shadow_bf16, void* stream) {
+  return tacorl_adam_step_range(n, p, g, m, v, lr, beta1, beta2, eps, step, step_dev, 1, grad_scale, sqnorm, max_norm,
+                                shadow_bf16, stream);
+}
+
+int tacorl_adam_step_range(long long n, float* p, const float* g, float* m, float* v, float lr, float beta1,
+                           float beta2, float eps, int step, int* step_dev, int increment_step, float grad_scale,
+                           const float* sqnorm, float max_norm, void* shadow_bf16, void* stream) {
   if (n == 0) return 0;
   TACORL_REQUIRE(p && g && m && v && (step >= 1 || step_dev), "adam_step: bad arguments");
-  if (step_dev) {
+  if (step_dev && increment_step) {
     increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
     TACORL_LAUNCH_CHECK();
-    if (step < 1) step = 1;
   }
+  if (step_dev && step < 1) step = 1;
   TACORL_REQUIRE(((uintptr_t)p % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
                      ((uintptr_t)v % 16 == 0) && ((uintptr_t)shadow_bf16 % 8 == 0),
                  "adam_step: buffers must be 16-byte aligned");

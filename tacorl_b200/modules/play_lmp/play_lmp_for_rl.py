@@ -170,11 +170,12 @@ class PlayLMP(LightningModule):
     _flat_opt = None
 
     def _overlap_grad_sync(self, emb_states):
-        """Data parallel: everything behind the vision encoders (RNNs, decoder, MLPs = 99.7 % of the parameters)
-        has its final gradient before the encoders' backward starts.  A hook on the embeddings starts the
-        all-reduce of that slice at exactly that moment, so it overlaps the encoder backward."""
+        """Everything behind the vision encoders (RNNs, decoder, MLPs = 99.7 % of the parameters) has its final
+        gradient before the encoders' backward starts.  A hook on the embeddings starts the all-reduce of that slice
+        (data parallel) and its Adam update (optimizer.early_step) at exactly that moment, on side streams, so both
+        overlap the encoder backward."""
         opt = self._flat_opt
-        if opt is None or opt.grad_sync is None or not torch.is_grad_enabled():
+        if opt is None or not torch.is_grad_enabled() or (opt.grad_sync is None and not opt.early_step):
             return
         enc_ids = {id(p) for p in self.perceptual_encoder.parameters()}
         rest = [p for p in opt.param_groups[0]["params"] if id(p) not in enc_ids]

@@ -805,12 +805,13 @@ def cql_alpha_loss(log_pi, log_alpha, target_entropy):
 
 # --------------------------------------------------------------------------------------- optimiser kernels
 def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, sqnorm=None, max_norm=0.0,
-              step_dev=None, shadow=None):
-    """step_dev: optional int32 device tensor holding the step count (incremented by the call).
+              step_dev=None, shadow=None, increment=True):
+    """step_dev: optional int32 device tensor holding the step count (incremented by the call unless increment=False:
+    the later slices of a step that is applied slice by slice).
     shadow: optional bf16 tensor of p.numel() elements that receives a bf16 copy of the updated parameters."""
     sd = ctypes.c_void_p(step_dev.data_ptr()) if step_dev is not None else None
-    L.call("tacorl_adam_step", p.numel(), L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), float(lr), float(beta1),
-           float(beta2), float(eps), int(step), sd, float(grad_scale), L.ptr(sqnorm), float(max_norm),
+    L.call("tacorl_adam_step_range", p.numel(), L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), float(lr), float(beta1),
+           float(beta2), float(eps), int(step), sd, int(increment), float(grad_scale), L.ptr(sqnorm), float(max_norm),
            L.ptr_any(shadow), L.stream())
 
 

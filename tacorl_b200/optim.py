@@ -87,19 +87,48 @@ class FlatAdam(torch.optim.Optimizer):
 
     def begin_overlapped_sync(self, params):
         """Call when the gradients of `params` (a contiguous run, e.g. everything behind the vision encoder) are
-        final while backward is still running: their slice of the flat gradient is gathered and its all-reduce is
-        started on the side stream, overlapping the rest of backward.  step() then only exchanges what is left."""
-        if self.grad_sync is None:
-            return
+        final while backward is still running.  Their slice of the flat gradient is gathered; with data parallelism
+        its all-reduce starts on the side stream; and -- when no global-norm clip couples the slices -- the Adam update
+        of the slice follows on that same side stream, so that exchange AND update of 99.7 % of the parameters hide
+        under the encoder backward.  step() then only handles what is left."""
         r = self._range_of(params)
         if r is None:
             return
+        early = self.early_step and self.max_grad_norm is None and self.pbuf.flat.is_cuda
+        if self.grad_sync is None and not early:
+            return
         lo, hi, e0, e1 = r
         self.gather_grads(lo, hi)
-        self.grad_sync.start(self.flat_grad[e0:e1])
+        if self.grad_sync is not None:
+            self.grad_sync.start(self.flat_grad[e0:e1])
         self._synced = (lo, hi, e0, e1)
+        if early:
+            dev = self.pbuf.flat.device
+            if self._early_stream is None:
+                self._early_stream = torch.cuda.Stream(device=dev)
+            stream = self._early_stream
+            sync_stream = getattr(self.grad_sync, "_stream", None) if self.grad_sync is not None else None
+            # after the slice's all-reduce (own stream, so that the later exchange of the encoder slice does not queue
+            # behind this update), or straight after the gather
+            stream.wait_stream(sync_stream if sync_stream is not None else torch.cuda.current_stream(dev))
+            with torch.cuda.stream(stream):
+                self.step_count += 1
+                self._adam_range(e0, e1, increment=True)
+            self._early = (e0, e1, stream)
 
+    # update slices whose gradient is final early on a side stream (see begin_overlapped_sync).  Off by default: it assumes
+    # ONE backward pass per step() (no gradient accumulation); runtime.play_lmp_step_fn, which owns that structure, enables it
+    early_step = False
     _synced = None
+    _early = None
+    _early_stream = None
+
+    def _adam_range(self, e0, e1, increment, sq=None):
+        g = self.param_groups[0]
+        ops.adam_step(self.pbuf.flat[e0:e1], self.flat_grad[e0:e1], self.exp_avg[e0:e1], self.exp_avg_sq[e0:e1], g["lr"],
+                      self.step_count, g["betas"][0], g["betas"][1], g["eps"], self.grad_scale, sq,
+                      float(self.max_grad_norm) if self.max_grad_norm is not None else 0.0, self._step_dev,
+                      None if self.shadow is None else self.shadow[e0:e1], increment)
 
     def gather_grads(self, lo=0, hi=None):
         ps = self.param_groups[0]["params"][lo:hi]
@@ -192,34 +221,38 @@ class FlatAdam(torch.optim.Optimizer):
     def step(self, closure=None, gathered=False):
         loss = closure() if closure is not None else None
         self._slots_taken.clear()
-        if self._synced is not None and self.grad_sync is not None:
-            lo, hi, e0, e1 = self._synced          # [lo,hi) already gathered and in flight on the side stream
+        rest = [(0, self.pbuf.numel)]
+        if self._synced is not None:
+            lo, hi, e0, e1 = self._synced          # [lo,hi) already gathered (and in flight on the side stream)
             n = len(self.param_groups[0]["params"])
             if not gathered:
                 if lo > 0:
                     self.gather_grads(0, lo)
                 if hi < n:
                     self.gather_grads(hi, n)
-            if e0 > 0:
-                self.grad_sync.start(self.flat_grad[:e0])
-            if e1 < self.pbuf.numel:
-                self.grad_sync.start(self.flat_grad[e1:])
-            self.grad_sync.finish()
+            rest = [(a, b) for a, b in ((0, e0), (e1, self.pbuf.numel)) if b > a]
+            if self.grad_sync is not None:
+                for a, b in rest:
+                    self.grad_sync.start(self.flat_grad[a:b])
+                self.grad_sync.finish()
             self._synced = None
         else:
             if not gathered:
                 self.gather_grads()
             if self.grad_sync is not None:
                 self.grad_sync(self.flat_grad)
-        g = self.param_groups[0]
+        if self._early is not None:                # the big slice was updated early: only the remaining slices are left
+            e0, e1, stream = self._early
+            for a, b in rest:
+                self._adam_range(a, b, increment=False)
+            torch.cuda.current_stream(self.pbuf.flat.device).wait_stream(stream)
+            self._early = None
+            return loss
         self.step_count += 1
         sq = None
         if self.max_grad_norm is not None:
             sq = ops.sqnorm(self.flat_grad, self._sqnorm)
-        ops.adam_step(self.pbuf.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], self.step_count,
-                      g["betas"][0], g["betas"][1], g["eps"], self.grad_scale, sq,
-                      float(self.max_grad_norm) if self.max_grad_norm is not None else 0.0, self._step_dev,
-                      self.shadow)
+        self._adam_range(0, self.pbuf.numel, increment=True, sq=sq)
         return loss
 
     def set_grad(self, flat_values):

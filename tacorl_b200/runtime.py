@@ -145,7 +145,11 @@ class GraphedTrainStep:
         self._staged = True
 
 
-def play_lmp_step_fn(module, optimizer):
+def play_lmp_step_fn(module, optimizer, early_step=True):
+    """One PlayLMP optimiser step.  early_step: this function runs exactly one backward pass per step(), so the update
+    of the parameters behind the encoders may start as soon as their gradients are final (FlatAdam.early_step)."""
+    optimizer.early_step = bool(early_step)
+
     def step(batch):
         optimizer.zero_grad(set_to_none=True)
         loss = module.training_step(batch, 0)

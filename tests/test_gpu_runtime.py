@@ -227,3 +227,29 @@ def test_rnn_gradient_slots_survive_accumulation_and_kept_grads():
     out.square().sum().backward()
     for p, f in zip(rnn.parameters(), fresh1):
         assert rel_err(p.grad, f) < 1e-6
+
+
+def test_early_adam_slice_update_is_bit_identical_to_one_pass():
+    """FlatAdam.early_step: the parameters behind the encoders are updated on a side stream as soon as their gradients
+    are final (under the encoder backward), the rest at step(): same kernel, same device step count -> same bits."""
+    from tacorl_b200 import ops, runtime
+    ops.set_precision("fp32")
+    B, T, H, W = 2, 8, 84, 84
+    results = []
+    for early in (False, True):
+        m = build_play_lmp("tanh_net", ("rgb_static",), 64, 16, T)
+        shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
+        m.load_state_dict(S.synth_state_dict(shapes, 4))
+        m.to(DEV)
+        opt = m.configure_optimizers()
+        fn = runtime.play_lmp_step_fn(m, opt, early_step=early)
+        batch = to_dev(S.synth_play_batch(B, T, H, W, 4))
+        batch = {"states": batch["states"], "actions": batch["actions"]}
+        torch.manual_seed(3)
+        for _ in range(3):
+            fn(batch)
+        torch.cuda.synchronize()
+        assert int(opt._step_dev) == 3 and opt.step_count == 3
+        results.append((opt.flat_params.clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone()))
+    for a, b in zip(*results):
+        assert torch.equal(a, b)
