@@ -282,7 +282,7 @@ def measure_workload(ctx, name, precision, steps, warmup, e2e=True, sample_clock
     h2d = nbytes(host)
     graphed = None
     if not args.no_graph:
-        graphed = runtime.GraphedTrainStep(eager_step, resident, device=dev, warmup=3)
+        graphed = runtime.GraphedTrainStep(eager_step, resident, device=dev, warmup=3, buffers=2)
         ctx.graphs.append(graphed)
 
     def step(_s):
@@ -320,15 +320,24 @@ def measure_workload(ctx, name, precision, steps, warmup, e2e=True, sample_clock
         if graphed is not None and os.environ.get("BENCH_E2E_SYNC", "") != "1":
             pinned = [torch.empty((), dtype=torch.float32, pin_memory=True) for _ in range(2)]
             done = [torch.cuda.Event() for _ in range(2)]
+            stepped = [torch.cuda.Event() for _ in range(2)]
+            rb = torch.cuda.Stream(device=dev)       # loss read-back stream: the main stream carries graph launches only
+            main = torch.cuda.current_stream(dev)
+            for e in done:
+                e.record(main)
 
             def read(i):
                 done[i % 2].synchronize()
                 losses.append(float(pinned[i % 2]))
 
             def fn(s):
+                main.wait_event(done[s % 2])         # (long complete) the slot's previous read-back, before its loss is rewritten
                 loss = graphed()
-                pinned[s % 2].copy_(loss, non_blocking=True)
-                done[s % 2].record(torch.cuda.current_stream(dev))
+                stepped[s % 2].record(main)
+                with torch.cuda.stream(rb):
+                    rb.wait_event(stepped[s % 2])
+                    pinned[s % 2].copy_(loss, non_blocking=True)
+                    done[s % 2].record(rb)
                 graphed.prefetch(host)
                 if s > 0:
                     read(s - 1)

@@ -233,6 +233,29 @@ int tacorl_cql_actor_loss(int mode, int B, const float* log_pi, const float* a, 
                           const float* log_alpha, float target_entropy, float* out, float* d_log_alpha,
                           float* d_log_pi, float* da, float* db, void* stream);
 
+/* ---- fused small-MLP chains (fp32): a whole Linear -> act -> Linear ... stack in ONE launch, forward or backward.
+ * Replaces the per-layer launches behind VisualGoalEncoder.forward (goal_encoder.py:29-33), MLPPolicy.forward
+ * (actor.py:252-270: 3 x Linear+SiLU, then fc_mean | fc_log_std as ONE layer of two weight segments) and
+ * MLPQNetwork.forward (critic.py:92-97).  <= 4 layers, widths <= 256 and multiples of 4 (the last layer's output width
+ * is free), the last layer has no activation.  The input may be the concatenation of two tensors along the feature
+ * dim (state | goal, embedding | action): no torch.cat.  z: (rows, sum of the hidden widths) receives the
+ * pre-activations of layers 0 .. L-2 (the backward pass's saved tensors).  bwd: dW / db per segment may be NULL
+ * (gradient w.r.t. the input only); dx0 / dx1 may be NULL. */
+typedef struct tacorl_mlp_layer {
+  const float* W0; const float* b0; int n0;     /* first weight segment: (n0, in) row-major, bias (n0) or NULL */
+  const float* W1; const float* b1; int n1;     /* optional second segment stacked behind it (n1 = 0: none) */
+  int in; int act;                              /* input width; activation on the output (TACORL_ACT_*) */
+  float* dW0; float* db0; float* dW1; float* db1;   /* backward outputs */
+} tacorl_mlp_layer;
+size_t tacorl_mlp_chain_ws_bytes(int L, int rows, const tacorl_mlp_layer* layers);
+int tacorl_mlp_chain_fwd(int L, int rows, const tacorl_mlp_layer* layers, const float* x0, int xin0, long long ldx0,
+                         const float* x1, int xin1, long long ldx1, float* z, long long ldz, float* out, long long ldo,
+                         void* stream);
+int tacorl_mlp_chain_bwd(int L, int rows, const tacorl_mlp_layer* layers, const float* x0, int xin0, long long ldx0,
+                         const float* x1, int xin1, long long ldx1, const float* z, long long ldz, const float* d_out,
+                         long long lddo, float* dx0, long long lddx0, float* dx1, long long lddx1, void* ws,
+                         size_t ws_bytes, void* stream);
+
 /* ---- optimiser side: Adam (play_lmp_for_rl.py:362-368, cql_offline_lightning.py:553-574) fused with
  * clip_grad_norm_ (:522-537) over flat buffers; Polyak (:229-232); sum of squares (ws >= 592 floats) */
 /* step: host-side step count (>=1) used for the bias corrections, OR step_dev != NULL: a device int that the
@@ -242,10 +265,11 @@ int tacorl_adam_step(long long n, float* p, const float* g, float* m, float* v, 
                      float max_norm, void* shadow_bf16, void* stream);
 /* One optimiser step applied slice by slice (a slice whose gradient is final early -- everything behind the vision
  * encoders -- is updated on a side stream while the encoder backward still runs): every slice of the step reads the same
- * device step count; only the FIRST call of a step passes increment_step = 1. */
+ * device step count; only the FIRST call of a step passes increment_step = 1.  background = 1: launch a small grid
+ * (one CTA per SM) that shares the SMs with whatever else is running instead of filling them. */
 int tacorl_adam_step_range(long long n, float* p, const float* g, float* m, float* v, float lr, float beta1,
-                           float beta2, float eps, int step, int* step_dev, int increment_step, float grad_scale,
-                           const float* sqnorm, float max_norm, void* shadow_bf16, void* stream);
+                           float beta2, float eps, int step, int* step_dev, int increment_step, int background,
+                           float grad_scale, const float* sqnorm, float max_norm, void* shadow_bf16, void* stream);
 int tacorl_polyak_update(long long n, float* target, const float* source, float tau, void* stream);
 int tacorl_sqnorm(long long n, const float* x, float* out, float* ws, void* stream);
 

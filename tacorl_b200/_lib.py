@@ -65,8 +65,11 @@ _SIGS = {
     "tacorl_cql_critic_loss": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _i,
                                _vp, _vp, _vp, _vp, _vp],
     "tacorl_cql_actor_loss": [_i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp],
+    "tacorl_mlp_chain_ws_bytes": [_i, _i, _vp],
+    "tacorl_mlp_chain_fwd": [_i, _i, _vp, _vp, _i, _ll, _vp, _i, _ll, _vp, _ll, _vp, _ll, _vp],
+    "tacorl_mlp_chain_bwd": [_i, _i, _vp, _vp, _i, _ll, _vp, _i, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _sz, _vp],
     "tacorl_adam_step": [_ll, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _vp, _f, _vp, _f, _vp, _vp],
-    "tacorl_adam_step_range": [_ll, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _vp, _i, _f, _vp, _f, _vp, _vp],
+    "tacorl_adam_step_range": [_ll, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _vp, _i, _i, _f, _vp, _f, _vp, _vp],
     "tacorl_polyak_update": [_ll, _vp, _vp, _f, _vp],
     "tacorl_sqnorm": [_ll, _vp, _vp, _vp, _vp],
     "tacorl_last_error": [],
@@ -78,6 +81,7 @@ _SIGS = {
 }
 _RESTYPES = {
     "tacorl_lmp_encoder_ws_bytes": _sz, "tacorl_rnn_layer_ws_bytes": _sz, "tacorl_rnn_layer2_ws_bytes": _sz,
+    "tacorl_mlp_chain_ws_bytes": _sz,
     "tacorl_last_error": ctypes.c_char_p, "tacorl_launch_count": ctypes.c_ulonglong,
     "tacorl_rnn_seq_timeouts": ctypes.c_uint,
 }
@@ -86,6 +90,12 @@ EXPORTED = tuple(_SIGS)
 
 class TacorlLibraryError(RuntimeError):
     pass
+
+
+class MlpLayer(ctypes.Structure):
+    """tacorl_mlp_layer (include/tacorl_b200.h)."""
+    _fields_ = [("W0", _vp), ("b0", _vp), ("n0", _i), ("W1", _vp), ("b1", _vp), ("n1", _i), ("in_", _i), ("act", _i),
+                ("dW0", _vp), ("db0", _vp), ("dW1", _vp), ("db1", _vp)]
 
 
 def lib():

@@ -17,6 +17,7 @@ constexpr int kOptBlocks = 148 * 4;
 //   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
 // g is first multiplied by grad_scale * clip_coef, clip_coef = min(1, max_norm / (sqrt(*sqnorm)*grad_scale + 1e-6))
 // when sqnorm != nullptr (clip_grad_norm_ semantics on the already-scaled gradient).
+template <int UN>
 __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __restrict__ g,
                             float* __restrict__ m, float* __restrict__ v, float lr, float b1, float b2,
                             float eps, float bc1, float bc2_sqrt, float grad_scale,
@@ -36,20 +37,30 @@ __global__ void adam_kernel(long long n, float* __restrict__ p, const float* __r
   const long long n4 = n >> 2;
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
   float4* p4 = (float4*)p; const float4* g4 = (const float4*)g; float4* m4 = (float4*)m; float4* v4 = (float4*)v;
-  for (long long i = tid; i < n4; i += nth) {
-    float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
-#define ADAMC(c)                                                   \
-    { const float gx = gg.c * gs;                                  \
-      mm.c = b1 * mm.c + (1.f - b1) * gx;                          \
-      vv.c = b2 * vv.c + (1.f - b2) * gx * gx;                     \
-      pp.c -= step * mm.c / (sqrtf(vv.c) / bc2_sqrt + eps); }
-    ADAMC(x) ADAMC(y) ADAMC(z) ADAMC(w)
+  for (long long i0 = tid; i0 < n4; i0 += nth * UN) {
+    float4 pp[UN], gg[UN], mm[UN], vv[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {          // every load of the iteration in flight before the first use
+      const long long i = i0 + u * nth;
+      if (i < n4) { pp[u] = p4[i]; gg[u] = g4[i]; mm[u] = m4[i]; vv[u] = v4[i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long i = i0 + u * nth;
+      if (i >= n4) break;
+#define ADAMC(c)                                                               \
+      { const float gx = gg[u].c * gs;                                         \
+        mm[u].c = b1 * mm[u].c + (1.f - b1) * gx;                              \
+        vv[u].c = b2 * vv[u].c + (1.f - b2) * gx * gx;                         \
+        pp[u].c -= step * mm[u].c / (sqrtf(vv[u].c) / bc2_sqrt + eps); }
+      ADAMC(x) ADAMC(y) ADAMC(z) ADAMC(w)
 #undef ADAMC
-    p4[i] = pp; m4[i] = mm; v4[i] = vv;
-    if (shadow) {     // bf16 copy of the updated parameters: the tensor-core operands of the next step
-      const __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
-      reinterpret_cast<uint2*>(shadow)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo),
-                                                        *reinterpret_cast<const uint32_t*>(&hi));
+      p4[i] = pp[u]; m4[i] = mm[u]; v4[i] = vv[u];
+      if (shadow) {     // bf16 copy of the updated parameters: the tensor-core operands of the next step
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(pp[u].x, pp[u].y), hi = __floats2bfloat162_rn(pp[u].z, pp[u].w);
+        reinterpret_cast<uint2*>(shadow)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo),
+                                                          *reinterpret_cast<const uint32_t*>(&hi));
+      }
     }
   }
   for (long long i = (n4 << 2) + tid; i < n; i += nth) {
@@ -114,19 +125,19 @@ using namespace tacorl;
 extern "C" {
 
 int tacorl_adam_step_range(long long n, float* p, const float* g, float* m, float* v, float lr, float beta1,
-                           float beta2, float eps, int step, int* step_dev, int increment_step, float grad_scale,
-                           const float* sqnorm, float max_norm, void* shadow_bf16, void* stream);
+                           float beta2, float eps, int step, int* step_dev, int increment_step, int background,
+                           float grad_scale, const float* sqnorm, float max_norm, void* shadow_bf16, void* stream);
 
 int tacorl_adam_step(long long n, float* p, const float* g, float* m, float* v, float lr, float beta1,
                      float beta2, float eps, int step, int* step_dev, float grad_scale, const float* sqnorm,
                      float max_norm, void* shadow_bf16, void* stream) {
-  return tacorl_adam_step_range(n, p, g, m, v, lr, beta1, beta2, eps, step, step_dev, 1, grad_scale, sqnorm, max_norm,
+  return tacorl_adam_step_range(n, p, g, m, v, lr, beta1, beta2, eps, step, step_dev, 1, 0, grad_scale, sqnorm, max_norm,
                                 shadow_bf16, stream);
 }
 
 int tacorl_adam_step_range(long long n, float* p, const float* g, float* m, float* v, float lr, float beta1,
-                           float beta2, float eps, int step, int* step_dev, int increment_step, float grad_scale,
-                           const float* sqnorm, float max_norm, void* shadow_bf16, void* stream) {
+                           float beta2, float eps, int step, int* step_dev, int increment_step, int background,
+                           float grad_scale, const float* sqnorm, float max_norm, void* shadow_bf16, void* stream) {
   if (n == 0) return 0;
   TACORL_REQUIRE(p && g && m && v && (step >= 1 || step_dev), "adam_step: bad arguments");
   if (step_dev && increment_step) {
@@ -139,10 +150,20 @@ int tacorl_adam_step_range(long long n, float* p, const float* g, float* m, floa
                  "adam_step: buffers must be 16-byte aligned");
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
-  int blocks = (int)min((long long)kOptBlocks, (n / 4 + 255) / 256 + 1);
-  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(n, p, g, m, v, lr, beta1, beta2, eps, bc1, sqrtf(bc2),
-                                                       grad_scale, sqnorm, max_norm, step_dev,
-                                                       (__nv_bfloat16*)shadow_bf16);
+  if (background) {
+    // meant to run UNDER other kernels (the encoder backward): one 256-thread CTA per SM (the foreground grid of
+    // 4 CTAs per SM takes 57 K of an SM's 64 K registers and starves everything else), two 16-byte loads per array
+    // in flight per thread instead
+    int blocks = (int)min((long long)148, (n / 8 + 255) / 256 + 1);
+    adam_kernel<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(n, p, g, m, v, lr, beta1, beta2, eps, bc1, sqrtf(bc2),
+                                                            grad_scale, sqnorm, max_norm, step_dev,
+                                                            (__nv_bfloat16*)shadow_bf16);
+  } else {
+    int blocks = (int)min((long long)kOptBlocks, (n / 4 + 255) / 256 + 1);
+    adam_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(n, p, g, m, v, lr, beta1, beta2, eps, bc1, sqrtf(bc2),
+                                                            grad_scale, sqnorm, max_norm, step_dev,
+                                                            (__nv_bfloat16*)shadow_bf16);
+  }
   TACORL_LAUNCH_CHECK();
   return 0;
 }

@@ -203,12 +203,10 @@ class TACORL(LightningModule):
         return torch.cat([e, goal_emb], dim=-1), goal_emb
 
     @staticmethod
-    def _q_mlp(qnet, x, detach_params=False):
-        """MLPQNetwork.forward (critic.py:92-97); detach_params: gradient w.r.t. the input only."""
-        f = (lambda t: t.detach()) if detach_params else (lambda t: t)
-        for fc in qnet.fc_layers:
-            x = ops.linear(x, f(fc.weight), f(fc.bias), "silu")
-        return ops.linear(x, f(qnet.out.weight), f(qnet.out.bias), None)
+    def _q_mlp(qnet, emb, action, detach_params=False):
+        """MLPQNetwork.forward on cat(emb, action) (critic.py:24-30, 92-97), one fused launch each way;
+        detach_params: gradient w.r.t. the input only."""
+        return qnet((emb, action), detach_params=detach_params)
 
     def compute_update(self, batch, optimize: bool = True, log_type: str = "train"):
         states, plan, next_states, rewards, dones = batch
@@ -239,8 +237,8 @@ class TACORL(LightningModule):
             plp = dist_a.log_prob(value=plan)
             actor_loss, aout = ops.CqlActorLossFn.apply(1, curr_log_pi, plp, None, self.log_alpha)
         else:
-            qa1 = self._q_mlp(self.q1.critic.Q, torch.cat([q1_e.detach(), curr_actions], dim=-1), True)
-            qa2 = self._q_mlp(self.q2.critic.Q, torch.cat([q2_e.detach(), curr_actions], dim=-1), True)
+            qa1 = self._q_mlp(self.q1.critic.Q, q1_e.detach(), curr_actions, True)
+            qa2 = self._q_mlp(self.q2.critic.Q, q2_e.detach(), curr_actions, True)
             actor_loss, aout = ops.CqlActorLossFn.apply(2, curr_log_pi, qa1, qa2, self.log_alpha)
         log("alpha", aout[1])
 
@@ -251,8 +249,8 @@ class TACORL(LightningModule):
             next_actions, _ = TanhNormal(mean_n, std_n).sample_and_logprob()
             t1_e, _ = self._emb(self.target_q1, nxt, goal)
             t2_e, _ = self._emb(self.target_q2, nxt, goal)
-            tq1 = self._q_mlp(self.target_q1.critic.Q, torch.cat([t1_e, next_actions], dim=-1))
-            tq2 = self._q_mlp(self.target_q2.critic.Q, torch.cat([t2_e, next_actions], dim=-1))
+            tq1 = self._q_mlp(self.target_q1.critic.Q, t1_e, next_actions)
+            tq2 = self._q_mlp(self.target_q2.critic.Q, t2_e, next_actions)
             # ---- sampled actions for the conservative term (:238-282); draw order = reference's
             rand_actions = rng.uniform((n * B, Ld), -1.0, 1.0, plan.device)
             ac, zc = TanhNormal(mean.detach(), std.detach()).sample_n(n, return_pre_tanh_value=True)
@@ -261,8 +259,8 @@ class TACORL(LightningModule):
             lp_next = ops.tanh_logprob(mean_n, std_n, zn, False)
             acts_all = torch.cat([plan, rand_actions, ac.reshape(n * B, Ld), an.reshape(n * B, Ld)], dim=0)
         reps = 1 + 3 * n
-        q1_all = self._q_mlp(self.q1.critic.Q, torch.cat([q1_e.repeat(reps, 1), acts_all], dim=-1))
-        q2_all = self._q_mlp(self.q2.critic.Q, torch.cat([q2_e.repeat(reps, 1), acts_all], dim=-1))
+        q1_all = self._q_mlp(self.q1.critic.Q, q1_e.repeat(reps, 1), acts_all)
+        q2_all = self._q_mlp(self.q2.critic.Q, q2_e.repeat(reps, 1), acts_all)
         rand_density = math.log(0.5 ** Ld)
         q1_loss, q2_loss, scal, d_lap = ops.CqlCriticLossFn.apply(
             q1_all, q2_all, lp_curr, lp_next, tq1, tq2, rewards * 1.0, dones * 1.0,

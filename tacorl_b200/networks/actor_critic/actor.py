@@ -40,11 +40,13 @@ class MLPPolicy(nn.Module):
         return x
 
     def forward(self, policy_input):
-        x = self.get_last_hidden_state(policy_input)
-        w = torch.cat([self.fc_mean.weight, self.fc_log_std.weight], dim=0)
-        b = torch.cat([self.fc_mean.bias, self.fc_log_std.bias], dim=0)
-        lead = x.shape[:-1]
-        mean, std = ops.gauss_head(ops.linear(x.reshape(-1, x.shape[-1]), w, b))
+        """policy_input: one tensor, or a (state_emb, goal_emb) pair that the fused kernel concatenates itself.
+        The SiLU trunk and the fc_mean | fc_log_std heads run as ONE launch each way (ops.mlp_chain)."""
+        layers = [(fc.weight, fc.bias) for fc in self.fc_layers]
+        layers.append([(self.fc_mean.weight, self.fc_mean.bias), (self.fc_log_std.weight, self.fc_log_std.bias)])
+        raw = ops.mlp_chain(policy_input, layers, ("silu",) * len(self.fc_layers))
+        lead = raw.shape[:-1]
+        mean, std = ops.gauss_head(raw.reshape(-1, raw.shape[-1]))
         return mean.view(*lead, -1), std.view(*lead, -1)
 
 
@@ -62,8 +64,7 @@ class Actor(nn.Module):
         self.policy = instantiate(policy_cfg)
 
     def forward(self, state_emb: torch.Tensor, goal_emb: Optional[torch.Tensor] = None):
-        x = torch.cat([state_emb, goal_emb], dim=-1) if goal_emb is not None else state_emb
-        return self.policy(x)
+        return self.policy((state_emb, goal_emb) if goal_emb is not None else state_emb)
 
     def get_dist(self, state_emb, goal_emb=None):
         mean, std = self.forward(state_emb, goal_emb)

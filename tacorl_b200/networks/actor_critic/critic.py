@@ -2,6 +2,7 @@
 import torch
 import torch.nn as nn
 
+from ... import ops
 from ...utils.config import instantiate, to_container
 from ..layers import Linear
 
@@ -18,11 +19,12 @@ class MLPQNetwork(nn.Module):
         self.out.weight.data.uniform_(-init_w, init_w)
         self.out.bias.data.uniform_(-init_w, init_w)
 
-    def forward(self, q_input):
-        x = q_input
-        for fc in self.fc_layers:
-            x = fc(x, act="silu")
-        return self.out(x)
+    def forward(self, q_input, detach_params: bool = False):
+        """q_input: one tensor or an (embedding, action) pair.  detach_params: gradient w.r.t. the input only.
+        One fused launch each way (ops.mlp_chain)."""
+        f = (lambda t: t.detach()) if detach_params else (lambda t: t)
+        layers = [(f(fc.weight), f(fc.bias)) for fc in self.fc_layers] + [(f(self.out.weight), f(self.out.bias))]
+        return ops.mlp_chain(q_input, layers, ("silu",) * len(self.fc_layers))
 
 
 class Critic(nn.Module):
@@ -35,4 +37,4 @@ class Critic(nn.Module):
     def forward(self, obs: torch.Tensor, action: torch.Tensor):
         if len(action.shape) == 2 and action.shape[0] == 1 and len(obs.shape) == 1:
             obs = obs.unsqueeze(0)
-        return self.Q(torch.cat((obs, action), dim=-1))
+        return self.Q((obs, action))

@@ -2,6 +2,7 @@
 import torch
 import torch.nn as nn
 
+from ... import ops
 from ..layers import Linear, Marker
 
 
@@ -18,6 +19,5 @@ class VisualGoalEncoder(nn.Module):
                                  Linear(hidden_size, out_features))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        x = self.mlp[0](x, act="relu")
-        x = self.mlp[2](x, act="relu")
-        return self.mlp[4](x)
+        # the three layers in one fused launch each way (ops.mlp_chain)
+        return ops.mlp_chain(x, [(self.mlp[i].weight, self.mlp[i].bias) for i in (0, 2, 4)], ("relu", "relu"))

@@ -209,6 +209,111 @@ def linear(x, W, b=None, act=None):
     return LinearFn.apply(x, W, b, L.ACTS[act] if not isinstance(act, int) else act)
 
 
+# --------------------------------------------------------------------------------------- fused MLP chains
+def _dp(t):
+    return None if t is None else t.data_ptr()
+
+
+class MlpChainFn(Function):
+    """Linear -> act -> ... -> Linear in one launch each way (tacorl_mlp_chain_{fwd,bwd}).
+    spec = (acts, segs): acts[l] for the hidden layers; segs[l] = number of (W, b) pairs stacked in layer l (1 or 2).
+    params: per layer, per segment: W, b."""
+
+    @staticmethod
+    def _layers(spec, params, in0, grads=None):
+        acts, segs = spec
+        arr = (L.MlpLayer * len(segs))()
+        i, width = 0, in0
+        for l, ns in enumerate(segs):
+            e = arr[l]
+            W0, b0 = params[i], params[i + 1]
+            e.W0, e.b0, e.n0 = _dp(W0), _dp(b0), W0.shape[0]
+            if grads is not None:
+                e.dW0, e.db0 = _dp(grads[i]), _dp(grads[i + 1])
+            if ns == 2:
+                W1, b1 = params[i + 2], params[i + 3]
+                e.W1, e.b1, e.n1 = _dp(W1), _dp(b1), W1.shape[0]
+                if grads is not None:
+                    e.dW1, e.db1 = _dp(grads[i + 2]), _dp(grads[i + 3])
+            e.in_ = width
+            e.act = acts[l] if l < len(acts) else L.ACT_NONE
+            width = e.n0 + e.n1
+            i += 2 * ns
+        return arr, width
+
+    @staticmethod
+    def forward(ctx, spec, x0, x1, *params):
+        lead = x0.shape[:-1]
+        x0 = _c(x0.reshape(-1, x0.shape[-1]))
+        x1 = _c(x1.reshape(-1, x1.shape[-1])) if x1 is not None else None
+        params = [None if p is None else _c(p) for p in params]
+        rows = x0.shape[0]
+        in0 = x0.shape[1] + (x1.shape[1] if x1 is not None else 0)
+        arr, out_w = MlpChainFn._layers(spec, params, in0)
+        nl = len(spec[1])
+        zw = sum(arr[l].n0 + arr[l].n1 for l in range(nl - 1))
+        z = torch.empty(rows, max(zw, 1), device=x0.device, dtype=torch.float32)
+        out = torch.empty(rows, out_w, device=x0.device, dtype=torch.float32)
+        L.call("tacorl_mlp_chain_fwd", nl, rows, ctypes.byref(arr), L.ptr(x0), x0.shape[1], x0.shape[1],
+               L.ptr(x1), x1.shape[1] if x1 is not None else 0, x1.shape[1] if x1 is not None else 0,
+               L.ptr(z), z.shape[1], L.ptr(out), out_w, L.stream())
+        ctx.spec, ctx.lead, ctx.has_x1 = spec, lead, x1 is not None
+        ctx.save_for_backward(x0, x1, z, *params)
+        return out.view(*lead, out_w)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x0, x1, z, *params = ctx.saved_tensors
+        rows = x0.shape[0]
+        d_out = _c(d_out.reshape(rows, -1))
+        need = ctx.needs_input_grad
+        # a layer's weights either all receive a gradient or none does (detached parameters: input gradient only)
+        want_w = any(need[3:])
+        grads = [torch.empty_like(p) if (want_w and p is not None) else None for p in params]
+        in0 = x0.shape[1] + (x1.shape[1] if x1 is not None else 0)
+        arr, _ = MlpChainFn._layers(ctx.spec, params, in0, grads)
+        dx0 = torch.empty_like(x0) if need[1] else None
+        dx1 = torch.empty_like(x1) if (x1 is not None and need[2]) else None
+        nl = len(ctx.spec[1])
+        nbytes = L.query("tacorl_mlp_chain_ws_bytes", nl, rows, ctypes.byref(arr))
+        ws = L.workspace(nbytes, x0.device, "mlp_chain")
+        L.call("tacorl_mlp_chain_bwd", nl, rows, ctypes.byref(arr), L.ptr(x0), x0.shape[1], x0.shape[1],
+               L.ptr(x1), x1.shape[1] if x1 is not None else 0, x1.shape[1] if x1 is not None else 0,
+               L.ptr(z), z.shape[1], L.ptr(d_out), d_out.shape[1], L.ptr(dx0), x0.shape[1],
+               L.ptr(dx1), x1.shape[1] if x1 is not None else 0, ctypes.c_void_p(ws.data_ptr()), ws.numel(), L.stream())
+        gx0 = dx0.view(*ctx.lead, x0.shape[1]) if dx0 is not None else None
+        gx1 = dx1.view(*ctx.lead, x1.shape[1]) if dx1 is not None else None
+        return (None, gx0, gx1, *[g if need[3 + i] else None for i, g in enumerate(grads)])
+
+
+def mlp_chain(xs, layers, acts):
+    """y = Linear_L(... act_1(Linear_1(cat(xs))) ...) in one fused launch (fp32; tacorl_mlp_chain_fwd/bwd).
+    xs: one tensor or a pair concatenated along the last dim; layers: per layer a (W, b) pair or a list of two pairs
+    stacked along the output dim; acts: activation names of the hidden layers (len(layers) - 1 entries).
+    Shapes outside the kernel's range (widths > 256 or not multiples of 4, > 4 layers, > 256 rows) run layer by layer."""
+    xs = list(xs) if isinstance(xs, (list, tuple)) else [xs]
+    segs = [[l] if torch.is_tensor(l[0]) else list(l) for l in layers]
+    acts_i = tuple(L.ACTS[a] if not isinstance(a, int) else a for a in acts)
+    in0 = sum(x.shape[-1] for x in xs)
+    widths = [in0] + [sum(W.shape[0] for W, _ in sg) for sg in segs]
+    ok = (len(segs) <= 4 and len(xs) <= 2 and all(len(sg) <= 2 for sg in segs) and xs[0].is_cuda
+          and all(w % 4 == 0 and w <= 256 for w in widths[:-1]) and widths[-1] <= 256
+          and all(x.dtype == torch.float32 for x in xs) and xs[0].numel() // xs[0].shape[-1] <= 256)
+    if not ok:
+        x = xs[0] if len(xs) == 1 else torch.cat(xs, dim=-1)
+        for l, sg in enumerate(segs):
+            W = sg[0][0] if len(sg) == 1 else torch.cat([w for w, _ in sg], dim=0)
+            b = sg[0][1] if len(sg) == 1 else torch.cat([bb for _, bb in sg], dim=0)
+            x = linear(x, W, b, acts_i[l] if l < len(acts_i) else None)
+        return x
+    flat = []
+    for sg in segs:
+        for W, b in sg:
+            flat += [W, b]
+    spec = (acts_i, tuple(len(sg) for sg in segs))
+    return MlpChainFn.apply(spec, xs[0], xs[1] if len(xs) == 2 else None, *flat)
+
+
 # --------------------------------------------------------------------------------------- encoder
 class LMPEncoderFn(Function):
     """LMPVisionEncoder forward/backward as one op (tacorl_lmp_encoder_{fwd,bwd})."""
@@ -805,14 +910,15 @@ def cql_alpha_loss(log_pi, log_alpha, target_entropy):
 
 # --------------------------------------------------------------------------------------- optimiser kernels
 def adam_step(p, g, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, sqnorm=None, max_norm=0.0,
-              step_dev=None, shadow=None, increment=True):
+              step_dev=None, shadow=None, increment=True, background=False):
     """step_dev: optional int32 device tensor holding the step count (incremented by the call unless increment=False:
     the later slices of a step that is applied slice by slice).
-    shadow: optional bf16 tensor of p.numel() elements that receives a bf16 copy of the updated parameters."""
+    shadow: optional bf16 tensor of p.numel() elements that receives a bf16 copy of the updated parameters.
+    background: small grid that shares the SMs with concurrently running kernels (the early slice of FlatAdam)."""
     sd = ctypes.c_void_p(step_dev.data_ptr()) if step_dev is not None else None
     L.call("tacorl_adam_step_range", p.numel(), L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), float(lr), float(beta1),
-           float(beta2), float(eps), int(step), sd, int(increment), float(grad_scale), L.ptr(sqnorm), float(max_norm),
-           L.ptr_any(shadow), L.stream())
+           float(beta2), float(eps), int(step), sd, int(increment), int(background), float(grad_scale), L.ptr(sqnorm),
+           float(max_norm), L.ptr_any(shadow), L.stream())
 
 
 def polyak_update(target, source, tau):

@@ -113,7 +113,7 @@ class FlatAdam(torch.optim.Optimizer):
             stream.wait_stream(sync_stream if sync_stream is not None else torch.cuda.current_stream(dev))
             with torch.cuda.stream(stream):
                 self.step_count += 1
-                self._adam_range(e0, e1, increment=True)
+                self._adam_range(e0, e1, increment=True, background=True)
             self._early = (e0, e1, stream)
 
     # update slices whose gradient is final early on a side stream (see begin_overlapped_sync).  Off by default: it assumes
@@ -123,12 +123,12 @@ class FlatAdam(torch.optim.Optimizer):
     _early = None
     _early_stream = None
 
-    def _adam_range(self, e0, e1, increment, sq=None):
+    def _adam_range(self, e0, e1, increment, sq=None, background=False):
         g = self.param_groups[0]
         ops.adam_step(self.pbuf.flat[e0:e1], self.flat_grad[e0:e1], self.exp_avg[e0:e1], self.exp_avg_sq[e0:e1], g["lr"],
                       self.step_count, g["betas"][0], g["betas"][1], g["eps"], self.grad_scale, sq,
                       float(self.max_grad_norm) if self.max_grad_norm is not None else 0.0, self._step_dev,
-                      None if self.shadow is None else self.shadow[e0:e1], increment)
+                      None if self.shadow is None else self.shadow[e0:e1], increment, background)
 
     def gather_grads(self, lo=0, hi=None):
         ps = self.param_groups[0]["params"][lo:hi]

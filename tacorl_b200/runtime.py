@@ -60,23 +60,32 @@ class GraphedTrainStep:
     tensors a step mutates: they are saved before the warm-up steps a capture needs and restored afterwards, so
     building a graph does not train on the example batch."""
 
-    def __init__(self, step_fn, example_batch, device=None, warmup=3, mode_key=None, preserve=None):
+    def __init__(self, step_fn, example_batch, device=None, warmup=3, mode_key=None, preserve=None, buffers=1):
+        """buffers=2: two sets of static input buffers, one captured graph per set (sharing one memory pool), used
+        alternately: `prefetch()` copies the next batch host->device straight into the set the running step is NOT
+        reading, so a host-fed loop needs no staging->static device copy between replays."""
         device = device or torch.device("cuda", torch.cuda.current_device())
         self.device = device
-        self.static = _clone_to_static(example_batch, device)
+        self.statics = [_clone_to_static(example_batch, device) for _ in range(max(1, int(buffers)))]
+        self._cur = 0
         self.step_fn = step_fn
         self.warmup = warmup
         self.mode_key = mode_key if mode_key is not None else getattr(step_fn, "mode_key", None)
         self.preserve = preserve if preserve is not None else getattr(step_fn, "preserve", None)
         self._graphs = {}
+        self._pool = None
         self.replays = 0
         self.captures = 0
         self._select(self._key())
 
+    @property
+    def static(self):
+        return self.statics[self._cur]
+
     def _key(self):
         return self.mode_key() if self.mode_key is not None else None
 
-    def _capture(self):
+    def _capture(self, static):
         from . import _lib
         device = self.device
         snaps = _snapshot(self.preserve()) if self.preserve is not None else None
@@ -84,13 +93,15 @@ class GraphedTrainStep:
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
             for _ in range(self.warmup):
-                self.step_fn(self.static)
+                self.step_fn(static)
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
         graph = torch.cuda.CUDAGraph()
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()      # graphs of one runner never run concurrently: one pool
         n0 = _lib.launch_count()
-        with torch.cuda.graph(graph):
-            out = self.step_fn(self.static)
+        with torch.cuda.graph(graph, pool=self._pool):
+            out = self.step_fn(static)
             out = out.detach() if torch.is_tensor(out) else None
         # kernels of libtacorl_b200.so recorded in the graph = launched again by every replay
         launches = _lib.launch_count() - n0
@@ -101,46 +112,65 @@ class GraphedTrainStep:
         return graph, out, launches
 
     def _select(self, key):
-        if key not in self._graphs:
-            self._graphs[key] = self._capture()
-        self.graph, self.out, self.launches_per_replay = self._graphs[key]
-        self._active_key = key
+        k = (key, self._cur)
+        if k not in self._graphs:
+            self._graphs[k] = self._capture(self.statics[self._cur])
+        self.graph, self.out, self.launches_per_replay = self._graphs[k]
+        self._active_key = k
 
     def __call__(self, batch=None):
-        key = self._key()
-        if key != self._active_key:
-            self._select(key)
+        """Returns the step's output tensor; with buffers > 1 it is only valid until the next call (shared pool)."""
+        main = torch.cuda.current_stream()
         if batch is not None:
             _copy_into(self.static, batch)
         elif self._staged:
-            # inputs prefetched by `prefetch()`: wait for the H2D, move them into the graph's static buffers
-            main = torch.cuda.current_stream()
-            main.wait_event(self._ready)
-            _copy_into(self.static, self._staging)
-            self._consumed.record(main)
+            main.wait_event(self._ready)              # the H2D of this step's inputs
+            if len(self.statics) > 1:
+                self._cur = self._staged_buf           # ... which went straight into the other buffer set
+            else:
+                _copy_into(self.static, self._staging)
+                self._consumed.record(main)
             self._staged = False
+        key = self._key()
+        if (key, self._cur) != self._active_key:
+            self._select(key)
         from . import ops
         ops.refresh_shadows()      # parameters edited through torch since the last replay (checkpoint load, ...)
         self.graph.replay()
+        if len(self.statics) > 1 and self._free is not None:
+            self._free[self._cur].record(main)         # this buffer set may be refilled once the replay has finished
         self.replays += 1
         return self.out
 
     _staged = False
     _staging = None
+    _free = None
 
     def prefetch(self, host_batch):
         """Start the host->device copy of the NEXT step's (pinned) batch on a side stream so it overlaps the
         step that is running; the following `__call__()` consumes it (double buffering, like a pinned
         DataLoader with non_blocking copies)."""
         if self._staging is None:
-            self._staging = _clone_to_static(self.static, next(iter(_tensors(self.static))).device)
             self._copy_stream = torch.cuda.Stream()
             self._ready = torch.cuda.Event()
-            self._consumed = torch.cuda.Event()
-            self._consumed.record(torch.cuda.current_stream())
+            if len(self.statics) > 1:
+                self._staging = True
+                self._free = [torch.cuda.Event() for _ in self.statics]
+                for e in self._free:
+                    e.record(torch.cuda.current_stream())
+            else:
+                self._staging = _clone_to_static(self.static, next(iter(_tensors(self.static))).device)
+                self._consumed = torch.cuda.Event()
+                self._consumed.record(torch.cuda.current_stream())
         with torch.cuda.stream(self._copy_stream):
-            self._copy_stream.wait_event(self._consumed)
-            _copy_into(self._staging, host_batch)
+            if len(self.statics) > 1:
+                target = (self._cur + 1) % len(self.statics)
+                self._copy_stream.wait_event(self._free[target])
+                _copy_into(self.statics[target], host_batch)
+                self._staged_buf = target
+            else:
+                self._copy_stream.wait_event(self._consumed)
+                _copy_into(self._staging, host_batch)
             self._ready.record(self._copy_stream)
         self._staged = True
 

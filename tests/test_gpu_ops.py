@@ -429,3 +429,58 @@ def test_uint8_frames_equal_prenormalised_float_frames(prec):
             assert_close(f"grad {k}", a, b, tol * 10, atol=1e-6)
     finally:
         ops.set_precision("fp32")
+
+
+@pytest.mark.parametrize("rows,ins,widths,acts,two_seg,detach", [
+    (64, (32,), (256, 256, 32), ("relu", "relu"), False, False),          # goal encoder
+    (64, (32, 32), (256, 256, 256, 32), ("silu",) * 3, True, False),      # MLPPolicy on (state, goal): fc_mean | fc_log_std
+    (832, (64, 16), (256, 256, 256, 1), ("silu",) * 3, False, False),     # MLPQNetwork over 13 * B rows: layer-by-layer route
+    (256, (64, 16), (256, 256, 256, 1), ("silu",) * 3, False, False),     # 16 row blocks: partial slabs + reduction
+    (64, (64, 16), (256, 256, 256, 1), ("silu",) * 3, False, True),       # actor loss through Q: input gradient only
+    (3, (32,), (64, 64, 32), ("relu", "relu"), False, False),
+    (100, (128, 32), (256, 64), ("silu",), True, False),                  # 2 row blocks, ragged
+])
+def test_fused_mlp_chain_vs_fp64(rows, ins, widths, acts, two_seg, detach):
+    """ops.mlp_chain (one launch forward, one backward) against a plain fp64 evaluation: values, input gradients, every
+    weight / bias gradient (incl. the per-row-block partial reduction and the two-segment last layer)."""
+    from tacorl_b200 import ops
+    ops.set_precision("fp32")
+    g = torch.Generator().manual_seed(rows + sum(widths))
+    xs = [torch.randn(rows, i, generator=g) for i in ins]
+    dims = [sum(ins)] + list(widths)
+    layers = []
+    for l in range(len(widths)):
+        bound = 1.0 / dims[l] ** 0.5
+        if two_seg and l == len(widths) - 1:
+            h = widths[l] // 2
+            layers.append([((torch.rand(h, dims[l], generator=g) * 2 - 1) * bound, torch.randn(h, generator=g) * 0.1),
+                           ((torch.rand(widths[l] - h, dims[l], generator=g) * 2 - 1) * bound, torch.randn(widths[l] - h, generator=g) * 0.1)])
+        else:
+            layers.append([((torch.rand(widths[l], dims[l], generator=g) * 2 - 1) * bound, torch.randn(widths[l], generator=g) * 0.1)])
+    cot = torch.randn(rows, widths[-1], generator=g)
+    # fp64 reference
+    x64 = [x.double().requires_grad_(True) for x in xs]
+    l64 = [[(W.double().requires_grad_(True), b.double().requires_grad_(True)) for W, b in sg] for sg in layers]
+    h = torch.cat(x64, dim=-1)
+    for l, sg in enumerate(l64):
+        W = torch.cat([w for w, _ in sg], 0)
+        b = torch.cat([bb for _, bb in sg], 0)
+        h = torch.nn.functional.linear(h, W, b)
+        if l < len(acts):
+            h = torch.relu(h) if acts[l] == "relu" else torch.nn.functional.silu(h)
+    (h * cot.double()).sum().backward()
+    # CUDA
+    xd = [x.to(DEV).requires_grad_(True) for x in xs]
+    ld = [[(W.to(DEV).requires_grad_(not detach), b.to(DEV).requires_grad_(not detach)) for W, b in sg] for sg in layers]
+    out = ops.mlp_chain(xd if len(xd) > 1 else xd[0], [sg if len(sg) > 1 else sg[0] for sg in ld], acts)
+    (out * cot.to(DEV)).sum().backward()
+    assert_close("out", out, h, 2e-6)
+    for a, b in zip(xd, x64):
+        assert_close("dx", a.grad, b.grad, 1e-5)
+    for sgd, sg64 in zip(ld, l64):
+        for (W, b), (W64, b64) in zip(sgd, sg64):
+            if detach:
+                assert W.grad is None and b.grad is None
+            else:
+                assert_close("dW", W.grad, W64.grad, 1e-5)
+                assert_close("db", b.grad, b64.grad, 1e-5)
