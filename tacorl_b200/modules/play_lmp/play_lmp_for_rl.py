@@ -105,6 +105,9 @@ class PlayLMP(LightningModule):
         pp_goal = self.goal_encoder(pp_goal)
         pp_dist = self.plan_proposal.get_dist(pp_state, pp_goal)
         pr_states = self._cat([emb_states[k] for k in self.plan_recognition_modalities])
+        if self._sync_active():
+            pr_states = pr_states.view_as(pr_states)      # own autograd node: its gradient = "the recogniser's BPTT is done"
+            self._sync_when_grad_of(pr_states, [self.plan_recognition])
         pr_dist = self.plan_recognition(pr_states)
         return emb_states, pp_dist, pr_dist, pp_goal
 
@@ -113,6 +116,7 @@ class PlayLMP(LightningModule):
         kl_loss = self.compute_kl_loss(pr_dist=pr_dist, pp_dist=pp_dist, stage=stage)
         ad_states = self._cat([emb_states[k] for k in self.action_decoder_modalities])
         latent_plan = pr_dist.rsample()
+        self._sync_when_grad_of(latent_plan, [self.action_decoder])       # decoder BPTT done -> its slice can go
         mean_shape = pr_dist.normal.mean.shape if isinstance(pr_dist, TanhNormal) else pr_dist.mean.shape
         dec = self.action_decoder
         if self.add_random_plan_loss or not hasattr(dec, "loss_and_act_two_plans"):
@@ -169,22 +173,56 @@ class PlayLMP(LightningModule):
 
     _flat_opt = None
 
+    def _sync_active(self):
+        opt = self._flat_opt
+        return opt is not None and torch.is_grad_enabled() and (opt.grad_sync is not None or opt.early_step)
+
+    def _sync_when_grad_of(self, tensor, modules):
+        """Start the gradient exchange / early update of `modules`' parameters as soon as the gradient w.r.t. `tensor`
+        (their only input that requires one) exists, i.e. their backward pass is complete."""
+        if not self._sync_active() or not tensor.requires_grad:
+            return
+        opt = self._flat_opt
+        ids = set()
+        for m in modules:
+            ids |= {id(p) for p in m.parameters()}
+        params = [p for p in opt.param_groups[0]["params"] if id(p) in ids]
+
+        def hook(grad):
+            opt.begin_overlapped_sync(params)
+            return None
+
+        tensor.register_hook(hook)
+
     def _overlap_grad_sync(self, emb_states):
         """Everything behind the vision encoders (RNNs, decoder, MLPs = 99.7 % of the parameters) has its final
         gradient before the encoders' backward starts.  A hook on the embeddings starts the all-reduce of that slice
         (data parallel) and its Adam update (optimizer.early_step) at exactly that moment, on side streams, so both
-        overlap the encoder backward."""
-        opt = self._flat_opt
-        if opt is None or not torch.is_grad_enabled() or (opt.grad_sync is None and not opt.early_step):
+        overlap the encoder backward.  (The decoder and the plan recogniser are started even earlier, as their own
+        BPTT finishes: compute_loss / process_batch.)"""
+        if not self._sync_active():
             return
+        opt = self._flat_opt
         enc_ids = {id(p) for p in self.perceptual_encoder.parameters()}
-        rest = [p for p in opt.param_groups[0]["params"] if id(p) not in enc_ids]
+        groups, run = [], []
+        for p in opt.param_groups[0]["params"]:        # contiguous runs of non-encoder parameters
+            if id(p) in enc_ids:
+                if run:
+                    groups.append(run)
+                run = []
+            else:
+                run.append(p)
+        if run:
+            groups.append(run)
         pending = [len(emb_states)]
 
         def hook(grad):
             pending[0] -= 1
             if pending[0] == 0:
-                opt.begin_overlapped_sync(rest)
+                for g in groups:
+                    # (runs the decoder / recogniser hooks already handled are skipped inside; what is left of a run
+                    # that contains them is picked up by step())
+                    opt.begin_overlapped_sync(g)
             return None
 
         for v in emb_states.values():

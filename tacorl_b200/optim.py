@@ -65,6 +65,7 @@ class FlatAdam(torch.optim.Optimizer):
         self._pparam = {p.data_ptr(): p for p in ps}       # slot hand-out checks the owning parameter's .grad
         self._flat_version = self.pbuf.flat._version
         self._slots_taken = set()
+        self._ranges = []          # (param lo, param hi, element lo, element hi) runs already exchanged / updated this step
         if self.pbuf.flat.is_cuda:
             self.shadow = torch.zeros(self.pbuf.numel, device=self.pbuf.flat.device, dtype=torch.bfloat16)
             ops.register_shadow_owner(self)
@@ -86,11 +87,11 @@ class FlatAdam(torch.optim.Optimizer):
         return lo, hi + 1, self.pbuf.offsets[lo], end
 
     def begin_overlapped_sync(self, params):
-        """Call when the gradients of `params` (a contiguous run, e.g. everything behind the vision encoder) are
-        final while backward is still running.  Their slice of the flat gradient is gathered; with data parallelism
-        its all-reduce starts on the side stream; and -- when no global-norm clip couples the slices -- the Adam update
-        of the slice follows on that same side stream, so that exchange AND update of 99.7 % of the parameters hide
-        under the encoder backward.  step() then only handles what is left."""
+        """Call when the gradients of `params` (a contiguous run: a whole sub-network) are final while backward is
+        still running.  Their slice of the flat gradient is gathered; with data parallelism its all-reduce starts on
+        the side stream; and -- when no global-norm clip couples the slices -- the Adam update of the slice follows, so
+        that exchange AND update hide under the rest of the backward pass.  May be called several times per step with
+        disjoint runs (decoder, plan recogniser, ... as their BPTT finishes); step() handles whatever is left."""
         r = self._range_of(params)
         if r is None:
             return
@@ -98,29 +99,36 @@ class FlatAdam(torch.optim.Optimizer):
         if self.grad_sync is None and not early:
             return
         lo, hi, e0, e1 = r
+        if any(not (hi <= a or b <= lo) for a, b, _, _ in self._ranges):
+            return                                     # (already handled this step)
         self.gather_grads(lo, hi)
         if self.grad_sync is not None:
             self.grad_sync.start(self.flat_grad[e0:e1])
-        self._synced = (lo, hi, e0, e1)
+        first = not self._ranges
+        self._ranges.append((lo, hi, e0, e1))
         if early:
             dev = self.pbuf.flat.device
             if self._early_stream is None:
                 self._early_stream = torch.cuda.Stream(device=dev)
             stream = self._early_stream
             sync_stream = getattr(self.grad_sync, "_stream", None) if self.grad_sync is not None else None
-            # after the slice's all-reduce (own stream, so that the later exchange of the encoder slice does not queue
-            # behind this update), or straight after the gather
+            # after the slice's all-reduce (own stream, so that later exchanges do not queue behind this update), or
+            # straight after the gather
             stream.wait_stream(sync_stream if sync_stream is not None else torch.cuda.current_stream(dev))
             with torch.cuda.stream(stream):
-                self.step_count += 1
-                self._adam_range(e0, e1, increment=True, background=True)
-            self._early = (e0, e1, stream)
+                if first:
+                    self.step_count += 1
+                # full-size grid: measured on the B200, a background-sized grid (one CTA per SM, tacorl_adam_step_range
+                # background = 1) does run under the encoder backward, but the convolution kernels it shares the SMs with
+                # slow down by more than the update takes (step 3.39 -> 3.57 ms; profiles/r02)
+                self._adam_range(e0, e1, increment=first, background=self.early_background)
+            self._early = True
 
     # update slices whose gradient is final early on a side stream (see begin_overlapped_sync).  Off by default: it assumes
     # ONE backward pass per step() (no gradient accumulation); runtime.play_lmp_step_fn, which owns that structure, enables it
     early_step = False
-    _synced = None
-    _early = None
+    early_background = False
+    _early = False
     _early_stream = None
 
     def _adam_range(self, e0, e1, increment, sq=None, background=False):
@@ -147,6 +155,8 @@ class FlatAdam(torch.optim.Optimizer):
 
     def zero_grad(self, set_to_none=True):
         self._slots_taken.clear()
+        if not self._early:
+            self._ranges = []
         return super().zero_grad(set_to_none=set_to_none)
 
     # ---- checkpointing: torch.optim.Adam's layout ({"state": {i: {step, exp_avg, exp_avg_sq}}, "param_groups": [...]}),
@@ -221,38 +231,40 @@ class FlatAdam(torch.optim.Optimizer):
     def step(self, closure=None, gathered=False):
         loss = closure() if closure is not None else None
         self._slots_taken.clear()
-        rest = [(0, self.pbuf.numel)]
-        if self._synced is not None:
-            lo, hi, e0, e1 = self._synced          # [lo,hi) already gathered (and in flight on the side stream)
-            n = len(self.param_groups[0]["params"])
-            if not gathered:
-                if lo > 0:
-                    self.gather_grads(0, lo)
-                if hi < n:
-                    self.gather_grads(hi, n)
-            rest = [(a, b) for a, b in ((0, e0), (e1, self.pbuf.numel)) if b > a]
-            if self.grad_sync is not None:
-                for a, b in rest:
-                    self.grad_sync.start(self.flat_grad[a:b])
-                self.grad_sync.finish()
-            self._synced = None
-        else:
-            if not gathered:
-                self.gather_grads()
-            if self.grad_sync is not None:
-                self.grad_sync(self.flat_grad)
-        if self._early is not None:                # the big slice was updated early: only the remaining slices are left
-            e0, e1, stream = self._early
-            for a, b in rest:
+        n, numel = len(self.param_groups[0]["params"]), self.pbuf.numel
+        done = sorted(self._ranges)
+        self._ranges = []
+        # complement of the runs handled early, in parameter-index space and in element space
+        rest_p, rest_e, p0, x0 = [], [], 0, 0
+        for lo, hi, e0, e1 in done:
+            if lo > p0:
+                rest_p.append((p0, lo))
+            if e0 > x0:
+                rest_e.append((x0, e0))
+            p0, x0 = hi, e1
+        if p0 < n:
+            rest_p.append((p0, n))
+        if x0 < numel:
+            rest_e.append((x0, numel))
+        if not gathered:
+            for a, b in rest_p:
+                self.gather_grads(a, b)
+        if self.grad_sync is not None:
+            for a, b in rest_e:
+                self.grad_sync.start(self.flat_grad[a:b])
+            self.grad_sync.finish()
+        if self._early:                            # some slices were updated early: only the remaining ones are left
+            for a, b in rest_e:
                 self._adam_range(a, b, increment=False)
-            torch.cuda.current_stream(self.pbuf.flat.device).wait_stream(stream)
-            self._early = None
+            torch.cuda.current_stream(self.pbuf.flat.device).wait_stream(self._early_stream)
+            self._early = False
             return loss
+        assert not done or self.grad_sync is not None
         self.step_count += 1
         sq = None
         if self.max_grad_norm is not None:
             sq = ops.sqnorm(self.flat_grad, self._sqnorm)
-        self._adam_range(0, self.pbuf.numel, increment=True, sq=sq)
+        self._adam_range(0, numel, increment=True, sq=sq)
         return loss
 
     def set_grad(self, flat_values):

@@ -12,13 +12,30 @@ SM_RESERVE_FOR_COLLECTIVES = 16   # SMs left out of the persistent conv grids wh
 
 class BucketedAllReduce:
     """All-reduces a flat gradient buffer in fixed-size buckets on a side stream (CUDA) so the exchange of
-    early buckets overlaps whatever the caller still runs on the main stream."""
+    early buckets overlaps whatever the caller still runs on the main stream.
+    wire_dtype=torch.bfloat16: every bucket is cast to bf16, summed over the ranks in bf16 and cast back into the fp32
+    buffer (half the NVLink bytes; used with the bf16 compute path, whose gradients carry bf16 operand rounding anyway)."""
 
-    def __init__(self, world_size, bucket_elems=16 << 20, group=None):
+    def __init__(self, world_size, bucket_elems=16 << 20, group=None, wire_dtype=None):
         self.world = world_size
         self.bucket = bucket_elems
         self.group = group
+        self.wire_dtype = wire_dtype
         self._stream = None
+        self._stage = None
+
+    def _reduce(self, flat):
+        for o in range(0, flat.numel(), self.bucket):
+            chunk = flat[o:o + self.bucket]
+            if self.wire_dtype is not None and chunk.is_cuda:
+                if self._stage is None or self._stage.numel() < self.bucket or self._stage.device != chunk.device:
+                    self._stage = torch.empty(self.bucket, device=chunk.device, dtype=self.wire_dtype)
+                st = self._stage[:chunk.numel()]
+                st.copy_(chunk)
+                dist.all_reduce(st, op=dist.ReduceOp.SUM, group=self.group)
+                chunk.copy_(st)
+            else:
+                dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
 
     def start(self, flat):
         """Enqueue the all-reduce of `flat` on the side stream (after everything already queued on the current
@@ -31,11 +48,9 @@ class BucketedAllReduce:
             self._device = flat.device
             self._stream.wait_stream(torch.cuda.current_stream(flat.device))
             with torch.cuda.stream(self._stream):
-                for o in range(0, flat.numel(), self.bucket):
-                    dist.all_reduce(flat[o:o + self.bucket], op=dist.ReduceOp.SUM, group=self.group)
+                self._reduce(flat)
         else:
-            for o in range(0, flat.numel(), self.bucket):
-                dist.all_reduce(flat[o:o + self.bucket], op=dist.ReduceOp.SUM, group=self.group)
+            self._reduce(flat)
 
     def finish(self):
         if self._stream is not None:
@@ -48,10 +63,15 @@ class BucketedAllReduce:
         self.finish()
 
 
-def attach_data_parallel(optimizer, world_size, group=None, bucket_elems=16 << 20):
+def attach_data_parallel(optimizer, world_size, group=None, bucket_elems=16 << 20, wire_dtype="auto"):
     """Make a FlatAdam average its gradient over `world_size` ranks before the update (DDP semantics:
-    mean of local-mean gradients; clip-by-norm acts on the reduced gradient, cql_offline_lightning.py:521-537)."""
-    optimizer.grad_sync = BucketedAllReduce(world_size, bucket_elems, group)
+    mean of local-mean gradients; clip-by-norm acts on the reduced gradient, cql_offline_lightning.py:521-537).
+    wire_dtype: "auto" = bf16 on the wire when the bf16 compute path is active, fp32 otherwise; None = fp32."""
+    if wire_dtype == "auto":
+        from . import ops
+        flat0 = getattr(optimizer, "flat_params", None)
+        wire_dtype = torch.bfloat16 if (ops.get_precision() == "bf16" and flat0 is not None and flat0.is_cuda) else None
+    optimizer.grad_sync = BucketedAllReduce(world_size, bucket_elems, group, wire_dtype)
     optimizer.grad_scale = 1.0 / world_size
     flat = getattr(optimizer, "flat_params", None)
     if world_size > 1 and flat is not None and flat.is_cuda and "TACORL_SM_RESERVE" not in os.environ:
