@@ -105,7 +105,7 @@ class PlayLMP(LightningModule):
         pp_goal = self.goal_encoder(pp_goal)
         pp_dist = self.plan_proposal.get_dist(pp_state, pp_goal)
         pr_states = self._cat([emb_states[k] for k in self.plan_recognition_modalities])
-        if self._sync_active():
+        if self.early_subnet_sync and self._sync_active():
             pr_states = pr_states.view_as(pr_states)      # own autograd node: its gradient = "the recogniser's BPTT is done"
             self._sync_when_grad_of(pr_states, [self.plan_recognition])
         pr_dist = self.plan_recognition(pr_states)
@@ -177,10 +177,15 @@ class PlayLMP(LightningModule):
         opt = self._flat_opt
         return opt is not None and torch.is_grad_enabled() and (opt.grad_sync is not None or opt.early_step)
 
+    # Exchange / update the decoder's and the recogniser's slices as soon as their own BPTT finishes (instead of when
+    # the embeddings' gradient exists).  Off: measured at N = 2, the extra NCCL / Adam grids then run while the persistent
+    # recurrence kernels of the other sub-network need 120-128 co-resident SMs, and the step gets slower (3.51 -> 3.67 ms).
+    early_subnet_sync = False
+
     def _sync_when_grad_of(self, tensor, modules):
         """Start the gradient exchange / early update of `modules`' parameters as soon as the gradient w.r.t. `tensor`
         (their only input that requires one) exists, i.e. their backward pass is complete."""
-        if not self._sync_active() or not tensor.requires_grad:
+        if not self.early_subnet_sync or not self._sync_active() or not tensor.requires_grad:
             return
         opt = self._flat_opt
         ids = set()

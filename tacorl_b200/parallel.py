@@ -66,11 +66,13 @@ class BucketedAllReduce:
 def attach_data_parallel(optimizer, world_size, group=None, bucket_elems=16 << 20, wire_dtype="auto"):
     """Make a FlatAdam average its gradient over `world_size` ranks before the update (DDP semantics:
     mean of local-mean gradients; clip-by-norm acts on the reduced gradient, cql_offline_lightning.py:521-537).
-    wire_dtype: "auto" = bf16 on the wire when the bf16 compute path is active, fp32 otherwise; None = fp32."""
+    wire_dtype: "auto" = fp32 unless TACORL_WIRE=bf16; torch.bfloat16 = compressed exchange; None = fp32."""
     if wire_dtype == "auto":
-        from . import ops
+        # measured (profiles/r02): at N = 2 the two cast passes cost more than the halved NVLink bytes save (3.50 -> 3.60
+        # ms/step), so fp32 stays the default; TACORL_WIRE=bf16 selects the compressed exchange
         flat0 = getattr(optimizer, "flat_params", None)
-        wire_dtype = torch.bfloat16 if (ops.get_precision() == "bf16" and flat0 is not None and flat0.is_cuda) else None
+        want = os.environ.get("TACORL_WIRE", "fp32") == "bf16"
+        wire_dtype = torch.bfloat16 if (want and flat0 is not None and flat0.is_cuda) else None
     optimizer.grad_sync = BucketedAllReduce(world_size, bucket_elems, group, wire_dtype)
     optimizer.grad_scale = 1.0 / world_size
     flat = getattr(optimizer, "flat_params", None)
