@@ -685,18 +685,22 @@ rnn_seq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t ph = (uint32_t)step & 1u;
     float4 cold[RS_MAXE], gt[RS_MAXE];
     if (warp == RS_EPI / 32) {
+      if (step > 0 && !dead) {      // one lane per producing tile, polled in parallel
+        const unsigned want = (unsigned)(RS_KS * step);
+        bool bad = false;
+        for (int j = j_lo + lane; j <= j_hi; j += 32) {
+          unsigned spins = 0;
+          while (ld_acquire_gpu(sa.flags + j) < want) {
+            if (++spins > (1u << 21)) { bad = true; atomicAdd(&g_rnn_seq_timeouts, 1u); break; }
+          }
+        }
+        if (__any_sync(0xffffffffu, bad)) dead = true;
+        __threadfence();
+        __syncwarp();
+      }
       if (lane == 0) {
         SQ_STAMP(0)
         if (step == 0) mbar_wait(w_bar, 0);
-        else if (!dead) {
-          const unsigned want = (unsigned)(RS_KS * step);
-          for (int j = j_lo; j <= j_hi && !dead; ++j) {
-            unsigned spins = 0;
-            while (ld_acquire_gpu(sa.flags + j) < want) {
-              if (++spins > (1u << 21)) { dead = true; atomicAdd(&g_rnn_seq_timeouts, 1u); break; }
-            }
-          }
-        }
         SQ_STAMP(1)
         asm volatile("fence.proxy.async.global;" ::: "memory");
         for (int s = 0; s < kb_per_cta; ++s) {
@@ -924,17 +928,23 @@ rnn_wave_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const uint32_t ph = (uint32_t)step & 1u;
     float4 cold[RS_MAXE], gt[RS_MAXE];
     if (warp == RS_EPI / 32) {
-      if (lane == 0) {
-        if (step == 0) mbar_wait(w_bar, 0);
-        else if (!dead) {
-          const unsigned want = (unsigned)(RW_KS * step);
-          for (int j = j_lo; j <= j_hi && !dead; ++j) {
-            unsigned spins = 0;
-            while (ld_acquire_gpu(sa.flags + j) < want) {
-              if (++spins > (1u << 21)) { dead = true; atomicAdd(&g_rnn_seq_timeouts, 1u); break; }
-            }
+      // the producing tiles' arrival counters are polled by one lane each, in parallel (a dependent chain of up to four
+      // L2 round trips by a single lane cost ~1 us per step)
+      if (step > 0 && !dead) {
+        const unsigned want = (unsigned)(RW_KS * step);
+        bool bad = false;
+        for (int j = j_lo + lane; j <= j_hi; j += 32) {
+          unsigned spins = 0;
+          while (ld_acquire_gpu(sa.flags + j) < want) {
+            if (++spins > (1u << 21)) { bad = true; atomicAdd(&g_rnn_seq_timeouts, 1u); break; }
           }
         }
+        if (__any_sync(0xffffffffu, bad)) dead = true;
+        __threadfence();          // the lanes' acquires, made cumulative for lane 0's TMA issue below
+        __syncwarp();
+      }
+      if (lane == 0) {
+        if (step == 0) mbar_wait(w_bar, 0);
         asm volatile("fence.proxy.async.global;" ::: "memory");
         for (int s = 0; s < kb_per_cta; ++s) {
           const uint32_t bar = smem_u32(bars + s);
