@@ -666,8 +666,9 @@ def run_ours(args):
             os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         # the gradient all-reduce runs under the encoder backward: 16 NCCL channels on the 16 SMs the persistent
         # convolution kernels leave free (parallel.attach_data_parallel; scripts/n2_reserve_sweep.sh)
-        os.environ.setdefault("NCCL_MAX_NCHANNELS", "16")
-        os.environ.setdefault("NCCL_MIN_NCHANNELS", "16")
+        from tacorl_b200.parallel import collective_channels
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", str(collective_channels(world)))
+        os.environ.setdefault("NCCL_MIN_NCHANNELS", str(collective_channels(world)))
         # NCCL announces its version on stdout when the image sets NCCL_DEBUG: send its log to stderr, and route
         # fd 1 to stderr while the communicator comes up, so that stdout carries the JSON line and nothing else
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")

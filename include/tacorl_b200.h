@@ -233,6 +233,24 @@ int tacorl_cql_actor_loss(int mode, int B, const float* log_pi, const float* a, 
                           const float* log_alpha, float target_entropy, float* out, float* d_log_alpha,
                           float* d_log_pi, float* da, float* db, void* stream);
 
+/* ---- device-side input pipeline: the per-sample work of the reference's DataLoader workers on uint8
+ * frames resident in HBM.  Random quantities are inputs (drawn by the host in the reference's order).
+ * window_gather_u8: out[b][t] = store[start[b] + min(t, window[b]-1)] (pad_sequence by repetition,
+ *   play_dataset.py:282-330), each frame shifted by (shift[b][t] - pad) pixels with edge clamping = RandomShiftsAug
+ *   (utils/transforms.py:265-299: replicate-pad by `pad`, integer shift in [0, 2 pad]); shift NULL = no augmentation.
+ * actions_gather_pad: same windows over a (frames, A) fp32 store; zero_pad = 1: steps past the window are zero except
+ *   the last channel, which repeats (the "rel" action modalities, play_dataset.py:291-301).
+ * color_jitter_u8: ScaleImageTensor (u8/255) -> torchvision ColorJitter ops in the per-frame order `order` (three op
+ *   ids packed 4 bits each, first op lowest: 0 brightness, 1 contrast, 3 hue, 0xF none) with per-frame factors
+ *   (brightness, contrast, hue) -> Normalize(mean, std): utils/transforms.py:87-101, 302-330.  order NULL = no jitter.
+ *   mean_ws: N floats of scratch. */
+int tacorl_window_gather_u8(const unsigned char* store, long long frames, int C, int H, int W, const int* start,
+                            const int* window, const int* shift, int pad, int B, int T, unsigned char* out, void* stream);
+int tacorl_actions_gather_pad(const float* store, long long frames, int A, const int* start, const int* window, int B,
+                              int T, int zero_pad, float* out, void* stream);
+int tacorl_color_jitter_u8(const unsigned char* x, long long N, int H, int W, const int* order, const float* factors,
+                           float norm_mean, float norm_std, float* mean_ws, float* out, void* stream);
+
 /* ---- fused small-MLP chains (fp32): a whole Linear -> act -> Linear ... stack in ONE launch, forward or backward.
  * Replaces the per-layer launches behind VisualGoalEncoder.forward (goal_encoder.py:29-33), MLPPolicy.forward
  * (actor.py:252-270: 3 x Linear+SiLU, then fc_mean | fc_log_std as ONE layer of two weight segments) and

@@ -10,6 +10,13 @@ import torch.distributed as dist
 SM_RESERVE_FOR_COLLECTIVES = 16   # SMs left out of the persistent conv grids when gradients are exchanged (one per NCCL channel)
 
 
+def collective_channels(world_size):
+    """NCCL channels = SMs reserved for the overlapped gradient all-reduce.  Measured (ms/step, PlayLMP bf16, 64 windows
+    per GPU): N = 2 (round 1, scripts/n2_reserve_sweep.sh): 8 -> 4.30, 16 -> 3.96, 24 -> 4.01, 32 -> 4.07;
+    N = 8 (round 2, scripts/n8_sweep.sh): 8 -> 3.915, 16 -> 3.905, 24 -> 3.79, 32 -> 3.79 (bf16 wire 3.77, tree 4.65)."""
+    return 16 if world_size <= 2 else 24
+
+
 class BucketedAllReduce:
     """All-reduces a flat gradient buffer in fixed-size buckets on a side stream (CUDA) so the exchange of
     early buckets overlaps whatever the caller still runs on the main stream.
@@ -79,7 +86,7 @@ def attach_data_parallel(optimizer, world_size, group=None, bucket_elems=16 << 2
     if world_size > 1 and flat is not None and flat.is_cuda and "TACORL_SM_RESERVE" not in os.environ:
         # the all-reduce of the non-encoder slice overlaps the encoder backward: keep SMs free for its channels
         from . import _lib
-        _lib.lib().tacorl_set_sm_reserve(SM_RESERVE_FOR_COLLECTIVES)
+        _lib.lib().tacorl_set_sm_reserve(collective_channels(world_size))
     return optimizer
 
 

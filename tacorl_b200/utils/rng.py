@@ -57,6 +57,15 @@ def uniform(shape, lo, hi, device):
     return torch.empty(shape, device=device, dtype=torch.float32).uniform_(lo, hi)
 
 
+def randint(shape, lo, hi, device):
+    """torch.randint(lo, hi, shape) as drawn by RandomShiftsAug (utils/transforms.py:287-289), as int32."""
+    if _TAPE is not None:
+        t = _TAPE.popleft()
+        assert tuple(t.shape) == tuple(shape), f"noise tape shape {tuple(t.shape)} != requested {tuple(shape)}"
+        return t.to(device=device, dtype=torch.int32).contiguous()
+    return torch.randint(lo, hi, shape, device=device).to(torch.int32)
+
+
 def dropout_mask(shape, p, device, training=True):
     """Pre-scaled keep mask (keep / (1-p)) of F.dropout, or None when dropout is inactive."""
     if not training or p == 0.0:

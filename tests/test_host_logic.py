@@ -260,3 +260,43 @@ def test_committed_ncu_launch_lists_parse_and_carry_our_kernels():
         assert k in names, k
     enc = list(rows(os.path.join(ROOT, "profiles", "r01_encoder_launches_final.csv")))
     assert any("conv_dgrad2_kernel" in n for _, n, _ in enc)
+
+
+def test_transform_oracle_matches_the_reference_classes():
+    """oracle/transforms_oracle.py (the checker of the device-side input pipeline) against the unmodified reference
+    RandomShiftsAug / ColorTransform / PlayDataset.pad_* (utils/transforms.py:265-330, play_dataset.py:312-330)."""
+    from oracle import ref_loader as R
+    from oracle import transforms_oracle as TO
+    if not R.reference_available():
+        pytest.skip("reference not present")
+    R.import_reference()
+    import numpy as np
+    from tacorl.utils.transforms import ColorTransform, RandomShiftsAug
+    g = torch.Generator().manual_seed(0)
+    x = torch.randint(0, 256, (6, 3, 32, 32), generator=g).float()
+    pad = 3
+    shift = torch.randint(0, 2 * pad + 1, (6, 1, 1, 2), generator=g)
+    orig = torch.randint
+    torch.randint = lambda *a, **k: shift.to(k.get("dtype", torch.float32))
+    try:
+        want = RandomShiftsAug(pad)(x)
+    finally:
+        torch.randint = orig
+    assert torch.equal(TO.random_shifts(x, pad, shift), want)
+    # integer shift with edge clamping is what the grid_sample formulation evaluates to
+    p = torch.nn.functional.pad(x, (pad,) * 4, "replicate")
+    for n in range(6):
+        sx, sy = int(shift[n, 0, 0, 0]), int(shift[n, 0, 0, 1])
+        assert (want[n] - p[n, :, sy:sy + 32, sx:sx + 32]).abs().max() < 5e-3
+    # ColorTransform: same torch / numpy seeds -> same draws -> same image as the restated op chain
+    from tacorl_b200.utils.transforms import OP_NONE, draw_color_jitter_params
+    img = torch.rand(3, 3, 16, 16, generator=g)
+    ct = ColorTransform(contrast=0.1, brightness=0.1, hue=0.02)
+    torch.manual_seed(5); np.random.seed(5)
+    want = ct(img)
+    torch.manual_seed(5); np.random.seed(5)
+    order, fac = draw_color_jitter_params(3, 0.1, 0.1, 0.02)
+    for n in range(3):
+        ops = [(int(order[n]) >> (4 * k)) & 0xF for k in range(3)]
+        got = TO.color_jitter(img[n], [o for o in ops if o != OP_NONE], float(fac[n, 0]), float(fac[n, 1]), float(fac[n, 2]))
+        assert torch.allclose(got, want[n], atol=1e-6), n
