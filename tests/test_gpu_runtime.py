@@ -297,3 +297,42 @@ def test_double_buffered_graphs_consume_prefetched_batches_in_order():
     torch.cuda.synchronize()
     assert torch.equal(g.statics[g._cur]["actions"].cpu(), hosts[seq[-1]]["actions"])
     assert torch.equal(g.statics[1 - g._cur]["actions"].cpu(), hosts[seq[-2]]["actions"])
+
+
+def test_trainer_fit_checkpoints_and_resumes_across_the_bc_epoch_boundary(tmp_path):
+    """tacorl_b200.trainer.Trainer (the part of pl.Trainer scripts/train.py:28-75 uses): manual-optimisation TACORL,
+    epochs of 2 steps with bc_epochs = 1 -> the actor loss switches graphs after the first epoch; Lightning-format
+    checkpoints; a second Trainer resumes from last.ckpt with every optimiser's moments and step count."""
+    from tacorl_b200 import trainer as TR
+    from tests.gpu_util import build_tacorl
+
+    def fresh():
+        lmp = build_play_lmp("tanh_net", ("rgb_static",), 64, 16, 8)
+        t = build_tacorl(lmp, bc_epochs=1)
+        shapes = {k: list(v.shape) for k, v in t.state_dict().items()}
+        t.load_state_dict(S.synth_state_dict(shapes, 6))
+        return t
+
+    hb = S.synth_play_batch(3, 8, 84, 84, 6, with_goal=True)
+    batch = {k: hb[k] for k in ("states", "actions", "goal", "disp")}
+    t = fresh()
+    torch.manual_seed(1)
+    tr = TR.Trainer(max_steps=5, precision="fp32", default_root_dir=tmp_path, steps_per_epoch=2)
+    tr.fit(t, lambda s: batch)
+    assert tr.global_step == 5 and t.current_epoch == 2
+    opts = t.optimizers()
+    assert [o.steps_done for o in opts] == [5] * 6
+    last = tmp_path / "saved_models" / "last.ckpt"
+    assert last.is_file() and (tmp_path / "saved_models" / "tacorl_epoch_01_.ckpt").is_file()
+    ck = torch.load(last, weights_only=False)
+    assert ck["epoch"] == 2 and ck["global_step"] == 5 and len(ck["optimizer_states"]) == 6
+    assert float(ck["optimizer_states"][1]["state"][0]["step"]) == 5.0
+    # resume in a fresh module
+    t2 = fresh()
+    tr2 = TR.Trainer(max_steps=7, precision="fp32", default_root_dir=tmp_path / "resumed", steps_per_epoch=2)
+    tr2.fit(t2, lambda s: batch, ckpt_path=last)
+    assert tr2.global_step == 7 and [o.steps_done for o in t2.optimizers()] == [7] * 6
+    sd1 = {k: v.cpu() for k, v in t.state_dict().items()}
+    moved = [k for k, v in t2.state_dict().items() if v.dtype.is_floating_point and not torch.equal(v.cpu(), sd1[k])]
+    assert any(k.startswith("actor.") for k in moved) and any(k.startswith("q1.") for k in moved)
+    assert not [k for k in moved if k.startswith(("perceptual_encoder.", "plan_recognition."))]     # frozen LMP parts

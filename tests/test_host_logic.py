@@ -300,3 +300,63 @@ def test_transform_oracle_matches_the_reference_classes():
         ops = [(int(order[n]) >> (4 * k)) & 0xF for k in range(3)]
         got = TO.color_jitter(img[n], [o for o in ops if o != OP_NONE], float(fac[n, 0]), float(fac[n, 1]), float(fac[n, 2]))
         assert torch.allclose(got, want[n], atol=1e-6), n
+
+
+def test_reference_lightning_checkpoint_resumes_in_the_b200_modules(tmp_path):
+    """A run directory as the reference leaves it (`.hydra/config.yaml` with the reference `_target_`, a Lightning-format
+    `.ckpt` holding the reference module's state_dict and its torch.optim.Adam state) is picked up by the B200 loader:
+    class path remapped, weights identical, Adam moments / step restored into FlatAdam (utils/networks.py:90-117,
+    scripts/train.py:48-66).  CPU only: no kernel runs."""
+    import yaml
+    from oracle import ref_loader as R
+    from oracle import ref_loader_cfg as RC
+    from oracle import synth as S
+    if not R.reference_available():
+        pytest.skip("reference not present")
+    ref = R.build_reference_play_lmp(pr_kind="tanh_net", rnn_hidden=32, dropout_p=0.0, max_window=8)
+    opt = ref.configure_optimizers()
+    batch = S.synth_play_batch(2, 8, 84, 84, 3)
+    for s in range(2):
+        torch.manual_seed(10 + s)
+        opt.zero_grad()
+        ref.training_step(S.clone_batch(batch), s).backward()
+        opt.step()
+    run = tmp_path / "run"
+    (run / ".hydra").mkdir(parents=True)
+    (run / "saved_models").mkdir()
+    cfg = RC.play_lmp_cfg(pr_kind="tanh_net", rnn_hidden=32, dropout_p=0.0, max_window=8)
+    cfg["_target_"] = "tacorl.modules.play_lmp.play_lmp_for_rl.PlayLMP"
+    cfg["_recursive_"] = False
+    yaml.safe_dump({"module": cfg}, open(run / ".hydra" / "config.yaml", "w"))
+    torch.save({"epoch": 3, "global_step": 2, "pytorch-lightning_version": "1.6.5", "state_dict": ref.state_dict(),
+                "optimizer_states": [opt.state_dict()], "lr_schedulers": []}, run / "saved_models" / "tacorl_epoch_03_.ckpt")
+    from tacorl_b200 import trainer as TR
+    from tacorl_b200.modules.play_lmp.play_lmp_for_rl import PlayLMP
+    from tacorl_b200.utils.networks import get_checkpoint_i_from_dir, load_pl_module_from_checkpoint
+    m = load_pl_module_from_checkpoint(run, epoch=3)
+    assert type(m) is PlayLMP
+    for k, v in ref.state_dict().items():
+        assert torch.equal(m.state_dict()[k], v), k
+    ckpt = TR.restore_checkpoint(m, get_checkpoint_i_from_dir(run, 3))
+    assert ckpt["global_step"] == 2 and m.current_epoch == 3
+    o = m.optimizers()[0]
+    assert o.step_count == 2
+    ref_params = [p for p in ref.parameters() if p.requires_grad]
+    mine = o.param_groups[0]["params"]
+    assert len(ref_params) == len(mine)
+    for i, (rp, off) in enumerate(zip(ref_params, o.pbuf.offsets)):
+        st = opt.state.get(rp)
+        if not st:
+            continue
+        assert torch.equal(o.exp_avg[off:off + rp.numel()].view(rp.shape), st["exp_avg"]), i
+        assert torch.equal(o.exp_avg_sq[off:off + rp.numel()].view(rp.shape), st["exp_avg_sq"]), i
+    # and back: a checkpoint written by this package has the layout the reference's Lightning run expects
+    out = TR.save_checkpoint(m, tmp_path / "out" / "last.ckpt", epoch=4, global_step=7)
+    back = torch.load(out, weights_only=False)
+    assert set(back) >= {"epoch", "global_step", "state_dict", "optimizer_states", "pytorch-lightning_version"}
+    ref2 = R.build_reference_play_lmp(pr_kind="tanh_net", rnn_hidden=32, dropout_p=0.0, max_window=8)
+    ref2.load_state_dict(back["state_dict"], strict=True)
+    opt2 = ref2.configure_optimizers()
+    opt2.load_state_dict(back["optimizer_states"][0])
+    rp2 = [p for p in ref2.parameters() if p.requires_grad]
+    assert float(opt2.state[rp2[0]]["step"]) == 2.0
