@@ -195,12 +195,46 @@ class TACORL(LightningModule):
 
     # ------------------------------------------------------------------------------ CQL update
     def _emb(self, wrapper, obs_img, goal_img, goal_emb=None):
-        """Visual*Wrapper.get_emb_representation with the goal embedding optionally re-used."""
-        e = wrapper.encoder.get_state_from_observation(obs_img, modalities=wrapper.env_modalities)
-        if goal_emb is None:
-            g = wrapper.encoder.get_state_from_observation(goal_img, modalities=wrapper.goal_modalities)
-            goal_emb = wrapper.goal_encoder(g) if wrapper.goal_encoder is not None else g
+        """Visual*Wrapper.get_emb_representation with the goal embedding optionally re-used.  Observation and goal
+        frames of a view go through that view's encoder as ONE batch (same weights, independent frames: identical
+        values; half the kernel launches of these small 64-frame passes, one weight-gradient pass instead of two)."""
+        enc = wrapper.encoder
+        if goal_emb is not None:
+            return torch.cat([enc.get_state_from_observation(obs_img, modalities=wrapper.env_modalities), goal_emb], dim=-1), goal_emb
+        B = next(iter(obs_img.values())).shape[0]
+        parts = {}
+        for m in dict.fromkeys(list(wrapper.env_modalities) + list(wrapper.goal_modalities)):
+            srcs = ([obs_img[m]] if m in wrapper.env_modalities else []) + ([goal_img[m]] if m in wrapper.goal_modalities else [])
+            if len(srcs) == 2 and srcs[0].shape == srcs[1].shape and srcs[0].dtype == srcs[1].dtype:
+                out = enc.networks[m](self._stack_frames(srcs))
+                parts[(m, "obs")], parts[(m, "goal")] = out[:B], out[B:]
+            else:
+                if m in wrapper.env_modalities:
+                    parts[(m, "obs")] = enc.networks[m](obs_img[m])
+                if m in wrapper.goal_modalities:
+                    parts[(m, "goal")] = enc.networks[m](goal_img[m])
+        cat = lambda ts: ts[0] if len(ts) == 1 else torch.cat(ts, dim=-1)
+        e = cat([parts[(m, "obs")] for m in wrapper.env_modalities])
+        g = cat([parts[(m, "goal")] for m in wrapper.goal_modalities])
+        goal_emb = wrapper.goal_encoder(g) if wrapper.goal_encoder is not None else g
         return torch.cat([e, goal_emb], dim=-1), goal_emb
+
+    @staticmethod
+    def _stack_frames(srcs):
+        """cat along the batch dim.  uint8 frames are copied through an int32 view: torch's byte-wise cat / strided copy
+        kernels run at 0.2-0.4 TB/s (78 us per 15 MB pair of 64-frame batches, measured), 4-byte elements at > 2 TB/s."""
+        n = sum(t.shape[0] for t in srcs)
+        out = torch.empty((n,) + tuple(srcs[0].shape[1:]), device=srcs[0].device, dtype=srcs[0].dtype)
+        wide = srcs[0].dtype == torch.uint8 and srcs[0].shape[-1] % 4 == 0
+        o = 0
+        for t in srcs:
+            dst = out[o:o + t.shape[0]]
+            if wide and t.stride(-1) == 1 and all(st % 4 == 0 for st in t.stride()[:-1]) and t.storage_offset() % 4 == 0:
+                dst.view(torch.int32).copy_(t.view(torch.int32))
+            else:
+                dst.copy_(t)
+            o += t.shape[0]
+        return out
 
     @staticmethod
     def _q_mlp(qnet, emb, action, detach_params=False):
