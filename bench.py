@@ -338,7 +338,8 @@ def measure_workload(ctx, name, precision, steps, warmup, e2e=True, sample_clock
                     rb.wait_event(stepped[s % 2])
                     pinned[s % 2].copy_(loss, non_blocking=True)
                     done[s % 2].record(rb)
-                graphed.prefetch(host)
+                if not os.environ.get("BENCH_E2E_NO_H2D"):        # (diagnostic knob: never set for a reported number)
+                    graphed.prefetch(host)
                 if s > 0:
                     read(s - 1)
                 if s == steps - 1:

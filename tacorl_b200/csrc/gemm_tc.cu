@@ -613,6 +613,23 @@ struct SeqArgs {
   unsigned* flags;                        // [tiles] arrival counters, zero before the launch
 };
 __device__ unsigned g_rnn_seq_timeouts = 0;   // flag waits that gave up (never expected; read by tacorl_rnn_seq_timeouts)
+// Arrival counters of the persistent recurrence kernels: [lane][tile].  Zero at module load and SELF-CLEANING: the last
+// CTA of a launch to finish (nobody polls any more by then) resets them, so no launch needs a memset in front of it
+// (8 memset nodes + their launch gaps per training step otherwise).  Persistent launches never overlap (chained).
+__device__ unsigned g_rnn_flags[2][32];
+__device__ unsigned g_rnn_done = 0;
+__device__ __forceinline__ void rnn_launch_epilogue(int tid) {
+  if (tid == 0) {
+    __threadfence();
+    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+    if (atomicAdd(&g_rnn_done, 1u) == total - 1) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) (&g_rnn_flags[0][0])[i] = 0;
+      __threadfence();
+      g_rnn_done = 0;
+    }
+  }
+}
 #ifdef TACORL_STEP_PROFILE                    // stage stamps of one CTA at step 8 (scripts/prof/step_prof.cu)
 __device__ long long g_seq_prof[16];
 #define SQ_STAMP(i) if (step == 8 && blockIdx.x == 1 && blockIdx.y == 3) g_seq_prof[i] = clock64();
@@ -690,7 +707,7 @@ rnn_seq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         bool bad = false;
         for (int j = j_lo + lane; j <= j_hi; j += 32) {
           unsigned spins = 0;
-          while (ld_acquire_gpu(sa.flags + j) < want) {
+          while (ld_acquire_gpu(&g_rnn_flags[0][j]) < want) {
             if (++spins > (1u << 21)) { bad = true; atomicAdd(&g_rnn_seq_timeouts, 1u); break; }
           }
         }
@@ -830,7 +847,7 @@ rnn_seq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("fence.proxy.async.global;" ::: "memory");
       if (tid == 0) { SQ_STAMP(9) }
       asm volatile("bar.sync 1, %0;" ::"n"(RS_EPI) : "memory");
-      if (tid == 0) { __threadfence(); red_release_gpu_add(sa.flags + tile, 1u); SQ_STAMP(10) }
+      if (tid == 0) { __threadfence(); red_release_gpu_add(&g_rnn_flags[0][tile], 1u); SQ_STAMP(10) }
 #pragma unroll
       for (int i = 0; i < RS_MAXE; ++i) {
         const int e = tid + i * RS_EPI;
@@ -846,6 +863,7 @@ rnn_seq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
+  rnn_launch_epilogue(tid);
 }
 
 // ------------------------------------------------------------------------------------------ two-lane persistent recurrence
@@ -935,7 +953,7 @@ rnn_wave_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         bool bad = false;
         for (int j = j_lo + lane; j <= j_hi; j += 32) {
           unsigned spins = 0;
-          while (ld_acquire_gpu(sa.flags + j) < want) {
+          while (ld_acquire_gpu(&g_rnn_flags[blockIdx.z][j]) < want) {
             if (++spins > (1u << 21)) { bad = true; atomicAdd(&g_rnn_seq_timeouts, 1u); break; }
           }
         }
@@ -1062,7 +1080,7 @@ rnn_wave_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       }
       asm volatile("fence.proxy.async.global;" ::: "memory");
       asm volatile("bar.sync 1, %0;" ::"n"(RS_EPI) : "memory");
-      if (tid == 0) { __threadfence(); red_release_gpu_add(sa.flags + tile, 1u); }
+      if (tid == 0) { __threadfence(); red_release_gpu_add(&g_rnn_flags[blockIdx.z][tile], 1u); }
 #pragma unroll
       for (int i = 0; i < RS_MAXE; ++i) {
         const int e = tid + i * RS_EPI;
@@ -1078,6 +1096,7 @@ rnn_wave_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
+  rnn_launch_epilogue(tid);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -1200,6 +1219,7 @@ int rnn_seq_mode() { rnn_seq_enabled(); return g_rnn_seq_enabled; }
 // launches of the same capture (an event recorded elsewhere cannot be waited on there; the graph launch itself is
 // stream-ordered after earlier work).
 static cudaEvent_t g_chain_ev[64] = {};
+static cudaStream_t g_chain_stream[64] = {};
 static unsigned long long g_chain_capture[64] = {};
 static bool g_chain_recorded[64] = {};
 static int chain_slot(cudaStream_t st, int* dev, unsigned long long* cid) {
@@ -1215,14 +1235,16 @@ static int chain_slot(cudaStream_t st, int* dev, unsigned long long* cid) {
 static int persistent_chain_enter(cudaStream_t st) {
   int dev; unsigned long long cid; int rc;
   if ((rc = chain_slot(st, &dev, &cid))) return rc;
-  if (g_chain_recorded[dev] && g_chain_capture[dev] == cid) TACORL_CHECK_CUDA(cudaStreamWaitEvent(st, g_chain_ev[dev], 0));
+  // (a launch on the stream of the previous persistent launch is ordered behind it already)
+  if (g_chain_recorded[dev] && g_chain_capture[dev] == cid && g_chain_stream[dev] != st)
+    TACORL_CHECK_CUDA(cudaStreamWaitEvent(st, g_chain_ev[dev], 0));
   return 0;
 }
 static int persistent_chain_leave(cudaStream_t st) {
   int dev; unsigned long long cid; int rc;
   if ((rc = chain_slot(st, &dev, &cid))) return rc;
   TACORL_CHECK_CUDA(cudaEventRecord(g_chain_ev[dev], st));
-  g_chain_recorded[dev] = true; g_chain_capture[dev] = cid;
+  g_chain_recorded[dev] = true; g_chain_capture[dev] = cid; g_chain_stream[dev] = st;
   return 0;
 }
 
@@ -1280,7 +1302,6 @@ int rnn_seq_tc(const void* Ab, int T, const void* W, long long ldw, int M, int N
     TACORL_REQUIRE(r == CUDA_SUCCESS, "rnn_seq: cuTensorMapEncodeTiled failed (%d) K=%d M=%d T=%d", (int)r, K, M, T);
   }
   if ((rc = make_tmap(&tw, W, K, N, ldw, 64, NT))) return rc;
-  TACORL_CHECK_CUDA(cudaMemsetAsync(flags, 0, (size_t)tiles * sizeof(unsigned), st));
   SeqArgs sa;
   sa.n_steps = n_steps; sa.tau0 = tau0; sa.dtau = dtau; sa.beta = beta; sa.C = C; sa.ldc = ldc; sa.c_ts = c_ts;
   sa.gate = gate; sa.ldgate = ldgate; sa.gate_ts = gate_ts; sa.Cb = (__nv_bfloat16*)Cb; sa.cb_ts = (long long)M * N;
@@ -1364,7 +1385,6 @@ int rnn_wave_tc(const WaveLaneHost* lanes, int n_lanes, int T, int M, int N, int
     d.n_steps = l < n_lanes ? h.n_steps : 0; d.tau0 = h.tau0; d.dtau = h.dtau; d.act = h.act; d.beta = h.beta;
     d.C = h.C; d.ldc = h.ldc; d.c_ts = h.c_ts; d.gate = h.gate; d.ldgate = h.ldgate; d.gate_ts = h.gate_ts;
     d.Cb = (__nv_bfloat16*)h.Cb; d.ldcb = h.ldcb; d.cb_ts = h.cb_ts; d.flags = h.flags;
-    if (l < n_lanes) TACORL_CHECK_CUDA(cudaMemsetAsync(h.flags, 0, (size_t)tiles * sizeof(unsigned), st));
   }
   if ((rc = persistent_chain_enter(st))) return rc;
   void* args[] = {&ta[0], &tw[0], &ta[1], &tw[1], &wa, (void*)&M, (void*)&Mpad, (void*)&N, (void*)&NT, (void*)&kb};

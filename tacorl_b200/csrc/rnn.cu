@@ -431,7 +431,8 @@ static int layer2_fwd_bf16(int T, int B, int I, int H, int D, const float* x, lo
   for (int d = 0; d < D; ++d) {
     const int n = n_steps[d], t_lo = d ? T - n : 0, t0 = d ? T - 1 : 0;
     TcArgs in;   // pre-activations of the active steps: out[t, :, dH:(d+1)H] = x[t] W_ih^T + (b_ih + b_hh)
-    in.C = out + (long long)t_lo * B * ldo + (long long)d * H; in.ldc = ldo; in.bias = L.bsum[d]; in.split_k = 1;
+    in.C = out + (long long)t_lo * B * ldo + (long long)d * H; in.ldc = ldo; in.bias = L.bsum[d];
+    in.split_k = n * B <= 128 ? 0 : 1;      // a single step (the top layer's reverse direction): the cluster split-K kernel
     if ((rc = gemm_tc_bf16(L.xb + (long long)t_lo * B * L.ldxb, L.ldxb, 0, L.wih[d], Ip, 0, n * B, H, I, in, L.sk, L.sk_bytes, st)))
       return rc;
     // first step: h_init = 0
