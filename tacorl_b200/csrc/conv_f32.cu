@@ -176,7 +176,9 @@ __global__ void softargmax_fwd_kernel(const float* __restrict__ y, int P, int OW
 // ---- vectorised variants (C % 4 == 0): thread (cq, g) owns 4 consecutive channels (one 16-byte load per position)
 // and scans positions g, g+G, ...; 256-thread CTAs (C = 64, G = 16) so that several CTAs share an SM and every thread
 // keeps 8 x 16 bytes in flight: the scalar kernels above run 1024-thread CTAs at one CTA per SM (register limit) and
-// reach 1.7 TB/s (ncu, round 1); these are bound by HBM.
+// reach 1.7 TB/s (ncu, round 1); these reach 3.2 TB/s.  (Tried and measured slower, round 2: 512-thread CTAs that put the
+// whole 113 KB frame in flight in one batch per thread, 54 / 58 us against 36 / 44 us: with one CTA per SM the load phase
+// of one frame no longer overlaps the exponentials of another.)
 template <int G>
 __global__ void __launch_bounds__(256)
 softargmax_fwd_v4_kernel(const float* __restrict__ y, int P, int OW, int C, const float* __restrict__ temperature,
