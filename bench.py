@@ -641,6 +641,8 @@ def teardown(ctx):
     ctx.graphs.clear()
     gc.collect()
     ctx.barrier()
+    from tacorl_b200 import parallel
+    parallel.NativeAllReduce.shutdown()          # the library's own communicator (tacorl_dp_allreduce_*)
     done = threading.Event()
 
     def destroy():

@@ -233,6 +233,18 @@ int tacorl_cql_actor_loss(int mode, int B, const float* log_pi, const float* a, 
                           const float* log_alpha, float target_entropy, float* out, float* d_log_alpha,
                           float* d_log_pi, float* da, float* db, void* stream);
 
+/* ---- data-parallel gradient exchange (dp_allreduce_{init,enqueue,wait}); replaces Lightning's DDP over
+ * gloo (config/trainer/default.yaml:1-4, scripts/train.py:73-75).  One communicator per process (one process per GPU).
+ * unique_id: rank 0 fills 128 bytes that the host broadcasts to the other ranks by any means; init: every rank.
+ * enqueue: in-place sum over the ranks of buf[0..n) (dtype 0 = fp32, 1 = bf16), ordered after everything queued on
+ * `stream`, executed on the library's own communication stream (returns at once; capturable in a CUDA graph);
+ * wait: `stream` waits for every exchange enqueued so far.  NCCL is dlopen()ed (TACORL_NCCL_LIB overrides the path). */
+int tacorl_dp_unique_id(void* id128);
+int tacorl_dp_allreduce_init(const void* id128, int rank, int world);
+int tacorl_dp_allreduce_enqueue(void* buf, long long n, int dtype, void* stream);
+int tacorl_dp_allreduce_wait(void* stream);
+int tacorl_dp_allreduce_destroy(void);
+
 /* ---- device-side input pipeline: the per-sample work of the reference's DataLoader workers on uint8
  * frames resident in HBM.  Random quantities are inputs (drawn by the host in the reference's order).
  * window_gather_u8: out[b][t] = store[start[b] + min(t, window[b]-1)] (pad_sequence by repetition,

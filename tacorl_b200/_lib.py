@@ -65,6 +65,11 @@ _SIGS = {
     "tacorl_cql_critic_loss": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _i,
                                _vp, _vp, _vp, _vp, _vp],
     "tacorl_cql_actor_loss": [_i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp],
+    "tacorl_dp_unique_id": [_vp],
+    "tacorl_dp_allreduce_init": [_vp, _i, _i],
+    "tacorl_dp_allreduce_enqueue": [_vp, _ll, _i, _vp],
+    "tacorl_dp_allreduce_wait": [_vp],
+    "tacorl_dp_allreduce_destroy": [],
     "tacorl_window_gather_u8": [_vp, _ll, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "tacorl_actions_gather_pad": [_vp, _ll, _i, _vp, _vp, _i, _i, _i, _vp, _vp],
     "tacorl_color_jitter_u8": [_vp, _ll, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _vp],

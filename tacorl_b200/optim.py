@@ -111,10 +111,11 @@ class FlatAdam(torch.optim.Optimizer):
             if self._early_stream is None:
                 self._early_stream = torch.cuda.Stream(device=dev)
             stream = self._early_stream
-            sync_stream = getattr(self.grad_sync, "_stream", None) if self.grad_sync is not None else None
             # after the slice's all-reduce (own stream, so that later exchanges do not queue behind this update), or
             # straight after the gather
-            stream.wait_stream(sync_stream if sync_stream is not None else torch.cuda.current_stream(dev))
+            stream.wait_stream(torch.cuda.current_stream(dev))
+            if self.grad_sync is not None:
+                self.grad_sync.wait_on(stream)
             with torch.cuda.stream(stream):
                 if first:
                     self.step_count += 1

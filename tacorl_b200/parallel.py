@@ -63,6 +63,11 @@ class BucketedAllReduce:
         if self._stream is not None:
             torch.cuda.current_stream(self._device).wait_stream(self._stream)
 
+    def wait_on(self, stream):
+        """`stream` waits for every exchange enqueued so far."""
+        if self._stream is not None:
+            stream.wait_stream(self._stream)
+
     _device = None
 
     def __call__(self, flat):
@@ -70,17 +75,82 @@ class BucketedAllReduce:
         self.finish()
 
 
-def attach_data_parallel(optimizer, world_size, group=None, bucket_elems=16 << 20, wire_dtype="auto"):
+class NativeAllReduce:
+    """The same exchange through the library's own NCCL communicator (tacorl_dp_allreduce_{init,enqueue,wait}): no
+    torch.distributed call on the data path.  torch.distributed (any backend) is only used once, to hand rank 0's
+    ncclUniqueId to the other ranks."""
+    _ready = False
+
+    @classmethod
+    def ensure_init(cls, world_size, group=None):
+        if cls._ready:
+            return
+        import ctypes
+        from . import _lib
+        rank = dist.get_rank(group)
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            _lib.call("tacorl_dp_unique_id", buf)
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        _lib.call("tacorl_dp_allreduce_init", ctypes.create_string_buffer(box[0], 128), rank, world_size)
+        cls._ready = True
+
+    @classmethod
+    def shutdown(cls):
+        if cls._ready:
+            from . import _lib
+            _lib.call("tacorl_dp_allreduce_destroy")
+            cls._ready = False
+
+    def __init__(self, world_size, bucket_elems=16 << 20, group=None):
+        self.world, self.bucket, self.group = world_size, bucket_elems, group
+        self.ensure_init(world_size, group)
+
+    def start(self, flat):
+        if self.world <= 1 or flat.numel() == 0:
+            return
+        from . import _lib
+        assert flat.is_cuda and flat.dtype in (torch.float32, torch.bfloat16)
+        for o in range(0, flat.numel(), self.bucket):
+            chunk = flat[o:o + self.bucket]
+            _lib.call("tacorl_dp_allreduce_enqueue", _lib.ptr_any(chunk), chunk.numel(),
+                      1 if chunk.dtype == torch.bfloat16 else 0, _lib.stream())
+
+    def wait_on(self, stream):
+        """`stream` waits for every exchange enqueued so far."""
+        from . import _lib
+        with torch.cuda.stream(stream):
+            _lib.call("tacorl_dp_allreduce_wait", _lib.stream())
+
+    def finish(self):
+        from . import _lib
+        _lib.call("tacorl_dp_allreduce_wait", _lib.stream())
+
+    def __call__(self, flat):
+        self.start(flat)
+        self.finish()
+
+
+def attach_data_parallel(optimizer, world_size, group=None, bucket_elems=16 << 20, wire_dtype="auto", native="auto"):
     """Make a FlatAdam average its gradient over `world_size` ranks before the update (DDP semantics:
     mean of local-mean gradients; clip-by-norm acts on the reduced gradient, cql_offline_lightning.py:521-537).
-    wire_dtype: "auto" = fp32 unless TACORL_WIRE=bf16; torch.bfloat16 = compressed exchange; None = fp32."""
+    wire_dtype: "auto" = fp32 unless TACORL_WIRE=bf16; torch.bfloat16 = compressed exchange; None = fp32.
+    native: exchange through the library's own NCCL communicator (tacorl_dp_allreduce_*; CUDA, fp32 wire) instead of
+    torch.distributed's; "auto" = yes unless TACORL_NATIVE_NCCL=0."""
     if wire_dtype == "auto":
         # measured (profiles/r02): at N = 2 the two cast passes cost more than the halved NVLink bytes save (3.50 -> 3.60
         # ms/step), so fp32 stays the default; TACORL_WIRE=bf16 selects the compressed exchange
         flat0 = getattr(optimizer, "flat_params", None)
         want = os.environ.get("TACORL_WIRE", "fp32") == "bf16"
         wire_dtype = torch.bfloat16 if (want and flat0 is not None and flat0.is_cuda) else None
-    optimizer.grad_sync = BucketedAllReduce(world_size, bucket_elems, group, wire_dtype)
+    flat1 = getattr(optimizer, "flat_params", None)
+    if native == "auto":
+        native = os.environ.get("TACORL_NATIVE_NCCL", "1") != "0"
+    if native and world_size > 1 and flat1 is not None and flat1.is_cuda and wire_dtype is None:
+        optimizer.grad_sync = NativeAllReduce(world_size, bucket_elems, group)
+    else:
+        optimizer.grad_sync = BucketedAllReduce(world_size, bucket_elems, group, wire_dtype)
     optimizer.grad_scale = 1.0 / world_size
     flat = getattr(optimizer, "flat_params", None)
     if world_size > 1 and flat is not None and flat.is_cuda and "TACORL_SM_RESERVE" not in os.environ:

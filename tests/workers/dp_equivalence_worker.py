@@ -115,6 +115,8 @@ def main():
     del g
     gc.collect()
     torch.cuda.synchronize()
+    out["native_nccl"] = bool(parallel.NativeAllReduce._ready)
+    parallel.NativeAllReduce.shutdown()
     done = threading.Event()
 
     def destroy():
