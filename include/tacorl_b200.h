@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TACORL_B200_ABI_VERSION 6
+#define TACORL_B200_ABI_VERSION 7
 
 #define TACORL_PREC_F32 0
 #define TACORL_PREC_BF16 1
@@ -274,8 +274,10 @@ int tacorl_color_jitter_u8(const unsigned char* x, long long N, int H, int W, co
 typedef struct tacorl_mlp_layer {
   const float* W0; const float* b0; int n0;     /* first weight segment: (n0, in) row-major, bias (n0) or NULL */
   const float* W1; const float* b1; int n1;     /* optional second segment stacked behind it (n1 = 0: none) */
+  const float* W2; const float* b2; int n2;     /* optional third segment (n2 = 0: none; needs n1 > 0):
+                                                 * fc_mean | fc_log_std | gripper_action of a discrete-gripper MLPPolicy */
   int in; int act;                              /* input width; activation on the output (TACORL_ACT_*) */
-  float* dW0; float* db0; float* dW1; float* db1;   /* backward outputs */
+  float* dW0; float* db0; float* dW1; float* db1; float* dW2; float* db2;   /* backward outputs */
 } tacorl_mlp_layer;
 size_t tacorl_mlp_chain_ws_bytes(int L, int rows, const tacorl_mlp_layer* layers);
 int tacorl_mlp_chain_fwd(int L, int rows, const tacorl_mlp_layer* layers, const float* x0, int xin0, long long ldx0,

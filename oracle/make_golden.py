@@ -100,6 +100,30 @@ def golden_tacorl(name, pr_kind, B, T, H, W, rnn_hidden, epoch, steps=2, seed=13
     print("wrote", name, {k: round(v, 5) for k, v in rec["steps"][0]["scalars"].items()})
 
 
+def golden_cql(name, B, H, W, epoch, steps=2, seed=29, **overrides):
+    """Flat-CQL baseline: CQL_Offline of config/experiment/cql_real_world.yaml, discrete-gripper actor.
+    (seed 29: with seeds 23 / 31 the clipped gripper-bias / conv-bias gradients of consecutive steps nearly cancel inside
+    Adam's first moment, and fp32 summation order alone moves the parameter by 2e-4 -- an ill-conditioned fixture.)"""
+    torch.manual_seed(0)
+    m = R.build_reference_cql(**overrides)
+    m.train()
+    m.current_epoch = epoch
+    shapes = _shapes(m)
+    _load_synth(m, seed)
+    batch = S.synth_cql_batch(B, H, W, seed)
+    rec = {"kind": "cql_flat", "B": B, "H": H, "W": W, "seed": seed, "epoch": epoch, "shapes": shapes,
+           "noise_seed_base": 3000, "target_entropy": float(m.target_entropy),
+           "deterministic_backup": bool(m.deterministic_backup), "steps": []}
+    for s in range(steps):
+        torch.manual_seed(3000 + s)
+        m.training_step(S.clone_batch(batch), s)
+        rec["steps"].append({
+            "scalars": _scalars(m.logged),
+            "params": {k: S.fingerprint(v) for k, v in m.state_dict().items() if v.dtype.is_floating_point}})
+    json.dump(rec, open(os.path.join(OUT, name + ".json"), "w"))
+    print("wrote", name, {k: round(v, 5) for k, v in rec["steps"][0]["scalars"].items()})
+
+
 def golden_encoder(name, sizes, seed=17):
     R.import_reference()
     from tacorl.networks.visual_encoders.encoder import LMPVisionEncoder
@@ -200,6 +224,8 @@ FIXTURES = {
     "tacorl_multiview_q": lambda: golden_tacorl("tacorl_multiview_q", "tanh_net", 3, 8, 96, 128, 64, epoch=7,
                                                 modalities=("rgb_static", "rgb_gripper"),
                                                 goal_modalities=("rgb_static", "rgb_gripper"), latent_plan_dim=32),
+    "cql_flat_bc": lambda: golden_cql("cql_flat_bc", 4, 84, 84, epoch=0),
+    "cql_flat_q": lambda: golden_cql("cql_flat_q", 4, 84, 84, epoch=7),
 }
 
 

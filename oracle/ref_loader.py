@@ -75,3 +75,14 @@ def build_reference_tacorl(play_lmp, **overrides):
     cfg = tacorl_cfg()
     cfg.update(overrides)
     return T.TACORL(**copy.deepcopy(cfg))
+
+
+def build_reference_cql(**overrides):
+    """The flat-CQL baseline, CQL_Offline as composed by config/experiment/cql_real_world.yaml."""
+    import_reference()
+    from tacorl.modules.cql.cql_offline_lightning import CQL_Offline
+    from .ref_loader_cfg import cql_offline_cfg
+
+    cfg = cql_offline_cfg()
+    cfg.update(overrides)
+    return CQL_Offline(**copy.deepcopy(cfg))

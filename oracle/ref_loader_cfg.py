@@ -146,3 +146,38 @@ def tacorl_cfg():
     }
 
 
+
+
+def actor_discrete_gripper_cfg():
+    # config/networks/actor_critic/actor/discrete_gripper.yaml + policy/discrete_gripper.yaml
+    cfg = actor_cfg()
+    cfg["discrete_gripper"] = True
+    cfg["policy"]["discrete_gripper"] = True
+    return cfg
+
+
+def cql_offline_cfg():
+    # config/module/cql_offline_goal_cond.yaml + experiment/cql_real_world.yaml (real_world: no simulator)
+    return {
+        "actor": actor_discrete_gripper_cfg(),
+        "critic": critic_cfg(),
+        "actor_encoder": representation_cfg(),
+        "critic_encoder": representation_cfg(),
+        "goal_encoder": goal_encoder_cfg(),
+        "transform_manager": {},
+        "discount": 0.99,
+        "actor_lr": 1e-4,
+        "critic_lr": 3e-4,
+        "conservative_weight": 1.0,
+        "n_action_samples": 4,
+        "with_lagrange": True,
+        "reward_scale": 10.0,
+        "deterministic_backup": False,
+        "bc_epochs": 5,
+        "with_dr3": False,
+        "with_vib": False,
+        "real_world": True,
+        "obs_modalities": ["rgb_static"],
+        "goal_modalities": ["rgb_static"],
+        "action_dim": 7,
+    }

@@ -99,13 +99,26 @@ def synth_play_batch(B, T, H, W, seed, modalities=("rgb_static",), gripper_hw=(8
     return batch
 
 
+def synth_cql_batch(B, H, W, seed, modalities=("rgb_static",), goal_modalities=("rgb_static",), gripper_hw=(84, 84)):
+    """Transition batch of the flat-CQL baseline (GoalCondReplayBufferDataset.get_transition,
+    datamodule/dataset/goal_cond_replay_buffer_dataset.py:277-296): reward = terminal = [goal is the next step]."""
+    g = _gen(seed, "cql_batch")
+    hw = lambda m: (H, W) if m == "rgb_static" else tuple(gripper_hw)
+    obs = {m: synth_images((B, 3) + hw(m), seed, "obs_" + m) for m in modalities}
+    nxt = {m: synth_images((B, 3) + hw(m), seed, "next_" + m) for m in modalities}
+    goal = {m: synth_images((B, 3) + hw(m), seed, "cqlgoal_" + m) for m in goal_modalities}
+    actions = torch.rand(B, 7, generator=g) * 2 - 1
+    actions[..., -1] = torch.where(actions[..., -1] > 0, 1.0, -1.0)
+    hit = (torch.rand(B, generator=g) < 0.3).long()
+    hit[0], hit[-1] = 1, 0
+    return {"observations": {"observation": obs, "goal": goal}, "actions": actions,
+            "next_observations": {"observation": nxt, "goal": goal}, "rewards": hit.clone(), "terminals": hit.clone()}
+
+
 def clone_batch(batch):
     """Fresh dict per call (the reference mutates batch['states'] in place,
     play_lmp_for_rl.py:188-190)."""
-    out = {}
-    for k, v in batch.items():
-        out[k] = {kk: vv.clone() for kk, vv in v.items()} if isinstance(v, dict) else v.clone()
-    return out
+    return {k: clone_batch(v) if isinstance(v, dict) else v.clone() for k, v in batch.items()}
 
 
 def fingerprint(t, seed=7, name="probe"):

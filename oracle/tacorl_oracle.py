@@ -651,6 +651,210 @@ def tacorl_training_step(P, opt, batch, noise, cfg=None, epoch=0):
     return logged, grads
 
 
+# ----------------------------------------------------------------------------- flat CQL baseline
+def mlp_policy_gripper(P, pre, x):
+    """MLPPolicy.forward with discrete_gripper=True, networks/actor_critic/actor.py:252-270:
+    (mean, std) over the continuous dims + 2 open/close logits from the same trunk."""
+    h = x
+    for i in range(_num_fc_layers(P, pre)):
+        h = F.silu(F.linear(h, P[pre + f"fc_layers.{i}.weight"], P[pre + f"fc_layers.{i}.bias"]))
+    mean = torch.clamp(F.linear(h, P[pre + "fc_mean.weight"], P[pre + "fc_mean.bias"]), MEAN_MIN, MEAN_MAX)
+    log_std = torch.clamp(F.linear(h, P[pre + "fc_log_std.weight"], P[pre + "fc_log_std.bias"]),
+                          LOG_SIG_MIN, LOG_SIG_MAX)
+    logits = F.linear(h, P[pre + "gripper_action.weight"], P[pre + "gripper_action.bias"])
+    return mean, log_std.exp(), logits
+
+
+def gumbel_argmax(logits, u, clamp):
+    """Index drawn by GumbelSoftmax, utils/distributions.py:28-48 (temperature 0.5 does not move the argmax):
+    sample():            argmax(normalised_logits - log(-log(u))), u ~ uniform_(0, 1)                     (clamp False)
+    rsample(hard=True):  argmax of the relaxed sample = argmax(normalised_logits + gumbel(clamp_probs(u))) (clamp True;
+                         torch ExpRelaxedCategorical.rsample, clamp_probs eps = float32 eps)
+    `logits` of a torch Categorical-family distribution are normalised: logits - logsumexp(logits)."""
+    norm = logits - logits.logsumexp(dim=-1, keepdim=True)
+    if clamp:
+        eps = torch.finfo(u.dtype).eps
+        u = u.clamp(min=eps, max=1 - eps)
+    return torch.argmax(norm - torch.log(-torch.log(u)), dim=-1)
+
+
+def gripper_log_prob(logits, index):
+    """GumbelSoftmax.log_prob of a class index, utils/distributions.py:50-58: log_softmax(logits)[index], keepdim."""
+    onehot = F.one_hot(index.long(), logits.shape[-1]).to(logits.dtype)
+    return (onehot * F.log_softmax(logits, dim=-1)).sum(dim=-1, keepdim=True)
+
+
+def cql_losses(P, batch, noise, cfg, epoch=0, alpha_override=None):
+    """Forward values of one CQL_Offline.training_step of the flat baseline (modules/cql/cql_offline_lightning.py:
+    470-516 with config/module/cql_offline_goal_cond.yaml: discrete-gripper actor, entropy-regularised backup,
+    Lagrange) for the CURRENT parameters P; alpha_override as in tacorl_losses.
+
+    batch: observations / next_observations = {"observation": {mod: (B,3,H,W)}, "goal": {mod: (B,3,H,W)}},
+           actions (B,7) with the last channel in {-1,+1}, rewards (B,), terminals (B,)
+           (datamodule/dataset/goal_cond_replay_buffer_dataset.py:277-296).
+    noise: eps_actor (B,6), u_actor (B,2), eps_next (B,6), u_next (B,2), rand_actions (n*B,7),
+           eps_curr (n,B,6), u_curr (n,B,2), eps_nextn (n,B,6), u_nextn (n,B,2)   (draw order: draw_cql_noise)."""
+    n = cfg.get("n_action_samples", 4)
+    discount = cfg.get("discount", 0.99)
+    reward_scale = cfg.get("reward_scale", 10.0)
+    target_entropy = cfg.get("target_entropy", -7.0)
+    gap = cfg.get("lagrange_thresh", 5.0)
+    bc_epochs = cfg.get("bc_epochs", 5)
+    det_backup = cfg.get("deterministic_backup", False)
+    mods = list(cfg.get("modalities", ["rgb_static"]))
+    goal_mods = list(cfg.get("goal_modalities", mods[:1]))
+    obs, goal = batch["observations"]["observation"], batch["observations"]["goal"]
+    nxt = batch["next_observations"]["observation"]
+    actions = batch["actions"].float()
+    B = actions.shape[0]
+    rew = batch["rewards"].float().reshape(B, 1)
+    done = batch["terminals"].int().reshape(B, 1)           # overwrite_batch, :119-148
+    emb = lambda pre, o: visual_emb(P, pre, o, goal, mods, goal_mods)
+    pol = "actor.actor.policy."
+    out = {}
+    # --- actor & alpha, :439-468 + Actor.get_actions(reparameterize=True), actor.py:66-98
+    mu_a, std_a, lg_a = mlp_policy_gripper(P, pol, emb("actor.", obs))
+    z = mu_a + std_a * noise["eps_actor"]
+    grip_idx = gumbel_argmax(lg_a, noise["u_actor"], clamp=True)
+    curr_log_pi = tanh_normal_log_prob(mu_a, std_a, pre_tanh=z) + gripper_log_prob(lg_a, grip_idx)
+    curr_actions = torch.cat([torch.tanh(z), grip_idx.unsqueeze(-1).to(z.dtype) * 2.0 - 1], dim=-1)
+    out["alpha_loss"] = -(P["log_alpha"][0] * (curr_log_pi + target_entropy).detach()).mean()
+    alpha = P["log_alpha"][0].exp() if alpha_override is None else alpha_override
+    out["alpha"] = alpha
+    q1_emb, q2_emb = emb("q1.", obs), emb("q2.", obs)
+    if epoch < bc_epochs:
+        # Actor.log_prob, actor.py:143-156
+        plp = tanh_normal_log_prob(mu_a, std_a, value=actions[..., :-1]) \
+            + gripper_log_prob(lg_a, actions[..., -1] / 2 + 0.5)
+        out["actor_loss"] = (alpha * curr_log_pi - plp).mean()
+    else:
+        qv = torch.min(q_value(P, "q1.", q1_emb, curr_actions), q_value(P, "q2.", q2_emb, curr_actions))
+        out["actor_loss"] = (alpha * curr_log_pi - qv).mean()
+    # --- Bellman, :284-314
+    with torch.no_grad():
+        mu_n, std_n, lg_n = mlp_policy_gripper(P, pol, emb("actor.", nxt))
+        zn1 = mu_n + std_n * noise["eps_next"]
+        gi_n = gumbel_argmax(lg_n, noise["u_next"], clamp=False)
+        next_log_pi = tanh_normal_log_prob(mu_n, std_n, pre_tanh=zn1) + gripper_log_prob(lg_n, gi_n)
+        next_actions = torch.cat([torch.tanh(zn1), gi_n.unsqueeze(-1).to(zn1.dtype) * 2.0 - 1], dim=-1)
+        tq = torch.min(q_value(P, "target_q1.", emb("target_q1.", nxt), next_actions),
+                       q_value(P, "target_q2.", emb("target_q2.", nxt), next_actions))
+        if not det_backup:
+            tq = tq - alpha.detach() * next_log_pi
+        q_target = reward_scale * rew + (1 - done) * discount * tq
+    q1_data = q_value(P, "q1.", q1_emb, actions)
+    q2_data = q_value(P, "q2.", q2_emb, actions)
+    out["bellman_q1_loss"] = F.mse_loss(q1_data, q_target)
+    out["bellman_q2_loss"] = F.mse_loss(q2_data, q_target)
+    # --- conservative, :238-282, 316-406
+    A = actions.shape[-1]
+    rand_a = noise["rand_actions"].clone()
+    rand_a[..., -1] = torch.where(rand_a[..., -1] >= 0, 1.0, -1.0)
+    rep = lambda e: e.unsqueeze(0).expand(n, *e.shape).reshape(n * B, -1)
+
+    def sample_n(mu, std, lg, eps, u):          # Actor.sample_n_with_log_prob, actor.py:117-141
+        zz = mu + std * eps
+        gi = gumbel_argmax(lg.unsqueeze(0).expand(n, *lg.shape), u, clamp=False)
+        lp = tanh_normal_log_prob(mu, std, pre_tanh=zz) + gripper_log_prob(lg, gi)
+        return torch.cat([torch.tanh(zz), gi.unsqueeze(-1).to(zz.dtype) * 2 - 1], dim=-1), lp
+
+    with torch.no_grad():
+        ac, lpc = sample_n(mu_a.detach(), std_a.detach(), lg_a.detach(), noise["eps_curr"], noise["u_curr"])
+        an, lpn = sample_n(mu_n, std_n, lg_n, noise["eps_nextn"], noise["u_nextn"])
+    rand_density = math.log(0.5 ** A)
+    for i, (qe, name) in enumerate(((q1_emb, "q1."), (q2_emb, "q2."))):
+        qr = q_value(P, name, rep(qe), rand_a).view(n, B).t()
+        qc = q_value(P, name, rep(qe), ac.reshape(n * B, A)).view(n, B).t()
+        qn = q_value(P, name, rep(qe), an.reshape(n * B, A)).view(n, B).t()
+        cat = torch.cat([qr - rand_density, qc - lpc.squeeze(-1).t(), qn - lpn.squeeze(-1).t()], dim=1)
+        qd = q1_data if i == 0 else q2_data
+        cons = torch.logsumexp(cat, dim=1).mean() - qd.mean()
+        out[f"q{i+1}_data"], out[f"q{i+1}_random"], out[f"q{i+1}_policy"] = qd.mean(), qr.mean(), qc.mean()
+        out[f"cons_raw_q{i+1}"] = cons
+    alpha_prime = torch.clamp(P["log_alpha_prime"][0].exp(), min=0.0, max=1e6)
+    out["alpha_prime"] = alpha_prime
+    out["conservative_q1_loss"] = alpha_prime * (out["cons_raw_q1"] - gap)
+    out["conservative_q2_loss"] = alpha_prime * (out["cons_raw_q2"] - gap)
+    out["alpha_prime_loss"] = (-out["conservative_q1_loss"] - out["conservative_q2_loss"]) * 0.5
+    out["q1_loss"] = out["bellman_q1_loss"] + out["conservative_q1_loss"]
+    out["q2_loss"] = out["bellman_q2_loss"] + out["conservative_q2_loss"]
+    return out
+
+
+def draw_cql_noise(B, action_dim=7, n=4, generator=None, device="cpu"):
+    """The reference's RNG draws for one flat CQL_Offline.training_step, in order:
+    rsample randn (B,A-1) -> RelaxedOneHotCategorical.rsample torch.rand (B,2) -> sample normal (B,A-1) ->
+    GumbelSoftmax.sample uniform_ (B,2) -> uniform_(-1,1) (n*B,A) -> [normal (n,B,A-1), uniform_ (n,B,2)] x 2."""
+    from torch.distributions.utils import _standard_normal
+    kw = dict(device=device)
+    C = action_dim - 1
+
+    def nrm(*shape):
+        return torch.empty(*shape, **kw).normal_(generator=generator)
+
+    def uni(*shape):
+        return torch.empty(*shape, **kw).uniform_(0, 1, generator=generator)
+
+    d = {}
+    if generator is None:
+        d["eps_actor"] = _standard_normal((B, C), dtype=torch.float32, device=torch.device(device))
+    else:
+        d["eps_actor"] = torch.randn(B, C, generator=generator, **kw)
+    d["u_actor"] = torch.rand(B, 2, generator=generator, **kw)
+    d["eps_next"] = nrm(B, C)
+    d["u_next"] = uni(B, 2)
+    d["rand_actions"] = torch.zeros(n * B, action_dim, **kw).uniform_(-1.0, 1.0, generator=generator)
+    d["eps_curr"] = nrm(n, B, C)
+    d["u_curr"] = uni(n, B, 2)
+    d["eps_nextn"] = nrm(n, B, C)
+    d["u_nextn"] = uni(n, B, 2)
+    return d
+
+
+CQL_NOISE_ORDER = ("eps_actor", "u_actor", "eps_next", "u_next", "rand_actions", "eps_curr", "u_curr", "eps_nextn",
+                   "u_nextn")
+
+
+def cql_training_step(P, opt, batch, noise, cfg=None, epoch=0):
+    """One flat CQL_Offline.training_step with optimisation in the reference's order (:470-542):
+    alpha Adam -> [losses with the NEW alpha, OLD alpha'] -> alpha' Adam -> actor clip+Adam -> q1 clip+Adam ->
+    q2 clip+Adam -> Polyak.  Same conventions as tacorl_training_step."""
+    cfg = cfg or {}
+    lrs = {"alpha": cfg.get("actor_lr", 1e-4), "actor": cfg.get("actor_lr", 1e-4),
+           "q1": cfg.get("critic_lr", 3e-4), "q2": cfg.get("critic_lr", 3e-4),
+           "alpha_prime": cfg.get("critic_lr", 3e-4)}
+    tau = cfg.get("tau", 0.005)
+    clip = cfg.get("clip_grad_val", 1.0)
+    groups = tacorl_param_groups(P)
+
+    def step(group, loss, do_clip=False):
+        ps = [P[k] for k in groups[group]]
+        gs = list(torch.autograd.grad(loss, ps, retain_graph=True, allow_unused=True))
+        gs = [torch.zeros_like(p) if g is None else g.clone() for p, g in zip(ps, gs)]
+        if do_clip:
+            clip_grad_norm(gs, clip)
+        with torch.no_grad():
+            adam_step(ps, gs, opt[group], lrs[group])
+        return gs
+
+    out = cql_losses(P, batch, noise, cfg, epoch)
+    logged = {"alpha_loss": out["alpha_loss"].detach().clone()}
+    grads = {"alpha": step("alpha", out["alpha_loss"])}
+    out = cql_losses(P, batch, noise, cfg, epoch)
+    for k in ("alpha", "actor_loss", "bellman_q1_loss", "bellman_q2_loss", "conservative_q1_loss",
+              "conservative_q2_loss", "q1_loss", "q2_loss", "alpha_prime", "alpha_prime_loss",
+              "q1_data", "q1_random", "q1_policy", "q2_data", "q2_random", "q2_policy"):
+        logged[k] = out[k].detach().clone()
+    grads["alpha_prime"] = step("alpha_prime", out["alpha_prime_loss"])
+    grads["actor"] = step("actor", out["actor_loss"], do_clip=cfg.get("clip_grad", True))
+    grads["q1"] = step("q1", out["q1_loss"], do_clip=cfg.get("clip_grad", True))
+    grads["q2"] = step("q2", out["q2_loss"], do_clip=cfg.get("clip_grad", True))
+    with torch.no_grad():
+        for q in ("q1", "q2"):
+            polyak_update([P["target_" + k] for k in groups[q]], [P[k] for k in groups[q]], tau)
+    return logged, grads
+
+
 def trainable_names(P):
     return [k for k, v in P.items() if v.dtype.is_floating_point and not _is_buffer(k)]
 

@@ -102,8 +102,9 @@ class TacorlLibraryError(RuntimeError):
 
 class MlpLayer(ctypes.Structure):
     """tacorl_mlp_layer (include/tacorl_b200.h)."""
-    _fields_ = [("W0", _vp), ("b0", _vp), ("n0", _i), ("W1", _vp), ("b1", _vp), ("n1", _i), ("in_", _i), ("act", _i),
-                ("dW0", _vp), ("db0", _vp), ("dW1", _vp), ("db1", _vp)]
+    _fields_ = [("W0", _vp), ("b0", _vp), ("n0", _i), ("W1", _vp), ("b1", _vp), ("n1", _i),
+                ("W2", _vp), ("b2", _vp), ("n2", _i), ("in_", _i), ("act", _i),
+                ("dW0", _vp), ("db0", _vp), ("dW1", _vp), ("db1", _vp), ("dW2", _vp), ("db2", _vp)]
 
 
 def lib():

@@ -31,11 +31,13 @@ constexpr int MC_PAD = 4;
 constexpr int MC_LD = MC_MAXW + MC_PAD;
 constexpr int MC_MAXL = 4;
 
+constexpr int MC_SEGS = 3;
 struct McLayer {
-  const float* W[2]; const float* b[2];   // up to two weight segments stacked along the output dim (fc_mean | fc_log_std)
-  int n[2];                               // output rows of each segment (n[1] may be 0)
+  const float* W[MC_SEGS]; const float* b[MC_SEGS];   // up to three weight segments stacked along the output dim
+                                                      // (fc_mean | fc_log_std | gripper_action)
+  int n[MC_SEGS];                         // output rows of each segment (n[1], n[2] may be 0)
   int in, out, act;                       // act applied to this layer's output (ACT_NONE for the last layer)
-  float* dW[2]; float* db[2];             // backward outputs (may be null: gradient w.r.t. the input only)
+  float* dW[MC_SEGS]; float* db[MC_SEGS]; // backward outputs (may be null: gradient w.r.t. the input only)
   long long part_off;                     // offset of this layer's [out][in + 1] block inside one partial slab
 };
 struct McChain {
@@ -65,8 +67,17 @@ __device__ __forceinline__ void mc_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// output row n of a layer -> (segment, row inside the segment)
+__device__ __forceinline__ int mc_seg(const McLayer& l, int n, int& nn) {
+  if (n < l.n[0]) { nn = n; return 0; }
+  if (n < l.n[0] + l.n[1]) { nn = n - l.n[0]; return 1; }
+  nn = n - l.n[0] - l.n[1];
+  return 2;
+}
 __device__ __forceinline__ const float* mc_wrow(const McLayer& l, int n) {
-  return n < l.n[0] ? l.W[0] + (long long)n * l.in : l.W[1] + (long long)(n - l.n[0]) * l.in;
+  int nn;
+  const int sg = mc_seg(l, n, nn);
+  return l.W[sg] + (long long)nn * l.in;
 }
 
 // Tile loader: dst[r][4*q .. 4*q+3] = src(r, q) for r < nrows, q < ncols4, with MC_UN independent 16-byte loads in flight
@@ -177,7 +188,9 @@ __global__ void __launch_bounds__(MC_THREADS, 2) mlp_chain_fwd_kernel(const __gr
         acc1 = fmaf(a1.x, w.x, acc1); acc1 = fmaf(a1.y, w.y, acc1); acc1 = fmaf(a1.z, w.z, acc1); acc1 = fmaf(a1.w, w.w, acc1);
       }
       const int n = n0 + j;
-      const float bias = n < l.n[0] ? (l.b[0] ? l.b[0][n] : 0.f) : (l.b[1] ? l.b[1][n - l.n[0]] : 0.f);
+      int bn;
+      const int bsg = mc_seg(l, n, bn);
+      const float bias = l.b[bsg] ? l.b[bsg][bn] : 0.f;
       const float z[2] = {acc0 + bias, acc1 + bias};
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
@@ -298,8 +311,7 @@ __global__ void __launch_bounds__(MC_THREADS, 2) mlp_chain_bwd_kernel(const __gr
             const int n = n0 + nb + q;
             if (nb + q < nc) {
               if (c.part) c.part[(long long)rb * c.part_stride + l.part_off + (long long)n * (l.in + 1) + k] = acc[q];
-              else if (n < l.n[0]) l.dW[0][(long long)n * l.in + k] = acc[q];
-              else l.dW[1][(long long)(n - l.n[0]) * l.in + k] = acc[q];
+              else { int nn; const int sg = mc_seg(l, n, nn); l.dW[sg][(long long)nn * l.in + k] = acc[q]; }
             }
           }
         }
@@ -309,8 +321,7 @@ __global__ void __launch_bounds__(MC_THREADS, 2) mlp_chain_bwd_kernel(const __gr
         float s = 0.f;
         for (int r = 0; r < MC_ROWS; ++r) s += Ds[r * MC_LD + n];
         if (c.part) c.part[(long long)rb * c.part_stride + l.part_off + (long long)n * (l.in + 1) + l.in] = s;
-        else if (n < l.n[0]) { if (l.db[0]) l.db[0][n] = s; }
-        else if (l.db[1]) l.db[1][n - l.n[0]] = s;
+        else { int nn; const int sg = mc_seg(l, n, nn); if (l.db[sg]) l.db[sg][nn] = s; }
       }
     }
     // ---- dX for my slice of input columns: dX[r][k] = sum_n dZ[r][n] W[n][k]; thread = (column j, rows 2g, 2g+1)
@@ -354,7 +365,8 @@ __global__ void mlp_chain_reduce_kernel(const McChain c, int row_blocks) {
       float s = 0.f;
       for (int rb = 0; rb < row_blocks; ++rb) s += c.part[(long long)rb * c.part_stride + l.part_off + i];
       const int n = (int)(i / (l.in + 1)), k = (int)(i - (long long)n * (l.in + 1));
-      const int seg = n < l.n[0] ? 0 : 1, nn = seg ? n - l.n[0] : n;
+      int nn;
+      const int seg = mc_seg(l, n, nn);
       if (k < l.in) l.dW[seg][(long long)nn * l.in + k] = s;
       else if (l.db[seg]) l.db[seg][nn] = s;
     }
@@ -368,9 +380,10 @@ static int mc_check(const McChain& c, bool bwd) {
   for (int i = 0; i < c.L; ++i) {
     const McLayer& l = c.layer[i];
     TACORL_REQUIRE(l.in == in, "mlp_chain: layer %d expects %d inputs, gets %d", i, l.in, in);
-    TACORL_REQUIRE(l.in % 4 == 0 && l.in <= MC_MAXW && l.out >= 1 && l.out <= MC_MAXW && l.n[0] + l.n[1] == l.out,
+    TACORL_REQUIRE(l.in % 4 == 0 && l.in <= MC_MAXW && l.out >= 1 && l.out <= MC_MAXW && l.n[0] + l.n[1] + l.n[2] == l.out,
                    "mlp_chain: layer %d has unsupported dims (in %d, out %d)", i, l.in, l.out);
-    TACORL_REQUIRE(l.W[0] && (l.n[1] == 0 || l.W[1]), "mlp_chain: null weight pointer in layer %d", i);
+    TACORL_REQUIRE(l.W[0] && (l.n[1] == 0 || l.W[1]) && (l.n[2] == 0 || l.W[2]), "mlp_chain: null weight pointer in layer %d", i);
+    TACORL_REQUIRE(l.n[1] > 0 || l.n[2] == 0, "mlp_chain: layer %d uses segment 2 without segment 1", i);
     TACORL_REQUIRE(i == c.L - 1 || l.out % 4 == 0, "mlp_chain: hidden width %d must be a multiple of 4", l.out);
     in = l.out;
   }
@@ -411,9 +424,10 @@ static int mc_build(McChain& c, int L, int rows, const tacorl_mlp_layer* layers,
   for (int i = 0; i < L; ++i) {
     McLayer& l = c.layer[i];
     const tacorl_mlp_layer& s = layers[i];
-    l.W[0] = s.W0; l.W[1] = s.W1; l.b[0] = s.b0; l.b[1] = s.b1; l.n[0] = s.n0; l.n[1] = s.n1;
-    l.in = s.in; l.out = s.n0 + s.n1; l.act = i == L - 1 ? ACT_NONE : s.act;
-    l.dW[0] = s.dW0; l.dW[1] = s.dW1; l.db[0] = s.db0; l.db[1] = s.db1;
+    l.W[0] = s.W0; l.W[1] = s.W1; l.W[2] = s.W2; l.b[0] = s.b0; l.b[1] = s.b1; l.b[2] = s.b2;
+    l.n[0] = s.n0; l.n[1] = s.n1; l.n[2] = s.n2;
+    l.in = s.in; l.out = s.n0 + s.n1 + s.n2; l.act = i == L - 1 ? ACT_NONE : s.act;
+    l.dW[0] = s.dW0; l.dW[1] = s.dW1; l.dW[2] = s.dW2; l.db[0] = s.db0; l.db[1] = s.db1; l.db[2] = s.db2;
     l.part_off = poff; poff += (long long)l.out * (l.in + 1);
     c.zoff[i] = zoff; if (i < L - 1) zoff += l.out;
   }
@@ -426,7 +440,7 @@ static int mc_build(McChain& c, int L, int rows, const tacorl_mlp_layer* layers,
 
 size_t tacorl_mlp_chain_ws_bytes(int L, int rows, const tacorl_mlp_layer* layers) {
   size_t slab = 0;
-  for (int i = 0; i < L; ++i) slab += (size_t)(layers[i].n0 + layers[i].n1) * (layers[i].in + 1);
+  for (int i = 0; i < L; ++i) slab += (size_t)(layers[i].n0 + layers[i].n1 + layers[i].n2) * (layers[i].in + 1);
   const size_t rb = (size_t)cdiv(rows, MC_ROWS);
   return 2 * (size_t)rows * MC_MAXW * 4 + (rb > 1 ? rb * slab * 4 : 0) + 1024;
 }

@@ -216,7 +216,7 @@ def _dp(t):
 
 class MlpChainFn(Function):
     """Linear -> act -> ... -> Linear in one launch each way (tacorl_mlp_chain_{fwd,bwd}).
-    spec = (acts, segs): acts[l] for the hidden layers; segs[l] = number of (W, b) pairs stacked in layer l (1 or 2).
+    spec = (acts, segs): acts[l] for the hidden layers; segs[l] = number of (W, b) pairs stacked in layer l (1..3).
     params: per layer, per segment: W, b."""
 
     @staticmethod
@@ -226,18 +226,14 @@ class MlpChainFn(Function):
         i, width = 0, in0
         for l, ns in enumerate(segs):
             e = arr[l]
-            W0, b0 = params[i], params[i + 1]
-            e.W0, e.b0, e.n0 = _dp(W0), _dp(b0), W0.shape[0]
-            if grads is not None:
-                e.dW0, e.db0 = _dp(grads[i]), _dp(grads[i + 1])
-            if ns == 2:
-                W1, b1 = params[i + 2], params[i + 3]
-                e.W1, e.b1, e.n1 = _dp(W1), _dp(b1), W1.shape[0]
+            for sg in range(ns):
+                W, b = params[i + 2 * sg], params[i + 2 * sg + 1]
+                setattr(e, f"W{sg}", _dp(W)); setattr(e, f"b{sg}", _dp(b)); setattr(e, f"n{sg}", W.shape[0])
                 if grads is not None:
-                    e.dW1, e.db1 = _dp(grads[i + 2]), _dp(grads[i + 3])
+                    setattr(e, f"dW{sg}", _dp(grads[i + 2 * sg])); setattr(e, f"db{sg}", _dp(grads[i + 2 * sg + 1]))
             e.in_ = width
             e.act = acts[l] if l < len(acts) else L.ACT_NONE
-            width = e.n0 + e.n1
+            width = e.n0 + e.n1 + e.n2
             i += 2 * ns
         return arr, width
 
@@ -251,7 +247,7 @@ class MlpChainFn(Function):
         in0 = x0.shape[1] + (x1.shape[1] if x1 is not None else 0)
         arr, out_w = MlpChainFn._layers(spec, params, in0)
         nl = len(spec[1])
-        zw = sum(arr[l].n0 + arr[l].n1 for l in range(nl - 1))
+        zw = sum(arr[l].n0 + arr[l].n1 + arr[l].n2 for l in range(nl - 1))
         z = torch.empty(rows, max(zw, 1), device=x0.device, dtype=torch.float32)
         out = torch.empty(rows, out_w, device=x0.device, dtype=torch.float32)
         L.call("tacorl_mlp_chain_fwd", nl, rows, ctypes.byref(arr), L.ptr(x0), x0.shape[1], x0.shape[1],
@@ -288,7 +284,7 @@ class MlpChainFn(Function):
 
 def mlp_chain(xs, layers, acts):
     """y = Linear_L(... act_1(Linear_1(cat(xs))) ...) in one fused launch (fp32; tacorl_mlp_chain_fwd/bwd).
-    xs: one tensor or a pair concatenated along the last dim; layers: per layer a (W, b) pair or a list of two pairs
+    xs: one tensor or a pair concatenated along the last dim; layers: per layer a (W, b) pair or a list of up to three pairs
     stacked along the output dim; acts: activation names of the hidden layers (len(layers) - 1 entries).
     Shapes outside the kernel's range (widths > 256 or not multiples of 4, > 4 layers, > 256 rows) run layer by layer."""
     xs = list(xs) if isinstance(xs, (list, tuple)) else [xs]
@@ -296,7 +292,7 @@ def mlp_chain(xs, layers, acts):
     acts_i = tuple(L.ACTS[a] if not isinstance(a, int) else a for a in acts)
     in0 = sum(x.shape[-1] for x in xs)
     widths = [in0] + [sum(W.shape[0] for W, _ in sg) for sg in segs]
-    ok = (len(segs) <= 4 and len(xs) <= 2 and all(len(sg) <= 2 for sg in segs) and xs[0].is_cuda
+    ok = (len(segs) <= 4 and len(xs) <= 2 and all(len(sg) <= 3 for sg in segs) and xs[0].is_cuda
           and all(w % 4 == 0 and w <= 256 for w in widths[:-1]) and widths[-1] <= 256
           and all(x.dtype == torch.float32 for x in xs) and xs[0].numel() // xs[0].shape[-1] <= 256)
     if not ok:

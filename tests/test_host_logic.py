@@ -23,7 +23,7 @@ def test_shared_library_exports_every_declared_symbol():
     missing = [n for n in declared if not hasattr(L, n)]
     assert not missing, missing
     assert declared == set(_lib.EXPORTED), declared ^ set(_lib.EXPORTED)
-    assert _lib.lib().tacorl_abi_version() == 6
+    assert _lib.lib().tacorl_abi_version() == 7
     assert _lib.launch_count() == 0          # nothing may have launched on a CPU-only box
 
 

@@ -81,6 +81,26 @@ def test_tacorl_steps_match_reference(name):
             _check_fp(f"{name}/step{s}/param/{k}", P[k], fp)
 
 
+@pytest.mark.parametrize("name", ["cql_flat_bc", "cql_flat_q"])
+def test_flat_cql_steps_match_reference(name):
+    """the flat-CQL baseline (discrete-gripper actor, entropy-regularised backup)."""
+    rec = _load(name)
+    P = O.params_from(S.synth_state_dict(rec["shapes"], rec["seed"]))
+    batch = S.synth_cql_batch(rec["B"], rec["H"], rec["W"], rec["seed"])
+    opt = O.new_tacorl_opt_state(P)
+    cfg = {"target_entropy": rec["target_entropy"], "deterministic_backup": rec["deterministic_backup"]}
+    keys = ["alpha", "alpha_loss", "actor_loss", "q1_loss", "q2_loss", "bellman_q1_loss", "bellman_q2_loss",
+            "conservative_q1_loss", "conservative_q2_loss", "alpha_prime", "alpha_prime_loss", "q1_data", "q1_random",
+            "q1_policy", "q2_data", "q2_random", "q2_policy"]
+    for s, step in enumerate(rec["steps"]):
+        torch.manual_seed(rec["noise_seed_base"] + s)
+        noise = O.draw_cql_noise(rec["B"])
+        logged, _ = O.cql_training_step(P, opt, S.clone_batch(batch), noise, cfg, rec["epoch"])
+        _check_scalars(logged, step["scalars"], keys)
+        for k, fp in step["params"].items():
+            _check_fp(f"{name}/step{s}/param/{k}", P[k], fp)
+
+
 def test_encoder_shapes_match_reference():
     rec = _load("encoder_shapes")
     sd = S.synth_state_dict(rec["shapes"], rec["seed"])
