@@ -183,6 +183,16 @@ int tacorl_softplus_head_fwd(int rows, int L, const float* raw, float min_std, f
                              void* stream);
 int tacorl_softplus_head_bwd(int rows, int L, const float* raw, const float* dmean, const float* dstd,
                              float* draw, void* stream);
+/* ---- discrete open/close gripper head of the flat-CQL baseline: GumbelSoftmax of utils/distributions.py:15-58 as used
+ * by Actor.get_actions / sample_n_with_log_prob / log_prob (actor.py:66-156).  logits: (rows0, 2); u: (rows, 2) uniforms
+ * (row r reads logits row r % rows0: the n sampled copies of sample_n share the logits); index: class id 0 / 1 as float,
+ * action = 2 * index - 1.  clamp_u = 1: the rsample path (torch clamp_probs), 0: GumbelSoftmax.sample. */
+int tacorl_gripper_gumbel(int rows, int rows0, const float* logits, const float* u, int clamp_u, float* index,
+                          float* action, void* stream);
+/* logp[r] = log_softmax(logits[r % rows0])[index[r]]  (GumbelSoftmax.log_prob of a class index, :50-58) */
+int tacorl_gripper_logprob(int rows, int rows0, const float* logits, const float* index, float* logp, void* stream);
+int tacorl_gripper_logprob_bwd(int rows, const float* logits, const float* index, const float* dlogp, float* dlogits,
+                               void* stream);
 /* balanced KL of the underlying Normals, play_lmp_for_rl.py:259-285; grads are d kl / d(.) */
 int tacorl_kl_balanced(int B, int L, const float* mu_q, const float* sd_q, const float* mu_p,
                        const float* sd_p, float kl_alpha, int balancing, float* kl_out, float* dmu_q,

@@ -53,6 +53,9 @@ _SIGS = {
     "tacorl_tanh_rsample_fwd": [_ll, _ll, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "tacorl_tanh_rsample_bwd": [_ll, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
     "tacorl_tanh_logprob": [_i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp],
+    "tacorl_gripper_gumbel": [_i, _i, _vp, _vp, _i, _vp, _vp, _vp],
+    "tacorl_gripper_logprob": [_i, _i, _vp, _vp, _vp, _vp],
+    "tacorl_gripper_logprob_bwd": [_i, _vp, _vp, _vp, _vp, _vp],
     "tacorl_posemb_fwd": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "tacorl_posemb_bwd": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "tacorl_attn_fwd": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],

@@ -82,3 +82,21 @@ def tacorl(play_lmp_dir="~/tacorl/models/play_lmp"):
             "discount": 0.95, "conservative_weight": 1.0, "reward_scale": 10.0, "n_action_samples": 4,
             "with_lagrange": True, "deterministic_backup": True, "bc_epochs": 5, "with_dr3": False,
             "with_vib": False, "real_world": True}
+
+
+def actor_discrete_gripper():                                     # networks/actor_critic/actor/discrete_gripper.yaml
+    cfg = actor()
+    cfg["discrete_gripper"] = True
+    cfg["policy"]["discrete_gripper"] = True
+    return cfg
+
+
+def cql_offline_goal_cond(obs_modalities=("rgb_static",), goal_modalities=("rgb_static",)):
+    """config/module/cql_offline_goal_cond.yaml + experiment/cql_real_world.yaml: the flat-CQL baseline."""
+    return {"_target_": "tacorl_b200.modules.cql.cql_offline_lightning.CQL_Offline", "_recursive_": False,
+            "actor": actor_discrete_gripper(), "critic": critic(), "actor_encoder": lmp_encoder(),
+            "critic_encoder": lmp_encoder(), "goal_encoder": goal_encoder(), "discount": 0.99, "actor_lr": 1e-4,
+            "critic_lr": 3e-4, "conservative_weight": 1.0, "n_action_samples": 4, "with_lagrange": True,
+            "reward_scale": 10.0, "deterministic_backup": False, "bc_epochs": 5, "with_dr3": False, "with_vib": False,
+            "real_world": True, "obs_modalities": list(obs_modalities), "goal_modalities": list(goal_modalities),
+            "action_dim": 7}

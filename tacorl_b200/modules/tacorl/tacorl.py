@@ -1,38 +1,28 @@
-"""Mirror of TACORL(CQL_Offline): /root/reference/src/tacorl/modules/tacorl/tacorl.py:21-300 and
-modules/cql/cql_offline_lightning.py:24-574 (the parts config/module/tacorl.yaml exercises:
-offline CQL with Lagrange, deterministic backup, BC warm-up epochs; DR3 / VIB are off).
+"""Mirror of TACORL(CQL_Offline): /root/reference/src/tacorl/modules/tacorl/tacorl.py:21-300 on top of
+modules/cql/cql_offline_lightning.py (config/module/tacorl.yaml: offline CQL over latent plans with Lagrange,
+deterministic backup, BC warm-up epochs; DR3 / VIB are off).
 
 Same ctor kwargs, same `training_step(batch)` contract (manual optimisation, returns None, steps its own
-optimisers in the reference's order), same state_dict layout.  The update is
-restructured for the device (SURVEY.md §0 finding 7-i, Appendix E):
-  * each (network, image) pair is encoded ONCE and the 32-float embedding is repeated over the
-    n_action_samples copies, instead of pushing 4 identical image copies through the encoder;
-  * gradients the reference computes and then throws away (q-network weights from the actor loss,
-    log_alpha / log_alpha_prime deposits) are never computed;
-  * every scalar loss (Bellman, conservative logsumexp, Lagrange, actor, alpha) comes out of two fused
-    kernels, value and gradient in one pass; log values stay on the device (no host sync per metric).
+optimisers in the reference's order), same state_dict layout.  The CQL update itself
+(`compute_update`, restructured for the device) is inherited from tacorl_b200.modules.cql.cql_offline_lightning.
 """
 import copy
-import math
 from pathlib import Path
 from typing import List
 
 import torch
 import torch.nn as nn
 
-from ... import ops
 from ...networks.actor_critic.visual_actor_wrapper import VisualActorWrapper
 from ...networks.actor_critic.visual_critic_wrapper import VisualCriticWrapper
-from ...optim import FlatAdam, FlatBuffer, polyak_update
-from ...utils import rng
+from ...optim import FlatAdam
 from ...utils.config import instantiate, to_container
-from ...utils.distributions import TanhNormal
-from ...utils.lightning import LightningModule
 from ...utils.misc import set_parameter_requires_grad
 from ...utils.networks import load_pl_module_from_checkpoint
+from ..cql.cql_offline_lightning import CQL_Offline
 
 
-class TACORL(LightningModule):
+class TACORL(CQL_Offline):
     def __init__(self, play_lmp_dir: str = "~/tacorl/models/play_lmp", lmp_epoch_to_load: int = -1,
                  overwrite_lmp_cfg: dict = {}, finetune_action_decoder: bool = False,
                  action_decoder_lr: float = 1e-4,
@@ -47,44 +37,25 @@ class TACORL(LightningModule):
                  with_vib: bool = False, vib_coefficient: float = 0.01, real_world: bool = False,
                  obs_modalities: List[str] = [], goal_modalities: List[str] = [], action_dim: int = 7,
                  play_lmp: nn.Module = None, *args, **kwargs):
-        super().__init__()
-        if with_dr3 or with_vib:
-            raise NotImplementedError("DR3 / VIB regularisers are disabled in config/module/tacorl.yaml")
-        if not deterministic_backup:
-            raise NotImplementedError("config/module/tacorl.yaml uses deterministic_backup: True")
-        self.play_lmp_dir = Path(play_lmp_dir).expanduser()
-        self.lmp_epoch_to_load = lmp_epoch_to_load
-        self.overwrite_lmp_cfg = overwrite_lmp_cfg
-        self._play_lmp_module = play_lmp
-        self.finetune_action_decoder = finetune_action_decoder
-        self.action_decoder_lr = action_decoder_lr
-        self.real_world = real_world
-        self.env = None
-        self.transform_manager = instantiate(transform_manager) if transform_manager else None
-        self.deterministic_backup = deterministic_backup
-        self.actor_lr, self.critic_lr = actor_lr, critic_lr
-        self.critic_cfg, self.critic_encoder_cfg = critic, critic_encoder
-        self.discount, self.reward_scale, self.tau = discount, reward_scale, tau
-        self.bc_epochs = bc_epochs
-        self.clip_grad, self.clip_grad_val = clip_grad, clip_grad_val
-        self.action_dim = action_dim
-        self.build_networks()
-        # heuristic target entropy from the LOW-LEVEL action dim (cql_offline_lightning.py:93-98; Appendix E.11)
-        self.target_entropy = -float(action_dim)
-        self.log_alpha = nn.Parameter(torch.zeros(1), requires_grad=True)
-        self.conservative_weight = conservative_weight
-        self.n_action_samples = n_action_samples
-        self.temp = temp
-        self.with_lagrange = with_lagrange
-        if with_lagrange:
-            self.target_action_gap = lagrange_thresh
-            self.log_alpha_prime = nn.Parameter(torch.zeros(1), requires_grad=True)
-        self.automatic_optimization = False
-        self._target_bufs = None
-        self.save_hyperparameters()
+        self._pre_init = dict(play_lmp_dir=Path(play_lmp_dir).expanduser(), lmp_epoch_to_load=lmp_epoch_to_load,
+                              overwrite_lmp_cfg=overwrite_lmp_cfg, _play_lmp_module=play_lmp,
+                              finetune_action_decoder=finetune_action_decoder, action_decoder_lr=action_decoder_lr)
+        super().__init__(env=env, actor=actor, critic=critic, actor_encoder=actor_encoder, critic_encoder=critic_encoder,
+                         goal_encoder=goal_encoder, transform_manager=transform_manager, discount=discount, tau=tau,
+                         actor_lr=actor_lr, critic_lr=critic_lr, deterministic_backup=deterministic_backup,
+                         reward_scale=reward_scale, bc_epochs=bc_epochs, clip_grad=clip_grad, clip_grad_val=clip_grad_val,
+                         conservative_weight=conservative_weight, lagrange_thresh=lagrange_thresh,
+                         n_action_samples=n_action_samples, temp=temp, with_lagrange=with_lagrange, with_dr3=with_dr3,
+                         dr3_coefficient=dr3_coefficient, with_vib=with_vib, vib_coefficient=vib_coefficient,
+                         real_world=real_world, obs_modalities=obs_modalities, goal_modalities=goal_modalities,
+                         action_dim=action_dim)
 
     # ------------------------------------------------------------------------------ build (tacorl.py:44-126)
     def build_networks(self):
+        # (the TACO-RL fields are set here: CQL_Offline.__init__ calls build_networks, and attributes cannot be
+        # assigned on an nn.Module before its own __init__ ran)
+        for k, v in self.__dict__.pop("_pre_init").items():
+            setattr(self, k, v)
         play_lmp = self._play_lmp_module
         if play_lmp is None:
             play_lmp = load_pl_module_from_checkpoint(self.play_lmp_dir, epoch=self.lmp_epoch_to_load,
@@ -129,23 +100,11 @@ class TACORL(LightningModule):
 
     # ------------------------------------------------------------------------------ optimisers
     def configure_optimizers(self):                              # cql…py:553-574 + tacorl.py:289-300
-        clip = float(self.clip_grad_val) if self.clip_grad else None
-        req = lambda mod: [p for p in mod.parameters() if p.requires_grad]
-        opts = [FlatAdam([self.log_alpha], lr=self.actor_lr),
-                FlatAdam(req(self.actor), lr=self.actor_lr, max_grad_norm=clip),
-                FlatAdam(req(self.q1), lr=self.critic_lr, max_grad_norm=clip),
-                FlatAdam(req(self.q2), lr=self.critic_lr, max_grad_norm=clip)]
-        if self.with_lagrange:
-            opts.append(FlatAdam([self.log_alpha_prime], lr=self.critic_lr))
+        opts = super().configure_optimizers()
         if self.finetune_action_decoder:
-            opts.append(FlatAdam(req(self.action_decoder), lr=self.action_decoder_lr))
-        # Polyak pairs target.parameters() with source.parameters() by order (:229-232): same flat layout
-        self._target_bufs = (FlatBuffer(list(self.target_q1.parameters())), FlatBuffer(list(self.target_q2.parameters())))
+            opts.append(FlatAdam([p for p in self.action_decoder.parameters() if p.requires_grad],
+                                 lr=self.action_decoder_lr))
         return opts
-
-    @staticmethod
-    def soft_update_from_to(source_flat, target_buf, tau):
-        polyak_update(target_buf, source_flat, tau)
 
     # ------------------------------------------------------------------------------ frozen LMP (tacorl.py:128-252)
     def get_emb_states(self, states, modalities: List[str] = []):
@@ -192,136 +151,6 @@ class TACORL(LightningModule):
                 action_loss = self.action_decoder.loss(latent_plan=latent_plan, perceptual_emb=ad_states[:, :-1],
                                                        actions=actions[:, :-1])
         self.log(f"{log_type}/action_loss", action_loss, on_step=True, on_epoch=True, sync_dist=True)
-
-    # ------------------------------------------------------------------------------ CQL update
-    def _emb(self, wrapper, obs_img, goal_img, goal_emb=None):
-        """Visual*Wrapper.get_emb_representation with the goal embedding optionally re-used.  Observation and goal
-        frames of a view go through that view's encoder as ONE batch (same weights, independent frames: identical
-        values; half the kernel launches of these small 64-frame passes, one weight-gradient pass instead of two)."""
-        enc = wrapper.encoder
-        if goal_emb is not None:
-            return torch.cat([enc.get_state_from_observation(obs_img, modalities=wrapper.env_modalities), goal_emb], dim=-1), goal_emb
-        B = next(iter(obs_img.values())).shape[0]
-        parts = {}
-        for m in dict.fromkeys(list(wrapper.env_modalities) + list(wrapper.goal_modalities)):
-            srcs = ([obs_img[m]] if m in wrapper.env_modalities else []) + ([goal_img[m]] if m in wrapper.goal_modalities else [])
-            if len(srcs) == 2 and srcs[0].shape == srcs[1].shape and srcs[0].dtype == srcs[1].dtype:
-                out = enc.networks[m](self._stack_frames(srcs))
-                parts[(m, "obs")], parts[(m, "goal")] = out[:B], out[B:]
-            else:
-                if m in wrapper.env_modalities:
-                    parts[(m, "obs")] = enc.networks[m](obs_img[m])
-                if m in wrapper.goal_modalities:
-                    parts[(m, "goal")] = enc.networks[m](goal_img[m])
-        cat = lambda ts: ts[0] if len(ts) == 1 else torch.cat(ts, dim=-1)
-        e = cat([parts[(m, "obs")] for m in wrapper.env_modalities])
-        g = cat([parts[(m, "goal")] for m in wrapper.goal_modalities])
-        goal_emb = wrapper.goal_encoder(g) if wrapper.goal_encoder is not None else g
-        return torch.cat([e, goal_emb], dim=-1), goal_emb
-
-    @staticmethod
-    def _stack_frames(srcs):
-        """cat along the batch dim.  uint8 frames are copied through an int32 view: torch's byte-wise cat / strided copy
-        kernels run at 0.2-0.4 TB/s (78 us per 15 MB pair of 64-frame batches, measured), 4-byte elements at > 2 TB/s."""
-        n = sum(t.shape[0] for t in srcs)
-        out = torch.empty((n,) + tuple(srcs[0].shape[1:]), device=srcs[0].device, dtype=srcs[0].dtype)
-        wide = srcs[0].dtype == torch.uint8 and srcs[0].shape[-1] % 4 == 0
-        o = 0
-        for t in srcs:
-            dst = out[o:o + t.shape[0]]
-            if wide and t.stride(-1) == 1 and all(st % 4 == 0 for st in t.stride()[:-1]) and t.storage_offset() % 4 == 0:
-                dst.view(torch.int32).copy_(t.view(torch.int32))
-            else:
-                dst.copy_(t)
-            o += t.shape[0]
-        return out
-
-    @staticmethod
-    def _q_mlp(qnet, emb, action, detach_params=False):
-        """MLPQNetwork.forward on cat(emb, action) (critic.py:24-30, 92-97), one fused launch each way;
-        detach_params: gradient w.r.t. the input only."""
-        return qnet((emb, action), detach_params=detach_params)
-
-    def compute_update(self, batch, optimize: bool = True, log_type: str = "train"):
-        states, plan, next_states, rewards, dones = batch
-        obs, goal, nxt = states["observation"], states["goal"], next_states["observation"]
-        opts = self.optimizers()
-        alpha_opt, actor_opt, q1_opt, q2_opt = opts[:4]
-        n = self.n_action_samples
-        B, Ld = plan.shape
-        log = lambda k, v: self.log(f"{log_type}/{k}", v, on_step=True)
-
-        # ---- actor forward + alpha (cql…py:439-457)
-        a_in, a_goal = self._emb(self.actor, obs, goal)
-        mean, std = self.actor.actor(a_in)
-        dist_a = TanhNormal(mean, std)
-        curr_actions, z = dist_a.rsample_with_pretanh()
-        curr_log_pi = dist_a.log_prob(curr_actions, z)
-        alpha_loss, d_log_alpha = ops.cql_alpha_loss(curr_log_pi, self.log_alpha, self.target_entropy)
-        if optimize:
-            alpha_opt.set_grad(d_log_alpha)
-            alpha_opt.step(gathered=True)        # alpha is stepped BEFORE it is read for the actor loss (:451-456)
-
-        # ---- critic embeddings: one encoder pass per (network, image)
-        q1_e, _ = self._emb(self.q1, obs, goal)
-        q2_e, _ = self._emb(self.q2, obs, goal)
-
-        # ---- actor loss (:459-466)
-        if self.current_epoch < self.bc_epochs:
-            plp = dist_a.log_prob(value=plan)
-            actor_loss, aout = ops.CqlActorLossFn.apply(1, curr_log_pi, plp, None, self.log_alpha)
-        else:
-            qa1 = self._q_mlp(self.q1.critic.Q, q1_e.detach(), curr_actions, True)
-            qa2 = self._q_mlp(self.q2.critic.Q, q2_e.detach(), curr_actions, True)
-            actor_loss, aout = ops.CqlActorLossFn.apply(2, curr_log_pi, qa1, qa2, self.log_alpha)
-        log("alpha", aout[1])
-
-        # ---- Bellman target (:284-308), no grad
-        with torch.no_grad():
-            an_in, _ = self._emb(self.actor, nxt, goal, goal_emb=a_goal.detach())
-            mean_n, std_n = self.actor.actor(an_in)
-            next_actions, _ = TanhNormal(mean_n, std_n).sample_and_logprob()
-            t1_e, _ = self._emb(self.target_q1, nxt, goal)
-            t2_e, _ = self._emb(self.target_q2, nxt, goal)
-            tq1 = self._q_mlp(self.target_q1.critic.Q, t1_e, next_actions)
-            tq2 = self._q_mlp(self.target_q2.critic.Q, t2_e, next_actions)
-            # ---- sampled actions for the conservative term (:238-282); draw order = reference's
-            rand_actions = rng.uniform((n * B, Ld), -1.0, 1.0, plan.device)
-            ac, zc = TanhNormal(mean.detach(), std.detach()).sample_n(n, return_pre_tanh_value=True)
-            lp_curr = ops.tanh_logprob(mean.detach(), std.detach(), zc, False)
-            an, zn = TanhNormal(mean_n, std_n).sample_n(n, return_pre_tanh_value=True)
-            lp_next = ops.tanh_logprob(mean_n, std_n, zn, False)
-            acts_all = torch.cat([plan, rand_actions, ac.reshape(n * B, Ld), an.reshape(n * B, Ld)], dim=0)
-        reps = 1 + 3 * n
-        q1_all = self._q_mlp(self.q1.critic.Q, q1_e.repeat(reps, 1), acts_all)
-        q2_all = self._q_mlp(self.q2.critic.Q, q2_e.repeat(reps, 1), acts_all)
-        rand_density = math.log(0.5 ** Ld)
-        q1_loss, q2_loss, scal, d_lap = ops.CqlCriticLossFn.apply(
-            q1_all, q2_all, lp_curr, lp_next, tq1, tq2, rewards * 1.0, dones * 1.0,
-            self.log_alpha_prime if self.with_lagrange else None, n, rand_density, self.discount, self.reward_scale,
-            self.target_action_gap if self.with_lagrange else 0.0, self.conservative_weight, self.temp,
-            self.with_lagrange)
-        for i, k in enumerate(ops.CQL_SCALARS):
-            if self.with_lagrange or k not in ("alpha_prime", "alpha_prime_loss"):
-                log(k, scal[i])
-        log("actor_loss", actor_loss)
-        log("alpha_loss", alpha_loss[0])
-
-        if not optimize:
-            return
-        if self.with_lagrange:                   # alpha' steps from alpha_prime_loss alone (:400-404)
-            opts[4].set_grad(d_lap)
-            opts[4].step(gathered=True)
-        for o in (actor_opt, q1_opt, q2_opt):
-            o.zero_grad(set_to_none=True)
-        # actor, q1, q2 parameter sets are disjoint and every loss was built from pre-step values, so one
-        # backward pass yields the three gradients the reference obtains from three retained passes (:519-538)
-        torch.autograd.backward([actor_loss, q1_loss, q2_loss])
-        actor_opt.step()
-        q1_opt.step()
-        q2_opt.step()
-        self.soft_update_from_to(q1_opt.flat_params, self._target_bufs[0], self.tau)    # :541-542
-        self.soft_update_from_to(q2_opt.flat_params, self._target_bufs[1], self.tau)
 
     def training_step(self, batch, batch_idx=0):                 # tacorl.py:254-273
         latent_plan, emb_states = self.get_pr_latent_plan(batch, return_emb_states=True)

@@ -828,6 +828,45 @@ def tanh_logprob(mu, sd, z, from_value=False):
     return TanhLogProbFn.apply(mu, sd, z, from_value)
 
 
+# --------------------------------------------------------------------------------------- discrete gripper head
+def gripper_gumbel(logits, u, clamp):
+    """Class index (0 / 1, float, shape u.shape[:-1] + (1,)) drawn by GumbelSoftmax(logits) from the uniforms u
+    (tacorl_gripper_gumbel; no gradient: the reference keeps only the argmax of a draw, actor.py:84-91)."""
+    logits, u = _c(logits.detach()), _c(u)
+    rows, rows0 = u.numel() // 2, logits.numel() // 2
+    index = torch.empty(rows, device=u.device, dtype=torch.float32)
+    L.call("tacorl_gripper_gumbel", rows, rows0, L.ptr(logits), L.ptr(u), int(clamp), L.ptr(index), None, L.stream())
+    return index.view(*u.shape[:-1], 1)
+
+
+class GripperLogProbFn(Function):
+    """GumbelSoftmax.log_prob of class indices (distributions.py:50-58) -> (..., 1); gradient w.r.t. the logits."""
+
+    @staticmethod
+    def forward(ctx, logits, index):
+        logits, index = _c(logits), _c(index.to(torch.float32))
+        rows, rows0 = index.numel(), logits.numel() // 2
+        logp = torch.empty(rows, device=logits.device, dtype=torch.float32)
+        L.call("tacorl_gripper_logprob", rows, rows0, L.ptr(logits), L.ptr(index), L.ptr(logp), L.stream())
+        if ctx.needs_input_grad[0]:
+            assert rows == rows0, "gradient through a broadcast gripper log_prob is not used by the reference"
+            ctx.save_for_backward(logits, index)
+        lead = index.shape[:-1] if index.dim() > 1 and index.shape[-1] == 1 else index.shape
+        return logp.view(*lead, 1)
+
+    @staticmethod
+    def backward(ctx, dlogp):
+        logits, index = ctx.saved_tensors
+        d = _c(dlogp.reshape(-1))
+        dlogits = torch.empty_like(logits)
+        L.call("tacorl_gripper_logprob_bwd", d.numel(), L.ptr(logits), L.ptr(index), L.ptr(d), L.ptr(dlogits), L.stream())
+        return dlogits, None
+
+
+def gripper_logprob(logits, index):
+    return GripperLogProbFn.apply(logits, index)
+
+
 # --------------------------------------------------------------------------------------- CQL
 CQL_SCALARS = ("bellman_q1_loss", "bellman_q2_loss", "conservative_q1_loss", "conservative_q2_loss",
                "alpha_prime", "alpha_prime_loss", "q1_loss", "q2_loss", "q1_data", "q1_random", "q1_policy",

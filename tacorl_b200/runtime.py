@@ -192,11 +192,12 @@ def play_lmp_step_fn(module, optimizer, early_step=True):
 
 
 def tacorl_step_fn(module):
+    """Step function of a manual-optimisation module: TACORL or the flat CQL_Offline baseline."""
     def step(batch):
         module.training_step(batch)
         return module.logged.get("train/q1_loss")
     opts = module.optimizers()
-    step.mode_key = lambda: (module.current_epoch < module.bc_epochs, bool(module.finetune_action_decoder),
+    step.mode_key = lambda: (module.current_epoch < module.bc_epochs, bool(getattr(module, "finetune_action_decoder", False)),
                              tuple(float(o.param_groups[0]["lr"]) for o in opts), bool(module.training))
     step.preserve = lambda: list(opts) + [b.flat for b in (module._target_bufs or ())]
     return step

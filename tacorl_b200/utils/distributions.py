@@ -1,4 +1,4 @@
-"""Mirror of /root/reference/src/tacorl/utils/distributions.py:61-153 (TanhNormal) on the
+"""Mirror of /root/reference/src/tacorl/utils/distributions.py:15-58 (GumbelSoftmax), :61-153 (TanhNormal) on the
 tacorl_b200 kernels, plus the diagonal Normal the reference gets from torch.distributions."""
 import torch
 
@@ -87,3 +87,26 @@ class TanhNormal:
     @property
     def stddev(self):
         return self.normal_std
+
+
+class GumbelSoftmax:
+    """The open/close gripper distribution of the discrete-gripper actor (distributions.py:15-58).  Every call site of
+    the reference reduces a draw to its class index (actor.py:84-91, 128-129), so draws return the index (float 0 / 1,
+    trailing dim 1); `hard` relaxed samples are not materialised."""
+
+    def __init__(self, temperature: float = 0.5, logits=None):
+        self.temperature = temperature            # (does not move the argmax of a draw)
+        self.logits = logits
+
+    def sample(self, sample_shape=()):                           # distributions.py:28-38: uniform_(0, 1), no clamp
+        shape = tuple(sample_shape) + tuple(self.logits.shape)
+        u = rng.uniform(shape, 0.0, 1.0, self.logits.device)
+        return ops.gripper_gumbel(self.logits, u, clamp=False)
+
+    def rsample_index(self):
+        """argmax(rsample(hard=True)) (distributions.py:40-48 + actor.py:84-85): torch.rand clamped by clamp_probs."""
+        u = rng.rand(tuple(self.logits.shape), self.logits.device)
+        return ops.gripper_gumbel(self.logits, u, clamp=True)
+
+    def log_prob(self, index):                                   # distributions.py:50-58
+        return ops.gripper_logprob(self.logits, index)

@@ -42,10 +42,7 @@ def build_play_lmp(pr_kind="tanh_net", modalities=("rgb_static",), rnn_hidden=20
 
 
 def to_dev(batch):
-    out = {}
-    for k, v in batch.items():
-        out[k] = {kk: vv.to(DEV) for kk, vv in v.items()} if isinstance(v, dict) else v.to(DEV)
-    return out
+    return {k: to_dev(v) if isinstance(v, dict) else v.to(DEV) for k, v in batch.items()}
 
 
 def play_lmp_tape(noise, B, goal_dim=32):
@@ -66,6 +63,21 @@ def build_tacorl(lmp, precision="fp32", **overrides):
     cfg["_target_"] = "tacorl.modules.tacorl.tacorl.TACORL"                # reference path, remapped
     cfg["_recursive_"] = False
     return instantiate(cfg, play_lmp=lmp)
+
+
+def build_cql_flat(precision="fp32", **overrides):
+    from tacorl_b200 import ops
+    from tacorl_b200.utils.config import instantiate
+    ops.set_precision(precision)
+    cfg = RC.cql_offline_cfg()
+    cfg.update(overrides)
+    cfg["_target_"] = "tacorl.modules.cql.cql_offline_lightning.CQL_Offline"   # reference path, remapped
+    cfg["_recursive_"] = False
+    return instantiate(cfg)
+
+
+def cql_tape(noise):
+    return [noise[k] for k in O.CQL_NOISE_ORDER]
 
 
 def tacorl_tape(noise):

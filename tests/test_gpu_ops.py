@@ -439,6 +439,8 @@ def test_uint8_frames_equal_prenormalised_float_frames(prec):
     (64, (64, 16), (256, 256, 256, 1), ("silu",) * 3, False, True),       # actor loss through Q: input gradient only
     (3, (32,), (64, 64, 32), ("relu", "relu"), False, False),
     (100, (128, 32), (256, 64), ("silu",), True, False),                  # 2 row blocks, ragged
+    (64, (32, 32), (256, 256, 256, 14), ("silu",) * 3, 3, False),         # discrete-gripper MLPPolicy: mean | log_std | gripper
+    (40, (64,), (256, 14), ("silu",), 3, False),                          # three segments through the partial-slab reduction
 ])
 def test_fused_mlp_chain_vs_fp64(rows, ins, widths, acts, two_seg, detach):
     """ops.mlp_chain (one launch forward, one backward) against a plain fp64 evaluation: values, input gradients, every
@@ -452,9 +454,9 @@ def test_fused_mlp_chain_vs_fp64(rows, ins, widths, acts, two_seg, detach):
     for l in range(len(widths)):
         bound = 1.0 / dims[l] ** 0.5
         if two_seg and l == len(widths) - 1:
-            h = widths[l] // 2
-            layers.append([((torch.rand(h, dims[l], generator=g) * 2 - 1) * bound, torch.randn(h, generator=g) * 0.1),
-                           ((torch.rand(widths[l] - h, dims[l], generator=g) * 2 - 1) * bound, torch.randn(widths[l] - h, generator=g) * 0.1)])
+            parts = [6, 6, widths[l] - 12] if two_seg == 3 else [widths[l] // 2, widths[l] - widths[l] // 2]
+            layers.append([((torch.rand(h, dims[l], generator=g) * 2 - 1) * bound, torch.randn(h, generator=g) * 0.1)
+                           for h in parts])
         else:
             layers.append([((torch.rand(widths[l], dims[l], generator=g) * 2 - 1) * bound, torch.randn(widths[l], generator=g) * 0.1)])
     cot = torch.randn(rows, widths[-1], generator=g)

@@ -48,6 +48,11 @@ def test_product_package_never_imports_the_oracle():
 def _build(kind, rec):
     from oracle import ref_loader_cfg as RC
     from tacorl_b200.utils.config import instantiate
+    if kind == "cql_flat":
+        cfg = RC.cql_offline_cfg()
+        cfg["_target_"] = "tacorl.modules.cql.cql_offline_lightning.CQL_Offline"     # the REFERENCE class path
+        cfg["_recursive_"] = False
+        return instantiate(cfg)
     latent = rec["shapes"]["plan_recognition.mean_fc.weight"][0]
     cfg = RC.play_lmp_cfg(pr_kind=rec["pr_kind"], modalities=tuple(rec.get("modalities", ["rgb_static"])),
                           rnn_hidden=rec["rnn_hidden"], latent_plan_dim=latent, max_window=rec["T"],
@@ -65,7 +70,8 @@ def _build(kind, rec):
 
 @pytest.mark.parametrize("name,kind", [("playlmp_birnn_84", "play_lmp"), ("playlmp_multiview", "play_lmp"),
                                        ("tacorl_bc_84", "tacorl"), ("tacorl_defaultpr_84", "tacorl"),
-                                       ("tacorl_transformer_84", "tacorl"), ("tacorl_multiview_bc", "tacorl")])
+                                       ("tacorl_transformer_84", "tacorl"), ("tacorl_multiview_bc", "tacorl"),
+                                       ("cql_flat_bc", "cql_flat")])
 def test_state_dict_layout_equals_reference(name, kind):
     """Keys, order and shapes of the mirrors' state_dict == the reference's (recorded in the goldens)."""
     rec = json.load(open(os.path.join(GOLD, name + ".json")))
@@ -78,6 +84,9 @@ def test_state_dict_layout_equals_reference(name, kind):
         frozen = [n for n, p in m.named_parameters() if not p.requires_grad]
         assert frozen and all(n.startswith(("perceptual_encoder.", "plan_recognition.")) for n in frozen)
         assert m.target_entropy == rec["target_entropy"]
+    if kind == "cql_flat":
+        assert m.target_entropy == rec["target_entropy"] and m.actor.discrete_gripper
+        assert m.deterministic_backup == rec["deterministic_backup"]
 
 
 def test_frozen_lmp_runs_in_eval_mode_inside_get_pr_latent_plan():
