@@ -62,7 +62,7 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--global-batch", type=int, default=512, help="windows per step over all GPUs (strong scaling)")
     ap.add_argument("--workload", default="play_lmp",
-                    choices=["play_lmp", "tacorl", "play_lmp_multiview", "tacorl_multiview"])
+                    choices=["play_lmp", "tacorl", "play_lmp_multiview", "tacorl_multiview", "cql_flat"])
     ap.add_argument("--input", default="u8", choices=["u8", "f32"],
                     help="frame dtype fed to the step: u8 = raw uint8 frames, scale+normalise fused on the device; "
                          "f32 = pre-normalised float32 (the reference DataLoader's output)")
@@ -108,12 +108,25 @@ WORKLOADS = {
                              "gripper 3x84x84 for observation and goal, latent plan 32, BASELINE configs[3]",
                              metric="tacorl_multiview_train_frames_per_sec",
                              flop=TACORL_FLOP_PER_WINDOW + (27 * 13.9e6 + 6 * 22.9e6)),
+    # the paper's flat baseline.  A "window" is one transition = 3 frames (observation, next, goal);
+    # 11 encoder forwards (actor: obs+goal, next; q1, q2: obs+goal; targets: next+goal) + 6 backward frames per transition
+    "cql_flat": dict(module="cql", mods=("rgb_static",), goal_mods=("rgb_static",), latent=16, frames=3,
+                     desc="flat CQL_Offline baseline (cql_offline_goal_cond / cql_real_world): discrete-gripper actor, "
+                          "twin visual critics, entropy-regularised backup, Lagrange, n_action_samples 4, BC epoch; "
+                          "one transition = observation + next observation + goal image, static 3x200x200",
+                     metric="cql_flat_train_frames_per_sec", flop=(11 * 96.8e6 + 6 * 164e6)),
 }
+
+
+def frames_per_window(wl):
+    return wl.get("frames", T_FRAMES)
 
 
 def host_batch(wl, B, seed, u8):
     """Synthetic CALVIN-shaped batch in pinned host memory (SURVEY 8(d) "Synthetic inputs")."""
     from tacorl_b200.utils import synthetic
+    if wl["module"] == "cql":
+        return cql_host_batch(B, seed, u8)
     b = synthetic.play_batch(B, T_FRAMES, IMG, IMG, seed=seed, with_goal=(wl["module"] == "tacorl"),
                              modalities=wl["mods"], goal_modalities=wl["goal_mods"], gripper_hw=(GRIP, GRIP))
     out = {"states": dict(b["states"]), "actions": b["actions"]}
@@ -134,6 +147,24 @@ def host_batch(wl, B, seed, u8):
     return out
 
 
+def cql_host_batch(B, seed, u8):
+    """Transition batch of GoalCondReplayBufferDataset.get_transition (goal_cond_replay_buffer_dataset.py:277-296) in
+    pinned host memory."""
+    g = torch.Generator().manual_seed(seed)
+
+    def img():
+        t = torch.randint(0, 256, (B, 3, IMG, IMG), generator=g, dtype=torch.uint8)
+        return (t if u8 else t.float() / 127.5 - 1.0).pin_memory()
+
+    obs, nxt, goal = {"rgb_static": img()}, {"rgb_static": img()}, {"rgb_static": img()}
+    actions = torch.rand(B, 7, generator=g) * 2 - 1
+    actions[:, -1] = torch.where(actions[:, -1] > 0, 1.0, -1.0)
+    hit = (torch.rand(B, generator=g) < 0.3).long()
+    return {"observations": {"observation": obs, "goal": goal}, "actions": actions.pin_memory(),
+            "next_observations": {"observation": nxt, "goal": goal}, "rewards": hit.clone().pin_memory(),
+            "terminals": hit.clone().pin_memory()}
+
+
 def nbytes(batch):
     n = 0
     for v in batch.values():
@@ -151,6 +182,16 @@ def build_ours(wl, dev, world, precision):
     from tacorl_b200.utils.config import instantiate
     ops.set_precision(precision)
     torch.manual_seed(0)
+    if wl["module"] == "cql":
+        m = instantiate(configs.cql_offline_goal_cond(wl["mods"], wl["goal_mods"]))
+        synthetic.init_like_reference(m, seed=0)
+        m.to(dev)
+        m.train()
+        opts = m.optimizers()
+        if world > 1:
+            for o in opts:
+                parallel.attach_data_parallel(o, world)
+        return m, opts, runtime.tacorl_step_fn(m)
     lmp = instantiate(configs.play_lmp_for_rl("tanh_net", modalities=wl["mods"], latent_plan_dim=wl["latent"],
                                               goal_modalities=wl["goal_mods"]))
     if wl["module"] == "play_lmp":
@@ -302,7 +343,7 @@ def measure_workload(ctx, name, precision, steps, warmup, e2e=True, sample_clock
         launches += graphed.launches_per_replay * (graphed.replays - r0)
     clk = clocks.stop() if clocks else None
     ms = total_ms / steps
-    frames = world * B * T_FRAMES
+    frames = world * B * frames_per_window(wl)
     res = {"metric": wl["metric"], "value": frames / (ms / 1e3), "unit": "frames/s", "ms_per_step": ms,
            "windows_per_sec": world * B / (ms / 1e3), "gpu_launches": launches, "launches_per_step": launches / steps,
            "cuda_graph": graphed is not None, "workload": wl["desc"],
@@ -467,6 +508,8 @@ def reference_kind():
 
 def reference_batch(wl, B, seed=1):
     from oracle import synth as S
+    if wl["module"] == "cql":
+        return S.synth_cql_batch(B, IMG, IMG, seed, modalities=wl["mods"], goal_modalities=wl["goal_mods"])
     return S.synth_play_batch(B, T_FRAMES, IMG, IMG, seed, modalities=wl["mods"], gripper_hw=(GRIP, GRIP),
                               with_goal=(wl["module"] == "tacorl"), goal_modalities=wl["goal_mods"])
 
@@ -476,9 +519,13 @@ def build_reference(wl, device="cpu"):
     from oracle import ref_loader as R
     from oracle import synth as S
     torch.manual_seed(0)
-    lmp = R.build_reference_play_lmp(pr_kind="tanh_net", rnn_hidden=RNN_H, dropout_p=0.0, max_window=T_FRAMES,
-                                     modalities=wl["mods"], goal_modalities=wl["goal_mods"], latent_plan_dim=wl["latent"])
-    m = lmp if wl["module"] == "play_lmp" else R.build_reference_tacorl(lmp)
+    if wl["module"] == "cql":
+        m = R.build_reference_cql(obs_modalities=list(wl["mods"]), goal_modalities=list(wl["goal_mods"]))
+    else:
+        lmp = R.build_reference_play_lmp(pr_kind="tanh_net", rnn_hidden=RNN_H, dropout_p=0.0, max_window=T_FRAMES,
+                                         modalities=wl["mods"], goal_modalities=wl["goal_mods"],
+                                         latent_plan_dim=wl["latent"])
+        m = lmp if wl["module"] == "play_lmp" else R.build_reference_tacorl(lmp)
     shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
     m.load_state_dict(S.synth_state_dict(shapes, 0))
     m.to(device)
@@ -496,7 +543,7 @@ def build_reference(wl, device="cpu"):
         m.optimizers()
 
         def step(batch, s):
-            m.training_step(batch)
+            m.training_step(batch, s) if wl["module"] == "cql" else m.training_step(batch)
             return m.logged.get("train/q1_loss")
     return m, step
 
@@ -505,7 +552,17 @@ def port_step(wl, B):
     """Fallback when the reference tree did not travel: the oracle port of the same step."""
     from oracle import synth as S
     from oracle import tacorl_oracle as O
-    from tests.gpu_util import build_play_lmp, build_tacorl
+    from tests.gpu_util import build_cql_flat, build_play_lmp, build_tacorl
+    if wl["module"] == "cql":
+        m = build_cql_flat()
+        shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
+        P = O.params_from(S.synth_state_dict(shapes, 0))
+        opt = O.new_tacorl_opt_state(P)
+
+        def step(batch, s):
+            torch.manual_seed(1000 + s)
+            return O.cql_training_step(P, opt, batch, O.draw_cql_noise(B), {}, 0)[0]["q1_loss"]
+        return step
     lmp = build_play_lmp("tanh_net", wl["mods"], RNN_H, wl["latent"], T_FRAMES, goal_modalities=wl["goal_mods"])
     m = lmp if wl["module"] == "play_lmp" else build_tacorl(lmp)        # shapes only (no kernels run)
     shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
@@ -556,7 +613,7 @@ def time_reference_gpu_eager(wl, B, steps=5, warmup=2):
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     out = {}
     batch = reference_batch(wl, B)
-    batch = {k: ({kk: vv.to(dev) for kk, vv in v.items()} if isinstance(v, dict) else v.to(dev)) for k, v in batch.items()}
+    batch = to_device(batch, dev)
     for mode in ("fp32_tf32conv", "bf16_autocast"):
         try:
             m, step = build_reference(wl, dev)
@@ -573,7 +630,7 @@ def time_reference_gpu_eager(wl, B, steps=5, warmup=2):
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / steps
-            out[mode] = {"ms_per_step": ms, "value": B * T_FRAMES / (ms / 1e3), "unit": "frames/s", "steps": steps,
+            out[mode] = {"ms_per_step": ms, "value": B * frames_per_window(wl) / (ms / 1e3), "unit": "frames/s", "steps": steps,
                          "loss": float(loss.detach()) if torch.is_tensor(loss) else None}
             del m, step
             torch.cuda.empty_cache()
@@ -597,12 +654,12 @@ def run_reference(args):
         w = WORKLOADS[name]
         times, kind = time_reference_cpu(w, B, steps, warmup, threads)
         ms = 1e3 * statistics.median(times)
-        fps = B * T_FRAMES / (ms / 1e3)
+        fps = B * frames_per_window(w) / (ms / 1e3)
         what = ("UNMODIFIED reference modules (oracle/_ref, vendored from /root/reference) + their own torch.optim.Adam"
                 if kind == "reference" else "oracle port of the reference step (the vendored reference tree is absent)")
         return {"metric": w["metric"], "value": fps, "unit": "frames/s", "ms_per_step": ms,
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "ms_per_step": ms,
-                                 "sample": f"median of {steps} timed steps (+{warmup} warm-up) of {B} windows x 16 frames: {what}, "
+                                 "sample": f"median of {steps} timed steps (+{warmup} warm-up) of {B} windows x {frames_per_window(w)} frames: {what}, "
                                            f"torch CPU fp32, {threads} threads"},
                 "workload": w["desc"]}
 
@@ -610,7 +667,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": main["metric"], "value": main["value"], "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "windows_per_step": B, "host": "cpu", "frames_per_window": T_FRAMES},
+            "config": {"workload": wl["desc"], "windows_per_step": B, "host": "cpu", "frames_per_window": frames_per_window(wl)},
             "cpu_baseline": main["cpu_baseline"],
             "e2e": {"value": main["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -693,7 +750,7 @@ def run_ours(args):
 
     main, h = measure_workload(ctx, args.workload, args.precision, args.steps, args.warmup, sample_clocks=True)
     rooflines = []
-    if "rgb_static" in wl["mods"] and args.precision == "bf16":
+    if "rgb_static" in wl["mods"] and args.precision == "bf16" and wl["module"] != "cql":
         try:
             if wl["module"] == "play_lmp":
                 rooflines.append(roofline_encoder(ctx, h, main["ms_per_step"], pk, pk_kind))
@@ -739,7 +796,7 @@ def run_ours(args):
             "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": wl["desc"], "windows_per_gpu": B, "global_windows": B * world,
-                       "frames_per_window": T_FRAMES, "parallelism": f"dp{world}", "precision": args.precision,
+                       "frames_per_window": frames_per_window(wl), "parallelism": f"dp{world}", "precision": args.precision,
                        "cuda_graph": main["cuda_graph"],
                        "input": "uint8 frames, ScaleImageTensor+Normalize fused into the first kernel" if args.input == "u8"
                                 else "float32 frames (pre-normalised on the host)",
@@ -758,10 +815,10 @@ def run_ours(args):
             try:
                 t, kind = time_reference_cpu(wl, B, args.cpu_steps, 1, threads)
                 cms = 1e3 * statistics.median(t)
-                line["cpu_baseline"] = {"value": B * T_FRAMES / (cms / 1e3), "unit": "frames/s", "cores": threads,
+                line["cpu_baseline"] = {"value": B * frames_per_window(wl) / (cms / 1e3), "unit": "frames/s", "cores": threads,
                                         "kind": kind, "ms_per_step": cms,
                                         "sample": f"median of {args.cpu_steps} timed steps (+1 warm-up) of the same {B} windows x "
-                                                  "16 frames workload: " + ("unmodified reference modules (oracle/_ref)"
+                                                  f"{frames_per_window(wl)} frames workload: " + ("unmodified reference modules (oracle/_ref)"
                                                   if kind == "reference" else "oracle port of the reference step") +
                                                   f", torch CPU fp32, {threads} threads"}
             except Exception as e:  # pragma: no cover
