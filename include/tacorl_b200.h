@@ -281,6 +281,9 @@ int tacorl_color_jitter_u8(const unsigned char* x, long long N, int H, int W, co
  * dim (state | goal, embedding | action): no torch.cat.  z: (rows, sum of the hidden widths) receives the
  * pre-activations of layers 0 .. L-2 (the backward pass's saved tensors).  bwd: dW / db per segment may be NULL
  * (gradient w.r.t. the input only); dx0 / dx1 may be NULL. */
+/* OR-ed into tacorl_mlp_layer.act of a ReLU layer: z receives relu(z) instead of the pre-activation (the backward pass
+ * reads the same buffer: relu'(z) and relu(z) are the same functions of either; LMPVisionEncoder's saved h4) */
+#define TACORL_MLP_SAVE_ACTIVATED 0x100
 typedef struct tacorl_mlp_layer {
   const float* W0; const float* b0; int n0;     /* first weight segment: (n0, in) row-major, bias (n0) or NULL */
   const float* W1; const float* b1; int n1;     /* optional second segment stacked behind it (n1 = 0: none) */

@@ -63,6 +63,39 @@ size_t tacorl_lmp_encoder_ws_bytes(int N, int H, int W, int hidden, int latent, 
   return tc > legacy ? tc : legacy;
 }
 
+// ------------------------------------------------------------------------------------------ FC head, small batches
+// Up to 256 frames (the 64 / 128-frame encoder calls of a TACO-RL / CQL step, rollouts): Linear(128, hidden) + ReLU +
+// Linear(hidden, latent) and its whole backward run as one fused cluster kernel each way (mlp_chain.cu, fp32 FFMA)
+// instead of 2 + 4 latency-bound GEMM launches with their casts, split-K reductions, column sums and ReLU gate.
+// h4 keeps its meaning (the post-ReLU activation): TACORL_MLP_SAVE_ACTIVATED.
+static bool fc_fused_ok(int N, int hidden, int latent) {
+  return N >= 1 && N <= 256 && hidden % 4 == 0 && hidden <= 256 && latent >= 1 && latent <= 256;
+}
+static void fc_layers(tacorl_mlp_layer* ly, const float* const* params, int hidden, int latent, float* const* grads) {
+  memset(ly, 0, 2 * sizeof(tacorl_mlp_layer));
+  ly[0].W0 = params[P_W4]; ly[0].b0 = params[P_B4]; ly[0].n0 = hidden; ly[0].in = 128;
+  ly[0].act = ACT_RELU | TACORL_MLP_SAVE_ACTIVATED;
+  ly[1].W0 = params[P_W5]; ly[1].b0 = params[P_B5]; ly[1].n0 = latent; ly[1].in = hidden; ly[1].act = ACT_NONE;
+  if (grads) {
+    ly[0].dW0 = grads[P_W4]; ly[0].db0 = grads[P_B4];
+    ly[1].dW0 = grads[P_W5]; ly[1].db0 = grads[P_B5];
+  }
+}
+static int fc_head_fwd_fused(int N, const float* const* params, int hidden, int latent, const float* feat, float* h4,
+                             float* emb, cudaStream_t st) {
+  tacorl_mlp_layer ly[2];
+  fc_layers(ly, params, hidden, latent, nullptr);
+  return tacorl_mlp_chain_fwd(2, N, ly, feat, 128, 128, nullptr, 0, 0, h4, hidden, emb, latent, st);
+}
+static int fc_head_bwd_fused(int N, const float* const* params, int hidden, int latent, const float* feat,
+                             const float* h4, const float* d_emb, float* const* grads, float* dfeat, void* ws,
+                             size_t ws_bytes, cudaStream_t st) {
+  tacorl_mlp_layer ly[2];
+  fc_layers(ly, params, hidden, latent, grads);
+  return tacorl_mlp_chain_bwd(2, N, ly, feat, 128, 128, nullptr, 0, 0, h4, hidden, d_emb, latent, dfeat, 128, nullptr, 0,
+                              ws, ws_bytes, st);
+}
+
 // ------------------------------------------------------------------------------------------ tensor-core path
 // conv stack as implicit GEMMs (conv_tc.cu): x -> space-to-depth bf16 -> conv1 -> conv2 -> conv3, NHWC bf16
 // activations, packed bf16 weights resident in shared memory, no im2col buffers.
@@ -95,6 +128,7 @@ static int enc_fwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
   if ((rc = conv_tc_conv2_fwd(y1b, N, g.H1, g.W1, g.H2, g.W2, wp2, params[P_B2], y2b, st))) return rc;
   if ((rc = conv_lin_conv3_fwd(y2b, N, g.H2, g.W2, g.H3, g.W3, wp3, params[P_B3], y3, st))) return rc;
   if ((rc = softargmax_fwd_f32(y3, N, g.H3, g.W3, 64, params[P_TEMP], feat, smax, ssum, st))) return rc;
+  if (fc_fused_ok(N, hidden, latent)) return fc_head_fwd_fused(N, params, hidden, latent, feat, h4, emb, st);
   GemmArgs f;
   f.transB = 1; f.M = N; f.N = hidden; f.K = 128; f.A = feat; f.lda = 128; f.B = params[P_W4]; f.ldb = 128;
   f.C = h4; f.ldc = hidden; f.bias = params[P_B4]; f.act = ACT_RELU; f.split_k = 1;
@@ -125,13 +159,16 @@ static int enc_bwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
   TACORL_REQUIRE(wd3 && wd2 && dh4 && dfeat && dtau && csws && skws && dy3b && dy2b && dy1b && xs,
                  "lmp_encoder_bwd(bf16): workspace too small (%zu bytes)", ws_bytes);
   int rc;
-  // ---- FC head (small GEMMs, fp32 operands staged to bf16)
-  GemmArgs a;
+  // ---- FC head (small batches: one fused kernel; else small GEMMs, fp32 operands staged to bf16)
+  const bool fc_fused = !accumulate && fc_fused_ok(N, hidden, latent);
+  if (fc_fused && (rc = fc_head_bwd_fused(N, params, hidden, latent, feat, h4, d_emb, grads, dfeat, skws, kSplitKWs, st)))
+    return rc;
+  GemmArgs a, b;
+  if (!fc_fused) {
   a.transA = 1; a.transB = 0; a.M = latent; a.N = hidden; a.K = N; a.A = d_emb; a.lda = latent; a.B = h4;
   a.ldb = hidden; a.C = grads[P_W5]; a.ldc = hidden; a.beta = beta0; a.split_k = 0;
   if ((rc = gemm_tc_from_f32(a, skws, kSplitKWs, st))) return rc;
   if ((rc = colsum_f32(N, latent, d_emb, latent, grads[P_B5], accumulate, st))) return rc;
-  GemmArgs b;
   b.M = N; b.N = hidden; b.K = latent; b.A = d_emb; b.lda = latent; b.B = params[P_W5]; b.ldb = hidden;
   b.C = dh4; b.ldc = hidden; b.split_k = 1;
   if ((rc = gemm_tc_from_f32(b, skws, kSplitKWs, st))) return rc;
@@ -141,6 +178,7 @@ static int enc_bwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
   if ((rc = colsum_f32(N, hidden, dh4, hidden, grads[P_B4], accumulate, st))) return rc;
   b.N = 128; b.K = hidden; b.A = dh4; b.lda = hidden; b.B = params[P_W4]; b.ldb = 128; b.C = dfeat; b.ldc = 128;
   if ((rc = gemm_tc_from_f32(b, skws, kSplitKWs, st))) return rc;
+  }
   // ---- soft-argmax backward (applies conv3's ReLU mask, writes the bf16 operand directly) and temperature gradient
   if ((rc = softargmax_bwd_bf16out(y3, N, g.H3, g.W3, 64, params[P_TEMP], feat, smax, ssum, dfeat, dy3b, dtau, st)))
     return rc;
@@ -234,6 +272,7 @@ static int enc_fwd(const void* xv, int x_u8, float x_scale, float x_shift, int N
     if ((rc = gemm_f32(a, nullptr, 0, st))) return rc;
   }
   if ((rc = softargmax_fwd_f32(y3, N, g.H3, g.W3, 64, params[P_TEMP], feat, smax, ssum, st))) return rc;
+  if (fc_fused_ok(N, hidden, latent)) return fc_head_fwd_fused(N, params, hidden, latent, feat, h4, emb, st);
   GemmArgs f;
   f.transB = 1; f.M = N; f.N = hidden; f.K = 128; f.A = feat; f.lda = 128; f.B = params[P_W4]; f.ldb = 128;
   f.C = h4; f.ldc = hidden; f.bias = params[P_B4]; f.act = ACT_RELU; f.split_k = 1;
@@ -302,12 +341,15 @@ int tacorl_lmp_encoder_bwd(const void* xv, int x_dtype, float x_scale, float x_s
   TACORL_REQUIRE(col && dy1c && dy2c, "lmp_encoder_bwd: workspace carve failed");
   int rc;
   // ---- FC head
-  GemmArgs a;
+  const bool fc_fused = !accumulate && fc_fused_ok(N, hidden, latent);
+  if (fc_fused && (rc = fc_head_bwd_fused(N, params, hidden, latent, feat, h4, d_emb, grads, dfeat, skws, kSplitKWs, st)))
+    return rc;
+  GemmArgs a, b;
+  if (!fc_fused) {
   a.transA = 1; a.transB = 0; a.M = latent; a.N = hidden; a.K = N; a.A = d_emb; a.lda = latent; a.B = h4;
   a.ldb = hidden; a.C = grads[P_W5]; a.ldc = hidden; a.beta = beta0; a.split_k = 0;
   if ((rc = gemm_f32(a, skws, kSplitKWs, st))) return rc;                 // dW5 = d_emb^T h4
   if ((rc = colsum_f32(N, latent, d_emb, latent, grads[P_B5], accumulate, st))) return rc;
-  GemmArgs b;
   b.M = N; b.N = hidden; b.K = latent; b.A = d_emb; b.lda = latent; b.B = params[P_W5]; b.ldb = hidden;
   b.C = dh4; b.ldc = hidden; b.split_k = 1;
   if ((rc = gemm_f32(b, skws, kSplitKWs, st))) return rc;                 // dh4 = d_emb W5
@@ -317,6 +359,7 @@ int tacorl_lmp_encoder_bwd(const void* xv, int x_dtype, float x_scale, float x_s
   if ((rc = colsum_f32(N, hidden, dh4, hidden, grads[P_B4], accumulate, st))) return rc;
   b.N = 128; b.K = hidden; b.A = dh4; b.lda = hidden; b.B = params[P_W4]; b.ldb = 128; b.C = dfeat; b.ldc = 128;
   if ((rc = gemm_f32(b, skws, kSplitKWs, st))) return rc;                 // dfeat = dh4 W4
+  }
   // ---- soft-argmax (also applies conv3's ReLU mask) and temperature grad
   if ((rc = softargmax_bwd_f32(y3, N, g.H3, g.W3, 64, params[P_TEMP], feat, smax, ssum, dfeat, dy3, dtau, st)))
     return rc;

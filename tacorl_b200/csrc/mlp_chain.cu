@@ -37,6 +37,7 @@ struct McLayer {
                                                       // (fc_mean | fc_log_std | gripper_action)
   int n[MC_SEGS];                         // output rows of each segment (n[1], n[2] may be 0)
   int in, out, act;                       // act applied to this layer's output (ACT_NONE for the last layer)
+  int zpost;                              // store act(z) instead of z in Z (ReLU only: the backward pass cannot tell)
   float* dW[MC_SEGS]; float* db[MC_SEGS]; // backward outputs (may be null: gradient w.r.t. the input only)
   long long part_off;                     // offset of this layer's [out][in + 1] block inside one partial slab
 };
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(MC_THREADS, 2) mlp_chain_fwd_kernel(const __gr
         if (li == c.L - 1) {
           if (row < c.rows) c.out[(long long)row * c.ldo + n] = z[r];
         } else {
-          if (row < c.rows) c.Z[(long long)row * c.ldz + c.zoff[li] + n] = z[r];
+          if (row < c.rows) c.Z[(long long)row * c.ldz + c.zoff[li] + n] = l.zpost ? mc_act(l.act, z[r]) : z[r];
           mc_push_all(An + lr * MC_LD + n, mc_act(l.act, z[r]));
         }
       }
@@ -426,7 +427,10 @@ static int mc_build(McChain& c, int L, int rows, const tacorl_mlp_layer* layers,
     const tacorl_mlp_layer& s = layers[i];
     l.W[0] = s.W0; l.W[1] = s.W1; l.W[2] = s.W2; l.b[0] = s.b0; l.b[1] = s.b1; l.b[2] = s.b2;
     l.n[0] = s.n0; l.n[1] = s.n1; l.n[2] = s.n2;
-    l.in = s.in; l.out = s.n0 + s.n1 + s.n2; l.act = i == L - 1 ? ACT_NONE : s.act;
+    l.in = s.in; l.out = s.n0 + s.n1 + s.n2; l.act = i == L - 1 ? ACT_NONE : (s.act & 0xFF);
+    l.zpost = (s.act & TACORL_MLP_SAVE_ACTIVATED) ? 1 : 0;
+    TACORL_REQUIRE(!l.zpost || l.act == ACT_RELU || l.act == ACT_NONE,
+                   "mlp_chain: TACORL_MLP_SAVE_ACTIVATED needs a ReLU layer (layer %d)", i);
     l.dW[0] = s.dW0; l.dW[1] = s.dW1; l.dW[2] = s.dW2; l.db[0] = s.db0; l.db[1] = s.db1; l.db[2] = s.db2;
     l.part_off = poff; poff += (long long)l.out * (l.in + 1);
     c.zoff[i] = zoff; if (i < L - 1) zoff += l.out;

@@ -13,6 +13,7 @@ from typing import List
 import torch
 import torch.nn as nn
 
+from ... import ops
 from ...networks.actor_critic.visual_actor_wrapper import VisualActorWrapper
 from ...networks.actor_critic.visual_critic_wrapper import VisualCriticWrapper
 from ...optim import FlatAdam
@@ -97,6 +98,8 @@ class TACORL(CQL_Offline):
         self.target_q2.load_state_dict(self.q2.state_dict())
         set_parameter_requires_grad(self.perceptual_encoder, requires_grad=False)
         set_parameter_requires_grad(self.plan_recognition, requires_grad=False)
+        ops.mark_frozen(self.perceptual_encoder)      # bf16 operand copies of frozen weights are cast once, not per step
+        ops.mark_frozen(self.plan_recognition)
 
     # ------------------------------------------------------------------------------ optimisers
     def configure_optimizers(self):                              # cql…py:553-574 + tacorl.py:289-300

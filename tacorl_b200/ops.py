@@ -72,6 +72,54 @@ def refresh_shadows():
     for o in list(_SHADOW_OWNERS):
         for p in o.param_groups[0]["params"]:
             shadow_of(p)
+    for key, (ref, ver, sh) in list(_FROZEN_SHADOWS.items()):
+        t = ref()
+        if t is None or t.data_ptr() != key or t.requires_grad:
+            del _FROZEN_SHADOWS[key]
+        elif t._version != ver:
+            with torch.no_grad():
+                sh.copy_(t.detach().reshape(-1))          # in place: captured graphs keep reading the same address
+            _FROZEN_SHADOWS[key] = (ref, t._version, sh)
+
+
+# bf16 twins of FROZEN parameters: modules registered with mark_frozen() (TACO-RL's frozen plan recogniser, tacorl.py:
+# 124-125), requires_grad False, owned by no optimiser.  Cast once and re-cast when the tensor's torch version counter
+# moves (load_state_dict, copy_).  Only registered parameters qualify: nothing that a kernel updates through raw
+# pointers (Polyak targets) may be cached, a captured graph would never see the refresh.
+_FROZEN_SHADOWS = {}
+_FROZEN_PARAMS = {}                 # id(parameter) -> weakref
+
+
+def mark_frozen(module):
+    """Declare every parameter of `module` frozen for good (the caller also sets requires_grad False)."""
+    for p in module.parameters():
+        _FROZEN_PARAMS[id(p)] = weakref.ref(p)
+
+
+def invalidate_frozen_shadows():
+    _FROZEN_SHADOWS.clear()
+
+
+def _frozen_shadow_of(t):
+    ref = _FROZEN_PARAMS.get(id(t))
+    if ref is None or ref() is not t or t.requires_grad or t.dtype != torch.float32:
+        return None
+    key = t.data_ptr()
+    hit = _FROZEN_SHADOWS.get(key)
+    if hit is not None:
+        ref, ver, sh = hit
+        if ref() is t and sh.numel() == t.numel():
+            if ver != t._version:
+                with torch.no_grad():
+                    sh.copy_(t.detach().reshape(-1))
+                _FROZEN_SHADOWS[key] = (ref, t._version, sh)
+            return sh
+    if torch.cuda.is_current_stream_capturing():
+        return None                                   # (never allocate a long-lived buffer from a graph's private pool)
+    with torch.no_grad():
+        sh = t.detach().reshape(-1).to(torch.bfloat16)
+    _FROZEN_SHADOWS[key] = (weakref.ref(t), t._version, sh)
+    return sh
 
 
 def shadow_of(t):
@@ -96,7 +144,7 @@ def shadow_of(t):
                     sh.copy_(t.detach().reshape(-1))
                 o._pver[ptr] = t._version
             return sh
-    return None
+    return _frozen_shadow_of(t)
 
 
 # ---- gradient slots.  FlatAdam owns one flat gradient buffer; a backward kernel that produces the whole gradient of a

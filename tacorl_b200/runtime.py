@@ -179,6 +179,11 @@ def play_lmp_step_fn(module, optimizer, early_step=True):
     """One PlayLMP optimiser step.  early_step: this function runs exactly one backward pass per step(), so the update
     of the parameters behind the encoders may start as soon as their gradients are final (FlatAdam.early_step)."""
     optimizer.early_step = bool(early_step)
+    import os
+    if os.environ.get("TACORL_EARLY_SUBNET") is not None:      # experiment switches (scripts/early_adam_sweep.sh)
+        module.early_subnet_sync = os.environ["TACORL_EARLY_SUBNET"] == "1"
+    if os.environ.get("TACORL_EARLY_BG") is not None:
+        optimizer.early_background = os.environ["TACORL_EARLY_BG"] == "1"
 
     def step(batch):
         optimizer.zero_grad(set_to_none=True)

@@ -336,3 +336,42 @@ def test_trainer_fit_checkpoints_and_resumes_across_the_bc_epoch_boundary(tmp_pa
     moved = [k for k, v in t2.state_dict().items() if v.dtype.is_floating_point and not torch.equal(v.cpu(), sd1[k])]
     assert any(k.startswith("actor.") for k in moved) and any(k.startswith("q1.") for k in moved)
     assert not [k for k in moved if k.startswith(("perceptual_encoder.", "plan_recognition."))]     # frozen LMP parts
+
+
+def test_frozen_lmp_weights_are_cast_once_and_follow_torch_side_edits():
+    """TACO-RL's frozen plan recogniser (tacorl.py:124-125): the bf16 operand copies of its weights are cached
+    (ops.mark_frozen) -- cast once, re-cast in place when the weights are edited through torch, also under a captured
+    graph; trainable and Polyak-updated parameters never enter that cache."""
+    from tacorl_b200 import ops, runtime
+    from tests.gpu_util import build_tacorl
+    try:
+        lmp = build_play_lmp("tanh_net", ("rgb_static",), 64, 16, 8)
+        t = build_tacorl(lmp, precision="bf16")
+        shapes = {k: list(v.shape) for k, v in t.state_dict().items()}
+        t.load_state_dict(S.synth_state_dict(shapes, 6))
+        t.to(DEV)
+        t.optimizers()
+        w = t.plan_recognition.birnn_model.weight_hh_l0
+        sh = ops.shadow_of(w)
+        assert sh is not None and sh.dtype == torch.bfloat16
+        assert torch.equal(sh.view_as(w), w.detach().to(torch.bfloat16))
+        assert ops.shadow_of(w).data_ptr() == sh.data_ptr()                 # cached: same buffer, no new cast
+        tq = next(iter(t.target_q1.critic.parameters()))
+        assert ops.shadow_of(tq) is None                                     # Polyak-updated: never cached
+        batch = to_dev(S.synth_play_batch(3, 8, 84, 84, 6, with_goal=True))
+        batch = {k: batch[k] for k in ("states", "actions", "goal", "disp")}
+        g = runtime.GraphedTrainStep(runtime.tacorl_step_fn(t), batch, warmup=2)
+        torch.manual_seed(1)
+        g()
+        a = float(t.logged["train/action_loss"])
+        with torch.no_grad():
+            for p in t.plan_recognition.parameters():
+                p.mul_(1.5)                                                   # bumps the version counters
+        torch.manual_seed(1)
+        g()
+        b = float(t.logged["train/action_loss"])
+        assert ops.shadow_of(w).data_ptr() == sh.data_ptr()
+        assert torch.equal(sh.view_as(w), w.detach().to(torch.bfloat16))    # refreshed in place before the replay
+        assert abs(a - b) > 1e-3 * max(1.0, abs(a))                          # the replay saw the new recogniser
+    finally:
+        ops.set_precision("fp32")
