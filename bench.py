@@ -288,6 +288,13 @@ class Ctx:
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.rank = int(os.environ.get("RANK", "0"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        # host threads and pinned staging buffers on the GPU's own NUMA node (every rank of a multi-GPU run pulls its
+        # 123 MB batch from host memory each step; TACORL_NUMA_BIND=0 disables, =1 forces it for a single rank too)
+        self.numa = {"bound": False, "why": "single rank"}
+        want = os.environ.get("TACORL_NUMA_BIND")
+        if want == "1" or (want is None and self.world > 1):
+            from tacorl_b200.utils.numa import bind_to_gpu_node
+            self.numa = bind_to_gpu_node(self.local)
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
         self.graphs = []          # every captured graph, released before the process group is destroyed
@@ -409,7 +416,7 @@ def measure_workload(ctx, name, precision, steps, warmup, e2e=True, sample_clock
             mode = "synchronous loss read every step"
         res["e2e"] = {"value": frames / (e2e_ms / 1e3), "unit": "frames/s", "ms_per_step": e2e_ms,
                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "loss_read": mode,
-                      "h2d_gbs_per_rank": h2d / (e2e_ms / 1e3) / 1e9}
+                      "h2d_gbs_per_rank": h2d / (e2e_ms / 1e3) / 1e9, "numa": ctx.numa}
         res["final_loss"] = losses[-1] if losses else None
         trace(f"{name}/{precision}: e2e {e2e_ms:.3f} ms/step")
     return res, {"module": m, "opts": opts, "resident": resident, "B": B, "host": host}

@@ -883,7 +883,19 @@ int conv_dgrad2_fused(const void* dy2b, int N, int H1, int W1, int H2, int W2, c
 // mode 3: conv3 dgrad Wp[t=(ky,kx)][c][oc]            = W3[oc][c][ky][kx]            (9 taps, BN=64)
 // mode 4: conv2 dgrad Wp[cls=(py,px)][t=(j,i)][c][oc] = W2[oc][c][py+2j][px+2i]      (4 classes x 4 taps, BN=32)
 // mode 5: conv2 dgrad Wp[t=(j,i)][cls*32 + c][oc]     = W2[oc][c][py+2j][px+2i]      (4 taps, BN=128: all classes fused)
-__global__ void cv_pack_kernel(int mode, const float* __restrict__ W, __nv_bfloat16* __restrict__ Wp, int total) {
+struct PackJobs {
+  int n;
+  int mode[3];
+  const float* W[3];
+  __nv_bfloat16* Wp[3];
+  int total[3];
+};
+// one launch packs up to three weight tensors (blockIdx.y = job): the 3 forward / 2 backward packs of an encoder pass
+__global__ void cv_pack_kernel(const PackJobs jobs) {
+  const int job = blockIdx.y;
+  const int mode = jobs.mode[job], total = jobs.total[job];
+  const float* __restrict__ W = jobs.W[job];
+  __nv_bfloat16* __restrict__ Wp = jobs.Wp[job];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int k = i & 63;
@@ -913,12 +925,24 @@ __global__ void cv_pack_kernel(int mode, const float* __restrict__ W, __nv_bfloa
   Wp[i] = __float2bfloat16(v);
 }
 
-int conv_tc_pack(int mode, const float* W, void* Wp, cudaStream_t st) {
+int conv_tc_pack_multi(int n, const int* modes, const float* const* Ws, void* const* Wps, cudaStream_t st) {
   static const int totals[6] = {9 * 64 * 64, 8 * 64 * 64, 4 * 32 * 64, 9 * 64 * 64, 16 * 32 * 64, 4 * 128 * 64};
-  TACORL_REQUIRE(mode >= 0 && mode < 6, "conv_tc_pack: bad mode");
-  cv_pack_kernel<<<cdiv(totals[mode], 256), 256, 0, st>>>(mode, W, (__nv_bfloat16*)Wp, totals[mode]);
+  TACORL_REQUIRE(n >= 1 && n <= 3, "conv_tc_pack: 1..3 tensors per launch");
+  PackJobs jobs;
+  jobs.n = n;
+  int most = 0;
+  for (int j = 0; j < n; ++j) {
+    TACORL_REQUIRE(modes[j] >= 0 && modes[j] < 6, "conv_tc_pack: bad mode");
+    jobs.mode[j] = modes[j]; jobs.W[j] = Ws[j]; jobs.Wp[j] = (__nv_bfloat16*)Wps[j]; jobs.total[j] = totals[modes[j]];
+    most = max(most, totals[modes[j]]);
+  }
+  cv_pack_kernel<<<dim3(cdiv(most, 256), n), 256, 0, st>>>(jobs);
   TACORL_LAUNCH_CHECK();
   return 0;
+}
+
+int conv_tc_pack(int mode, const float* W, void* Wp, cudaStream_t st) {
+  return conv_tc_pack_multi(1, &mode, &W, &Wp, st);
 }
 
 // fp32 NCHW image (N,3,H,W) -> bf16 space-to-depth(4) (N, SH, SW, 64), channel q = (py*4+px)*3 + c for q < 48, zero pad

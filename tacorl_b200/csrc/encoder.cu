@@ -119,9 +119,12 @@ static int enc_fwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
   TACORL_REQUIRE(wp1 && wp2 && wp3 && fcws && xs && y1b && y2b && y3 && feat && smax && ssum && h4,
                  "lmp_encoder_fwd(bf16): workspace too small (%zu bytes)", ws_bytes);
   int rc;
-  if ((rc = conv_tc_pack(2, params[P_W1], wp1, st))) return rc;
-  if ((rc = conv_tc_pack(1, params[P_W2], wp2, st))) return rc;
-  if ((rc = conv_tc_pack(0, params[P_W3], wp3, st))) return rc;
+  {
+    const int modes[3] = {2, 1, 0};
+    const float* Ws[3] = {params[P_W1], params[P_W2], params[P_W3]};
+    void* Wps[3] = {wp1, wp2, wp3};
+    if ((rc = conv_tc_pack_multi(3, modes, Ws, Wps, st))) return rc;
+  }
   if ((rc = x_u8 ? conv_tc_s2d_u8((const unsigned char*)xv, N, H, W, g.H1 + 1, g.W1 + 1, x_scale, x_shift, xs, st)
                  : conv_tc_s2d((const float*)xv, N, H, W, g.H1 + 1, g.W1 + 1, xs, st))) return rc;
   if ((rc = conv_lin_conv1_fwd(xs, N, g.H1, g.W1, wp1, params[P_B1], y1b, st))) return rc;
@@ -184,8 +187,12 @@ static int enc_bwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
     return rc;
   if ((rc = colsum_f32(N, 1, dtau, 1, grads[P_TEMP], accumulate, st))) return rc;
   // ---- per layer: weight + bias gradient (one kernel), then the data gradient gated by the input's ReLU
-  if ((rc = conv_tc_pack(3, params[P_W3], wd3, st))) return rc;
-  if ((rc = conv_tc_pack(5, params[P_W2], wd2, st))) return rc;
+  {
+    const int modes[2] = {3, 5};
+    const float* Ws[2] = {params[P_W3], params[P_W2]};
+    void* Wps[2] = {wd3, wd2};
+    if ((rc = conv_tc_pack_multi(2, modes, Ws, Wps, st))) return rc;
+  }
   if ((rc = conv_tc_wgrad(3, dy3b, y2, N, g.H2, g.W2, g.H3, g.W3, beta0, grads[P_W3], grads[P_B3], skws, kSplitKWs, st))) return rc;
   if ((rc = conv_tc_conv3_dgrad(dy3b, N, g.H2, g.W2, g.H3, g.W3, wd3, y2, dy2b, st))) return rc;
   if ((rc = conv_tc_wgrad(2, dy2b, y1, N, g.H1, g.W1, g.H2, g.W2, beta0, grads[P_W2], grads[P_B2], skws, kSplitKWs, st))) return rc;

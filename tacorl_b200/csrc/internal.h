@@ -77,6 +77,7 @@ static inline int gemm_any(int prec, const GemmArgs& g, float* ws, size_t ws_byt
 
 // ---- implicit-GEMM convolutions (conv_tc.cu); all activations NHWC bf16
 int conv_tc_pack(int mode, const float* W, void* Wp, cudaStream_t st);
+int conv_tc_pack_multi(int n, const int* modes, const float* const* Ws, void* const* Wps, cudaStream_t st);
 int conv_tc_s2d(const float* x, int N, int H, int W, int SH, int SW, void* xs, cudaStream_t st);
 int conv_tc_s2d_u8(const unsigned char* x, int N, int H, int W, int SH, int SW, float scale, float shift, void* xs,
                    cudaStream_t st);
