@@ -265,7 +265,10 @@ template <int G, typename OutT>
 __global__ void __launch_bounds__(256)
 softargmax_bwd_v4_kernel(const float* __restrict__ y, int P, int OW, int C, const float* __restrict__ temperature,
                          const float* __restrict__ feat, const float* __restrict__ smax, const float* __restrict__ ssum,
-                         const float* __restrict__ dfeat, OutT* __restrict__ dy, float* __restrict__ dtau_part) {
+                         const float* __restrict__ dfeat, OutT* __restrict__ dy, float* __restrict__ dtau_part,
+                         int out_w, int out_p) {
+  // out_w / out_p: row pitch (pixels) and pixels per frame of dy; larger than OW / P = dy is written into a frame with a
+  // zero right / bottom margin (the pitch of conv3's input: linear-shift weight gradient, conv_tc.cu)
   __shared__ float red[32];
   extern __shared__ float sm[];   // (col, row) coordinate of every position
   const int C4 = C >> 2;
@@ -273,10 +276,17 @@ softargmax_bwd_v4_kernel(const float* __restrict__ y, int P, int OW, int C, cons
   const long long n = blockIdx.x;
   const float tau = __ldg(temperature), inv_t = 1.f / tau;
   const float4* yp = reinterpret_cast<const float4*>(y + n * (long long)P * C);
-  OutT* dyp = dy + n * (long long)P * C;
+  OutT* dyp = dy + n * (long long)out_p * C;
   float2* xy = reinterpret_cast<float2*>(sm);
   for (int p = g * C4 + cq; p < P; p += G * C4) xy[p] = make_float2((float)(p % OW), (float)(p / OW));
   __syncthreads();
+  if (out_p != P) {                                      // zero margin
+    const int OH = P / OW;
+    for (int pp = g; pp < out_p; pp += G) {
+      const int yy = pp / out_w, xx = pp - yy * out_w;
+      if (yy >= OH || xx >= OW) sa_store4(dyp + (long long)pp * C + 4 * cq, 0.f, 0.f, 0.f, 0.f);
+    }
+  }
   float gx[4], gy[4], M[4], invS[4], dotg[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -309,7 +319,8 @@ softargmax_bwd_v4_kernel(const float* __restrict__ y, int P, int OW, int C, cons
         dt += dz * in[k];
         o[k] = in[k] > 0.f ? dz * inv_t : 0.f;
       }
-      sa_store4(dyp + (long long)p * C + 4 * cq, o[0], o[1], o[2], o[3]);
+      const int po = out_w == OW ? p : (int)q.y * out_w + (int)q.x;
+      sa_store4(dyp + (long long)po * C + 4 * cq, o[0], o[1], o[2], o[3]);
     }
   }
   dt = warp_sum(dt);
@@ -414,7 +425,8 @@ int softargmax_bwd_f32(const float* y, int N, int OH, int OW, int C, const float
   TACORL_REQUIRE((size_t)OH * OW * 8 <= 40 * 1024, "softargmax bwd: feature map of %d x %d positions is too large", OH, OW);
   if (sa_v4_ok(C, y, dy, 4)) {
     softargmax_bwd_v4_kernel<16, float><<<N, dim3(C / 4, 16), (size_t)OH * OW * 8, st>>>(y, OH * OW, OW, C, temperature, feat,
-                                                                                       smax, ssum, dfeat, dy, dtau_part);
+                                                                                       smax, ssum, dfeat, dy, dtau_part,
+                                                                                       OW, OH * OW);
     TACORL_LAUNCH_CHECK();
     return 0;
   }
@@ -428,16 +440,18 @@ int softargmax_bwd_f32(const float* y, int N, int OH, int OW, int C, const float
 // same, gradient written as bf16 (operand of the tensor-core conv3 weight / data gradient kernels)
 int softargmax_bwd_bf16out(const float* y, int N, int OH, int OW, int C, const float* temperature,
                            const float* feat, const float* smax, const float* ssum, const float* dfeat,
-                           void* dy_bf16, float* dtau_part, cudaStream_t st) {
+                           void* dy_bf16, float* dtau_part, int pad_h, int pad_w, cudaStream_t st) {
   if (N == 0) return 0;
   constexpr int G = 16;
   TACORL_REQUIRE((size_t)OH * OW * 8 <= 40 * 1024, "softargmax bwd: feature map of %d x %d positions is too large", OH, OW);
   if (sa_v4_ok(C, y, dy_bf16, 2)) {
     softargmax_bwd_v4_kernel<G, __nv_bfloat16><<<N, dim3(C / 4, G), (size_t)OH * OW * 8, st>>>(
-        y, OH * OW, OW, C, temperature, feat, smax, ssum, dfeat, (__nv_bfloat16*)dy_bf16, dtau_part);
+        y, OH * OW, OW, C, temperature, feat, smax, ssum, dfeat, (__nv_bfloat16*)dy_bf16, dtau_part, OW + pad_w,
+        (OH + pad_h) * (OW + pad_w));
     TACORL_LAUNCH_CHECK();
     return 0;
   }
+  TACORL_REQUIRE(pad_h == 0 && pad_w == 0, "softargmax bwd: padded gradient layout needs the 4-channel kernel");
   TACORL_REQUIRE(C * G <= 1024 && (C * G) % 32 == 0, "softargmax bwd: unsupported channel count");
   softargmax_bwd_kernel<G, __nv_bfloat16><<<N, dim3(C, G), (size_t)OH * OW * 8, st>>>(
       y, OH * OW, OW, C, temperature, feat, smax, ssum, dfeat, (__nv_bfloat16*)dy_bf16, dtau_part);

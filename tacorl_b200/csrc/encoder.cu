@@ -57,7 +57,7 @@ size_t tacorl_lmp_encoder_ws_bytes(int N, int H, int W, int hidden, int latent, 
   (void)latent;
   // implicit-GEMM tensor-core path: no col matrix, whole-batch bf16 gradient / s2d buffers instead
   size_t tc = (size_t)N * ((size_t)(g.H1 + 1) * (g.W1 + 1) * 128 + g.P1 * 64 + g.P2 * 128 + g.P3 * 64 * 6 +
-                           (g.P1 * 64 + g.P2 * 128) + (128 + 64 + 64 + hidden + 128 + hidden) * 4 + 4096) +
+                           (g.P1 * 64 + g.P2 * 128) + (size_t)(g.P2 - g.P3) * 128 + (128 + 64 + 64 + hidden + 128 + hidden) * 4 + 4096) +
               kSplitKWs + (32 << 20);
   size_t legacy = fixed + per_frame * chunk + (size_t)N * 3 * H * W * 4 + 4096;   // (+ fp32 copy of uint8 frames)
   return tc > legacy ? tc : legacy;
@@ -155,7 +155,10 @@ static int enc_bwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
   float* dtau = ar.take<float>(N);
   float* csws = ar.take<float>(592 * 64);
   float* skws = ar.take<float>(kSplitKWs / 4);
-  __nv_bfloat16* dy3b = ar.take<__nv_bfloat16>((size_t)N * g.P3 * 64);
+  // conv3's gradient lives at y2's pitch with a zero 2-pixel margin when the linear-shift weight gradient covers the shape
+  const bool lin3 = 128 + 2 * g.W2 + 3 <= 256 - 7;
+  const int pad3 = lin3 ? 2 : 0;
+  __nv_bfloat16* dy3b = ar.take<__nv_bfloat16>((size_t)N * (lin3 ? g.P2 : g.P3) * 64);
   __nv_bfloat16* dy2b = ar.take<__nv_bfloat16>((size_t)N * g.P2 * 64);
   __nv_bfloat16* dy1b = ar.take<__nv_bfloat16>((size_t)N * g.P1 * 32);
   __nv_bfloat16* xs = xs_saved ? (__nv_bfloat16*)xs_saved : ar.take<__nv_bfloat16>((size_t)N * (g.H1 + 1) * (g.W1 + 1) * 64);
@@ -183,7 +186,7 @@ static int enc_bwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
   if ((rc = gemm_tc_from_f32(b, skws, kSplitKWs, st))) return rc;
   }
   // ---- soft-argmax backward (applies conv3's ReLU mask, writes the bf16 operand directly) and temperature gradient
-  if ((rc = softargmax_bwd_bf16out(y3, N, g.H3, g.W3, 64, params[P_TEMP], feat, smax, ssum, dfeat, dy3b, dtau, st)))
+  if ((rc = softargmax_bwd_bf16out(y3, N, g.H3, g.W3, 64, params[P_TEMP], feat, smax, ssum, dfeat, dy3b, dtau, pad3, pad3, st)))
     return rc;
   if ((rc = colsum_f32(N, 1, dtau, 1, grads[P_TEMP], accumulate, st))) return rc;
   // ---- per layer: weight + bias gradient (one kernel), then the data gradient gated by the input's ReLU
@@ -193,8 +196,17 @@ static int enc_bwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
     void* Wps[2] = {wd3, wd2};
     if ((rc = conv_tc_pack_multi(2, modes, Ws, Wps, st))) return rc;
   }
-  if ((rc = conv_tc_wgrad(3, dy3b, y2, N, g.H2, g.W2, g.H3, g.W3, beta0, grads[P_W3], grads[P_B3], skws, kSplitKWs, st))) return rc;
-  if ((rc = conv_tc_conv3_dgrad(dy3b, N, g.H2, g.W2, g.H3, g.W3, wd3, y2, dy2b, st))) return rc;
+  if (lin3) {
+    if ((rc = conv_lin_conv3_wgrad(dy3b, y2, N, g.H2, g.W2, beta0, grads[P_W3], grads[P_B3], skws, kSplitKWs, st))) {
+      if (rc == 1) set_last_error("lmp_encoder_bwd: linear-shift weight gradient refused a shape it was selected for");
+      return rc;
+    }
+    // the margin of the padded gradient reads as zeros, exactly like the out-of-image taps TMA zero-fills
+    if ((rc = conv_tc_conv3_dgrad(dy3b, N, g.H2, g.W2, g.H2, g.W2, wd3, y2, dy2b, st))) return rc;
+  } else {
+    if ((rc = conv_tc_wgrad(3, dy3b, y2, N, g.H2, g.W2, g.H3, g.W3, beta0, grads[P_W3], grads[P_B3], skws, kSplitKWs, st))) return rc;
+    if ((rc = conv_tc_conv3_dgrad(dy3b, N, g.H2, g.W2, g.H3, g.W3, wd3, y2, dy2b, st))) return rc;
+  }
   if ((rc = conv_tc_wgrad(2, dy2b, y1, N, g.H1, g.W1, g.H2, g.W2, beta0, grads[P_W2], grads[P_B2], skws, kSplitKWs, st))) return rc;
   if ((rc = conv_dgrad2_fused(dy2b, N, g.H1, g.W1, g.H2, g.W2, wd2, y1, dy1b, st))) return rc;
   // ---- conv1 (weight gradient only; images receive no gradient)

@@ -77,6 +77,8 @@ static inline int gemm_any(int prec, const GemmArgs& g, float* ws, size_t ws_byt
 
 // ---- implicit-GEMM convolutions (conv_tc.cu); all activations NHWC bf16
 int conv_tc_pack(int mode, const float* W, void* Wp, cudaStream_t st);
+int conv_lin_conv3_wgrad(const void* dy3p, const void* y2b, int N, int H2, int W2, float beta, float* dW, float* db,
+                         float* ws, size_t ws_bytes, cudaStream_t st);
 int conv_tc_pack_multi(int n, const int* modes, const float* const* Ws, void* const* Wps, cudaStream_t st);
 int conv_tc_s2d(const float* x, int N, int H, int W, int SH, int SW, void* xs, cudaStream_t st);
 int conv_tc_s2d_u8(const unsigned char* x, int N, int H, int W, int SH, int SW, float scale, float shift, void* xs,
@@ -99,7 +101,7 @@ int conv_tc_conv2_dgrad(const void* dy2b, int N, int H1, int W1, int H2, int W2,
                         const void* y1b, void* dy1b, cudaStream_t st);
 int softargmax_bwd_bf16out(const float* y, int N, int OH, int OW, int C, const float* temperature, const float* feat,
                            const float* smax, const float* ssum, const float* dfeat, void* dy_bf16, float* dtau_part,
-                           cudaStream_t st);
+                           int pad_h, int pad_w, cudaStream_t st);
 int conv_tc_wgrad(int layer, const void* dyb, const void* src, int N, int SH, int SW, int RA, int RB, float beta,
                   float* dW, float* db, float* ws, size_t ws_bytes, cudaStream_t st);
 

@@ -97,6 +97,11 @@ def test_implicit_gemm_convs_match_torch(N, H, W):
     got = _run(6, dy3, y2b, None, None, N, H, W, (64 * 64 * 9 + 64,))
     assert_close("conv3 wgrad", got[:-64].view(64, 64, 3, 3), w.grad, 2e-4)
     assert_close("conv3 bias grad", got[-64:], dy3n.sum((0, 2, 3)), 2e-4)
+    # linear-shift form (what the encoder runs): dy3 stored at y2's pitch with zero margins, taps = shifted descriptors
+    dy3p = F.pad(dy3, (0, 0, 0, 2, 0, 2))
+    got_lin = _run(16, dy3p, y2b, None, None, N, H, W, (64 * 64 * 9 + 64,))
+    assert_close("conv3 wgrad (linear-shift)", got_lin[:-64].view(64, 64, 3, 3), w.grad, 2e-4)
+    assert_close("conv3 bias grad (linear-shift)", got_lin[-64:], dy3n.sum((0, 2, 3)), 2e-4)
     w = W2t.double().requires_grad_(True)
     (F.conv2d(y1n, w, stride=2) * dy2n).sum().backward()
     got = _run(7, dy2b, y1b, None, None, N, H, W, (64 * 32 * 16 + 64,))
