@@ -280,11 +280,11 @@ softargmax_bwd_v4_kernel(const float* __restrict__ y, int P, int OW, int C, cons
   float2* xy = reinterpret_cast<float2*>(sm);
   for (int p = g * C4 + cq; p < P; p += G * C4) xy[p] = make_float2((float)(p % OW), (float)(p / OW));
   __syncthreads();
-  if (out_p != P) {                                      // zero margin
-    const int OH = P / OW;
-    for (int pp = g; pp < out_p; pp += G) {
-      const int yy = pp / out_w, xx = pp - yy * out_w;
-      if (yy >= OH || xx >= OW) sa_store4(dyp + (long long)pp * C + 4 * cq, 0.f, 0.f, 0.f, 0.f);
+  if (out_p != P) {                                      // zero margin: right of every row, then the rows below
+    const int OH = P / OW, padw = out_w - OW, right = OH * padw, all = right + (out_p - OH * out_w);
+    for (int m = g; m < all; m += G) {
+      const int pp = m < right ? (m / padw) * out_w + OW + m % padw : OH * out_w + (m - right);
+      sa_store4(dyp + (long long)pp * C + 4 * cq, 0.f, 0.f, 0.f, 0.f);
     }
   }
   float gx[4], gy[4], M[4], invS[4], dotg[4];
@@ -319,7 +319,7 @@ softargmax_bwd_v4_kernel(const float* __restrict__ y, int P, int OW, int C, cons
         dt += dz * in[k];
         o[k] = in[k] > 0.f ? dz * inv_t : 0.f;
       }
-      const int po = out_w == OW ? p : (int)q.y * out_w + (int)q.x;
+      const int po = p + (int)q.y * (out_w - OW);
       sa_store4(dyp + (long long)po * C + 4 * cq, o[0], o[1], o[2], o[3]);
     }
   }

@@ -1384,32 +1384,34 @@ int conv_tc_wgrad(int layer, const void* dyb, const void* src, int N, int SH, in
 
 // ==========================================================================================
 // Linear-shift weight gradient (stride-1 layers whose source and gradient tensors share one pixel-row pitch).
-//   dW[oc][c][tap] = sum_p dY[p][oc] * X[p + shift(tap)][c],   p = linear pixel row over all frames
-// holds when dY is stored at the SOURCE's row pitch with zeros at the positions that are not outputs (the right / bottom
-// margin of every frame): a zero gradient row contributes nothing, whatever source row it is paired with.  Then a K block
-// of the implicit GEMM is simply 128 consecutive pixel rows: ONE TMA box of the source (128 + max shift rows) and one of
-// dY per stage, and every tap reads the same source window through a UMMA descriptor whose start address is advanced
-// by shift(tap) rows -- no per-tap gathers (the cp.async kernel above moves each source row once per tap and each dY row
-// once per tap group through the LSU).  Both operands are MN-major (pixels = K):
-//   A = source rows, M = 128 = TWO taps: M-atom 0 = channels of row p + shift, M-atom 1 = channels of row p + shift + 1
-//       (the atom stride of the descriptor is one pixel row, 128 bytes: the atoms overlap in shared memory),
-//   B = dY rows, N = 64 output channels.
-// One fp32 accumulator (128 lanes x 64 columns) per tap pair stays in TMEM over the CTA's whole pixel range; one more
-// (A = all ones) yields the bias gradient.  Partials -> fixed-order reduction kernel.
+//   dW[oc][c][ky][kx] = sum_p dY[p][oc] * X[p + ky*W + kx][c],   p = linear pixel row over all frames
+// holds when dY is stored at the SOURCE's row pitch W with zeros at the positions that are not outputs (the right /
+// bottom margin of every frame): a zero gradient row contributes nothing, whatever source row it is paired with.  Then a
+// K block of the implicit GEMM is simply 128 consecutive pixel rows: ONE TMA box of the source and one of dY per stage,
+// and the taps are UMMA descriptors into those two windows -- no per-tap gathers (the cp.async kernel above moves each
+// source row once per tap and each dY row once per tap group through the LSU).  Both operands are MN-major (pixels = K)
+// and the M / N atoms of a descriptor OVERLAP in shared memory: their stride is a row shift, not a tile size.
+//   B = source rows, N = 192 = the three taps kx = 0, 1, 2 of one kernel row: N-atom stride = 1 pixel row (128 bytes);
+//   A = dY rows,     M = 128 = two kernel rows: M-atom 0 = dY[p], M-atom 1 = dY[p + W] (stride = W pixel rows), because
+//       sum_p dY[p + W][oc] X[p + s][c] = sum_p' dY[p'][oc] X[p' + s - W][c] is the tap one kernel row above.
+// Two MMAs per 16 pixel rows cover all nine taps: D0 (B shifted by W) = taps ky = 1 (lanes 0-63) and ky = 0 (lanes
+// 64-127), D1 (B shifted by 2 W) = taps ky = 2 (lanes 0-63).  A third, N = 16 against an all-ones tile, is the bias
+// gradient.  The pixel range starts at p = -W (TMA zero-fills negative rows) so that M-atom 1 sees every gradient row.
+// fp32 accumulators stay in TMEM over the CTA's whole pixel range; partials -> fixed-order reduction kernel.
 namespace tacorl {
 
 constexpr int WL_KB = 128;          // pixel rows per K block
-constexpr int WL_STAGES = 4;
-constexpr int WL_MAXP = 6;          // tap pairs
+constexpr int WL_MAX_STAGES = 5;
 constexpr int WL_THREADS = 192;     // warp 0: TMA, warp 1: MMA issue, warps 2-5: TMEM drain
+constexpr int WL_COLS = 192 + 192 + 16;   // accumulator columns: D0 | D1 | bias
 
 struct WgradLinGeom {
-  int nkb;                          // K blocks in total
+  int nkb;                          // K blocks in total (pixel rows -W .. rows-1)
   int kb_per_cta;
-  int npairs;
-  int shift[WL_MAXP];               // source row shift of each pair's first tap
-  int load_rows;                    // source rows per stage (WL_KB + max shift + 1, multiple of 8)
-  float* partial;                   // [ctas][npairs + 1][128][64]
+  int W;                            // row pitch of both tensors (pixels)
+  int src_rows, dy_rows;            // rows per stage window (multiples of 8)
+  int stages;                       // smem ring depth (2 .. WL_MAX_STAGES)
+  float* partial;                   // [ctas][128 lanes][WL_COLS]
 };
 
 __global__ void __launch_bounds__(WL_THREADS, 1)
@@ -1417,23 +1419,22 @@ conv_wgrad_lin_kernel(const __grid_constant__ WgradLinGeom g, const __grid_const
                       const __grid_constant__ CUtensorMap tmD) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const uint32_t src_bytes = ((uint32_t)g.load_rows * 128 + 1023) & ~1023u;
-  constexpr uint32_t DY_BYTES = WL_KB * 128;
-  const uint32_t stage_bytes = src_bytes + DY_BYTES;
+  const uint32_t src_bytes = (uint32_t)g.src_rows * 128, dy_bytes = (uint32_t)g.dy_rows * 128;   // multiples of 1024
+  const uint32_t stage_bytes = src_bytes + dy_bytes;
   const uint32_t base = cv_smem(smem);
-  const uint32_t ones_tile = base + WL_STAGES * stage_bytes;       // 2 M-atoms x 16 K rows x 128 B of bf16 1.0
-  uint64_t* bars = (uint64_t*)(smem + WL_STAGES * stage_bytes + 4096);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * WL_STAGES + 1);
+  const int WL_STAGES = g.stages;
+  const uint32_t ones_tile = base + WL_STAGES * stage_bytes;       // 16 K rows x 128 B of bf16 1.0 (N = 16 uses 32 B of each)
+  uint64_t* bars = (uint64_t*)(smem + WL_STAGES * stage_bytes + 2048);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * WL_MAX_STAGES + 1);
   auto full_bar = [&](int s) { return cv_smem(bars + s); };
-  auto empty_bar = [&](int s) { return cv_smem(bars + WL_STAGES + s); };
-  const uint32_t done_bar = cv_smem(bars + 2 * WL_STAGES);
+  auto empty_bar = [&](int s) { return cv_smem(bars + WL_MAX_STAGES + s); };
+  const uint32_t done_bar = cv_smem(bars + 2 * WL_MAX_STAGES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb_begin = blockIdx.x * g.kb_per_cta;
   const int kb_end = min(g.nkb, kb_begin + g.kb_per_cta);
   const int nkb = max(0, kb_end - kb_begin);
-  const int nacc = g.npairs + 1;
 
-  for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x)
+  for (int i = threadIdx.x; i < 2048 / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(smem + WL_STAGES * stage_bytes)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
   if (threadIdx.x == 0) {
     for (int s = 0; s < WL_STAGES; ++s) { cv_mbar_init(full_bar(s), 1); cv_mbar_init(empty_bar(s), 1); }
@@ -1457,30 +1458,34 @@ conv_wgrad_lin_kernel(const __grid_constant__ WgradLinGeom g, const __grid_const
         const int s = i % WL_STAGES;
         cv_mbar_wait(empty_bar(s), ((i / WL_STAGES) & 1) ^ 1);
         const uint32_t st = base + s * stage_bytes;
-        const int row0 = (kb_begin + i) * WL_KB;
-        cv_mbar_expect_tx(full_bar(s), (uint32_t)g.load_rows * 128 + DY_BYTES);
-        cv_tma_2d(st, &tmS, 0, row0, full_bar(s));                 // rows past the end of the tensor arrive as zeros
-        cv_tma_2d(st + src_bytes, &tmD, 0, row0, full_bar(s));
+        const int row0 = (kb_begin + i) * WL_KB;                   // source window starts at pixel row p0 + W = row0
+        cv_mbar_expect_tx(full_bar(s), src_bytes + dy_bytes);
+        cv_tma_2d(st, &tmS, 0, row0, full_bar(s));                 // rows outside the tensor arrive as zeros
+        cv_tma_2d(st + src_bytes, &tmD, 0, row0 - g.W, full_bar(s));
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && nkb > 0) {
-      // A and B MN-major (bits 15, 16), D = f32, bf16 inputs, M = 128, N = 64
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                             ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint64_t ones_desc = cv_desc(ones_tile, 2048, 1024);
+      // A and B MN-major (bits 15, 16), D = f32, bf16 inputs, M = 128
+      const uint32_t idesc_hi = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc = idesc_hi | ((uint32_t)(192 >> 3) << 17);
+      const uint32_t idesc_b = idesc_hi | ((uint32_t)(16 >> 3) << 17);
+      const uint64_t ones_desc = cv_desc(ones_tile, 128, 1024);
+      const uint32_t wrow = (uint32_t)g.W * 128;
+      const uint64_t b0 = cv_desc(base, 128, 1024);                       // N-atom stride: one pixel row
+      const uint64_t a0 = cv_desc(base + src_bytes, wrow, 1024);          // M-atom stride: one image row
       for (int i = 0; i < nkb; ++i) {
         const int s = i % WL_STAGES;
         cv_mbar_wait(full_bar(s), (i / WL_STAGES) & 1);
         cv_fence_after();
-        const uint32_t a_src = base + s * stage_bytes, b_src = a_src + src_bytes;
-#pragma unroll 1
+        const uint64_t so = (uint64_t)((s * stage_bytes) >> 4);
+#pragma unroll
         for (int k = 0; k < WL_KB / 16; ++k) {      // 16 pixel rows (2048 B) per UMMA K step
-          const uint64_t bd = cv_desc(b_src + k * 2048, 8192, 1024);
           const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
-          for (int j = 0; j < g.npairs; ++j)
-            cv_mma(tmem_base + j * 64, cv_desc(a_src + (uint32_t)(g.shift[j] + 16 * k) * 128, 128, 1024), bd, idesc, acc);
-          cv_mma(tmem_base + g.npairs * 64, ones_desc, bd, idesc, acc);
+          const uint64_t ad = a0 + so + (uint64_t)(k * 128), bd = b0 + so + (uint64_t)(k * 128);
+          cv_mma(tmem_base, ad, bd, idesc, acc);
+          cv_mma(tmem_base + 192, ad, bd + (uint64_t)(wrow >> 4), idesc, acc);
+          cv_mma(tmem_base + 384, ad, ones_desc, idesc_b, acc);
         }
         cv_commit(empty_bar(s));
       }
@@ -1489,22 +1494,19 @@ conv_wgrad_lin_kernel(const __grid_constant__ WgradLinGeom g, const __grid_const
   } else {
     const int q = warp & 3;                     // TMEM lane quarter this warp may read
     if (nkb > 0) { cv_mbar_wait(done_bar, 0); cv_fence_after(); }
-    float* P = g.partial + ((long long)blockIdx.x * nacc * 128 + (q * 32 + lane)) * 64;
-    for (int j = 0; j < nacc; ++j) {
+    float* P = g.partial + ((long long)blockIdx.x * 128 + (q * 32 + lane)) * WL_COLS;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 16) {
-        uint32_t r[16];
-        if (nkb > 0) cv_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + j * 64 + c0, r);
-        else {
+    for (int c0 = 0; c0 < WL_COLS; c0 += 16) {
+      uint32_t r[16];
+      if (nkb > 0) cv_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
+      else {
 #pragma unroll
-          for (int x = 0; x < 16; ++x) r[x] = 0;
-        }
-        float* o = P + (long long)j * 128 * 64 + c0;
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-          reinterpret_cast<float4*>(o)[x] = make_float4(__uint_as_float(r[4 * x]), __uint_as_float(r[4 * x + 1]),
-                                                        __uint_as_float(r[4 * x + 2]), __uint_as_float(r[4 * x + 3]));
+        for (int x = 0; x < 16; ++x) r[x] = 0;
       }
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+        reinterpret_cast<float4*>(P + c0)[x] = make_float4(__uint_as_float(r[4 * x]), __uint_as_float(r[4 * x + 1]),
+                                                           __uint_as_float(r[4 * x + 2]), __uint_as_float(r[4 * x + 3]));
     }
   }
   cv_fence_before();
@@ -1515,20 +1517,22 @@ conv_wgrad_lin_kernel(const __grid_constant__ WgradLinGeom g, const __grid_const
   }
 }
 
-// partial [ctas][npairs + 1][128 lanes][64 oc] -> dW3[oc][c][ky][kx] (torch layout) and db3[oc]; fixed summation order.
-// pair j: ky = j / 2, lanes 0..63 = tap kx = 2 (j % 2), lanes 64..127 = tap kx + 1 (unused for j odd); lane % 64 = c.
+// partial [ctas][128 lanes][WL_COLS] -> dW3[oc][c][ky][kx] (torch layout) and db3[oc]; fixed summation order.
+// columns 0..191: D0 (col = kx*64 + c): lanes 0-63 = tap ky 1, lanes 64-127 = tap ky 0; 192..383: D1: lanes 0-63 = ky 2;
+// column 384: bias (lanes 0-63); lane % 64 = oc.
 __global__ void conv_wgrad_lin_reduce3_kernel(int ctas, const float* __restrict__ partial, float beta,
                                               float* __restrict__ dW, float* __restrict__ db) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;       // (acc j, lane, oc), oc fastest: coalesced partial reads
-  const int total = 7 * 128 * 64;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;       // (lane, column), column fastest: coalesced partial reads
+  const int total = 128 * WL_COLS;
   if (i >= total) return;
-  const int oc = i & 63, ln = (i >> 6) & 127, j = i >> 13;
+  const int col = i % WL_COLS, ln = i / WL_COLS, oc = ln & 63;
   int idx = -1;
   float* dst = dW;
-  if (j < 6) {
-    const int ky = j >> 1, kx = 2 * (j & 1) + (ln >> 6), c = ln & 63;
-    if (kx < 3) idx = ((oc * 64 + c) * 3 + ky) * 3 + kx;
-  } else if (ln == 0 && db) {
+  if (col < 384) {
+    const int d = col >= 192, cc = col - 192 * d, kx = cc >> 6, c = cc & 63;
+    const int ky = d ? (ln < 64 ? 2 : -1) : (ln < 64 ? 1 : 0);
+    if (ky >= 0) idx = ((oc * 64 + c) * 3 + ky) * 3 + kx;
+  } else if (col == 384 && ln < 64 && db) {
     idx = oc; dst = db;
   }
   if (idx < 0) return;
@@ -1539,22 +1543,25 @@ __global__ void conv_wgrad_lin_reduce3_kernel(int ctas, const float* __restrict_
 
 // conv3: y2b (N, H2, W2, 64) bf16, dy3p (N, H2, W2, 64) bf16 = the gradient w.r.t. conv3's pre-activation stored at y2's
 // pitch, zero outside the (H2-2) x (W2-2) valid outputs.  Returns 1 when the shape is outside the kernel's range.
+bool conv_lin_conv3_wgrad_ok(int W2) {
+  return cv_encode_fn() != nullptr && ((WL_KB + W2 + 2 + 7) & ~7) <= 256;
+}
+
 int conv_lin_conv3_wgrad(const void* dy3p, const void* y2b, int N, int H2, int W2, float beta, float* dW, float* db,
                          float* ws, size_t ws_bytes, cudaStream_t st) {
   if (N == 0) return 0;
   CvEncodeFn fn = cv_encode_fn();
   if (!fn) return 1;
   WgradLinGeom g = {};
-  g.npairs = 6;
-  for (int j = 0; j < 6; ++j) g.shift[j] = (j >> 1) * W2 + 2 * (j & 1);
-  const int max_shift = 2 * W2 + 2 + 1;
-  g.load_rows = (WL_KB + max_shift + 7) & ~7;
-  if (g.load_rows > 256) return 1;
+  g.W = W2;
+  g.src_rows = (WL_KB + W2 + 2 + 7) & ~7;          // window rows 0 .. 127 + W2 + 2 (D1, kx = 2)
+  g.dy_rows = (WL_KB + W2 + 7) & ~7;               // rows 0 .. 127 + W2 (M-atom 1)
+  if (g.src_rows > 256 || g.dy_rows > 256) return 1;
   const long long rows = (long long)N * H2 * W2;
-  g.nkb = (int)((rows + WL_KB - 1) / WL_KB);
+  g.nkb = (int)((rows + W2 + WL_KB - 1) / WL_KB);
   int ctas = persistent_ctas();
   if (ctas > g.nkb) ctas = g.nkb;
-  const size_t per_cta = (size_t)7 * 128 * 64 * sizeof(float);
+  const size_t per_cta = (size_t)128 * WL_COLS * sizeof(float);
   if ((size_t)ctas * per_cta > ws_bytes) ctas = (int)(ws_bytes / per_cta);
   TACORL_REQUIRE(ws && ctas >= 1, "conv_lin_wgrad: workspace too small");
   g.kb_per_cta = (g.nkb + ctas - 1) / ctas;
@@ -1565,15 +1572,18 @@ int conv_lin_conv3_wgrad(const void* dy3p, const void* y2b, int N, int H2, int W
   for (int which = 0; which < 2; ++which) {
     cuuint64_t dims[2] = {64, (cuuint64_t)rows};
     cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {64, (cuuint32_t)(which == 0 ? g.load_rows : WL_KB)};
+    cuuint32_t box[2] = {64, (cuuint32_t)(which == 0 ? g.src_rows : g.dy_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(which == 0 ? &ts : &td, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                     const_cast<void*>(which == 0 ? y2b : dy3p), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     TACORL_REQUIRE(r == CUDA_SUCCESS, "conv_lin_wgrad: cuTensorMapEncodeTiled failed (%d)", (int)r);
   }
-  const size_t src_bytes = ((size_t)g.load_rows * 128 + 1023) & ~(size_t)1023;
-  const size_t smem = WL_STAGES * (src_bytes + WL_KB * 128) + 4096 + (2 * WL_STAGES + 1) * 8 + 16 + 1024;
+  const size_t stage = (size_t)(g.src_rows + g.dy_rows) * 128;
+  const size_t fixed = 2048 + (2 * WL_MAX_STAGES + 1) * 8 + 16 + 1024;
+  g.stages = (int)std::min<size_t>(WL_MAX_STAGES, (227 * 1024 - fixed) / stage);
+  if (g.stages < 2) return 1;
+  const size_t smem = fixed + g.stages * stage;
   static size_t configured = 0;
   if (smem > configured) {
     TACORL_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1581,7 +1591,7 @@ int conv_lin_conv3_wgrad(const void* dy3p, const void* y2b, int N, int H2, int W
   }
   conv_wgrad_lin_kernel<<<ctas, WL_THREADS, smem, st>>>(g, ts, td);
   TACORL_LAUNCH_CHECK();
-  conv_wgrad_lin_reduce3_kernel<<<cdiv(7 * 128 * 64, 256), 256, 0, st>>>(ctas, ws, beta, dW, db);
+  conv_wgrad_lin_reduce3_kernel<<<cdiv(128 * WL_COLS, 256), 256, 0, st>>>(ctas, ws, beta, dW, db);
   TACORL_LAUNCH_CHECK();
   return 0;
 }

@@ -156,7 +156,7 @@ static int enc_bwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
   float* csws = ar.take<float>(592 * 64);
   float* skws = ar.take<float>(kSplitKWs / 4);
   // conv3's gradient lives at y2's pitch with a zero 2-pixel margin when the linear-shift weight gradient covers the shape
-  const bool lin3 = 128 + 2 * g.W2 + 3 <= 256 - 7;
+  const bool lin3 = conv_lin_conv3_wgrad_ok(g.W2);
   const int pad3 = lin3 ? 2 : 0;
   __nv_bfloat16* dy3b = ar.take<__nv_bfloat16>((size_t)N * (lin3 ? g.P2 : g.P3) * 64);
   __nv_bfloat16* dy2b = ar.take<__nv_bfloat16>((size_t)N * g.P2 * 64);

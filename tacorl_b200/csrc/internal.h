@@ -77,6 +77,7 @@ static inline int gemm_any(int prec, const GemmArgs& g, float* ws, size_t ws_byt
 
 // ---- implicit-GEMM convolutions (conv_tc.cu); all activations NHWC bf16
 int conv_tc_pack(int mode, const float* W, void* Wp, cudaStream_t st);
+bool conv_lin_conv3_wgrad_ok(int W2);
 int conv_lin_conv3_wgrad(const void* dy3p, const void* y2b, int N, int H2, int W2, float beta, float* dW, float* db,
                          float* ws, size_t ws_bytes, cudaStream_t st);
 int conv_tc_pack_multi(int n, const int* modes, const float* const* Ws, void* const* Wps, cudaStream_t st);
