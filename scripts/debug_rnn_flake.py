@@ -57,6 +57,10 @@ def rnn_check(bidir, last_only, use_h0, B=64, T=16, I=32, H=256):
             for k, w in zip(names, ws):
                 r2[k] = rel(w.grad, P["r." + k].grad)
             print(f"     again {again}: worst {max(r2.values()):.2e}; dx vs first run {rel(xd.grad, first_dx.cpu()):.2e}")
+        # the ReLU kink: units whose sign differs between the device's fp32 forward and the fp64 reference
+        flips = ((got.detach().cpu() > 0) != (want.detach() > 0)).sum().item()
+        tiny = (want.detach().abs() < 1e-6).sum().item()
+        print(f"     ReLU gates that differ (top layer output): {flips}; |reference output| < 1e-6 but nonzero-able: {tiny}")
         d = (first_dx - xd.grad).abs()
         nz = (d > 1e-5 * first_dx.abs().max()).nonzero()
         print("     differing dx elements:", nz.shape[0], "of", d.numel(), "first few", nz[:5].tolist(), "prec", ops.get_precision())
