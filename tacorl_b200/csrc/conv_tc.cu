@@ -513,6 +513,7 @@ struct Dgrad2Geom {
   int H1, W1, H2, W2;               // dy1 / y1 grid, dy2 grid
   int RA, RB;                       // pair-block grid: RA = ceil(H1 / 2), RB = ceil(W1 / 2)
   int tiles_x, tiles_y, num_tiles;
+  int OHp, OWp;                     // frame height / row pitch (pixels) of dy1: H1 / W1, or larger (zero margin written elsewhere)
 };
 
 __global__ void __launch_bounds__(CV_THREADS, 1)
@@ -608,13 +609,14 @@ conv_dgrad2_kernel(const __grid_constant__ Dgrad2Geom g, const __grid_constant__
       const bool row_ok = al < DG_PH - 1 && bl < DG_PW - 1 && a < g.RA && b < g.RB;
       // ReLU gates of the 2 x 2 output block (global latency): all in flight before blocking on the accumulator
       bool okc[4];
-      long long opixc[4];
+      long long opixc[4], dpixc[4];
       uint4 gate[4][4];
 #pragma unroll
       for (int cls = 0; cls < 4; ++cls) {
         const int oy = 2 * a + (cls >> 1), ox = 2 * b + (cls & 1);
         okc[cls] = row_ok && oy < g.H1 && ox < g.W1;
         opixc[cls] = okc[cls] ? ((long long)n * g.H1 + oy) * g.W1 + ox : 0;
+        dpixc[cls] = okc[cls] ? ((long long)n * g.OHp + oy) * g.OWp + ox : 0;
         const uint4* gp = reinterpret_cast<const uint4*>(y1 + opixc[cls] * 32);   // (pixel 0 of the tensor when masked)
 #pragma unroll
         for (int j = 0; j < 4; ++j) gate[cls][j] = __ldg(gp + j);
@@ -624,7 +626,7 @@ conv_dgrad2_kernel(const __grid_constant__ Dgrad2Geom g, const __grid_constant__
 #pragma unroll
       for (int cls = 0; cls < 4; ++cls) {
         const bool ok = okc[cls];
-        const long long opix = opixc[cls];
+        const long long opix = dpixc[cls];
         uint32_t r2[2][16];                  // both 16-column halves of the class in flight before the one wait
         cv_ld16_nowait(tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16) + cls * 32, r2[0]);
         cv_ld16_nowait(tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16) + cls * 32 + 16, r2[1]);
@@ -841,8 +843,22 @@ int conv_lin_conv1_fwd(const void* xs, int N, int H1, int W1, const void* wp, co
 }
 
 // conv2 data gradient, all four stride-parity classes in one kernel (weights packed with mode 5)
+// zero the right / bottom margin of an NHWC tensor stored in frames of Hp x Wp pixels whose valid part is H x W
+__global__ void cv_zero_margin_kernel(uint4* __restrict__ t, int N, int H, int W, int Hp, int Wp, int chunks) {
+  const int right = H * (Wp - W), all = right + (Hp - H) * Wp;
+  const long long total = (long long)N * all * chunks;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % chunks);
+    const long long r = i / chunks;
+    const int m = (int)(r % all);
+    const long long n = r / all;
+    const int pp = m < right ? (m / (Wp - W)) * Wp + W + m % (Wp - W) : H * Wp + (m - right);
+    t[(n * Hp * Wp + pp) * chunks + c] = make_uint4(0, 0, 0, 0);
+  }
+}
+
 int conv_dgrad2_fused(const void* dy2b, int N, int H1, int W1, int H2, int W2, const void* wp5, const void* y1b, void* dy1b,
-                      cudaStream_t st) {
+                      int out_pad, cudaStream_t st) {
   if (N == 0) return 0;
   CvEncodeFn fn = cv_encode_fn();
   TACORL_REQUIRE(fn, "conv_dgrad2: cuTensorMapEncodeTiled is not available");
@@ -850,6 +866,12 @@ int conv_dgrad2_fused(const void* dy2b, int N, int H1, int W1, int H2, int W2, c
   g.H1 = H1; g.W1 = W1; g.H2 = H2; g.W2 = W2; g.RA = (H1 + 1) / 2; g.RB = (W1 + 1) / 2;
   g.tiles_x = cdiv(g.RB, DG_PW - 1); g.tiles_y = cdiv(g.RA, DG_PH - 1);
   g.num_tiles = N * g.tiles_x * g.tiles_y;
+  g.OHp = H1 + out_pad; g.OWp = W1 + out_pad;
+  if (out_pad > 0) {
+    const long long total = (long long)N * (H1 * out_pad + out_pad * g.OWp) * 4;
+    cv_zero_margin_kernel<<<(int)min((long long)592, (total + 255) / 256), 256, 0, st>>>((uint4*)dy1b, N, H1, W1, g.OHp, g.OWp, 4);
+    TACORL_LAUNCH_CHECK();
+  }
   CUtensorMap tw, ta;
   int rc = cv_weight_tmap(&tw, wp5, 4, 128);
   if (rc) return rc;
@@ -1543,6 +1565,212 @@ __global__ void conv_wgrad_lin_reduce3_kernel(int ctas, const float* __restrict_
 
 // conv3: y2b (N, H2, W2, 64) bf16, dy3p (N, H2, W2, 64) bf16 = the gradient w.r.t. conv3's pre-activation stored at y2's
 // pitch, zero outside the (H2-2) x (W2-2) valid outputs.  Returns 1 when the shape is outside the kernel's range.
+// ---- conv1 (on the space-to-depth image: 2 x 2 taps, 32 output channels).  The gradient rows are 64 bytes wide, so dY
+// is the N operand in the 64-byte swizzle (N-atom = 32 channels) and the source the M operand:
+//   A = source rows, M = 128 = the taps dx = 0, 1 (M-atom stride = 1 pixel row);
+//   B = dY rows,     N = 64 = two kernel rows: N-atom 0 = dY[p], N-atom 1 = dY[p + W] (stride = W pixel rows of 64 B).
+// With A shifted by W, ONE MMA per 16 pixel rows covers all four taps: columns 0-31 = taps dy = 1, columns 32-63 = dy = 0.
+__device__ __forceinline__ uint64_t cv_desc64(uint32_t saddr, uint32_t lbo, uint32_t sbo) {   // 64-byte swizzle
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+constexpr int WL1_COLS = 64 + 32;         // accumulator columns: D | bias
+
+__global__ void __launch_bounds__(WL_THREADS, 1)
+conv_wgrad_lin1_kernel(const __grid_constant__ WgradLinGeom g, const __grid_constant__ CUtensorMap tmS,
+                       const __grid_constant__ CUtensorMap tmD) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t src_bytes = (uint32_t)g.src_rows * 128, dy_bytes = (uint32_t)g.dy_rows * 64;   // multiples of 1024
+  const uint32_t stage_bytes = src_bytes + dy_bytes;
+  const uint32_t base = cv_smem(smem);
+  const int NST = g.stages;
+  const uint32_t ones_tile = base + NST * stage_bytes;             // 2 M-atoms x 16 K rows x 128 B of bf16 1.0
+  uint64_t* bars = (uint64_t*)(smem + NST * stage_bytes + 4096);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * WL_MAX_STAGES + 1);
+  auto full_bar = [&](int s) { return cv_smem(bars + s); };
+  auto empty_bar = [&](int s) { return cv_smem(bars + WL_MAX_STAGES + s); };
+  const uint32_t done_bar = cv_smem(bars + 2 * WL_MAX_STAGES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb_begin = blockIdx.x * g.kb_per_cta;
+  const int kb_end = min(g.nkb, kb_begin + g.kb_per_cta);
+  const int nkb = max(0, kb_end - kb_begin);
+
+  for (int i = threadIdx.x; i < 4096 / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem + NST * stage_bytes)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; ++s) { cv_mbar_init(full_bar(s), 1); cv_mbar_init(empty_bar(s), 1); }
+    cv_mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(cv_smem(tmem_slot)), "r"(128) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  cv_fence_async();
+  cv_fence_before();
+  __syncthreads();
+  cv_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % NST;
+        cv_mbar_wait(empty_bar(s), ((i / NST) & 1) ^ 1);
+        const uint32_t st = base + s * stage_bytes;
+        const int row0 = (kb_begin + i) * WL_KB;
+        cv_mbar_expect_tx(full_bar(s), src_bytes + dy_bytes);
+        cv_tma_2d(st, &tmS, 0, row0, full_bar(s));
+        cv_tma_2d(st + src_bytes, &tmD, 0, row0 - g.W, full_bar(s));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nkb > 0) {
+      const uint32_t idesc_hi = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc = idesc_hi | ((uint32_t)(64 >> 3) << 17);
+      const uint32_t idesc_b = idesc_hi | ((uint32_t)(32 >> 3) << 17);
+      const uint64_t ones_desc = cv_desc(ones_tile, 2048, 1024);
+      const uint64_t a0 = cv_desc(base, 128, 1024);                               // M-atom stride: one pixel row
+      const uint64_t b0 = cv_desc64(base + src_bytes, (uint32_t)g.W * 64, 512);   // N-atom stride: one image row
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % NST;
+        cv_mbar_wait(full_bar(s), (i / NST) & 1);
+        cv_fence_after();
+        const uint64_t so = (uint64_t)((s * stage_bytes) >> 4);
+#pragma unroll
+        for (int k = 0; k < WL_KB / 16; ++k) {      // 16 pixel rows per UMMA K step: 2048 B of the source, 1024 B of dY
+          const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+          const uint64_t ad = a0 + so + (uint64_t)(k * 128), bd = b0 + so + (uint64_t)(k * 64);
+          cv_mma(tmem_base, ad, bd, idesc, acc);
+          cv_mma(tmem_base + 64, ones_desc, bd, idesc_b, acc);
+        }
+        cv_commit(empty_bar(s));
+      }
+      cv_commit(done_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    if (nkb > 0) { cv_mbar_wait(done_bar, 0); cv_fence_after(); }
+    float* P = g.partial + ((long long)blockIdx.x * 128 + (q * 32 + lane)) * WL1_COLS;
+#pragma unroll 1
+    for (int c0 = 0; c0 < WL1_COLS; c0 += 16) {
+      uint32_t r[16];
+      if (nkb > 0) cv_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
+      else {
+#pragma unroll
+        for (int x = 0; x < 16; ++x) r[x] = 0;
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+        reinterpret_cast<float4*>(P + c0)[x] = make_float4(__uint_as_float(r[4 * x]), __uint_as_float(r[4 * x + 1]),
+                                                           __uint_as_float(r[4 * x + 2]), __uint_as_float(r[4 * x + 3]));
+    }
+  }
+  cv_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    cv_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+  }
+}
+
+// partial [ctas][128 lanes = (dx, q)][WL1_COLS] -> dW1[oc][c][ky][kx] and db1[oc].  columns 0-31: tap dy = 1, 32-63: dy = 0
+// (oc = col % 32); columns 64-95: bias (any lane; lane 0 is used).  q = (py*4 + px)*3 + c < 48, ky = 4 dy + py, kx = 4 dx + px.
+__global__ void conv_wgrad_lin_reduce1_kernel(int ctas, const float* __restrict__ partial, float beta,
+                                              float* __restrict__ dW, float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = 128 * WL1_COLS;
+  if (i >= total) return;
+  const int col = i % WL1_COLS, ln = i / WL1_COLS;
+  int idx = -1;
+  float* dst = dW;
+  if (col < 64) {
+    const int oc = col & 31, dy = col < 32 ? 1 : 0, dx = ln >> 6, q = ln & 63;
+    if (q < 48) {
+      const int c = q % 3, pp = q / 3, py = pp >> 2, px = pp & 3;
+      idx = ((oc * 3 + c) * 8 + (4 * dy + py)) * 8 + (4 * dx + px);
+    }
+  } else if (ln == 0 && db) {
+    idx = col - 64; dst = db;
+  }
+  if (idx < 0) return;
+  float s = 0.f;
+  for (int z = 0; z < ctas; ++z) s += partial[(long long)z * total + i];
+  dst[idx] = beta != 0.f ? fmaf(beta, dst[idx], s) : s;
+}
+
+bool conv_lin_conv1_wgrad_ok(int Wp) {
+  return cv_encode_fn() != nullptr && ((WL_KB + Wp + 15) & ~15) <= 256;
+}
+
+// conv1: xs (N, Hp, Wp, 64) bf16 space-to-depth image, dy1p (N, Hp, Wp, 32) bf16 = the gradient w.r.t. conv1's
+// pre-activation at the image's pitch, zero in the last row / column of every frame.  1: shape outside the kernel's range.
+int conv_lin_conv1_wgrad(const void* dy1p, const void* xs, int N, int Hp, int Wp, float beta, float* dW, float* db,
+                         float* ws, size_t ws_bytes, cudaStream_t st) {
+  if (N == 0) return 0;
+  CvEncodeFn fn = cv_encode_fn();
+  if (!fn) return 1;
+  WgradLinGeom g = {};
+  g.W = Wp;
+  g.src_rows = (WL_KB + 1 + 7) & ~7;               // window rows 0 .. 127 + 1 (tap dx = 1)
+  g.dy_rows = (WL_KB + Wp + 15) & ~15;             // rows 0 .. 127 + Wp (N-atom 1); x 64 B must be a multiple of 1024
+  if (g.dy_rows > 256) return 1;
+  const long long rows = (long long)N * Hp * Wp;
+  g.nkb = (int)((rows + Wp + WL_KB - 1) / WL_KB);
+  int ctas = persistent_ctas();
+  if (ctas > g.nkb) ctas = g.nkb;
+  const size_t per_cta = (size_t)128 * WL1_COLS * sizeof(float);
+  if ((size_t)ctas * per_cta > ws_bytes) ctas = (int)(ws_bytes / per_cta);
+  TACORL_REQUIRE(ws && ctas >= 1, "conv_lin_wgrad: workspace too small");
+  g.kb_per_cta = (g.nkb + ctas - 1) / ctas;
+  ctas = (g.nkb + g.kb_per_cta - 1) / g.kb_per_cta;
+  g.partial = ws;
+  CUtensorMap ts, td;
+  TACORL_REQUIRE((((uintptr_t)xs | (uintptr_t)dy1p) & 15) == 0, "conv_lin_wgrad: tensors must be 16-byte aligned");
+  {
+    cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, (cuuint32_t)g.src_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&ts, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(xs), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TACORL_REQUIRE(r == CUDA_SUCCESS, "conv_lin_wgrad: cuTensorMapEncodeTiled(source) failed (%d)", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {32, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {64};
+    cuuint32_t box[2] = {32, (cuuint32_t)g.dy_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&td, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(dy1p), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TACORL_REQUIRE(r == CUDA_SUCCESS, "conv_lin_wgrad: cuTensorMapEncodeTiled(gradient) failed (%d)", (int)r);
+  }
+  const size_t stage = (size_t)g.src_rows * 128 + (size_t)g.dy_rows * 64;
+  const size_t fixed = 4096 + (2 * WL_MAX_STAGES + 1) * 8 + 16 + 1024;
+  g.stages = (int)std::min<size_t>(WL_MAX_STAGES, (227 * 1024 - fixed) / stage);
+  if (g.stages < 2) return 1;
+  const size_t smem = fixed + g.stages * stage;
+  static size_t configured = 0;
+  if (smem > configured) {
+    TACORL_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_lin1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  conv_wgrad_lin1_kernel<<<ctas, WL_THREADS, smem, st>>>(g, ts, td);
+  TACORL_LAUNCH_CHECK();
+  conv_wgrad_lin_reduce1_kernel<<<cdiv(128 * WL1_COLS, 256), 256, 0, st>>>(ctas, ws, beta, dW, db);
+  TACORL_LAUNCH_CHECK();
+  return 0;
+}
+
 bool conv_lin_conv3_wgrad_ok(int W2) {
   return cv_encode_fn() != nullptr && ((WL_KB + W2 + 2 + 7) & ~7) <= 256;
 }
@@ -1675,12 +1903,19 @@ extern "C" int tacorl_conv_tc_debug(int op, const float* in0, const float* in1, 
       if ((rc = conv_tc_pack(5, Wt, wp, st))) return rc;
       if ((rc = cast_bf16_2d(in0, 64, N * P2, 64, a0, 64, st))) return rc;
       if ((rc = cast_bf16_2d(in1, 32, N * P1, 32, a1, 32, st))) return rc;
-      if ((rc = conv_dgrad2_fused(a0, N, H1, W1, H2, W2, wp, a1, ob, st))) return rc;
+      if ((rc = conv_dgrad2_fused(a0, N, H1, W1, H2, W2, wp, a1, ob, 0, st))) return rc;
       return cv_to_f32(N * P1 * 32, ob, out, st);
     case 16: {   // conv3 weight gradient, linear-shift kernel: in0 = dy3 at y2's pitch (N, H2, W2, 64), zero margins
       if ((rc = cast_bf16_2d(in0, 64, N * P2, 64, a0, 64, st))) return rc;
       if ((rc = cast_bf16_2d(in1, 64, N * P2, 64, a1, 64, st))) return rc;
       rc = conv_lin_conv3_wgrad(a0, a1, N, H2, W2, 0.f, out, out + 64 * 64 * 9, wsf, 32 << 20, st);
+      if (rc == 1) set_last_error("conv_tc_debug: linear-shift weight gradient does not cover this shape");
+      return rc;
+    }
+    case 18: {   // conv1 weight gradient, linear-shift kernel: in0 = dy1 at the s2d image's pitch (N, H1+1, W1+1, 32)
+      if ((rc = cast_bf16_2d(in0, 32, (long long)N * (H1 + 1) * (W1 + 1), 32, a0, 32, st))) return rc;
+      if ((rc = conv_tc_s2d(in1, N, H, W, H1 + 1, W1 + 1, a1, st))) return rc;
+      rc = conv_lin_conv1_wgrad(a0, a1, N, H1 + 1, W1 + 1, 0.f, out, out + 32 * 3 * 64, wsf, 32 << 20, st);
       if (rc == 1) set_last_error("conv_tc_debug: linear-shift weight gradient does not cover this shape");
       return rc;
     }

@@ -57,7 +57,7 @@ size_t tacorl_lmp_encoder_ws_bytes(int N, int H, int W, int hidden, int latent, 
   (void)latent;
   // implicit-GEMM tensor-core path: no col matrix, whole-batch bf16 gradient / s2d buffers instead
   size_t tc = (size_t)N * ((size_t)(g.H1 + 1) * (g.W1 + 1) * 128 + g.P1 * 64 + g.P2 * 128 + g.P3 * 64 * 6 +
-                           (g.P1 * 64 + g.P2 * 128) + (size_t)(g.P2 - g.P3) * 128 + (128 + 64 + 64 + hidden + 128 + hidden) * 4 + 4096) +
+                           (g.P1 * 64 + g.P2 * 128) + (size_t)(g.P2 - g.P3) * 128 + (size_t)(g.H1 + g.W1 + 1) * 64 + (128 + 64 + 64 + hidden + 128 + hidden) * 4 + 4096) +
               kSplitKWs + (32 << 20);
   size_t legacy = fixed + per_frame * chunk + (size_t)N * 3 * H * W * 4 + 4096;   // (+ fp32 copy of uint8 frames)
   return tc > legacy ? tc : legacy;
@@ -160,7 +160,9 @@ static int enc_bwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
   const int pad3 = lin3 ? 2 : 0;
   __nv_bfloat16* dy3b = ar.take<__nv_bfloat16>((size_t)N * (lin3 ? g.P2 : g.P3) * 64);
   __nv_bfloat16* dy2b = ar.take<__nv_bfloat16>((size_t)N * g.P2 * 64);
-  __nv_bfloat16* dy1b = ar.take<__nv_bfloat16>((size_t)N * g.P1 * 32);
+  // conv1's gradient at the s2d image's pitch (one zero column / row of margin) for the linear-shift weight gradient
+  const bool lin1 = conv_lin_conv1_wgrad_ok(g.W1 + 1);
+  __nv_bfloat16* dy1b = ar.take<__nv_bfloat16>((size_t)N * (lin1 ? (size_t)(g.H1 + 1) * (g.W1 + 1) : (size_t)g.P1) * 32);
   __nv_bfloat16* xs = xs_saved ? (__nv_bfloat16*)xs_saved : ar.take<__nv_bfloat16>((size_t)N * (g.H1 + 1) * (g.W1 + 1) * 64);
   TACORL_REQUIRE(wd3 && wd2 && dh4 && dfeat && dtau && csws && skws && dy3b && dy2b && dy1b && xs,
                  "lmp_encoder_bwd(bf16): workspace too small (%zu bytes)", ws_bytes);
@@ -208,11 +210,16 @@ static int enc_bwd_tc(const void* xv, int x_u8, float x_scale, float x_shift, in
     if ((rc = conv_tc_conv3_dgrad(dy3b, N, g.H2, g.W2, g.H3, g.W3, wd3, y2, dy2b, st))) return rc;
   }
   if ((rc = conv_tc_wgrad(2, dy2b, y1, N, g.H1, g.W1, g.H2, g.W2, beta0, grads[P_W2], grads[P_B2], skws, kSplitKWs, st))) return rc;
-  if ((rc = conv_dgrad2_fused(dy2b, N, g.H1, g.W1, g.H2, g.W2, wd2, y1, dy1b, st))) return rc;
+  if ((rc = conv_dgrad2_fused(dy2b, N, g.H1, g.W1, g.H2, g.W2, wd2, y1, dy1b, lin1 ? 1 : 0, st))) return rc;
   // ---- conv1 (weight gradient only; images receive no gradient)
   if (!xs_saved)
   if ((rc = x_u8 ? conv_tc_s2d_u8((const unsigned char*)xv, N, H, W, g.H1 + 1, g.W1 + 1, x_scale, x_shift, xs, st)
                  : conv_tc_s2d((const float*)xv, N, H, W, g.H1 + 1, g.W1 + 1, xs, st))) return rc;
+  if (lin1) {
+    rc = conv_lin_conv1_wgrad(dy1b, xs, N, g.H1 + 1, g.W1 + 1, beta0, grads[P_W1], grads[P_B1], skws, kSplitKWs, st);
+    if (rc == 1) set_last_error("lmp_encoder_bwd: linear-shift weight gradient refused a shape it was selected for");
+    return rc;
+  }
   return conv_tc_wgrad(1, dy1b, xs, N, g.H1 + 1, g.W1 + 1, g.H1, g.W1, beta0, grads[P_W1], grads[P_B1], skws, kSplitKWs, st);
 }
 

@@ -77,6 +77,9 @@ static inline int gemm_any(int prec, const GemmArgs& g, float* ws, size_t ws_byt
 
 // ---- implicit-GEMM convolutions (conv_tc.cu); all activations NHWC bf16
 int conv_tc_pack(int mode, const float* W, void* Wp, cudaStream_t st);
+bool conv_lin_conv1_wgrad_ok(int Wp);
+int conv_lin_conv1_wgrad(const void* dy1p, const void* xs, int N, int Hp, int Wp, float beta, float* dW, float* db,
+                         float* ws, size_t ws_bytes, cudaStream_t st);
 bool conv_lin_conv3_wgrad_ok(int W2);
 int conv_lin_conv3_wgrad(const void* dy3p, const void* y2b, int N, int H2, int W2, float beta, float* dW, float* db,
                          float* ws, size_t ws_bytes, cudaStream_t st);
@@ -95,7 +98,7 @@ int conv_lin_conv1_fwd(const void* xs, int N, int H1, int W1, const void* wp, co
 int conv_lin_conv3_fwd(const void* y2b, int N, int H2, int W2, int H3, int W3, const void* wp, const float* bias,
                        float* y3, cudaStream_t st);
 int conv_dgrad2_fused(const void* dy2b, int N, int H1, int W1, int H2, int W2, const void* wp5, const void* y1b, void* dy1b,
-                      cudaStream_t st);
+                      int out_pad, cudaStream_t st);
 int conv_tc_conv3_dgrad(const void* dy3b, int N, int H2, int W2, int H3, int W3, const void* wp, const void* y2b,
                         void* dy2b, cudaStream_t st);
 int conv_tc_conv2_dgrad(const void* dy2b, int N, int H1, int W1, int H2, int W2, const void* wp_classes,

@@ -113,3 +113,7 @@ def test_implicit_gemm_convs_match_torch(N, H, W):
     got = _run(8, dy1b, x, None, None, N, H, W, (32 * 3 * 64 + 32,))
     assert_close("conv1 wgrad", got[:-32].view(32, 3, 8, 8), w.grad, 2e-4)
     assert_close("conv1 bias grad", got[-32:], dy1b.double().sum((0, 1, 2)), 2e-4)
+    # linear-shift form: dy1 at the s2d image's pitch (one zero row / column of margin), 64-byte swizzled N operand
+    got_lin = _run(18, F.pad(dy1b, (0, 0, 0, 1, 0, 1)), x, None, None, N, H, W, (32 * 3 * 64 + 32,))
+    assert_close("conv1 wgrad (linear-shift)", got_lin[:-32].view(32, 3, 8, 8), w.grad, 2e-4)
+    assert_close("conv1 bias grad (linear-shift)", got_lin[-32:], dy1b.double().sum((0, 1, 2)), 2e-4)
