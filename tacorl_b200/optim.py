@@ -3,6 +3,8 @@ flat buffers, and the hook where the data-parallel gradient all-reduce plugs in.
 
 Replaces torch.optim.Adam / clip_grad_norm_ / soft_update_from_to at the reference call sites
 (play_lmp_for_rl.py:362-368; cql_offline_lightning.py:229-232, 519-542, 553-574)."""
+import os
+
 import torch
 
 from . import ops
@@ -102,33 +104,40 @@ class FlatAdam(torch.optim.Optimizer):
         if any(not (hi <= a or b <= lo) for a, b, _, _ in self._ranges):
             return                                     # (already handled this step)
         self.gather_grads(lo, hi)
-        if self.grad_sync is not None:
-            self.grad_sync.start(self.flat_grad[e0:e1])
         first = not self._ranges
         self._ranges.append((lo, hi, e0, e1))
-        if early:
-            dev = self.pbuf.flat.device
-            if self._early_stream is None:
-                self._early_stream = torch.cuda.Stream(device=dev)
-            stream = self._early_stream
-            # after the slice's all-reduce (own stream, so that later exchanges do not queue behind this update), or
-            # straight after the gather
-            stream.wait_stream(torch.cuda.current_stream(dev))
+        if not early:
+            self.grad_sync.start(self.flat_grad[e0:e1])
+            return
+        dev = self.pbuf.flat.device
+        if self._early_stream is None:
+            self._early_stream = torch.cuda.Stream(device=dev)
+        stream = self._early_stream
+        # the update runs on its own stream (later exchanges must not queue behind it), after the gather ...
+        stream.wait_stream(torch.cuda.current_stream(dev))
+        if first:
+            self.step_count += 1
+        # ... and, with data parallelism, bucket by bucket behind the all-reduce: the update of bucket i overlaps the
+        # exchange of bucket i + 1 (the exchange keeps its own SMs -- the NCCL channels -- and the update is HBM-bound)
+        step = getattr(self.grad_sync, "bucket", None) if (self.grad_sync is not None and self.pipeline_early) else None
+        cuts = list(range(e0, e1, step)) if step else [e0]
+        for i, c0 in enumerate(cuts):
+            c1 = cuts[i + 1] if i + 1 < len(cuts) else e1
             if self.grad_sync is not None:
+                self.grad_sync.start(self.flat_grad[c0:c1])
                 self.grad_sync.wait_on(stream)
             with torch.cuda.stream(stream):
-                if first:
-                    self.step_count += 1
                 # full-size grid: measured on the B200, a background-sized grid (one CTA per SM, tacorl_adam_step_range
                 # background = 1) does run under the encoder backward, but the convolution kernels it shares the SMs with
                 # slow down by more than the update takes (step 3.39 -> 3.57 ms; profiles/r02)
-                self._adam_range(e0, e1, increment=first, background=self.early_background)
-            self._early = True
+                self._adam_range(c0, c1, increment=first and i == 0, background=self.early_background)
+        self._early = True
 
     # update slices whose gradient is final early on a side stream (see begin_overlapped_sync).  Off by default: it assumes
     # ONE backward pass per step() (no gradient accumulation); runtime.play_lmp_step_fn, which owns that structure, enables it
     early_step = False
     early_background = False
+    pipeline_early = os.environ.get("TACORL_PIPELINE_EARLY", "1") != "0"   # bucket-wise exchange -> update pipeline
     _early = False
     _early_stream = None
 
