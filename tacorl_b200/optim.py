@@ -7,7 +7,7 @@ import os
 
 import torch
 
-from . import ops
+from . import _lib, ops
 
 _ALIGN = 64   # elements (256 B): keeps every parameter view TMA/float4 friendly
 
@@ -106,6 +106,9 @@ class FlatAdam(torch.optim.Optimizer):
         self.gather_grads(lo, hi)
         first = not self._ranges
         self._ranges.append((lo, hi, e0, e1))
+        if self.grad_sync is not None and self.sm_reserve and self.pbuf.flat.is_cuda:
+            _lib.lib().tacorl_set_sm_reserve(int(self.sm_reserve))      # until step(): kernels under the exchange
+            self._reserved = True
         if not early:
             self.grad_sync.start(self.flat_grad[e0:e1])
             return
@@ -136,6 +139,8 @@ class FlatAdam(torch.optim.Optimizer):
     # update slices whose gradient is final early on a side stream (see begin_overlapped_sync).  Off by default: it assumes
     # ONE backward pass per step() (no gradient accumulation); runtime.play_lmp_step_fn, which owns that structure, enables it
     early_step = False
+    sm_reserve = 0            # SMs the persistent kernels leave to an overlapped exchange (parallel.attach_data_parallel)
+    _reserved = False
     early_background = False
     pipeline_early = os.environ.get("TACORL_PIPELINE_EARLY", "1") != "0"   # bucket-wise exchange -> update pipeline
     _early = False
@@ -241,6 +246,9 @@ class FlatAdam(torch.optim.Optimizer):
     def step(self, closure=None, gathered=False):
         loss = closure() if closure is not None else None
         self._slots_taken.clear()
+        if self._reserved:                         # the kernels that ran under the overlapped exchange are all launched
+            _lib.lib().tacorl_set_sm_reserve(0)
+            self._reserved = False
         n, numel = len(self.param_groups[0]["params"]), self.pbuf.numel
         done = sorted(self._ranges)
         self._ranges = []

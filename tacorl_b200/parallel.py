@@ -154,9 +154,10 @@ def attach_data_parallel(optimizer, world_size, group=None, bucket_elems=16 << 2
     optimizer.grad_scale = 1.0 / world_size
     flat = getattr(optimizer, "flat_params", None)
     if world_size > 1 and flat is not None and flat.is_cuda and "TACORL_SM_RESERVE" not in os.environ:
-        # the all-reduce of the non-encoder slice overlaps the encoder backward: keep SMs free for its channels
-        from . import _lib
-        _lib.lib().tacorl_set_sm_reserve(collective_channels(world_size))
+        # the all-reduce of the non-encoder slice overlaps the encoder backward: the persistent convolution kernels
+        # launched between the start of that exchange and step() leave one SM per NCCL channel free (FlatAdam sets and
+        # clears the reserve around that window; the forward pass and everything before the exchange use all SMs)
+        optimizer.sm_reserve = collective_channels(world_size)
     return optimizer
 
 
