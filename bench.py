@@ -69,6 +69,9 @@ def parse():
     ap.add_argument("--no-tacorl", action="store_true", help="skip the TACO-RL object of the PlayLMP line")
     ap.add_argument("--no-fp32", action="store_true", help="skip the short fp32-path measurement of the PlayLMP line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timeline", default=None,
+                    help="after the measurement, record the kernel timeline of ONE more graph replay (CUPTI through "
+                         "torch.profiler, every rank replays, rank 0 writes this JSON file): for shares and gaps only")
     ap.add_argument("--no-gpu-eager", action="store_true", help="reference arm: skip the torch-eager-on-GPU timings")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-steps", type=int, default=3, help="timed steps of the cpu_baseline leg of our own line")
@@ -358,6 +361,18 @@ def measure_workload(ctx, name, precision, steps, warmup, e2e=True, sample_clock
     if clk is not None:
         res["clocks"] = clk
     trace(f"{name}/{precision}: resident {ms:.3f} ms/step")
+    if ctx.args.timeline and graphed is not None and name == ctx.args.workload:
+        from torch.profiler import ProfilerActivity, profile
+        ctx.barrier()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            graphed()
+            torch.cuda.synchronize()
+        ctx.barrier()
+        if rank == 0:
+            evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None]
+            ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in evs), key=lambda t: t[0])
+            t0 = ks[0][0] if ks else 0
+            json.dump([{"start_us": a - t0, "dur_us": b - a, "name": n[:120]} for a, b, n in ks], open(ctx.args.timeline, "w"))
 
     if e2e:
         # end-to-end: pinned host batch -> H2D every step, loss read back every step.  With the graph runner the copy

@@ -88,7 +88,11 @@ int tacorl_dp_allreduce_init(const void* id128, int rank, int world) {
   NcclUniqueId id;
   memcpy(&id, id128, sizeof(id));
   TACORL_CHECK_NCCL(g_dp.init_rank(&g_dp.comm, world, id, rank));
-  TACORL_CHECK_CUDA(cudaStreamCreateWithFlags(&g_dp.stream, cudaStreamNonBlocking));
+  // highest priority: when a collective kernel is launched while compute grids fill the GPU (the early Adam update, the
+  // encoder backward), its channel CTAs take the next SMs that free up instead of queueing behind the pending compute CTAs
+  int prio_lo = 0, prio_hi = 0;
+  TACORL_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  TACORL_CHECK_CUDA(cudaStreamCreateWithPriority(&g_dp.stream, cudaStreamNonBlocking, prio_hi));
   TACORL_CHECK_CUDA(cudaEventCreateWithFlags(&g_dp.fork, cudaEventDisableTiming));
   TACORL_CHECK_CUDA(cudaEventCreateWithFlags(&g_dp.join, cudaEventDisableTiming));
   g_dp.rank = rank; g_dp.world = world; g_dp.pending = false;

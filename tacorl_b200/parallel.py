@@ -14,6 +14,9 @@ def collective_channels(world_size):
     """NCCL channels = SMs reserved for the overlapped gradient all-reduce.  Measured (ms/step, PlayLMP bf16, 64 windows
     per GPU): N = 2 (round 1, scripts/n2_reserve_sweep.sh): 8 -> 4.30, 16 -> 3.96, 24 -> 4.01, 32 -> 4.07;
     N = 8 (round 2, scripts/n8_sweep.sh): 8 -> 3.915, 16 -> 3.905, 24 -> 3.79, 32 -> 3.79 (bf16 wire 3.77, tree 4.65)."""
+    forced = os.environ.get("TACORL_NCCL_CHANNELS")
+    if forced:
+        return int(forced)
     return 16 if world_size <= 2 else 24
 
 
