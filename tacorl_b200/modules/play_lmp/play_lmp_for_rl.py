@@ -3,6 +3,8 @@ Same ctor kwargs (config/module/play_lmp_for_rl.yaml), same training_step contra
 scalar total loss; logs the same metric names), same state_dict layout."""
 from typing import Dict, List, Optional
 
+import os
+
 import torch
 
 from ... import ops
@@ -117,6 +119,7 @@ class PlayLMP(LightningModule):
         ad_states = self._cat([emb_states[k] for k in self.action_decoder_modalities])
         latent_plan = pr_dist.rsample()
         self._sync_when_grad_of(latent_plan, [self.action_decoder])       # decoder BPTT done -> its slice can go
+        self._exchange_when_grad_of(latent_plan, [self.action_decoder])
         mean_shape = pr_dist.normal.mean.shape if isinstance(pr_dist, TanhNormal) else pr_dist.mean.shape
         dec = self.action_decoder
         if self.add_random_plan_loss or not hasattr(dec, "loss_and_act_two_plans"):
@@ -195,6 +198,27 @@ class PlayLMP(LightningModule):
 
         def hook(grad):
             opt.begin_overlapped_sync(params)
+            return None
+
+        tensor.register_hook(hook)
+
+    # Data parallel: put the action decoder's gradients (13 M of 47 M parameters) on the wire as soon as its BPTT is done;
+    # the exchange then runs under the plan recogniser's BPTT (its 16 channel CTAs fit beside the recurrence's 128) and
+    # only two of three buckets are left when the embeddings' gradient exists.  Update still at the embeddings' hook.
+    early_decoder_exchange = os.environ.get("TACORL_EARLY_DECODER_EXCHANGE", "1") != "0"
+
+    def _exchange_when_grad_of(self, tensor, modules):
+        opt = self._flat_opt
+        if (not self.early_decoder_exchange or opt is None or opt.grad_sync is None or not torch.is_grad_enabled()
+                or not tensor.requires_grad or not getattr(opt, "sm_reserve", 0) or opt.sm_reserve + 128 > 148):
+            return
+        ids = set()
+        for m in modules:
+            ids |= {id(p) for p in m.parameters()}
+        params = [p for p in opt.param_groups[0]["params"] if id(p) in ids]
+
+        def hook(grad):
+            opt.begin_exchange_only(params)
             return None
 
         tensor.register_hook(hook)

@@ -68,6 +68,7 @@ class FlatAdam(torch.optim.Optimizer):
         self._flat_version = self.pbuf.flat._version
         self._slots_taken = set()
         self._ranges = []          # (param lo, param hi, element lo, element hi) runs already exchanged / updated this step
+        self._pre = []             # runs whose exchange was started ahead of their update (begin_exchange_only)
         if self.pbuf.flat.is_cuda:
             self.shadow = torch.zeros(self.pbuf.numel, device=self.pbuf.flat.device, dtype=torch.bfloat16)
             ops.register_shadow_owner(self)
@@ -88,6 +89,24 @@ class FlatAdam(torch.optim.Optimizer):
         end = self.pbuf.offsets[hi + 1] if hi + 1 < len(ps) else self.pbuf.numel
         return lo, hi + 1, self.pbuf.offsets[lo], end
 
+    def begin_exchange_only(self, params):
+        """Data parallel only: start the all-reduce of `params` (a contiguous run whose gradients are final) now and leave
+        their update to the begin_overlapped_sync() / step() call that covers them later.  Used for a sub-network whose
+        backward finishes long before the rest (the action decoder: its exchange then hides under the plan recogniser's
+        BPTT, where only the collective's own channel SMs are taken from nobody)."""
+        r = self._range_of(params)
+        if r is None or self.grad_sync is None or not self.pbuf.flat.is_cuda:
+            return
+        lo, hi, e0, e1 = r
+        if any(not (hi <= a or b <= lo) for a, b, _, _ in self._ranges + self._pre):
+            return
+        self.gather_grads(lo, hi)
+        if self.sm_reserve:
+            _lib.lib().tacorl_set_sm_reserve(int(self.sm_reserve))
+            self._reserved = True
+        self.grad_sync.start(self.flat_grad[e0:e1])
+        self._pre.append((lo, hi, e0, e1))
+
     def begin_overlapped_sync(self, params):
         """Call when the gradients of `params` (a contiguous run: a whole sub-network) are final while backward is
         still running.  Their slice of the flat gradient is gathered; with data parallelism its all-reduce starts on
@@ -103,14 +122,29 @@ class FlatAdam(torch.optim.Optimizer):
         lo, hi, e0, e1 = r
         if any(not (hi <= a or b <= lo) for a, b, _, _ in self._ranges):
             return                                     # (already handled this step)
-        self.gather_grads(lo, hi)
+        # sub-runs whose exchange was started earlier (begin_exchange_only): gathered and on the wire already
+        pre = sorted(q for q in self._pre if lo <= q[0] and q[1] <= hi)
+        self._pre = [q for q in self._pre if q not in pre]
+        plo = lo
+        for a, b, _, _ in pre:
+            if a > plo:
+                self.gather_grads(plo, a)
+            plo = b
+        if plo < hi:
+            self.gather_grads(plo, hi)
         first = not self._ranges
         self._ranges.append((lo, hi, e0, e1))
         if self.grad_sync is not None and self.sm_reserve and self.pbuf.flat.is_cuda:
             _lib.lib().tacorl_set_sm_reserve(int(self.sm_reserve))      # until step(): kernels under the exchange
             self._reserved = True
         if not early:
-            self.grad_sync.start(self.flat_grad[e0:e1])
+            x = e0
+            for _, _, a, b in pre:
+                if a > x:
+                    self.grad_sync.start(self.flat_grad[x:a])
+                x = b
+            if x < e1:
+                self.grad_sync.start(self.flat_grad[x:e1])
             return
         dev = self.pbuf.flat.device
         if self._early_stream is None:
@@ -123,11 +157,23 @@ class FlatAdam(torch.optim.Optimizer):
         # ... and, with data parallelism, bucket by bucket behind the all-reduce: the update of bucket i overlaps the
         # exchange of bucket i + 1 (the exchange keeps its own SMs -- the NCCL channels -- and the update is HBM-bound)
         step = getattr(self.grad_sync, "bucket", None) if (self.grad_sync is not None and self.pipeline_early) else None
-        cuts = list(range(e0, e1, step)) if step else [e0]
-        for i, c0 in enumerate(cuts):
-            c1 = cuts[i + 1] if i + 1 < len(cuts) else e1
+        # pieces in update order: the pre-exchanged sub-runs first (their all-reduce is done or well under way), then the
+        # rest bucket by bucket
+        pieces, x = [], e0
+        for _, _, a, b in pre:
+            if a > x:
+                pieces.append((x, a, True))
+            x = b
+        if x < e1:
+            pieces.append((x, e1, True))
+        todo = [(a, b, False) for _, _, a, b in pre]
+        for a, b, _ in pieces:
+            cs = list(range(a, b, step)) if step else [a]
+            todo += [(c, cs[j + 1] if j + 1 < len(cs) else b, True) for j, c in enumerate(cs)]
+        for i, (c0, c1, exchange) in enumerate(todo):
             if self.grad_sync is not None:
-                self.grad_sync.start(self.flat_grad[c0:c1])
+                if exchange:
+                    self.grad_sync.start(self.flat_grad[c0:c1])
                 self.grad_sync.wait_on(stream)
             with torch.cuda.stream(stream):
                 # full-size grid: measured on the B200, a background-sized grid (one CTA per SM, tacorl_adam_step_range
@@ -139,6 +185,7 @@ class FlatAdam(torch.optim.Optimizer):
     # update slices whose gradient is final early on a side stream (see begin_overlapped_sync).  Off by default: it assumes
     # ONE backward pass per step() (no gradient accumulation); runtime.play_lmp_step_fn, which owns that structure, enables it
     early_step = False
+    _pre = ()                 # (replaced by a list in __init__) sub-runs whose exchange started before their update was scheduled
     sm_reserve = 0            # SMs the persistent kernels leave to an overlapped exchange (parallel.attach_data_parallel)
     _reserved = False
     early_background = False
@@ -171,7 +218,7 @@ class FlatAdam(torch.optim.Optimizer):
     def zero_grad(self, set_to_none=True):
         self._slots_taken.clear()
         if not self._early:
-            self._ranges = []
+            self._ranges, self._pre = [], []
         return super().zero_grad(set_to_none=set_to_none)
 
     # ---- checkpointing: torch.optim.Adam's layout ({"state": {i: {step, exp_avg, exp_avg_sq}}, "param_groups": [...]}),
@@ -251,10 +298,11 @@ class FlatAdam(torch.optim.Optimizer):
             self._reserved = False
         n, numel = len(self.param_groups[0]["params"]), self.pbuf.numel
         done = sorted(self._ranges)
-        self._ranges = []
+        left_pre = sorted(self._pre)               # exchanged ahead of time, never covered by an early update
+        self._ranges, self._pre = [], []
         # complement of the runs handled early, in parameter-index space and in element space
         rest_p, rest_e, p0, x0 = [], [], 0, 0
-        for lo, hi, e0, e1 in done:
+        for lo, hi, e0, e1 in sorted(done + left_pre):
             if lo > p0:
                 rest_p.append((p0, lo))
             if e0 > x0:
@@ -272,12 +320,12 @@ class FlatAdam(torch.optim.Optimizer):
                 self.grad_sync.start(self.flat_grad[a:b])
             self.grad_sync.finish()
         if self._early:                            # some slices were updated early: only the remaining ones are left
-            for a, b in rest_e:
+            for a, b in rest_e + [(e0, e1) for _, _, e0, e1 in left_pre]:
                 self._adam_range(a, b, increment=False)
             torch.cuda.current_stream(self.pbuf.flat.device).wait_stream(self._early_stream)
             self._early = False
             return loss
-        assert not done or self.grad_sync is not None
+        assert not (done or left_pre) or self.grad_sync is not None
         self.step_count += 1
         sq = None
         if self.max_grad_norm is not None:
