@@ -205,7 +205,10 @@ class PlayLMP(LightningModule):
     # Data parallel: put the action decoder's gradients (13 M of 47 M parameters) on the wire as soon as its BPTT is done;
     # the exchange then runs under the plan recogniser's BPTT (its 16 channel CTAs fit beside the recurrence's 128) and
     # only two of three buckets are left when the embeddings' gradient exists.  Update still at the embeddings' hook.
-    early_decoder_exchange = os.environ.get("TACORL_EARLY_DECODER_EXCHANGE", "1") != "0"
+    # Opt-in: measured at N = 2 (profiles/r02/timeline_n2_dec1.json) the early exchange does hide (187 us under the BPTT),
+    # but the remaining buckets still queue behind the early Adam grids for their SMs and the step does not get shorter
+    # (3.47 vs 3.42 ms).
+    early_decoder_exchange = os.environ.get("TACORL_EARLY_DECODER_EXCHANGE", "0") == "1"
 
     def _exchange_when_grad_of(self, tensor, modules):
         opt = self._flat_opt
