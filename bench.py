@@ -43,9 +43,9 @@ ENC_BYTES_PER_FRAME = 2 * 120_000 + 2 * (153_664 + 67_712 + 56_448)        # 795
 # read by the data- and weight-gradient kernels), y3 kept in fp32 for the soft-argmax: 2 144 000 B per frame.
 ENC_BYTES_PER_FRAME_IMPL = 2_144_000
 # dram__bytes_read.sum + dram__bytes_write.sum over every launch of one encoder forward+backward pass under ncu
-# (scripts/profile_encoder.py, 1024 frames; profiles/r02_launches_summary.md "encoder pass": 3198 MB with float frames
-# - 368 MB the uint8 s2d does not read = 2830 MB; round 1 measured 2837 MB, profiles/r01_encoder_kernels_ncu.md)
-ENC_NCU_TRAFFIC_BYTES = 2.830e9
+# (scripts/profile_encoder.py, 1024 frames; profiles/r02_launches_summary.md section 4, final state of round 2: 3255 MB with
+# float frames - 368 MB the uint8 s2d does not read = 2887 MB; round 1 measured 2837 MB, profiles/r01_encoder_kernels_ncu.md)
+ENC_NCU_TRAFFIC_BYTES = 2.887e9
 PLAYLMP_FLOP_PER_WINDOW = 8.97e9        # BiRNN recogniser, 16 x 200x200 frames
 TACORL_FLOP_PER_WINDOW = 5.89e9         # 27 encoder fwd + 6 bwd frames, PR fwd, decoder fwd+bwd, MLPs
 RNN_H = 2048
