@@ -269,6 +269,13 @@ def test_committed_ncu_launch_lists_parse_and_carry_our_kernels():
         assert k in names, k
     enc = list(rows(os.path.join(ROOT, "profiles", "r01_encoder_launches_final.csv")))
     assert any("conv_dgrad2_kernel" in n for _, n, _ in enc)
+    # round 2, final state: the two-lane persistent recurrence, the fused MLP chains and the linear-shift weight gradients
+    step2 = list(rows(os.path.join(ROOT, "profiles", "r02", "r02_step_launches_final.csv")))
+    names2 = " ".join(n for _, n, _ in step2)
+    assert all(us > 0 for _, _, us in step2) and "skinny_cluster_kernel" not in names2
+    for k in ("tacorl::rnn_wave_kernel", "tacorl::mlp_chain_fwd_kernel", "tacorl::conv_wgrad_lin_kernel",
+              "tacorl::conv_wgrad_lin1_kernel", "tacorl::softargmax_bwd_v4_kernel"):
+        assert k in names2, k
 
 
 def test_transform_oracle_matches_the_reference_classes():
