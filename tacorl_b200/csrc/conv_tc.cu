@@ -516,7 +516,10 @@ struct Dgrad2Geom {
   int OHp, OWp;                     // frame height / row pitch (pixels) of dy1: H1 / W1, or larger (zero margin written elsewhere)
 };
 
-__global__ void __launch_bounds__(CV_THREADS, 1)
+// 8 epilogue warps: the four parity classes of a tile are drained by two warps per TMEM lane quarter (classes 0-1 / 2-3);
+// the kernel is epilogue-paced (gate loads + 4 x 64 B of packed bf16 per pixel block), not MMA- or DRAM-bound
+constexpr int DG_THREADS = 64 + 8 * 32;
+__global__ void __launch_bounds__(DG_THREADS, 1)
 conv_dgrad2_kernel(const __grid_constant__ Dgrad2Geom g, const __grid_constant__ CUtensorMap tmA,
                    const __grid_constant__ CUtensorMap tmW, const __nv_bfloat16* __restrict__ y1,
                    __nv_bfloat16* __restrict__ dy1) {
@@ -538,7 +541,7 @@ conv_dgrad2_kernel(const __grid_constant__ Dgrad2Geom g, const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < DG_STAGES; ++s) { cv_mbar_init(full_bar(s), 1); cv_mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { cv_mbar_init(tfull_bar(a), 1); cv_mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { cv_mbar_init(tfull_bar(a), 1); cv_mbar_init(tempty_bar(a), 8); }
     cv_mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -598,6 +601,7 @@ conv_dgrad2_kernel(const __grid_constant__ Dgrad2Geom g, const __grid_constant__
     }
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;                    // this warp's pair of parity classes
     const int r = q * 32 + lane;
     const int al = r / DG_PW, bl = r - al * DG_PW;
     uint32_t lt = 0;
@@ -608,25 +612,26 @@ conv_dgrad2_kernel(const __grid_constant__ Dgrad2Geom g, const __grid_constant__
       const int a = ty * (DG_PH - 1) + al, b = tx * (DG_PW - 1) + bl;
       const bool row_ok = al < DG_PH - 1 && bl < DG_PW - 1 && a < g.RA && b < g.RB;
       // ReLU gates of the 2 x 2 output block (global latency): all in flight before blocking on the accumulator
-      bool okc[4];
-      long long opixc[4], dpixc[4];
-      uint4 gate[4][4];
+      bool okc[2];
+      long long opixc[2], dpixc[2];
+      uint4 gate[2][4];
 #pragma unroll
-      for (int cls = 0; cls < 4; ++cls) {
-        const int oy = 2 * a + (cls >> 1), ox = 2 * b + (cls & 1);
-        okc[cls] = row_ok && oy < g.H1 && ox < g.W1;
-        opixc[cls] = okc[cls] ? ((long long)n * g.H1 + oy) * g.W1 + ox : 0;
-        dpixc[cls] = okc[cls] ? ((long long)n * g.OHp + oy) * g.OWp + ox : 0;
-        const uint4* gp = reinterpret_cast<const uint4*>(y1 + opixc[cls] * 32);   // (pixel 0 of the tensor when masked)
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int oy = 2 * a + half, ox = 2 * b + c2;     // class = 2 * half + c2 = (py, px) = (half, c2)
+        okc[c2] = row_ok && oy < g.H1 && ox < g.W1;
+        opixc[c2] = okc[c2] ? ((long long)n * g.H1 + oy) * g.W1 + ox : 0;
+        dpixc[c2] = okc[c2] ? ((long long)n * g.OHp + oy) * g.OWp + ox : 0;
+        const uint4* gp = reinterpret_cast<const uint4*>(y1 + opixc[c2] * 32);   // (pixel 0 of the tensor when masked)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) gate[cls][j] = __ldg(gp + j);
+        for (int j = 0; j < 4; ++j) gate[c2][j] = __ldg(gp + j);
       }
       cv_mbar_wait(tfull_bar(acc), (lt >> 1) & 1);
       cv_fence_after();
 #pragma unroll
-      for (int cls = 0; cls < 4; ++cls) {
-        const bool ok = okc[cls];
-        const long long opix = dpixc[cls];
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int cls = 2 * half + c2;
+        const bool ok = okc[c2];
+        const long long opix = dpixc[c2];
         uint32_t r2[2][16];                  // both 16-column halves of the class in flight before the one wait
         cv_ld16_nowait(tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16) + cls * 32, r2[0]);
         cv_ld16_nowait(tmem_base + acc * ACC_COLS + ((uint32_t)(q * 32) << 16) + cls * 32 + 16, r2[1]);
@@ -635,7 +640,7 @@ conv_dgrad2_kernel(const __grid_constant__ Dgrad2Geom g, const __grid_constant__
         for (int c0 = 0; c0 < 32; c0 += 16) {
           const uint32_t (&rr)[16] = r2[c0 / 16];
           if (!ok) continue;
-          const uint4 g0 = gate[cls][c0 / 8], g1 = gate[cls][c0 / 8 + 1];
+          const uint4 g0 = gate[c2][c0 / 8], g1 = gate[c2][c0 / 8 + 1];
           const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&g0);
           const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&g1);
           float v[16];
@@ -893,7 +898,7 @@ int conv_dgrad2_fused(const void* dy2b, int N, int H1, int W1, int H2, int W2, c
     configured = true;
   }
   const int ctas = g.num_tiles < persistent_ctas() ? g.num_tiles : persistent_ctas();
-  conv_dgrad2_kernel<<<ctas, CV_THREADS, smem, st>>>(g, ta, tw, (const __nv_bfloat16*)y1b, (__nv_bfloat16*)dy1b);
+  conv_dgrad2_kernel<<<ctas, DG_THREADS, smem, st>>>(g, ta, tw, (const __nv_bfloat16*)y1b, (__nv_bfloat16*)dy1b);
   TACORL_LAUNCH_CHECK();
   return 0;
 }
