@@ -43,7 +43,9 @@ def nhwc(t):
     return t.permute(0, 2, 3, 1).contiguous()
 
 
-@pytest.mark.parametrize("N,H,W", [(3, 84, 84), (2, 200, 200), (2, 150, 200), (5, 128, 128), (70, 84, 84)])
+# (400, 84, 84): more tiles than CTAs in every kernel -- each persistent CTA runs several rounds of its stage / accumulator
+# rings (the single-round shapes above cannot catch a ring-protocol error)
+@pytest.mark.parametrize("N,H,W", [(3, 84, 84), (2, 200, 200), (2, 150, 200), (5, 128, 128), (70, 84, 84), (400, 84, 84)])
 def test_implicit_gemm_convs_match_torch(N, H, W):
     g = torch.Generator().manual_seed(N * 1000 + H + W)
     H1, W1, H2, W2, H3, W3 = _geom(H, W)
