@@ -376,3 +376,18 @@ def test_reference_lightning_checkpoint_resumes_in_the_b200_modules(tmp_path):
     opt2.load_state_dict(back["optimizer_states"][0])
     rp2 = [p for p in ref2.parameters() if p.requires_grad]
     assert float(opt2.state[rp2[0]]["step"]) == 2.0
+
+
+def test_launch_side_helpers_numa_and_channel_choice(monkeypatch):
+    """utils/numa.py parses sysfs cpulists and reports instead of failing when the topology is not exposed;
+    parallel.collective_channels: 16 channels up to two ranks, 24 beyond, overridable for sweeps."""
+    from tacorl_b200 import parallel
+    from tacorl_b200.utils import numa
+    assert numa._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert numa._parse_cpulist("") == set()
+    rep = numa.bind_to_gpu_node(0)                       # no GPU / no NUMA information here: a report, no exception
+    assert rep["bound"] is False and "why" in rep
+    monkeypatch.delenv("TACORL_NCCL_CHANNELS", raising=False)
+    assert parallel.collective_channels(2) == 16 and parallel.collective_channels(8) == 24
+    monkeypatch.setenv("TACORL_NCCL_CHANNELS", "32")
+    assert parallel.collective_channels(2) == 32
