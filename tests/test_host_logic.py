@@ -391,3 +391,35 @@ def test_launch_side_helpers_numa_and_channel_choice(monkeypatch):
     assert parallel.collective_channels(2) == 16 and parallel.collective_channels(8) == 24
     monkeypatch.setenv("TACORL_NCCL_CHANNELS", "32")
     assert parallel.collective_channels(2) == 32
+
+
+def test_oracle_gumbel_gripper_draws_equal_the_reference_distribution():
+    """oracle.gumbel_argmax / gripper_log_prob (the checker of the gripper kernels) against the unmodified reference
+    GumbelSoftmax (utils/distributions.py:15-58) fed the same uniforms: sample(), rsample(hard=True) -> argmax, log_prob."""
+    from oracle import ref_loader as R
+    from oracle import tacorl_oracle as O
+    if not R.reference_available():
+        pytest.skip("reference not present")
+    R.import_reference()
+    from tacorl.utils.distributions import GumbelSoftmax
+    g = torch.Generator().manual_seed(5)
+    logits = torch.randn(64, 2, generator=g) * 2
+    u = torch.rand(64, 2, generator=g)
+    dist = GumbelSoftmax(temperature=0.5, logits=logits)
+    # sample(): torch.empty(...).uniform_(0, 1)
+    orig_uniform = torch.Tensor.uniform_
+    torch.Tensor.uniform_ = lambda self, *a, **k: self.copy_(u.expand_as(self))
+    try:
+        idx = dist.sample()
+    finally:
+        torch.Tensor.uniform_ = orig_uniform
+    assert torch.equal(idx, O.gumbel_argmax(logits, u, clamp=False))
+    # rsample(hard=True): torch.rand inside ExpRelaxedCategorical.rsample, clamped by clamp_probs
+    orig_rand = torch.rand
+    torch.rand = lambda *a, **k: u.clone()
+    try:
+        hard = dist.rsample(hard=True)
+    finally:
+        torch.rand = orig_rand
+    assert torch.equal(torch.argmax(hard, dim=-1), O.gumbel_argmax(logits, u, clamp=True))
+    assert torch.allclose(dist.log_prob(idx), O.gripper_log_prob(logits, idx), atol=1e-6)
